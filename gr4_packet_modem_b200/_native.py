@@ -1,0 +1,101 @@
+"""ctypes binding of include/b200sync.h.  Fails loudly when libb200sync.so is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200sync.so")
+
+
+class SdConfig(C.Structure):
+    _fields_ = [
+        ("fft_size", C.c_uint32),
+        ("samples_per_symbol", C.c_uint32),
+        ("rrc_taps", C.c_void_p),
+        ("n_rrc_taps", C.c_uint32),
+        ("syncword", C.c_void_p),
+        ("n_syncword", C.c_uint32),
+        ("constellation", C.c_void_p),
+        ("n_constellation", C.c_uint32),
+        ("min_freq_bin", C.c_int32),
+        ("max_freq_bin", C.c_int32),
+        ("time_threshold", C.c_uint64),
+        ("power_threshold", C.c_float),
+        ("device", C.c_int32),
+    ]
+
+
+class DetectionRecord(C.Structure):
+    _fields_ = [
+        ("index", C.c_uint64),
+        ("corr_re", C.c_float),
+        ("corr_im", C.c_float),
+        ("pow", C.c_float),
+        ("pow_left", C.c_float),
+        ("pow_right", C.c_float),
+        ("pow_prev", C.c_float),
+        ("pow_next", C.c_float),
+        ("noise_power", C.c_float),
+        ("freq_bin", C.c_int32),
+        ("_pad", C.c_int32),
+    ]
+
+
+class SyncwordTag(C.Structure):
+    _fields_ = [
+        ("index", C.c_uint64),
+        ("syncword_freq", C.c_double),
+        ("syncword_amplitude", C.c_float),
+        ("syncword_phase", C.c_float),
+        ("syncword_freq_bin", C.c_int32),
+        ("syncword_noise_power", C.c_float),
+        ("syncword_esn0_db", C.c_float),
+        ("syncword_time_est", C.c_float),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C gr4_packet_modem_b200/csrc).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.b200sync_last_error.restype = C.c_char_p
+    L.b200sync_abi_version.restype = C.c_int
+    L.b200sync_launch_count.restype = C.c_uint64
+    vp, sz, psz = C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)
+    L.b200sync_sd_create.argtypes = [C.POINTER(SdConfig), C.POINTER(vp)]
+    L.b200sync_sd_destroy.argtypes = [vp]
+    L.b200sync_sd_start.argtypes = [vp]
+    L.b200sync_sd_info.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_float),
+                                   C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+    L.b200sync_sd_process.argtypes = [vp, vp, sz, vp, psz, vp, sz, psz]
+    L.b200sync_sd_detect_device.argtypes = [vp, vp, sz, vp, vp, vp, sz, psz, psz]
+    L.b200sync_sd_detect_host.argtypes = [vp, vp, sz, vp, sz, psz, psz]
+    L.b200sync_sd_shard_phase1.argtypes = [vp, vp, C.c_uint64, sz, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, sz]
+    L.b200sync_sd_shard_phase2.argtypes = [vp, C.c_uint32, vp, sz, psz]
+    L.b200sync_sd_records_to_tags.argtypes = [vp, vp, sz, vp]
+    L.b200sync_sd_copy_metric.argtypes = [vp, vp, sz]
+    for name in ("b200sync_sd_create", "b200sync_sd_start", "b200sync_sd_info", "b200sync_sd_process",
+                 "b200sync_sd_detect_device", "b200sync_sd_detect_host", "b200sync_sd_shard_phase1",
+                 "b200sync_sd_shard_phase2", "b200sync_sd_records_to_tags", "b200sync_sd_copy_metric"):
+        getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+class B200SyncError(RuntimeError):
+    """Raised where the reference block would throw gr::exception."""
+
+
+def check(rc: int) -> int:
+    if rc < 0:
+        raise B200SyncError(f"libb200sync error {rc}: {lib().b200sync_last_error().decode()}")
+    return rc

@@ -1,0 +1,207 @@
+"""Host-side mirror of the reference's block interface for the hot path, on top of the
+C ABI (include/b200sync.h).  Same setting names, defaults, lifecycle and error behaviour as
+the reference blocks so the parity tests read like the reference's own QA:
+
+    reference (C++, GR4)                                   here
+    ----------------------------------------------------   -------------------------------
+    fg.emplaceBlock<SyncwordDetection>({{"rrc_taps",..}})   SyncwordDetection(rrc_taps=..)
+    start()                       PM/syncword_detection.hpp:143    .start()
+    processBulk(inSpan, outSpan)  PM/syncword_detection.hpp:204    .process_bulk(in_span)
+    out.publishTag(map, offset)   PM/syncword_detection.hpp:321    returned tag list
+    throw gr::exception(...)                                        raises B200SyncError
+
+All arithmetic happens in libb200sync.so on the GPU; nothing here computes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native
+from ._native import B200SyncError, DetectionRecord, SdConfig, SyncwordTag, check
+
+# numpy views of the C structs of include/b200sync.h (zero-copy, no per-record Python objects)
+RECORD_DTYPE = np.dtype([("index", "<u8"), ("corr_re", "<f4"), ("corr_im", "<f4"), ("pow", "<f4"),
+                         ("pow_left", "<f4"), ("pow_right", "<f4"), ("pow_prev", "<f4"), ("pow_next", "<f4"),
+                         ("noise_power", "<f4"), ("freq_bin", "<i4"), ("_pad", "<i4")])
+TAG_DTYPE = np.dtype([("index", "<u8"), ("syncword_freq", "<f8"), ("syncword_amplitude", "<f4"),
+                      ("syncword_phase", "<f4"), ("syncword_freq_bin", "<i4"), ("syncword_noise_power", "<f4"),
+                      ("syncword_esn0_db", "<f4"), ("syncword_time_est", "<f4")])
+assert RECORD_DTYPE.itemsize == C.sizeof(DetectionRecord) and TAG_DTYPE.itemsize == C.sizeof(SyncwordTag)
+
+
+def _tag_dict(t: SyncwordTag) -> dict:
+    """The property_map published by output_tag (PM/syncword_detection.hpp:106-114)."""
+    return {
+        "syncword_amplitude": t.syncword_amplitude,
+        "syncword_phase": t.syncword_phase,
+        "syncword_freq": t.syncword_freq,
+        "syncword_freq_bin": t.syncword_freq_bin,
+        "syncword_noise_power": t.syncword_noise_power,
+        "syncword_esn0_db": t.syncword_esn0_db,
+        "syncword_time_est": t.syncword_time_est,
+    }
+
+
+class SyncwordDetection:
+    """gr::packet_modem::SyncwordDetection on the GPU (PM/syncword_detection.hpp).
+
+    Settings are the reflected members of the reference block (:131-141, :361-372)."""
+
+    def __init__(self, rrc_taps, syncword, constellation, min_freq_bin: int = 0, max_freq_bin: int = 0,
+                 time_threshold: int = 768, power_threshold: float = 9.5, fft_size: int = 2048,
+                 samples_per_symbol: int = 4, device: int = 0):
+        self.fft_size = int(fft_size)
+        self.samples_per_symbol = int(samples_per_symbol)
+        self.rrc_taps = np.ascontiguousarray(rrc_taps, dtype=np.float32)
+        self.syncword = np.ascontiguousarray(syncword, dtype=np.uint8)
+        self.constellation = np.ascontiguousarray(constellation, dtype=np.complex64)
+        self.min_freq_bin = int(min_freq_bin)
+        self.max_freq_bin = int(max_freq_bin)
+        self.time_threshold = int(time_threshold)
+        self.power_threshold = float(power_threshold)
+        self.device = int(device)
+        self._h = C.c_void_p()
+        self._items_consumed = 0
+        self.start()
+
+    # -- lifecycle ---------------------------------------------------------------------
+    def start(self) -> None:
+        """Validate settings, build the syncword spectra, reset streaming state
+        (PM/syncword_detection.hpp:143-202).  Raises where the reference throws."""
+        L = _native.lib()
+        self._destroy()
+        cfg = SdConfig(self.fft_size, self.samples_per_symbol, self.rrc_taps.ctypes.data, self.rrc_taps.size,
+                       self.syncword.ctypes.data, self.syncword.size, self.constellation.ctypes.data,
+                       self.constellation.size, self.min_freq_bin, self.max_freq_bin, self.time_threshold,
+                       self.power_threshold, self.device)
+        h = C.c_void_p()
+        check(L.b200sync_sd_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self._items_consumed = 0
+        ss, st, dl, nh = C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_uint32()
+        sc = C.c_float()
+        check(L.b200sync_sd_info(self._h, C.byref(ss), C.byref(st), C.byref(sc), C.byref(nh), C.byref(dl)))
+        self._syncword_samples_size = ss.value
+        self.stride = st.value
+        self._syncword_self_corr = sc.value
+        self.num_hypotheses = nh.value
+        self.delay = dl.value
+
+    def _destroy(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _native.lib().b200sync_sd_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    # -- processBulk -------------------------------------------------------------------
+    def process_bulk(self, in_span, want_output: bool = True, max_tags: int = 4096):
+        """One processBulk(inSpan, outSpan) call with host spans.
+
+        Returns (status, consumed, out, tags): status "OK" or "INSUFFICIENT_INPUT_ITEMS"
+        (:215-227); `out` = the published output items (input delayed by 2*time_threshold+1,
+        :318-319); tags = [(offset_in_this_chunk, absolute_output_index, property_map)]."""
+        L = _native.lib()
+        x = np.ascontiguousarray(in_span, dtype=np.complex64)
+        out = np.empty(x.size, np.complex64) if want_output else None
+        tags = (SyncwordTag * max_tags)()
+        nc, nt = C.c_size_t(0), C.c_size_t(0)
+        rc = check(L.b200sync_sd_process(self._h, x.ctypes.data, x.size, out.ctypes.data if want_output else None,
+                                         C.byref(nc), tags, max_tags, C.byref(nt)))
+        base = self._items_consumed
+        self._items_consumed += nc.value
+        res = [(int(tags[i].index - base), int(tags[i].index), _tag_dict(tags[i])) for i in range(nt.value)]
+        status = "INSUFFICIENT_INPUT_ITEMS" if rc == 1 else "OK"
+        return status, nc.value, (out[:nc.value] if want_output else None), res
+
+    def run(self, x, chunk: int = 65536, want_output: bool = False):
+        """Drive process_bulk the way the GR4 runtime does: offer a span, advance by what was
+        consumed, re-offer the remainder (GR/Block.hpp:1537-1651)."""
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        pos, outs, tags = 0, [], []
+        while x.size - pos >= self.fft_size:
+            status, c, o, t = self.process_bulk(x[pos:pos + chunk], want_output)
+            if c == 0:
+                break
+            if want_output:
+                outs.append(o)
+            tags.extend(t)
+            pos += c
+        out = np.concatenate(outs) if outs else np.zeros(0, np.complex64)
+        return pos, out, tags
+
+    # -- offline bulk entry points -----------------------------------------------------
+    def _rec_buffer(self, max_recs: int) -> np.ndarray:
+        if getattr(self, "_recbuf", None) is None or self._recbuf.size < max_recs:
+            self._recbuf = np.empty(max_recs, RECORD_DTYPE)
+        return self._recbuf
+
+    def records_to_tags(self, recs: np.ndarray) -> np.ndarray:
+        """output_tag() on raw records (b200sync_sd_records_to_tags)."""
+        recs = np.ascontiguousarray(recs, dtype=RECORD_DTYPE)
+        tags = np.empty(recs.size, TAG_DTYPE)
+        check(_native.lib().b200sync_sd_records_to_tags(self._h, recs.ctypes.data, recs.size, tags.ctypes.data))
+        return tags
+
+    def detect_device(self, d_in_ptr: int, n: int, stream_ptr: int = 0, d_out_ptr: int = 0, max_recs: int = 0):
+        """Whole device-resident capture (b200sync_sd_detect_device).  d_in_ptr: device address of
+        n complex64 samples.  Returns (consumed, records, tags)."""
+        L = _native.lib()
+        if max_recs <= 0:
+            max_recs = n // (self.time_threshold + 1) + 2
+        recs = self._rec_buffer(max_recs)
+        nr, nc = C.c_size_t(0), C.c_size_t(0)
+        check(L.b200sync_sd_detect_device(self._h, C.c_void_p(d_in_ptr), n, C.c_void_p(d_out_ptr or None),
+                                          C.c_void_p(stream_ptr or None), recs.ctypes.data, max_recs, C.byref(nr),
+                                          C.byref(nc)))
+        r = recs[:nr.value].copy()
+        return nc.value, r, self.records_to_tags(r)
+
+    def detect_host(self, x, max_recs: int = 0):
+        """Whole host capture, H2D pipelined with compute (b200sync_sd_detect_host)."""
+        L = _native.lib()
+        if isinstance(x, np.ndarray):
+            x = np.ascontiguousarray(x, dtype=np.complex64)
+            ptr, n = x.ctypes.data, x.size
+        else:  # (address, n) of e.g. a pinned torch tensor
+            ptr, n = x
+        if max_recs <= 0:
+            max_recs = n // (self.time_threshold + 1) + 2
+        recs = self._rec_buffer(max_recs)
+        nr, nc = C.c_size_t(0), C.c_size_t(0)
+        check(L.b200sync_sd_detect_host(self._h, C.c_void_p(ptr), n, recs.ctypes.data, max_recs, C.byref(nr),
+                                        C.byref(nc)))
+        r = recs[:nr.value].copy()
+        return nc.value, r, self.records_to_tags(r)
+
+    def shard_phase1(self, d_in_ptr: int, first_sample_abs: int, n_in: int, first_block: int, n_blocks: int,
+                     total_blocks: int, stream_ptr: int = 0) -> np.ndarray:
+        L = _native.lib()
+        table = np.zeros(self.time_threshold + 1, np.uint16)
+        check(L.b200sync_sd_shard_phase1(self._h, C.c_void_p(d_in_ptr), first_sample_abs, n_in, first_block,
+                                         n_blocks, total_blocks, C.c_void_p(stream_ptr or None), table.ctypes.data,
+                                         table.size))
+        return table
+
+    def shard_phase2(self, entry_offset: int, max_recs: int):
+        L = _native.lib()
+        recs = self._rec_buffer(max(max_recs, 1))
+        nr = C.c_size_t(0)
+        check(L.b200sync_sd_shard_phase2(self._h, entry_offset, recs.ctypes.data, max_recs, C.byref(nr)))
+        r = recs[:nr.value].copy()
+        return r, self.records_to_tags(r)
+
+    def metric(self, n: int) -> np.ndarray:
+        """Per-sample winning correlation power of the last offline call (verification tap)."""
+        z = np.zeros(n, np.float32)
+        check(_native.lib().b200sync_sd_copy_metric(self._h, z.ctypes.data, n))
+        return z
+
+
+__all__ = ["SyncwordDetection", "DetectionRecord", "SyncwordTag", "B200SyncError", "RECORD_DTYPE", "TAG_DTYPE"]

@@ -1,0 +1,679 @@
+// api.cu — host side of libb200sync.so: the C ABI of include/b200sync.h.
+//
+// Host responsibilities (everything else runs on the GPU):
+//   * SyncwordDetection::start()  — settings validation and construction of the modulated,
+//     frequency-shifted syncword in the reference's own float/double arithmetic
+//     (PM/syncword_detection.hpp:143-182); the spectra themselves are computed by the GPU FFT;
+//   * the delay line of the block contract when the spans live in host memory
+//     (PM/syncword_detection.hpp:318-319) — a memcpy, the samples never needed the GPU;
+//   * SyncwordDetection::output_tag() (PM/syncword_detection.hpp:56-115) on the raw
+//     per-detection records the GPU returns;
+//   * buffer management and the streaming bookkeeping (_items_consumed, pending tags).
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <new>
+#include <numbers>
+#include <string>
+#include <vector>
+
+#include "b200sync_internal.h"
+
+using namespace b200sync;
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{ 0 };
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(B200SYNC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
+    } while (0)
+
+using c64 = std::complex<float>;
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+};
+
+}  // namespace
+
+struct b200sync_sd {
+    // settings (PM/syncword_detection.hpp:131-141)
+    uint32_t fft_size = 2048, sps = 4;
+    std::vector<float> rrc_taps;
+    std::vector<uint8_t> syncword;
+    std::vector<c64> constellation;
+    int min_bin = 0, max_bin = 0;
+    uint64_t time_threshold = 768;
+    float power_threshold = 9.5f;
+    int device = 0, num_sms = 148;
+    // derived (:148, :161-164, :236)
+    uint32_t L = 0, S = 0, K = 0;
+    float self_corr = 0.0f;
+    int T = 0;
+    uint64_t delay = 0;
+    // device constants
+    DevBuf<float2> d_tw, d_hperm;
+    // peak state + detection lists
+    DevBuf<PeakState> d_state;
+    DevBuf<unsigned long long> d_det_idx;
+    DevBuf<DetectionRecord> d_recs;
+    DevBuf<unsigned char> d_ws;
+    std::vector<DetectionRecord> h_recs;
+    // streaming (process): staging windows with absolute origins
+    cudaStream_t stream = nullptr;
+    DevBuf<float2> d_x, d_xtmp;
+    long long x_base = 0, x_end = 0;
+    DevBuf<float> d_z, d_ztmp;
+    long long z_base = 0, z_end = 0;
+    uint64_t consumed = 0;  // _items_consumed
+    long long lo_next = 0;  // first undecided sample
+    std::vector<c64> carry; // last `delay` input samples (delay line)
+    std::deque<b200sync_sd_tag> pending;
+    // offline
+    DevBuf<float> d_zoff;
+    DevBuf<float2> d_xoff;
+    size_t metric_n = 0;
+    const float* metric_ptr = nullptr;
+    long long metric_base = 0;
+    // shard
+    DevBuf<uint16_t> d_table;
+    struct {
+        const float2* d_in = nullptr;
+        long long in_base = 0, z_base = 0, lo = 0, hi = 0, P_total = 0;
+        cudaStream_t st = nullptr;
+        bool valid = false;
+    } shard;
+};
+
+namespace {
+
+int reset_state(b200sync_sd* sd, cudaStream_t st) {
+    CU(sd->d_state.ensure(1));
+    CU(cudaMemsetAsync(sd->d_state.p, 0, sizeof(PeakState), st));
+    return 0;
+}
+
+int ensure_det(b200sync_sd* sd, size_t cap) {
+    if (cap < 64) cap = 64;
+    CU(sd->d_det_idx.ensure(cap));
+    CU(sd->d_recs.ensure(cap));
+    return 0;
+}
+
+// correlate blocks [b0, b0+nb), then decide peaks on [lo, hi)
+int run_chunk(b200sync_sd* sd, const float2* d_in, long long in_base, float* d_z, long long z_base,
+              long long b0, long long nb, long long lo, long long hi, float2* d_out_delayed,
+              cudaStream_t st) {
+    CU(launch_correlate(d_in, in_base, d_z, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, b0, nb,
+                        sd->d_tw.p, d_out_delayed, 0, (int)sd->delay, sd->num_sms, st));
+    if (nb > 0) g_launches += 1;
+    if (hi > lo) {
+        const long long z_end = (b0 + nb) * (long long)sd->S;
+        CU(launch_peak_phase1(d_z, z_base, z_end, lo, hi, sd->T, sd->power_threshold, sd->d_ws.p,
+                              sd->d_ws.cap, nullptr, sd->num_sms, st));
+        CU(launch_peak_phase2(lo, hi, sd->T, sd->d_ws.p, sd->d_ws.cap, -1, sd->d_state.p,
+                              sd->d_det_idx.p, (unsigned)sd->d_det_idx.cap, sd->num_sms, st));
+        g_launches += 4;
+    }
+    return 0;
+}
+
+// refine the device-side detection list into host records (sorted by index)
+int collect_records(b200sync_sd* sd, const float2* d_in, long long in_base, const float* d_z,
+                    long long z_base, cudaStream_t st, std::vector<DetectionRecord>& out) {
+    PeakState hs{};
+    CU(cudaMemcpyAsync(&hs, sd->d_state.p, sizeof(PeakState), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    out.clear();
+    if (hs.det_count == 0) return 0;
+    if (hs.det_count > sd->d_det_idx.cap)
+        return fail(B200SYNC_ENOMEM, "internal detection list overflow");
+    const unsigned n = hs.det_count;
+    CU(launch_refine(d_in, in_base, d_z, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->min_bin,
+                     sd->d_tw.p, sd->d_det_idx.p, &sd->d_state.p->det_count, n, sd->d_recs.p,
+                     sd->num_sms, st));
+    g_launches += 1;
+    out.resize(n);
+    CU(cudaMemcpyAsync(out.data(), sd->d_recs.p, sizeof(DetectionRecord) * n, cudaMemcpyDeviceToHost, st));
+    // the list has been drained
+    CU(cudaMemsetAsync(&sd->d_state.p->det_count, 0, sizeof(unsigned int), st));
+    CU(cudaStreamSynchronize(st));
+    std::sort(out.begin(), out.end(),
+              [](const DetectionRecord& a, const DetectionRecord& b) { return a.index < b.index; });
+    return 0;
+}
+
+// SyncwordDetection::output_tag — PM/syncword_detection.hpp:56-115
+b200sync_sd_tag make_tag(const b200sync_sd* sd, const DetectionRecord& r) {
+    const double Ld = static_cast<double>(sd->L);
+    const double bin_spacing = std::numbers::pi / Ld;
+    double freq = static_cast<double>(r.freq_bin) * bin_spacing;
+    float phase = std::arg(c64(r.corr_re, r.corr_im));
+    float cpow;
+    if (r.freq_bin > sd->min_bin && r.freq_bin < sd->max_bin) {
+        const double a = r.pow_left, b = r.pow, c = r.pow_right;
+        const double quad = std::clamp((c - a) / (2.0 * (2.0 * b - (a + c))), -0.5, 0.5);
+        const double dfreq = quad * bin_spacing;
+        freq += dfreq;
+        phase -= static_cast<float>(dfreq * 0.5 * Ld);
+        if (phase >= std::numbers::pi_v<float>) phase -= 2.0f * std::numbers::pi_v<float>;
+        else if (phase < -std::numbers::pi_v<float>) phase += 2.0f * std::numbers::pi_v<float>;
+        cpow = static_cast<float>(b + (c - a) * (c - a) / (16.0 * (b - 0.5 * (a + c))));
+    } else {
+        cpow = r.pow;
+    }
+    const float amp = std::sqrt(cpow) / (static_cast<float>(sd->fft_size) * sd->self_corr);
+    const float spow = amp * amp * sd->self_corr;
+    const float esn0 = 10.0f * std::log10((spow * static_cast<float>(sd->sps)) /
+                                          (r.noise_power * static_cast<float>(sd->L)));
+    const double a = r.pow_prev, b = r.pow, c = r.pow_next;
+    const float time_est =
+        static_cast<float>(std::clamp((c - a) / (2.0 * (2.0 * b - (a + c))), -0.5, 0.5));
+    b200sync_sd_tag t{};
+    t.index = r.index + sd->delay;
+    t.syncword_freq = freq;
+    t.syncword_amplitude = amp;
+    t.syncword_phase = phase;
+    t.syncword_freq_bin = r.freq_bin;
+    t.syncword_noise_power = r.noise_power;
+    t.syncword_esn0_db = esn0;
+    t.syncword_time_est = time_est;
+    return t;
+}
+
+// start(): PM/syncword_detection.hpp:143-202
+int do_start(b200sync_sd* sd) {
+    if (sd->min_bin > sd->max_bin) return fail(B200SYNC_EINVAL, "min_freq_bin is greater than max_freq_bin");
+    if (sd->syncword.empty() || sd->rrc_taps.empty() || sd->constellation.empty() || sd->sps == 0)
+        return fail(B200SYNC_EINVAL, "syncword, rrc_taps and constellation must be non-empty");
+    for (uint8_t s : sd->syncword)
+        if (s >= sd->constellation.size()) return fail(B200SYNC_EINVAL, "syncword symbol outside constellation");
+    sd->L = static_cast<uint32_t>((sd->syncword.size() - 1) * sd->sps + sd->rrc_taps.size());
+    if (sd->L > sd->fft_size) return fail(B200SYNC_EINVAL, "fft_size too small");
+    if (sd->fft_size != (uint32_t)kFft)
+        return fail(B200SYNC_EUNSUPPORTED, "only fft_size = 2048 is implemented on the GPU path");
+    sd->K = static_cast<uint32_t>(sd->max_bin - sd->min_bin + 1);
+    if (sd->K > (uint32_t)kMaxHyp) return fail(B200SYNC_EUNSUPPORTED, "too many frequency hypotheses (max 129)");
+    if (sd->time_threshold > (uint64_t)kMaxTimeThreshold)
+        return fail(B200SYNC_EUNSUPPORTED, "time_threshold > 1023 is not implemented on the GPU path");
+    if (!(sd->power_threshold > 0.0f)) return fail(B200SYNC_EINVAL, "power_threshold must be positive");
+    sd->S = sd->fft_size - sd->L + 1;
+    sd->T = static_cast<int>(sd->time_threshold);
+    sd->delay = 2 * sd->time_threshold + 1;
+
+    std::vector<c64> sw(sd->L);
+    for (size_t j = 0; j < sd->syncword.size(); ++j)
+        for (size_t k = 0; k < sd->rrc_taps.size(); ++k) {
+            const c64 cst = sd->constellation[sd->syncword[j]];
+            const float t = sd->rrc_taps[k];
+            c64& d = sw[j * sd->sps + k];
+            d = c64(d.real() + cst.real() * t, d.imag() + cst.imag() * t);
+        }
+    sd->self_corr = 0.0f;
+    for (auto x : sw) sd->self_corr += x.real() * x.real() + x.imag() * x.imag();
+
+    std::vector<c64> td(static_cast<size_t>(sd->K) * kFft, c64(0.0f, 0.0f));
+    for (int bin = sd->min_bin; bin <= sd->max_bin; ++bin) {
+        double phase = 0.0;
+        const double incr = static_cast<double>(bin) * std::numbers::pi / static_cast<double>(sd->L);
+        c64* dst = td.data() + static_cast<size_t>(bin - sd->min_bin) * kFft;
+        for (uint32_t n = 0; n < sd->L; ++n) {
+            const float er = static_cast<float>(std::cos(phase)), ei = static_cast<float>(std::sin(phase));
+            const c64 x = sw[n];
+            dst[n] = c64(x.real() * er - x.imag() * ei, x.real() * ei + x.imag() * er);
+            phase += incr;
+            if (phase >= std::numbers::pi) phase -= 2.0 * std::numbers::pi;
+            else if (phase < std::numbers::pi) phase += 2.0 * std::numbers::pi;  // sic, :179-181
+        }
+    }
+    // twiddle table Wt[j] = exp(-2 pi i j / 2048) in float (fft2048.cuh arithmetic contract)
+    std::vector<float2> tw(kFft);
+    for (int j = 0; j < kFft; ++j) {
+        const double a = 2.0 * std::numbers::pi * static_cast<double>(j) / static_cast<double>(kFft);
+        tw[j] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(-std::sin(a)));
+    }
+    CU(cudaSetDevice(sd->device));
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, sd->device));
+    if (prop.major < 10)
+        return fail(B200SYNC_EUNSUPPORTED, "libb200sync is built for sm_100a; no Blackwell device found");
+    sd->num_sms = prop.multiProcessorCount;
+    if (!sd->stream) CU(cudaStreamCreateWithFlags(&sd->stream, cudaStreamNonBlocking));
+    CU(sd->d_tw.ensure(kFft));
+    CU(sd->d_hperm.ensure(static_cast<size_t>(sd->K) * kFft));
+    DevBuf<float2> d_td;
+    CU(d_td.ensure(td.size()));
+    CU(cudaMemcpyAsync(d_td.p, td.data(), td.size() * sizeof(float2), cudaMemcpyHostToDevice, sd->stream));
+    CU(cudaMemcpyAsync(sd->d_tw.p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, sd->stream));
+    CU(launch_template_spectra(d_td.p, sd->d_hperm.p, (int)sd->K, sd->d_tw.p, sd->stream));
+    g_launches += 1;
+    // streaming state (:191-201)
+    if (int rc = reset_state(sd, sd->stream)) return rc;
+    CU(cudaStreamSynchronize(sd->stream));
+    sd->consumed = 0;
+    sd->lo_next = 0;
+    sd->x_base = sd->x_end = 0;
+    sd->z_base = sd->z_end = 0;
+    sd->carry.assign(sd->delay, c64(0.0f, 0.0f));
+    sd->pending.clear();
+    sd->shard.valid = false;
+    return 0;
+}
+
+constexpr long long kOfflineChunkBlocks = 8192;  // ~14.4 M samples per chunk: zpow chunk stays in L2
+constexpr long long kStreamStepBlocks = 4096;    // max blocks per streaming step
+
+// slide a device window down so that it starts at absolute index `keep_from`
+template <typename T>
+int slide_window(DevBuf<T>& buf, DevBuf<T>& tmp, long long& base, long long end, long long keep_from,
+                 cudaStream_t st) {
+    if (keep_from <= base) return 0;
+    if (keep_from > end) keep_from = end;
+    const size_t n = static_cast<size_t>(end - keep_from);
+    if (n > 0) {
+        CU(tmp.ensure(n));
+        CU(cudaMemcpyAsync(tmp.p, buf.p + (keep_from - base), n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(buf.p, tmp.p, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    }
+    base = keep_from;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200sync_last_error(void) { return g_last_error.c_str(); }
+int b200sync_abi_version(void) { return 1; }
+uint64_t b200sync_launch_count(void) { return g_launches.load(); }
+
+int b200sync_sd_create(const b200sync_sd_config* cfg, b200sync_sd** out) {
+    if (!cfg || !out) return fail(B200SYNC_EINVAL, "null argument");
+    *out = nullptr;
+    if (!cfg->rrc_taps || !cfg->syncword || !cfg->constellation)
+        return fail(B200SYNC_EINVAL, "null settings array");
+    b200sync_sd* sd = new (std::nothrow) b200sync_sd();
+    if (!sd) return fail(B200SYNC_ENOMEM, "out of memory");
+    sd->fft_size = cfg->fft_size ? cfg->fft_size : 2048;
+    sd->sps = cfg->samples_per_symbol ? cfg->samples_per_symbol : 4;
+    sd->rrc_taps.assign(cfg->rrc_taps, cfg->rrc_taps + cfg->n_rrc_taps);
+    sd->syncword.assign(cfg->syncword, cfg->syncword + cfg->n_syncword);
+    sd->constellation.resize(cfg->n_constellation);
+    for (uint32_t i = 0; i < cfg->n_constellation; ++i)
+        sd->constellation[i] = c64(cfg->constellation[2 * i], cfg->constellation[2 * i + 1]);
+    sd->min_bin = cfg->min_freq_bin;
+    sd->max_bin = cfg->max_freq_bin;
+    sd->time_threshold = cfg->time_threshold;
+    sd->power_threshold = cfg->power_threshold;
+    sd->device = cfg->device;
+    const int rc = do_start(sd);
+    if (rc != 0) {
+        const std::string keep = g_last_error;
+        b200sync_sd_destroy(sd);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = sd;
+    return 0;
+}
+
+void b200sync_sd_destroy(b200sync_sd* sd) {
+    if (!sd) return;
+    cudaSetDevice(sd->device);
+    if (sd->stream) {
+        cudaStreamSynchronize(sd->stream);
+        cudaStreamDestroy(sd->stream);
+    }
+    delete sd;
+}
+
+int b200sync_sd_start(b200sync_sd* sd) {
+    if (!sd) return fail(B200SYNC_EINVAL, "null context");
+    return do_start(sd);
+}
+
+int b200sync_sd_info(const b200sync_sd* sd, uint32_t* syncword_samples, uint32_t* stride, float* self_corr,
+                     uint32_t* num_hypotheses, uint64_t* delay) {
+    if (!sd) return fail(B200SYNC_EINVAL, "null context");
+    if (syncword_samples) *syncword_samples = sd->L;
+    if (stride) *stride = sd->S;
+    if (self_corr) *self_corr = sd->self_corr;
+    if (num_hypotheses) *num_hypotheses = sd->K;
+    if (delay) *delay = sd->delay;
+    return 0;
+}
+
+int b200sync_sd_records_to_tags(const b200sync_sd* sd, const b200sync_detection_record* recs, size_t n,
+                                b200sync_sd_tag* tags) {
+    if (!sd || (!recs && n) || (!tags && n)) return fail(B200SYNC_EINVAL, "null argument");
+    for (size_t i = 0; i < n; ++i) tags[i] = make_tag(sd, recs[i]);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+int b200sync_sd_process(b200sync_sd* sd, const float* in, size_t n_in, float* out, size_t* n_consumed,
+                        b200sync_sd_tag* tags, size_t max_tags, size_t* n_tags) {
+    if (!sd || !n_consumed || !n_tags || (!in && n_in)) return fail(B200SYNC_EINVAL, "null argument");
+    *n_consumed = 0;
+    *n_tags = 0;
+    if (n_in < sd->fft_size) return 1;  // INSUFFICIENT_INPUT_ITEMS, consume(0)/publish(0) (:215-227)
+    CU(cudaSetDevice(sd->device));
+    cudaStream_t st = sd->stream;
+    const long long S = sd->S, F = sd->fft_size, T = sd->T;
+    const long long nb_total = (static_cast<long long>(n_in) - F) / S + 1;
+    const long long j_total = nb_total * S;
+    const long long C = static_cast<long long>(sd->consumed);
+    const float2* hin = reinterpret_cast<const float2*>(in);
+
+    long long done_blocks = 0;
+    while (done_blocks < nb_total) {
+        const long long nb = std::min(kStreamStepBlocks, nb_total - done_blocks);
+        const long long a0 = C + done_blocks * S;            // absolute first sample of this step
+        const long long need_end = a0 + (nb - 1) * S + F;    // absolute end of samples needed
+        const long long P_prev = a0, P = a0 + nb * S;
+        // --- input window: keep every block that may still hold an undecided peak
+        long long keep_x = (sd->lo_next / S) * S;
+        if (keep_x > a0) keep_x = a0;
+        const size_t x_need = static_cast<size_t>(need_end - keep_x);
+        if (sd->d_x.cap < x_need) {
+            DevBuf<float2> nx;
+            CU(nx.ensure(x_need + static_cast<size_t>(kStreamStepBlocks * S)));
+            if (sd->x_end > keep_x && sd->d_x.p)
+                CU(cudaMemcpyAsync(nx.p, sd->d_x.p + (keep_x - sd->x_base),
+                                   sizeof(float2) * static_cast<size_t>(sd->x_end - keep_x),
+                                   cudaMemcpyDeviceToDevice, st));
+            CU(cudaStreamSynchronize(st));
+            std::swap(sd->d_x.p, nx.p);
+            std::swap(sd->d_x.cap, nx.cap);
+            sd->x_base = keep_x;
+            if (sd->x_end < keep_x) sd->x_end = keep_x;
+        } else if (static_cast<size_t>(need_end - sd->x_base) > sd->d_x.cap) {
+            if (int rc = slide_window(sd->d_x, sd->d_xtmp, sd->x_base, sd->x_end, keep_x, st)) return rc;
+            if (sd->x_end < keep_x) sd->x_end = keep_x;
+        }
+        CU(cudaMemcpyAsync(sd->d_x.p + (a0 - sd->x_base), hin + (a0 - C),
+                           sizeof(float2) * static_cast<size_t>(need_end - a0), cudaMemcpyHostToDevice, st));
+        sd->x_end = need_end;
+        // --- metric window: [P_prev - 2T - 2, P)
+        long long keep_z = P_prev - 2 * T - 2;
+        if (keep_z < 0) keep_z = 0;
+        const size_t z_need = static_cast<size_t>(P - keep_z);
+        if (sd->d_z.cap < z_need) {
+            DevBuf<float> nz;
+            CU(nz.ensure(z_need + static_cast<size_t>(kStreamStepBlocks * S)));
+            if (sd->z_end > keep_z && sd->d_z.p)
+                CU(cudaMemcpyAsync(nz.p, sd->d_z.p + (keep_z - sd->z_base),
+                                   sizeof(float) * static_cast<size_t>(sd->z_end - keep_z),
+                                   cudaMemcpyDeviceToDevice, st));
+            CU(cudaStreamSynchronize(st));
+            std::swap(sd->d_z.p, nz.p);
+            std::swap(sd->d_z.cap, nz.cap);
+            sd->z_base = keep_z;
+        } else if (static_cast<size_t>(P - sd->z_base) > sd->d_z.cap) {
+            if (int rc = slide_window(sd->d_z, sd->d_ztmp, sd->z_base, sd->z_end, keep_z, st)) return rc;
+        }
+        // --- peaks decidable after this step: [lo_next, P - T - 1)
+        const long long lo = sd->lo_next;
+        long long hi = P - T - 1;
+        if (hi < lo) hi = lo;
+        const size_t ws = peak_workspace_bytes_sms(kStreamStepBlocks * S + T + 2, sd->T, sd->num_sms);
+        CU(sd->d_ws.ensure(ws));
+        if (int rc = ensure_det(sd, static_cast<size_t>((kStreamStepBlocks * S + T + 2) / (T + 1) + 2))) return rc;
+        if (int rc = run_chunk(sd, sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, a0 / S, nb, lo, hi, nullptr, st))
+            return rc;
+        sd->z_end = P;
+        sd->lo_next = hi;
+        std::vector<DetectionRecord> recs;
+        if (int rc = collect_records(sd, sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, st, recs)) return rc;
+        for (const auto& r : recs) sd->pending.push_back(make_tag(sd, r));
+        done_blocks += nb;
+    }
+
+    // delay line (:318-319): out[i] = stream[C + i - delay]
+    const size_t D = static_cast<size_t>(sd->delay);
+    const size_t j = static_cast<size_t>(j_total);
+    const c64* cin = reinterpret_cast<const c64*>(in);
+    if (out) {
+        c64* cout = reinterpret_cast<c64*>(out);
+        const size_t from_carry = std::min(D, j);
+        std::memcpy(cout, sd->carry.data(), from_carry * sizeof(c64));
+        if (j > D) std::memcpy(cout + D, cin, (j - D) * sizeof(c64));
+    }
+    if (j >= D) {
+        std::memcpy(sd->carry.data(), cin + (j - D), D * sizeof(c64));
+    } else {
+        std::memmove(sd->carry.data(), sd->carry.data() + j, (D - j) * sizeof(c64));
+        std::memcpy(sd->carry.data() + (D - j), cin, j * sizeof(c64));
+    }
+    sd->consumed += j;
+    *n_consumed = j;
+    // tags whose output index has now been published (:320-325)
+    size_t nt = 0;
+    while (!sd->pending.empty() && sd->pending.front().index < sd->consumed) {
+        if (nt >= max_tags) return fail(B200SYNC_ENOMEM, "tag buffer too small");
+        tags[nt++] = sd->pending.front();
+        sd->pending.pop_front();
+    }
+    *n_tags = nt;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+static int detect_resident(b200sync_sd* sd, const float2* d_in, size_t n, float2* d_out_delayed,
+                           cudaStream_t st, cudaEvent_t* chunk_ready, long long chunk_samples,
+                           b200sync_detection_record* recs, size_t max_recs, size_t* n_recs,
+                           size_t* n_consumed) {
+    const long long S = sd->S, F = sd->fft_size, T = sd->T;
+    *n_recs = 0;
+    *n_consumed = 0;
+    if (n < static_cast<size_t>(F)) return 0;
+    const long long nb_total = (static_cast<long long>(n) - F) / S + 1;
+    const long long P = nb_total * S;
+    CU(sd->d_zoff.ensure(static_cast<size_t>(P) + 64));
+    const long long chunk_range = kOfflineChunkBlocks * S + T + 2;
+    CU(sd->d_ws.ensure(peak_workspace_bytes_sms(chunk_range, sd->T, sd->num_sms)));
+    if (int rc = ensure_det(sd, static_cast<size_t>(P / (T + 1) + 2))) return rc;
+    if (int rc = reset_state(sd, st)) return rc;
+    if (d_out_delayed) {
+        const size_t zeros = std::min<size_t>(sd->delay, n);
+        CU(cudaMemsetAsync(d_out_delayed, 0, zeros * sizeof(float2), st));
+    }
+    long long lo = 0;
+    for (long long b0 = 0; b0 < nb_total; b0 += kOfflineChunkBlocks) {
+        const long long nb = std::min(kOfflineChunkBlocks, nb_total - b0);
+        if (chunk_ready) {
+            // wait until the H2D copy covering the last sample of this chunk has landed
+            const long long last_sample = (b0 + nb - 1) * S + F - 1;
+            CU(cudaStreamWaitEvent(st, chunk_ready[last_sample / chunk_samples], 0));
+        }
+        long long hi = (b0 + nb) * S - T - 1;
+        if (hi < lo) hi = lo;
+        if (int rc = run_chunk(sd, d_in, 0, sd->d_zoff.p, 0, b0, nb, lo, hi, d_out_delayed, st)) return rc;
+        lo = hi;
+    }
+    sd->metric_n = static_cast<size_t>(P);
+    sd->metric_ptr = sd->d_zoff.p;
+    sd->metric_base = 0;
+    if (int rc = collect_records(sd, d_in, 0, sd->d_zoff.p, 0, st, sd->h_recs)) return rc;
+    // only what the reference block would have tagged: output index < items published
+    size_t cnt = 0;
+    for (const auto& r : sd->h_recs) {
+        if (r.index + sd->delay >= static_cast<uint64_t>(P)) continue;
+        if (cnt >= max_recs) return fail(B200SYNC_ENOMEM, "record buffer too small");
+        recs[cnt++] = r;
+    }
+    *n_recs = cnt;
+    *n_consumed = static_cast<size_t>(P);
+    return 0;
+}
+
+int b200sync_sd_detect_device(b200sync_sd* sd, const void* d_in, size_t n, void* d_out_delayed,
+                              void* cuda_stream, b200sync_detection_record* recs, size_t max_recs,
+                              size_t* n_recs, size_t* n_consumed) {
+    if (!sd || !n_recs || !n_consumed || (!d_in && n) || (!recs && max_recs))
+        return fail(B200SYNC_EINVAL, "null argument");
+    CU(cudaSetDevice(sd->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    return detect_resident(sd, static_cast<const float2*>(d_in), n, static_cast<float2*>(d_out_delayed), st,
+                           nullptr, 0, recs, max_recs, n_recs, n_consumed);
+}
+
+int b200sync_sd_detect_host(b200sync_sd* sd, const float* in, size_t n, b200sync_detection_record* recs,
+                            size_t max_recs, size_t* n_recs, size_t* n_consumed) {
+    if (!sd || !n_recs || !n_consumed || (!in && n) || (!recs && max_recs))
+        return fail(B200SYNC_EINVAL, "null argument");
+    CU(cudaSetDevice(sd->device));
+    *n_recs = 0;
+    *n_consumed = 0;
+    if (n < sd->fft_size) return 0;
+    CU(sd->d_xoff.ensure(n));
+    // H2D on a copy stream in pieces, one event per piece; compute chases the copies
+    const long long piece = 4LL << 20;  // 4 Mi samples = 32 MiB per copy
+    const size_t npieces = (n + piece - 1) / piece;
+    cudaStream_t cs;
+    CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> ev(npieces);
+    int rc = 0;
+    size_t made = 0;
+    for (; made < npieces; ++made) {
+        if (cudaEventCreateWithFlags(&ev[made], cudaEventDisableTiming) != cudaSuccess) {
+            rc = fail(B200SYNC_ECUDA, "cudaEventCreate failed");
+            break;
+        }
+    }
+    if (rc == 0) {
+        for (size_t i = 0; i < npieces; ++i) {
+            const size_t off = i * piece;
+            const size_t cnt = std::min<size_t>(piece, n - off);
+            cudaError_t e = cudaMemcpyAsync(sd->d_xoff.p + off, reinterpret_cast<const float2*>(in) + off,
+                                            cnt * sizeof(float2), cudaMemcpyHostToDevice, cs);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[i], cs);
+            if (e != cudaSuccess) {
+                rc = fail(B200SYNC_ECUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
+                break;
+            }
+        }
+    }
+    if (rc == 0)
+        rc = detect_resident(sd, sd->d_xoff.p, n, nullptr, sd->stream, ev.data(), piece, recs, max_recs, n_recs,
+                             n_consumed);
+    cudaStreamSynchronize(cs);
+    cudaStreamSynchronize(sd->stream);
+    for (size_t i = 0; i < made; ++i) cudaEventDestroy(ev[i]);
+    cudaStreamDestroy(cs);
+    return rc;
+}
+
+int b200sync_sd_copy_metric(const b200sync_sd* sd, float* zpow, size_t n) {
+    if (!sd || !zpow) return fail(B200SYNC_EINVAL, "null argument");
+    if (!sd->metric_ptr || n > sd->metric_n) return fail(B200SYNC_EINVAL, "no metric of that length available");
+    CU(cudaSetDevice(sd->device));
+    CU(cudaMemcpy(zpow, sd->metric_ptr, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+int b200sync_sd_shard_phase1(b200sync_sd* sd, const void* d_in, uint64_t first_sample_abs, size_t n_in,
+                             uint64_t first_block, uint64_t n_blocks, uint64_t total_blocks,
+                             void* cuda_stream, uint16_t* table, size_t table_len) {
+    if (!sd || !d_in || !table) return fail(B200SYNC_EINVAL, "null argument");
+    if (table_len < static_cast<size_t>(sd->T) + 1) return fail(B200SYNC_ENOMEM, "table too small");
+    if (first_block + n_blocks > total_blocks || n_blocks == 0) return fail(B200SYNC_EINVAL, "bad shard");
+    CU(cudaSetDevice(sd->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const long long S = sd->S, F = sd->fft_size, T = sd->T;
+    const long long halo = (T + S) / S;  // blocks of metric context needed on each side
+    const long long fb = static_cast<long long>(first_block), nbk = static_cast<long long>(n_blocks);
+    const long long tb = static_cast<long long>(total_blocks);
+    const long long cb0 = std::max(0LL, fb - halo), cb1 = std::min(tb, fb + nbk + halo);
+    const long long P_total = tb * S;
+    const long long in_base = static_cast<long long>(first_sample_abs);
+    if (cb0 * S < in_base || (cb1 - 1) * S + F > in_base + static_cast<long long>(n_in))
+        return fail(B200SYNC_EINVAL, "shard input does not cover its halo blocks");
+    const long long dec_end = std::max(0LL, P_total - T - 1);
+    const long long lo = std::min(fb == 0 ? 0LL : fb * S, dec_end);
+    const long long hi = (fb + nbk == tb) ? dec_end : std::min((fb + nbk) * S, dec_end);
+    const long long z_base = cb0 * S;
+    CU(sd->d_zoff.ensure(static_cast<size_t>((cb1 - cb0) * S) + 64));
+    CU(sd->d_ws.ensure(peak_workspace_bytes_sms(hi - lo + 1, sd->T, sd->num_sms)));
+    if (int rc = ensure_det(sd, static_cast<size_t>((hi - lo) / (T + 1) + 2))) return rc;
+    if (int rc = reset_state(sd, st)) return rc;
+    CU(sd->d_table.ensure(static_cast<size_t>(T) + 1));
+    CU(launch_correlate(static_cast<const float2*>(d_in), in_base, sd->d_zoff.p, z_base, sd->d_hperm.p,
+                        (int)sd->K, (int)sd->S, cb0, cb1 - cb0, sd->d_tw.p, nullptr, 0, 0, sd->num_sms, st));
+    g_launches += 1;
+    if (hi > lo) {
+        CU(launch_peak_phase1(sd->d_zoff.p, z_base, cb1 * S, lo, hi, sd->T, sd->power_threshold, sd->d_ws.p,
+                              sd->d_ws.cap, sd->d_table.p, sd->num_sms, st));
+        g_launches += 3;
+        CU(cudaMemcpyAsync(table, sd->d_table.p, sizeof(uint16_t) * (T + 1), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    } else {
+        CU(cudaStreamSynchronize(st));
+        for (long long j = 0; j <= T; ++j) table[j] = static_cast<uint16_t>(j);  // empty range: identity
+    }
+    sd->shard.d_in = static_cast<const float2*>(d_in);
+    sd->shard.in_base = in_base;
+    sd->shard.z_base = z_base;
+    sd->shard.lo = lo;
+    sd->shard.hi = hi;
+    sd->shard.P_total = P_total;
+    sd->shard.st = st;
+    sd->shard.valid = true;
+    sd->metric_n = static_cast<size_t>((cb1 - cb0) * S);
+    sd->metric_ptr = sd->d_zoff.p;
+    sd->metric_base = z_base;
+    return 0;
+}
+
+int b200sync_sd_shard_phase2(b200sync_sd* sd, uint32_t entry_offset, b200sync_detection_record* recs,
+                             size_t max_recs, size_t* n_recs) {
+    if (!sd || !n_recs || (!recs && max_recs)) return fail(B200SYNC_EINVAL, "null argument");
+    if (!sd->shard.valid) return fail(B200SYNC_EINVAL, "shard_phase1 has not run");
+    if (entry_offset > static_cast<uint32_t>(sd->T)) return fail(B200SYNC_EINVAL, "entry offset out of range");
+    CU(cudaSetDevice(sd->device));
+    *n_recs = 0;
+    const auto& sh = sd->shard;
+    if (sh.hi > sh.lo) {
+        CU(launch_peak_phase2(sh.lo, sh.hi, sd->T, sd->d_ws.p, sd->d_ws.cap, static_cast<int>(entry_offset),
+                              sd->d_state.p, sd->d_det_idx.p, (unsigned)sd->d_det_idx.cap, sd->num_sms, sh.st));
+        g_launches += 2;
+    }
+    if (int rc = collect_records(sd, sh.d_in, sh.in_base, sd->d_zoff.p, sh.z_base, sh.st, sd->h_recs)) return rc;
+    size_t cnt = 0;
+    for (const auto& r : sd->h_recs) {
+        if (r.index + sd->delay >= static_cast<uint64_t>(sh.P_total)) continue;
+        if (cnt >= max_recs) return fail(B200SYNC_ENOMEM, "record buffer too small");
+        recs[cnt++] = r;
+    }
+    *n_recs = cnt;
+    sd->shard.valid = false;
+    return 0;
+}
+
+}  // extern "C"

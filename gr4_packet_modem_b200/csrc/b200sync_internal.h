@@ -1,0 +1,55 @@
+// b200sync_internal.h — declarations shared by the .cu translation units of libb200sync.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/b200sync.h"
+
+namespace b200sync {
+
+constexpr int kFft = 2048;         // the only fft_size the kernels implement (reference default)
+constexpr int kGroupThreads = 128; // threads cooperating on one FFT block
+constexpr int kCorrThreads = 512;  // 4 FFT groups per CTA, 1 persistent CTA per SM
+constexpr int kMaxHyp = 129;       // max frequency hypotheses (min/max_freq_bin = -/+64)
+constexpr int kMaxTimeThreshold = 1023;  // chain kernels keep one bitmap word per lane
+
+using DetectionRecord = b200sync_detection_record;
+
+// device-resident scalar state of the peak detector (a6): where the sequential
+// search of PM/syncword_detection.hpp:267-298 resumes, and the detection list size
+struct PeakState {
+    unsigned long long r_abs;  // next search start (absolute sample index)
+    unsigned int det_count;
+    unsigned int _pad;
+};
+
+// correlator.cu
+cudaError_t launch_template_spectra(const float2* d_td, float2* d_hperm, int K, const float2* d_tw,
+                                    cudaStream_t st);
+cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpow, long long z_base,
+                             const float2* d_hperm, int K, int S, long long b0, long long nb,
+                             const float2* d_tw, float2* d_out_delayed, long long out_base, int delay,
+                             int num_sms, cudaStream_t st);
+cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_zpow, long long z_base,
+                          const float2* d_hperm, int K, int S, int min_freq_bin, const float2* d_tw,
+                          const unsigned long long* d_det_idx, const unsigned int* d_det_count,
+                          unsigned int det_cap, DetectionRecord* d_recs, int num_sms, cudaStream_t st);
+
+// peaks.cu
+struct PeakWorkspace;  // opaque: bitmaps, tables, per-segment entry states
+size_t peak_workspace_bytes_sms(long long max_range, int T, int num_sms);
+// Decide peaks for p in [lo, hi) given zpow known on [.., hi+T] (indices < 0 read as 0).
+//   phase 1: candidate / threshold bitmaps + per-segment chain tables + range table
+//   phase 2: walk the chain from entry state j_in, append detections, update state
+cudaError_t launch_peak_phase1(const float* d_zpow, long long z_base, long long z_end, long long lo,
+                               long long hi, int T,
+                               float power_threshold, void* d_ws, size_t ws_bytes,
+                               uint16_t* d_range_table /*[T+1] or nullptr*/, int num_sms,
+                               cudaStream_t st);
+cudaError_t launch_peak_phase2(long long lo, long long hi, int T, void* d_ws, size_t ws_bytes,
+                               int j_in /*-1: derive from state->r_abs*/, PeakState* d_state,
+                               unsigned long long* d_det_idx, unsigned int det_cap, int num_sms,
+                               cudaStream_t st);
+
+}  // namespace b200sync

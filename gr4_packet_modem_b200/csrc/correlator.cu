@@ -1,0 +1,237 @@
+// correlator.cu — overlap-save syncword correlator for sm_100a.
+//
+// Replaces the hot loops of SyncwordDetection::processBulk
+// (PM/syncword_detection.hpp:236-252 forward FFT + per-hypothesis product + FFT,
+//  :299-313 per-sample best hypothesis) and the template construction FFT of
+// start() (:183-188).  One 128-thread group owns one 2048-sample block at a time:
+//   global (coalesced, streaming) -> registers -> FFT A -> spectrum stays in
+//   registers -> for each hypothesis: x conj-template (pre-permuted, L1/L2
+//   resident) -> FFT B -> |.|^2 -> running max in registers -> zpow (4 B/sample).
+// Nothing but the per-sample winning power leaves the SM.  The fields the estimator
+// needs (winning complex correlation, neighbour-bin powers, bin, block noise power,
+// PM/syncword_detection.hpp:326-342) are recomputed bit-identically by
+// refine_kernel for the sparse set of detected peaks only.
+#include "b200sync_internal.h"
+#include "fft2048.cuh"
+
+namespace b200sync {
+
+__device__ __forceinline__ void load_twiddles(float2* tw_s, const float2* __restrict__ tw_g) {
+    for (int i = threadIdx.x; i < kFft; i += blockDim.x) tw_s[i] = tw_g[i];
+}
+
+// ---------------------------------------------------------------------------------
+// Template spectra: Hperm[k][j][tid] = conj(FFT_A(shifted_syncword_k))[(tid+128*(j>>3)) + 256*(j&7)]
+// grid = K groups of 128 threads (one CTA each).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGroupThreads)
+template_spectra_kernel(const float2* __restrict__ td /*[K][2048] zero padded*/,
+                        float2* __restrict__ hperm, const float2* __restrict__ tw_g) {
+    __shared__ float2 tw_s[kFft];
+    __shared__ float2 xb[kXchgFloat2];
+    load_twiddles(tw_s, tw_g);
+    __syncthreads();
+    const int tid = threadIdx.x;
+    const int k = blockIdx.x;
+    float2 v[16], xs[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) v[n1] = td[(size_t)k * kFft + 128 * n1 + tid];
+    fft_a(v, xs, tw_s, xb, tid, 1);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        hperm[((size_t)k * 16 + j) * kGroupThreads + tid] = make_float2(xs[j].x, -xs[j].y);
+}
+
+// ---------------------------------------------------------------------------------
+// Main correlator.  Persistent: gridDim.x CTAs x (blockDim.x/128) groups; group gg
+// handles blocks gg, gg+G, ... of [b0, b0+nb).  Block b covers absolute samples
+// [b*S, b*S+2048) and produces zpow for [b*S, (b+1)*S).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCorrThreads, 1)
+correlate_kernel(const float2* __restrict__ in, long long in_base, float* __restrict__ zpow,
+                 long long z_base, const float2* __restrict__ hperm, int K, int S, long long b0,
+                 long long nb, const float2* __restrict__ tw_g, float2* __restrict__ out_delayed,
+                 long long out_base, int delay) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* tw_s = reinterpret_cast<float2*>(smem_raw);
+    const int g = threadIdx.x >> 7;
+    const int tid = threadIdx.x & 127;
+    float2* xb = tw_s + kFft + g * kXchgFloat2;
+    load_twiddles(tw_s, tw_g);
+    __syncthreads();
+    const int ngroups = blockDim.x >> 7;
+    const long long gstride = (long long)gridDim.x * ngroups;
+    const int bar_id = 1 + g;
+
+    for (long long blk = (long long)blockIdx.x * ngroups + g; blk < nb; blk += gstride) {
+        const long long s0 = (b0 + blk) * (long long)S;  // absolute first sample of the block
+        const float2* src = in + (s0 - in_base);
+        float2 v[16], xs[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) v[n1] = __ldcs(src + 128 * n1 + tid);
+        if (out_delayed != nullptr) {
+            // block contract: out[n] = in[n - delay] (PM/syncword_detection.hpp:318-319).
+            // This block owns samples [s0, s0+S); it has them in registers already.
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) {
+                const int i = 128 * n1 + tid;
+                if (i < S) out_delayed[s0 + i + delay - out_base] = v[n1];
+            }
+        }
+        fft_a(v, xs, tw_s, xb, tid, bar_id);
+
+        float best[16];
+#pragma unroll
+        for (int m1 = 0; m1 < 16; ++m1) best[m1] = -1.0f;  // :303
+        for (int k = 0; k < K; ++k) {
+            const float2* h = hperm + (size_t)k * 16 * kGroupThreads + tid;
+            float2 y[16], c[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = cmul(xs[j], __ldg(h + j * kGroupThreads));  // :247-249
+            fft_b(y, c, tw_s, xb, tid, bar_id);                                             // :250-251
+#pragma unroll
+            for (int m1 = 0; m1 < 16; ++m1) {
+                const float p = norm2(c[m1]);  // :307
+                best[m1] = (p > best[m1]) ? p : best[m1];  // strict >, first hypothesis wins ties (:308)
+            }
+        }
+        // time reversal: lag kk lives at index (F - kk) mod F (:300)
+        float* zdst = zpow + (s0 - z_base);
+#pragma unroll
+        for (int m1 = 0; m1 < 16; ++m1) {
+            const int m = 128 * m1 + tid;
+            const int kk = (kFft - m) & (kFft - 1);
+            if (kk < S) zdst[kk] = best[m1];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Refine: recompute, for each detected sample p, the HistoryItem fields of
+// PM/syncword_detection.hpp:326-342 with exactly the arithmetic of correlate_kernel.
+// One group per detection, grid-stride over the device-side detection count.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGroupThreads)
+refine_kernel(const float2* __restrict__ in, long long in_base, const float* __restrict__ zpow,
+              long long z_base, const float2* __restrict__ hperm, int K, int S, int min_freq_bin,
+              const float2* __restrict__ tw_g, const unsigned long long* __restrict__ det_idx,
+              const unsigned int* __restrict__ det_count, unsigned int det_cap,
+              DetectionRecord* __restrict__ recs) {
+    __shared__ float2 tw_s[kFft];
+    __shared__ float2 xb[kXchgFloat2];
+    __shared__ float xpow[kFft];
+    __shared__ float2 corr_s[kMaxHyp];
+    __shared__ float noise_s;
+    load_twiddles(tw_s, tw_g);
+    __syncthreads();
+    const int tid = threadIdx.x;
+    unsigned int n = *det_count;
+    if (n > det_cap) n = det_cap;
+    for (unsigned int d = blockIdx.x; d < n; d += gridDim.x) {
+        const long long p = (long long)det_idx[d];
+        const long long b = p / S;
+        const int kk = (int)(p - b * S);
+        const int m = (kFft - kk) & (kFft - 1);
+        const long long s0 = b * (long long)S;
+        const float2* src = in + (s0 - in_base);
+        float2 v[16], xs[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) v[n1] = __ldcs(src + 128 * n1 + tid);
+        fft_a(v, xs, tw_s, xb, tid, 1);
+        // noise power, sequential float sum over k = F/4 .. 3F/4-1 in index order (:257-265)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) xpow[(tid + 128 * (j >> 3)) + 256 * (j & 7)] = norm2(xs[j]);
+        __syncthreads();
+        if (tid == 0) {
+            float acc = 0.0f;
+            for (int f = kFft / 4; f < 3 * kFft / 4; ++f) acc = __fadd_rn(acc, xpow[f]);
+            noise_s = __fdiv_rn(acc, __fmul_rn((float)(kFft / 2), (float)kFft));
+        }
+        for (int k = 0; k < K; ++k) {
+            const float2* h = hperm + (size_t)k * 16 * kGroupThreads + tid;
+            float2 y[16], c[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = cmul(xs[j], __ldg(h + j * kGroupThreads));
+            fft_b(y, c, tw_s, xb, tid, 1);
+            if (tid == (m & 127)) {
+                float2 val = c[0];
+#pragma unroll
+                for (int m1 = 1; m1 < 16; ++m1) val = ((m >> 7) == m1) ? c[m1] : val;
+                corr_s[k] = val;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int best_freq = 0;  // :301-313
+            float2 z = make_float2(0.f, 0.f);
+            float zp = -1.0f;
+            for (int k = 0; k < K; ++k) {
+                const float q = norm2(corr_s[k]);
+                if (q > zp) { best_freq = k; z = corr_s[k]; zp = q; }
+            }
+            DetectionRecord r;
+            r.index = (unsigned long long)p;
+            r.corr_re = z.x;
+            r.corr_im = z.y;
+            r.pow = zp;
+            r.pow_left = best_freq > 0 ? norm2(corr_s[best_freq - 1]) : 0.0f;
+            r.pow_right = best_freq < K - 1 ? norm2(corr_s[best_freq + 1]) : 0.0f;
+            r.pow_prev = (p - 1 >= 0 && p - 1 >= z_base) ? zpow[p - 1 - z_base] : 0.0f;
+            r.pow_next = zpow[p + 1 - z_base];
+            r.noise_power = noise_s;
+            r.freq_bin = min_freq_bin + best_freq;
+            r._pad = 0;
+            recs[d] = r;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------
+cudaError_t launch_template_spectra(const float2* d_td, float2* d_hperm, int K, const float2* d_tw,
+                                    cudaStream_t st) {
+    template_spectra_kernel<<<K, kGroupThreads, 0, st>>>(d_td, d_hperm, d_tw);
+    return cudaGetLastError();
+}
+
+size_t correlate_smem_bytes(int groups) {
+    return sizeof(float2) * (size_t)(kFft + groups * kXchgFloat2);
+}
+
+cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpow, long long z_base,
+                             const float2* d_hperm, int K, int S, long long b0, long long nb,
+                             const float2* d_tw, float2* d_out_delayed, long long out_base, int delay,
+                             int num_sms, cudaStream_t st) {
+    if (nb <= 0) return cudaSuccess;
+    static bool attr_set = false;
+    const int groups = kCorrThreads / kGroupThreads;
+    const size_t smem = correlate_smem_bytes(groups);
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(correlate_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    long long want = (nb + groups - 1) / groups;
+    int grid = (int)(want < num_sms ? want : num_sms);
+    correlate_kernel<<<grid, kCorrThreads, smem, st>>>(d_in, in_base, d_zpow, z_base, d_hperm, K, S, b0,
+                                                        nb, d_tw, d_out_delayed, out_base, delay);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_zpow, long long z_base,
+                          const float2* d_hperm, int K, int S, int min_freq_bin, const float2* d_tw,
+                          const unsigned long long* d_det_idx, const unsigned int* d_det_count,
+                          unsigned int det_cap, DetectionRecord* d_recs, int num_sms, cudaStream_t st) {
+    int grid = num_sms * 4;
+    if ((unsigned)grid > det_cap) grid = (int)det_cap;
+    if (grid < 1) grid = 1;
+    refine_kernel<<<grid, kGroupThreads, 0, st>>>(d_in, in_base, d_zpow, z_base, d_hperm, K, S,
+                                                  min_freq_bin, d_tw, d_det_idx, d_det_count, det_cap,
+                                                  d_recs);
+    return cudaGetLastError();
+}
+
+}  // namespace b200sync

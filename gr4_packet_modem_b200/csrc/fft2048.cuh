@@ -1,0 +1,227 @@
+// fft2048.cuh — register/shared-memory FFT-2048 building blocks for sm_100a.
+//
+// The overlap-save correlator (PM/syncword_detection.hpp:236-252 in the reference)
+// needs, per 2048-sample block, one forward FFT and K "inverse-as-forward" FFTs.
+// On the CPU that is FFTW; here it is a 3-pass 16 x 16 x 8 decomposition executed by
+// a 128-thread group: every thread holds 16 complex points in registers, small DFTs
+// run entirely in registers, and the two transposes between passes go through a
+// padded shared-memory exchange buffer laid out so that every LDS.64/STS.64 warp
+// access is the minimum 2 wavefronts (no bank conflicts).
+//
+//   FFT "A" (samples -> spectrum), n = 128 n1 + 8 n2 + n3, k = k1 + 16 k2 + 256 k3
+//     pass A1  DFT16 over n1   x W_256^{n2 k1}            thread = (n2,n3) = tid
+//     pass A2  DFT16 over n2   x W_2048^{n3 (k1+16 k2)}   thread = (n3,k1)
+//     pass A3  DFT8  over n3                              thread owns p = k1+16 k2 in {tid, tid+128}
+//   FFT "B" (spectrum product -> correlation), f = f1 + 16 f2 + 256 f3, m = 128 m1 + 8 m2 + m3
+//     pass B1  DFT8  over f3   x W_2048^{(f1+16 f2) m3}   same ownership as A3 (no exchange!)
+//     pass B2  DFT16 over f2   x W_256^{f1 m2}            thread = (m3,f1)
+//     pass B3  DFT16 over f1                              thread = (m2,m3) = tid -> C[128 m1 + tid]
+//
+// A's output ordering is exactly B's input ordering, so the spectrum never has to be
+// un-permuted: the template spectra are stored pre-permuted instead.
+//
+// ARITHMETIC CONTRACT (mirrored bit-for-bit by oracle/oracle_fft.hpp, FftKind::Mirror):
+//   * every add/sub/mul is a separately rounded IEEE binary32 op (__fadd_rn etc. so
+//     nvcc never contracts them), except the complex multiply
+//         cmul(a,w) = ( fma(a.x, w.x, -(a.y*w.y)),  fma(a.x, w.y, a.y*w.x) )
+//     and the squared magnitude  norm2(z) = fma(z.y, z.y, z.x*z.x);
+//   * small DFTs are radix-2 decimation-in-frequency stages: (u,v) -> (u+v, (u-v)*w);
+//     w = 1 is skipped, w = -i is a swap/negate, w = W8^1 and W8^3 use
+//         (x,y)*W8^1 = ( c*(x+y),  c*(y-x) ),   (x,y)*W8^3 = ( c*(y-x), -(c*(x+y)) ),  c = float(sqrt(1/2));
+//     W16^{1,3,5,7} use cmul with constants equal to twiddle-table entries;
+//   * all inter-pass twiddles are entries of one table  Wt[j] = (float(cos(2 pi j/2048)), float(-sin(2 pi j/2048)))
+//     computed in double on the host; a statically-zero exponent skips the multiply.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b200sync_internal.h"
+
+namespace b200sync {
+
+constexpr int kXchgStrideA = 129;   // exchange layout 1: (a*129 + tid)
+constexpr int kXchgStrideP = 9;     // exchange layout 2: (p*9 + d)
+constexpr int kXchgFloat2 = 256 * kXchgStrideP;  // 2304 float2 = 18432 B (>= 16*129 = 2064)
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+    return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+    return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y));
+}
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
+    return make_float2(__fmaf_rn(a.x, w.x, -__fmul_rn(a.y, w.y)),
+                       __fmaf_rn(a.x, w.y, __fmul_rn(a.y, w.x)));
+}
+__device__ __forceinline__ float norm2(float2 z) { return __fmaf_rn(z.y, z.y, __fmul_rn(z.x, z.x)); }
+// (x,y) * -i
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
+
+#define B200_SQRT1_2 0.70710678118654752440f
+#define B200_COS_PI_8 0.92387953251128675613f
+#define B200_SIN_PI_8 0.38268343236508977173f
+
+// (x,y) * W8^1 = c(1-i)
+__device__ __forceinline__ float2 mul_w8_1(float2 a) {
+    return make_float2(__fmul_rn(B200_SQRT1_2, __fadd_rn(a.x, a.y)),
+                       __fmul_rn(B200_SQRT1_2, __fsub_rn(a.y, a.x)));
+}
+// (x,y) * W8^3 = -c(1+i)
+__device__ __forceinline__ float2 mul_w8_3(float2 a) {
+    return make_float2(__fmul_rn(B200_SQRT1_2, __fsub_rn(a.y, a.x)),
+                       -__fmul_rn(B200_SQRT1_2, __fadd_rn(a.x, a.y)));
+}
+
+// multiply by W16^e, e compile-time in [0,8)
+template <int E>
+__device__ __forceinline__ float2 mul_w16(float2 a) {
+    if constexpr (E == 0) return a;
+    else if constexpr (E == 1) return cmul(a, make_float2(B200_COS_PI_8, -B200_SIN_PI_8));
+    else if constexpr (E == 2) return mul_w8_1(a);
+    else if constexpr (E == 3) return cmul(a, make_float2(B200_SIN_PI_8, -B200_COS_PI_8));
+    else if constexpr (E == 4) return mul_mi(a);
+    else if constexpr (E == 5) return cmul(a, make_float2(-B200_SIN_PI_8, -B200_COS_PI_8));
+    else if constexpr (E == 6) return mul_w8_3(a);
+    else return cmul(a, make_float2(-B200_COS_PI_8, -B200_SIN_PI_8));
+}
+
+template <int HALF, int STEP, int I>
+__device__ __forceinline__ void bfly(float2& u, float2& v) {
+    const float2 s = cadd(u, v);
+    const float2 d = csub(u, v);
+    u = s;
+    v = mul_w16<I * STEP>(d);
+}
+
+// In-place radix-2 DIF DFT-16.  Input v[n], output v[bitrev4(k)] = X[k].
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+    // half = 8, twiddle W16^i
+    bfly<8, 1, 0>(v[0], v[8]);  bfly<8, 1, 1>(v[1], v[9]);
+    bfly<8, 1, 2>(v[2], v[10]); bfly<8, 1, 3>(v[3], v[11]);
+    bfly<8, 1, 4>(v[4], v[12]); bfly<8, 1, 5>(v[5], v[13]);
+    bfly<8, 1, 6>(v[6], v[14]); bfly<8, 1, 7>(v[7], v[15]);
+    // half = 4, twiddle W8^i = W16^{2i}
+#pragma unroll
+    for (int g = 0; g < 16; g += 8) {
+        bfly<4, 2, 0>(v[g + 0], v[g + 4]); bfly<4, 2, 1>(v[g + 1], v[g + 5]);
+        bfly<4, 2, 2>(v[g + 2], v[g + 6]); bfly<4, 2, 3>(v[g + 3], v[g + 7]);
+    }
+    // half = 2, twiddle W4^i = W16^{4i}
+#pragma unroll
+    for (int g = 0; g < 16; g += 4) {
+        bfly<2, 4, 0>(v[g + 0], v[g + 2]); bfly<2, 4, 1>(v[g + 1], v[g + 3]);
+    }
+    // half = 1
+#pragma unroll
+    for (int g = 0; g < 16; g += 2) bfly<1, 8, 0>(v[g], v[g + 1]);
+}
+
+// In-place radix-2 DIF DFT-8.  Input v[n], output v[bitrev3(k)] = X[k].
+__device__ __forceinline__ void dft8(float2 (&v)[8]) {
+    bfly<4, 2, 0>(v[0], v[4]); bfly<4, 2, 1>(v[1], v[5]);
+    bfly<4, 2, 2>(v[2], v[6]); bfly<4, 2, 3>(v[3], v[7]);
+#pragma unroll
+    for (int g = 0; g < 8; g += 4) {
+        bfly<2, 4, 0>(v[g + 0], v[g + 2]); bfly<2, 4, 1>(v[g + 1], v[g + 3]);
+    }
+#pragma unroll
+    for (int g = 0; g < 8; g += 2) bfly<1, 8, 0>(v[g], v[g + 1]);
+}
+
+__host__ __device__ constexpr int bitrev4(int k) {
+    return ((k & 1) << 3) | ((k & 2) << 1) | ((k & 4) >> 1) | ((k & 8) >> 3);
+}
+__host__ __device__ constexpr int bitrev3(int k) { return ((k & 1) << 2) | (k & 2) | ((k & 4) >> 2); }
+
+// 128-thread named barrier for one FFT group (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(int bar_id) {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kGroupThreads) : "memory");
+}
+
+// ---- FFT A: 2048 samples (registers v[n1] = x[128 n1 + tid]) -> spectrum -------------
+// On return xs[pi*8 + k3] = X[(tid + 128 pi) + 256 k3]   (pi in {0,1}).
+// `tw` is the 2048-entry twiddle table (shared memory), `xb` this group's exchange buffer.
+__device__ __forceinline__ void fft_a(float2 (&v)[16], float2 (&xs)[16], const float2* __restrict__ tw,
+                                      float2* __restrict__ xb, int tid, int bar_id) {
+    // pass A1
+    dft16(v);
+    {
+        const int n2 = tid >> 3;
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) {
+            float2 val = v[bitrev4(k1)];
+            if (k1 != 0) val = cmul(val, tw[8 * n2 * k1]);
+            xb[k1 * kXchgStrideA + tid] = val;
+        }
+    }
+    group_sync(bar_id);
+    // pass A2
+    const int n3 = tid >> 4, k1 = tid & 15;
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = xb[k1 * kXchgStrideA + n2 * 8 + n3];
+    group_sync(bar_id);
+    dft16(v);
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) {
+        float2 val = v[bitrev4(k2)];
+        val = cmul(val, tw[n3 * (k1 + 16 * k2)]);
+        xb[(k1 + 16 * k2) * kXchgStrideP + n3] = val;
+    }
+    group_sync(bar_id);
+    // pass A3
+#pragma unroll
+    for (int pi = 0; pi < 2; ++pi) {
+        float2 w[8];
+        const int p = tid + 128 * pi;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) w[d] = xb[p * kXchgStrideP + d];
+        dft8(w);
+#pragma unroll
+        for (int k3 = 0; k3 < 8; ++k3) xs[pi * 8 + k3] = w[bitrev3(k3)];
+    }
+    group_sync(bar_id);  // exchange buffer free again
+}
+
+// ---- FFT B: y[pi*8 + f3] = Y[(tid + 128 pi) + 256 f3] -> c[m1] = C[128 m1 + tid] ------
+// y is destroyed.  The exchange buffer must be free on entry and is free on return.
+__device__ __forceinline__ void fft_b(float2 (&y)[16], float2 (&c)[16], const float2* __restrict__ tw,
+                                      float2* __restrict__ xb, int tid, int bar_id) {
+    // pass B1
+#pragma unroll
+    for (int pi = 0; pi < 2; ++pi) {
+        float2 w[8];
+        const int p = tid + 128 * pi;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) w[d] = y[pi * 8 + d];
+        dft8(w);
+#pragma unroll
+        for (int m3 = 0; m3 < 8; ++m3) {
+            float2 val = w[bitrev3(m3)];
+            if (m3 != 0) val = cmul(val, tw[p * m3]);
+            xb[p * kXchgStrideP + m3] = val;
+        }
+    }
+    group_sync(bar_id);
+    // pass B2
+    const int m3 = tid >> 4, f1 = tid & 15;
+#pragma unroll
+    for (int f2 = 0; f2 < 16; ++f2) c[f2] = xb[(f1 + 16 * f2) * kXchgStrideP + m3];
+    group_sync(bar_id);
+    dft16(c);
+#pragma unroll
+    for (int m2 = 0; m2 < 16; ++m2) {
+        float2 val = c[bitrev4(m2)];
+        if (m2 != 0) val = cmul(val, tw[8 * f1 * m2]);
+        xb[f1 * kXchgStrideA + m2 * 8 + m3] = val;
+    }
+    group_sync(bar_id);
+    // pass B3
+#pragma unroll
+    for (int ff = 0; ff < 16; ++ff) y[ff] = xb[ff * kXchgStrideA + tid];
+    group_sync(bar_id);  // exchange buffer free again
+    dft16(y);
+#pragma unroll
+    for (int m1 = 0; m1 < 16; ++m1) c[m1] = y[bitrev4(m1)];
+}
+
+}  // namespace b200sync

@@ -1,0 +1,115 @@
+"""Seeded synthetic captures for tests and bench.py (not on the product data path).
+
+Signal model of BASELINE.json configs / SURVEY.md §8(d): back-to-back frames of
+  64-symbol BPSK syncword + 128 QPSK header symbols + QPSK payload ((bytes+4)*4 symbols),
+x4 RRC pulse shaping with the transmitter's taps (PM/packet_transmitter_rrc_taps.hpp:8-28),
+carrier frequency offset (what Rotator applies, apps/packet_transceiver.cpp:74-75) and complex
+AWGN with N0 = 0.32 * sps * 10^(-EsN0/10) (apps/packet_transceiver.cpp:48-52).
+
+Two generators with the same structure: numpy (host, any size that fits RAM) and torch
+(device, used by bench.py for the 2^30-sample capture).  They are NOT bit-identical to each
+other; parity tests always feed the same array to the GPU path and to the oracle.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .firdes import SYNCWORD, root_raised_cosine
+
+TX_POWER = 0.32  # apps/packet_transceiver.cpp:48
+
+
+def tx_rrc_taps(sps: int = 4) -> np.ndarray:
+    """PM/packet_transmitter_rrc_taps.hpp:8-28."""
+    rrc = root_raised_cosine(1.0, float(sps), 1.0, 0.35, sps * 11)
+    m = max(float(np.sum(np.abs(rrc[j::sps]))) for j in range(sps))
+    return (rrc * np.float32(0.9 / m)).astype(np.float32)
+
+
+def frame_symbols(rng: np.random.Generator, payload_bytes: int) -> np.ndarray:
+    nq = 128 + (payload_bytes + 4) * 4
+    q = rng.integers(0, 4, nq)
+    qpsk = ((1 - 2 * (q & 1)) + 1j * (1 - 2 * (q >> 1))) / math.sqrt(2.0)
+    sw = 1.0 - 2.0 * SYNCWORD.astype(np.float64)
+    return np.concatenate([sw.astype(np.complex128), qpsk])
+
+
+def packet_capture(n_samples: int, seed: int = 1, esn0_db: float = 20.0, cfo: float = 0.005,
+                   payload_bytes: int = 1500, sps: int = 4, gap_symbols: int = 0, noise_seed: int = 2,
+                   signal: bool = True) -> tuple[np.ndarray, np.ndarray]:
+    """Returns (capture complex64[n_samples], syncword_start_sample_indices)."""
+    rng = np.random.default_rng(seed)
+    taps = tx_rrc_taps(sps).astype(np.float64)
+    nsym = n_samples // sps + 2
+    syms = np.zeros(nsym, np.complex128)
+    starts = []
+    pos = 0
+    if signal:
+        while pos < nsym:
+            f = frame_symbols(rng, payload_bytes)
+            m = min(f.size, nsym - pos)
+            syms[pos:pos + m] = f[:m]
+            if m >= 64:
+                starts.append(pos * sps)
+            pos += f.size + gap_symbols
+    up = np.zeros(nsym * sps, np.complex128)
+    up[::sps] = syms
+    x = np.convolve(up, taps)[:n_samples]
+    if cfo != 0.0:
+        x = x * np.exp(1j * cfo * np.arange(n_samples, dtype=np.float64))
+    n0 = TX_POWER * sps * 10.0 ** (-0.1 * esn0_db)
+    nrng = np.random.default_rng(noise_seed)
+    noise = (nrng.standard_normal(n_samples) + 1j * nrng.standard_normal(n_samples)) * math.sqrt(n0 / 2.0)
+    x = (x + noise).astype(np.complex64)
+    return x, np.array([s for s in starts if s + 297 <= n_samples], dtype=np.int64)
+
+
+def packet_capture_torch(n_samples: int, device, seed: int = 1, esn0_db: float = 20.0, cfo: float = 0.005,
+                         payload_bytes: int = 1500, sps: int = 4, chunk: int = 1 << 24):
+    """Device-side generator for large captures: returns a torch.complex64 tensor of n_samples
+    on `device`.  Same frame structure and statistics as packet_capture()."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    taps = torch.tensor(tx_rrc_taps(sps), dtype=torch.float32, device=device)
+    ntaps = taps.numel()
+    frame_len = 64 + 128 + (payload_bytes + 4) * 4
+    sw = torch.tensor(1.0 - 2.0 * SYNCWORD.astype(np.float32), device=device)
+    out = torch.empty(n_samples, dtype=torch.complex64, device=device)
+    n0 = TX_POWER * sps * 10.0 ** (-0.1 * esn0_db)
+    hist = (ntaps + sps - 1) // sps  # symbols of filter memory
+    kernel = taps.flip(0).view(1, 1, -1)
+    for s0 in range(0, n_samples, chunk):
+        m = min(chunk, n_samples - s0)
+        sym0 = s0 // sps - hist
+        nsym = m // sps + hist + 2
+        idx = torch.arange(sym0, sym0 + nsym, device=device)
+        # symbols are a pure function of (seed, symbol index): chunking does not change the capture
+        h = (idx * 2654435761 + seed * 40503) & 0xFFFFFFFF
+        h = ((h ^ (h >> 15)) * 2246822519) & 0xFFFFFFFF
+        h = ((h ^ (h >> 13)) * 3266489917) & 0xFFFFFFFF
+        h = h ^ (h >> 16)
+        re = 1.0 - 2.0 * (h & 1).to(torch.float32)
+        im = 1.0 - 2.0 * ((h >> 1) & 1).to(torch.float32)
+        inframe = torch.remainder(idx, frame_len)
+        is_sw = (inframe < 64) & (idx >= 0)
+        re = torch.where(is_sw, sw[inframe.clamp(max=63)], re * (1.0 / math.sqrt(2.0)))
+        im = torch.where(is_sw, torch.zeros_like(im), im * (1.0 / math.sqrt(2.0)))
+        valid = (idx >= 0).to(torch.float32)
+        re, im = re * valid, im * valid
+        up = torch.zeros(2, 1, nsym * sps, dtype=torch.float32, device=device)
+        up[0, 0, ::sps] = re
+        up[1, 0, ::sps] = im
+        up = torch.nn.functional.pad(up, (ntaps - 1, 0))
+        y = torch.nn.functional.conv1d(up, kernel)  # causal FIR: y[n] = sum_k taps[k] up[n-k]
+        off = s0 - sym0 * sps
+        sig = torch.complex(y[0, 0, off:off + m], y[1, 0, off:off + m])
+        n = torch.arange(s0, s0 + m, device=device, dtype=torch.float64)
+        ph = torch.remainder(n * cfo, 2.0 * math.pi).to(torch.float32)
+        sig = sig * torch.complex(torch.cos(ph), torch.sin(ph))
+        noise = torch.randn(m, 2, generator=g, device=device, dtype=torch.float32) * math.sqrt(n0 / 2.0)
+        out[s0:s0 + m] = sig + torch.view_as_complex(noise)
+    return out

@@ -1,0 +1,158 @@
+/* b200sync.h — C ABI of libb200sync.so: the B200 (sm_100a) receiver-synchronisation
+ * hot path of gr4-packet-modem.
+ *
+ * The reference has no C ABI for DSP: its blocks are header-only C++ classes called
+ * by the GNU Radio 4.0 runtime (gr::Block<T>::workInternal -> T::processBulk).  The
+ * entry points below are what a cgo/JNI/ctypes/C++ binding of that block contract
+ * needs; each one names the reference interface it stands in for.  Paths:
+ *   PM/ = blocks/include/gnuradio-4.0/packet-modem/   (reference repository)
+ *
+ * Conventions
+ *   - complex samples are interleaved float32 (re, im), i.e. std::complex<float>;
+ *   - every function returns 0 on success or a negative B200SYNC_E* code; the
+ *     message of the last failure on the calling thread is b200sync_last_error();
+ *   - a context is NOT thread-safe (like a GR4 block instance: one worker thread per
+ *     block, GR/Scheduler.hpp:387-398); distinct contexts may be used concurrently;
+ *   - there is no CPU fallback: if no sm_100-class device is usable, create fails.
+ */
+#ifndef B200SYNC_H
+#define B200SYNC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SYNC_OK 0
+#define B200SYNC_EINVAL (-1)      /* bad argument / setting (gr::exception in the reference) */
+#define B200SYNC_ECUDA (-2)       /* CUDA runtime failure                                     */
+#define B200SYNC_ENOMEM (-3)      /* caller buffer too small / allocation failed             */
+#define B200SYNC_EUNSUPPORTED (-4)/* valid in the reference, not implemented on the GPU path */
+
+const char* b200sync_last_error(void);
+/* ABI version of this header (bumped on incompatible change). */
+int b200sync_abi_version(void);
+/* Number of kernel launches issued by this process so far (bench.py's gpu_launches). */
+uint64_t b200sync_launch_count(void);
+
+/* ------------------------------------------------------------------------------
+ * SyncwordDetection                                   PM/syncword_detection.hpp
+ * ------------------------------------------------------------------------------ */
+
+/* The reflected settings of the block, PM/syncword_detection.hpp:131-141, 361-372. */
+typedef struct b200sync_sd_config {
+    uint32_t fft_size;            /* default 2048 (only 2048 is implemented)            */
+    uint32_t samples_per_symbol;  /* default 4                                          */
+    const float* rrc_taps;        /* rrc_taps                                           */
+    uint32_t n_rrc_taps;
+    const uint8_t* syncword;      /* syncword (symbol indices into constellation)       */
+    uint32_t n_syncword;
+    const float* constellation;   /* constellation, interleaved (re, im)                */
+    uint32_t n_constellation;
+    int32_t min_freq_bin;         /* default 0                                          */
+    int32_t max_freq_bin;         /* default 0                                          */
+    uint64_t time_threshold;      /* default 768                                        */
+    float power_threshold;        /* default 9.5                                        */
+    int32_t device;               /* CUDA device ordinal                                */
+} b200sync_sd_config;
+
+/* Raw per-detection fields = the HistoryItem of PM/syncword_detection.hpp:17-29 for the
+ * detected sample plus its neighbours' powers (:321-323), computed on the GPU. */
+typedef struct b200sync_detection_record {
+    uint64_t index;        /* absolute INPUT sample index where the syncword starts     */
+    float corr_re, corr_im;/* HistoryItem::correlation                                  */
+    float pow;             /* HistoryItem::correlation_power                            */
+    float pow_left;        /* correlation_power_left  (0 at the lowest bin)             */
+    float pow_right;       /* correlation_power_right (0 at the highest bin)            */
+    float pow_prev;        /* previous_item.correlation_power                           */
+    float pow_next;        /* next_item.correlation_power                               */
+    float noise_power;     /* HistoryItem::fft_noise_power                              */
+    int32_t freq_bin;      /* HistoryItem::freq_bin                                     */
+    int32_t _pad;
+} b200sync_detection_record;
+
+/* The tag SyncwordDetection::output_tag() publishes, PM/syncword_detection.hpp:106-114. */
+typedef struct b200sync_sd_tag {
+    uint64_t index;          /* absolute OUTPUT stream index (= record.index + 2*time_threshold + 1) */
+    double syncword_freq;
+    float syncword_amplitude;
+    float syncword_phase;
+    int32_t syncword_freq_bin;
+    float syncword_noise_power;
+    float syncword_esn0_db;
+    float syncword_time_est;
+} b200sync_sd_tag;
+
+typedef struct b200sync_sd b200sync_sd;
+
+/* emplaceBlock<SyncwordDetection>({settings}) + start(): validates the settings
+ * (PM/syncword_detection.hpp:145-152), builds the modulated syncword and its K conjugated
+ * spectra (:154-189, spectra by the GPU FFT) and resets the streaming state (:191-201). */
+int b200sync_sd_create(const b200sync_sd_config* cfg, b200sync_sd** out);
+void b200sync_sd_destroy(b200sync_sd* sd);
+/* start() again: reset streaming state, keep settings. */
+int b200sync_sd_start(b200sync_sd* sd);
+
+/* Derived quantities (read-only): _syncword_samples_size (:148), stride (:236),
+ * _syncword_self_corr (:161-164), number of hypotheses, output delay 2T+1. */
+int b200sync_sd_info(const b200sync_sd* sd, uint32_t* syncword_samples, uint32_t* stride,
+                     float* self_corr, uint32_t* num_hypotheses, uint64_t* delay);
+
+/* processBulk(inSpan, outSpan), PM/syncword_detection.hpp:204-356, HOST spans.
+ *   in, n_in      the ConsumableSpan offered by the runtime
+ *   out           the PublishableSpan (same length); may be NULL to skip the delayed copy
+ *   *n_consumed   items consumed == items published (a multiple of the stride; 0 and
+ *                 return value 1 == INSUFFICIENT_INPUT_ITEMS when n_in < fft_size, :215-227)
+ *   tags          tags to publish; tag.index - (items consumed before this call) is the
+ *                 offset to pass to out.publishTag(); at most max_tags, count in *n_tags.
+ * Host<->device copies happen inside this call. */
+int b200sync_sd_process(b200sync_sd* sd, const float* in, size_t n_in, float* out, size_t* n_consumed,
+                        b200sync_sd_tag* tags, size_t max_tags, size_t* n_tags);
+
+/* Offline bulk entry point over a DEVICE-resident capture (no reference counterpart: a
+ * 65536-item GR ring chunk is far too small to fill a B200).  Equivalent to start()
+ * followed by one processBulk over the whole capture: runs blocks while j + fft_size <= n.
+ *   d_in          device pointer, n complex samples
+ *   d_out_delayed optional device pointer (>= n items): receives out[i] = in[i - delay]
+ *   cuda_stream   cudaStream_t (NULL = default stream); work is enqueued and completed
+ *                 before return (records come back to host memory)
+ *   recs          host array; receives the records of every tag the reference block would
+ *                 have published (index + delay < items consumed), sorted by index. */
+int b200sync_sd_detect_device(b200sync_sd* sd, const void* d_in, size_t n, void* d_out_delayed,
+                              void* cuda_stream, b200sync_detection_record* recs, size_t max_recs,
+                              size_t* n_recs, size_t* n_consumed);
+
+/* Same over a HOST capture: chunks are staged through pinned double buffers so H2D
+ * copies overlap compute.  `in` may be pageable or pinned. */
+int b200sync_sd_detect_host(b200sync_sd* sd, const float* in, size_t n, b200sync_detection_record* recs,
+                            size_t max_recs, size_t* n_recs, size_t* n_consumed);
+
+/* Time-sharded operation (one context per GPU).  The shard owns FFT
+ * blocks [first_block, first_block + n_blocks) of a longer stream; d_in points at absolute
+ * sample first_sample_abs and must cover every block the shard computes (one extra block
+ * of halo on each side that exists in the stream).
+ *   phase 1 computes zpow and the shard's chain table: entry search offset j (0..T) at the
+ *           shard's first decided sample -> exit offset, written to table[T+1];
+ *   phase 2 takes the true entry offset (composition of the previous shards' tables, done by
+ *           the caller) and returns the shard's detection records. */
+int b200sync_sd_shard_phase1(b200sync_sd* sd, const void* d_in, uint64_t first_sample_abs, size_t n_in,
+                             uint64_t first_block, uint64_t n_blocks, uint64_t total_blocks,
+                             void* cuda_stream, uint16_t* table, size_t table_len);
+int b200sync_sd_shard_phase2(b200sync_sd* sd, uint32_t entry_offset, b200sync_detection_record* recs,
+                             size_t max_recs, size_t* n_recs);
+
+/* output_tag(), PM/syncword_detection.hpp:56-115, evaluated on the host in the reference's
+ * own float/double mix from the raw records. */
+int b200sync_sd_records_to_tags(const b200sync_sd* sd, const b200sync_detection_record* recs, size_t n,
+                                b200sync_sd_tag* tags);
+
+/* Debug/verification tap: copy the per-sample winning correlation power of the last
+ * detect_device/detect_host call (zpow[0..n)) to host memory. */
+int b200sync_sd_copy_metric(const b200sync_sd* sd, float* zpow, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SYNC_H */

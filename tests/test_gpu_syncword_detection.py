@@ -1,0 +1,179 @@
+"""GPU parity tests for SyncwordDetection: CUDA path (through the C ABI) vs the CPU oracle.
+
+Bars (BASELINE.json north_star):
+  * detected sample indices and detection counts: bit-exact;
+  * vs the oracle's MIRROR arithmetic: every float of the metric and of the records bit-exact;
+  * vs the oracle's independent RADIX-2 arithmetic: |df| < 1e-5 rad/sample, |dphi| < 1e-3 rad,
+    amplitude / time estimate within 1e-4.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_FREQ = 1e-5   # rad/sample
+TOL_PHASE = 1e-3  # rad
+TOL_AMP = 1e-4
+TOL_TIME = 1e-3
+
+
+def _gpu(rx_params, **kw):
+    from gr4_packet_modem_b200 import SyncwordDetection
+
+    return SyncwordDetection(**rx_params, **kw)
+
+
+def _qa_stimulus(oracle, rx_params, freq_error, nsym=200000, seed=1234):
+    """The stimulus of test/qa_syncword_detection.cpp:24-76 with a fixed seed."""
+    from gr4_packet_modem_b200.firdes import SYNCWORD
+
+    rng = np.random.default_rng(seed)
+    sym = rng.integers(0, 2, nsym).astype(np.uint8)
+    locs = [100, 1000, 1250, 10000, 13721, 43124, 58000, 127018]
+    for l in locs:
+        sym[l:l + 64] = SYNCWORD
+    x = oracle.interpolating_fir(rx_params["constellation"][sym], rx_params["rrc_taps"], 4)
+    return oracle.rotator(x, freq_error), locs
+
+
+def _wrap(d):
+    return (d + np.pi) % (2 * np.pi) - np.pi
+
+
+@pytest.mark.parametrize("freq_error", [0.0, 0.005, 0.015, -0.005, -0.015])
+def test_reference_qa_assertions_streaming(oracle, rx_params, freq_error):
+    """test/qa_syncword_detection.cpp:99-146 against the GPU block, driven in 65536-item chunks."""
+    x, locs = _qa_stimulus(oracle, rx_params, freq_error)
+    sd = _gpu(rx_params, min_freq_bin=-4, max_freq_bin=4, power_threshold=20.0)
+    consumed, out, tags = sd.run(x, want_output=True)
+    delay = 2 * 768 + 1
+    assert consumed <= x.size and consumed + 2048 > x.size
+    assert np.all(out[:delay] == 0)
+    assert np.array_equal(out[delay:], x[:consumed - delay])
+    assert len(tags) == len(locs)
+    for (off, idx, m), loc in zip(tags, locs):
+        assert idx == delay + 4 * loc
+        assert 0.95 < m["syncword_amplitude"] < 1.01
+        assert m["syncword_esn0_db"] >= 30.0
+        assert abs(m["syncword_freq"] - freq_error) < 5e-4
+        assert m["syncword_freq_bin"] == round(freq_error / (np.pi / 297))
+        assert m["syncword_noise_power"] < 5e-4
+        if freq_error == 0.0:
+            assert abs(m["syncword_phase"]) < 1e-6
+        assert abs(m["syncword_time_est"]) < 0.05
+
+
+@pytest.mark.parametrize("esn0_db,thr,bins", [(20.0, 9.5, 4), (0.0, 9.5, 4), (3.0, 6.0, 1), (20.0, 9.5, 0)])
+def test_offline_bit_exact_vs_mirror_oracle(oracle, rx_params, esn0_db, thr, bins):
+    """Whole pipeline bit-for-bit: metric, detection set, raw records, estimates."""
+    from gr4_packet_modem_b200.stimulus import packet_capture
+
+    n = 1 << 20
+    x, _ = packet_capture(n, seed=3, esn0_db=esn0_db, cfo=0.005, payload_bytes=200)
+    sd = _gpu(rx_params, min_freq_bin=-bins, max_freq_bin=bins, power_threshold=thr)
+    consumed, recs, tags = sd.detect_host(x)
+    o = oracle.SyncwordDetection(**rx_params, min_freq_bin=-bins, max_freq_bin=bins, power_threshold=thr,
+                                 fft_kind=oracle.FFT_MIRROR, record_metric=True)
+    oc, _, otags = o.run(x, chunk=1 << 20)
+    assert consumed == oc
+    zp, _ = o.metric(oc)
+    assert np.array_equal(sd.metric(consumed).view(np.uint32), zp.view(np.uint32)), "metric not bit-exact"
+    assert (recs["index"] + sd.delay).tolist() == [t.index for t in otags]
+    assert len(recs) > 0
+    for r, t, ot in zip(recs, tags, otags):
+        for a, b in [(r["corr_re"], ot.corr_re), (r["corr_im"], ot.corr_im), (r["pow"], ot.pow),
+                     (r["pow_prev"], ot.pow_prev), (r["pow_next"], ot.pow_next), (r["noise_power"], ot.noise_power)]:
+            assert np.float32(a).view(np.uint32) == np.float32(b).view(np.uint32)
+        assert r["freq_bin"] == ot.freq_bin
+        if -bins < r["freq_bin"] < bins:
+            assert np.float32(r["pow_left"]) == np.float32(ot.pow_left)
+            assert np.float32(r["pow_right"]) == np.float32(ot.pow_right)
+        assert t["syncword_freq"] == ot.freq
+        assert np.float32(t["syncword_amplitude"]) == np.float32(ot.amplitude)
+        assert np.float32(t["syncword_phase"]) == np.float32(ot.phase)
+        assert np.float32(t["syncword_time_est"]) == np.float32(ot.time_est)
+        assert np.float32(t["syncword_esn0_db"]) == np.float32(ot.esn0_db)
+
+
+def test_offline_vs_independent_oracle(oracle, rx_params):
+    """Config 1/2 signal model (20 dB, CFO 0.005): indices exact, estimates within tolerance, against
+    the oracle arithmetic that shares nothing with the GPU FFT."""
+    from gr4_packet_modem_b200.stimulus import packet_capture
+
+    n = 1 << 21
+    x, starts = packet_capture(n, seed=1, esn0_db=20.0, cfo=0.005, payload_bytes=1500)
+    sd = _gpu(rx_params, min_freq_bin=-4, max_freq_bin=4, power_threshold=9.5)
+    consumed, recs, tags = sd.detect_host(x)
+    o = oracle.SyncwordDetection(**rx_params, min_freq_bin=-4, max_freq_bin=4, power_threshold=9.5,
+                                 fft_kind=oracle.FFT_RADIX2, record_metric=True)
+    oc, _, otags = o.run(x, chunk=1 << 20)
+    assert consumed == oc
+    assert tags["index"].tolist() == [t.index for t in otags]
+    # every true syncword far enough from the end is found, at exactly its start sample
+    found = set(recs["index"].tolist())
+    for s in starts:
+        if s + sd.delay < consumed:
+            assert int(s) in found
+    zp, _ = o.metric(oc)
+    z = sd.metric(consumed)
+    assert np.linalg.norm(z - zp) / np.linalg.norm(zp) < 1e-5
+    for t, ot in zip(tags, otags):
+        assert abs(t["syncword_freq"] - ot.freq) < TOL_FREQ
+        assert abs(_wrap(t["syncword_phase"] - ot.phase)) < TOL_PHASE
+        assert abs(t["syncword_amplitude"] - ot.amplitude) < TOL_AMP
+        assert abs(t["syncword_time_est"] - ot.time_est) < TOL_TIME
+        assert t["syncword_freq_bin"] == ot.freq_bin
+        assert abs(t["syncword_esn0_db"] - ot.esn0_db) < 1e-2
+
+
+@pytest.mark.parametrize("chunk", [2048, 5000, 65536, 300000])
+def test_streaming_equals_offline_and_oracle(oracle, rx_params, chunk):
+    """processBulk in arbitrary chunkings gives the same tags at the same indices (state carried across
+    calls: _items_consumed, history, pending detections), same delayed output."""
+    from gr4_packet_modem_b200.stimulus import packet_capture
+
+    n = 600000
+    x, _ = packet_capture(n, seed=5, esn0_db=6.0, cfo=-0.012, payload_bytes=100)
+    sd = _gpu(rx_params, min_freq_bin=-2, max_freq_bin=2, power_threshold=9.5)
+    consumed, out, tags = sd.run(x, chunk=chunk, want_output=True)
+    o = oracle.SyncwordDetection(**rx_params, min_freq_bin=-2, max_freq_bin=2, power_threshold=9.5,
+                                 fft_kind=oracle.FFT_MIRROR)
+    oc, oout, otags = o.run(x, chunk=chunk, want_output=True)
+    assert consumed == oc
+    assert np.array_equal(out, oout)
+    assert [i for _, i, _ in tags] == [t.index for t in otags]
+    assert len(tags) > 3
+    for (_, _, m), ot in zip(tags, otags):
+        assert m["syncword_freq"] == ot.freq
+        assert np.float32(m["syncword_phase"]) == np.float32(ot.phase)
+
+
+def test_edge_inputs(oracle, rx_params):
+    """Empty / short / all-zero / exactly-one-block inputs (reference guards :215-227; the
+    benchmark's NullSource input, benchmarks/README.md:50-53)."""
+    sd = _gpu(rx_params, min_freq_bin=-4, max_freq_bin=4)
+    status, c, out, tags = sd.process_bulk(np.zeros(100, np.complex64))
+    assert status == "INSUFFICIENT_INPUT_ITEMS" and c == 0 and tags == []
+    status, c, out, tags = sd.process_bulk(np.zeros(2048, np.complex64))
+    assert status == "OK" and c == sd.stride == 1752 and tags == []
+    sd.start()
+    z = np.zeros(1 << 18, np.complex64)
+    consumed, recs, tags = sd.detect_host(z)
+    assert consumed == ((z.size - 2048) // 1752 + 1) * 1752 and len(recs) == 0
+    assert np.all(sd.metric(consumed) == 0.0)
+    # a constant (DC) input: heavy ties in the metric; must agree with the oracle exactly
+    dc = np.full(1 << 16, 0.25 + 0.5j, np.complex64)
+    consumed, recs, tags = sd.detect_host(dc)
+    o = oracle.SyncwordDetection(**rx_params, min_freq_bin=-4, max_freq_bin=4, fft_kind=oracle.FFT_MIRROR)
+    oc, _, otags = o.run(dc, chunk=1 << 16)
+    assert consumed == oc and (recs["index"] + sd.delay).tolist() == [t.index for t in otags]
+
+
+def test_settings_errors(rx_params):
+    """start() throws like the reference (PM/syncword_detection.hpp:145-152)."""
+    from gr4_packet_modem_b200.blocks import B200SyncError
+
+    with pytest.raises(B200SyncError, match="min_freq_bin is greater than max_freq_bin"):
+        _gpu(rx_params, min_freq_bin=2, max_freq_bin=1)
+    with pytest.raises(B200SyncError, match="fft_size too small"):
+        _gpu(dict(rx_params, syncword=np.zeros(600, np.uint8)))
