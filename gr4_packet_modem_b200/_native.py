@@ -83,9 +83,12 @@ def lib():
     L.b200sync_sd_shard_phase2.argtypes = [vp, C.c_uint32, vp, sz, psz]
     L.b200sync_sd_records_to_tags.argtypes = [vp, vp, sz, vp]
     L.b200sync_sd_copy_metric.argtypes = [vp, vp, sz]
+    pf = C.POINTER(C.c_float)
+    L.b200sync_sd_last_timings.argtypes = [vp, pf, pf, pf]
     for name in ("b200sync_sd_create", "b200sync_sd_start", "b200sync_sd_info", "b200sync_sd_process",
                  "b200sync_sd_detect_device", "b200sync_sd_detect_host", "b200sync_sd_shard_phase1",
-                 "b200sync_sd_shard_phase2", "b200sync_sd_records_to_tags", "b200sync_sd_copy_metric"):
+                 "b200sync_sd_shard_phase2", "b200sync_sd_records_to_tags", "b200sync_sd_copy_metric",
+                 "b200sync_sd_last_timings"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L

@@ -197,6 +197,12 @@ class SyncwordDetection:
         r = recs[:nr.value].copy()
         return r, self.records_to_tags(r)
 
+    def last_timings(self) -> dict:
+        """Device milliseconds of the stages of the last offline call (CUDA events)."""
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        check(_native.lib().b200sync_sd_last_timings(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"correlate_ms": a.value, "peaks_ms": b.value, "refine_ms": c.value}
+
     def metric(self, n: int) -> np.ndarray:
         """Per-sample winning correlation power of the last offline call (verification tap)."""
         z = np.zeros(n, np.float32)

@@ -100,6 +100,9 @@ struct b200sync_sd {
     size_t metric_n = 0;
     const float* metric_ptr = nullptr;
     long long metric_base = 0;
+    // device-side stage timing of the last offline call (CUDA events on the caller's stream)
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    bool ev_valid = false;
     // shard
     DevBuf<uint16_t> d_table;
     struct {
@@ -264,6 +267,8 @@ int do_start(b200sync_sd* sd) {
         return fail(B200SYNC_EUNSUPPORTED, "libb200sync is built for sm_100a; no Blackwell device found");
     sd->num_sms = prop.multiProcessorCount;
     if (!sd->stream) CU(cudaStreamCreateWithFlags(&sd->stream, cudaStreamNonBlocking));
+    for (auto& e : sd->ev)
+        if (!e) CU(cudaEventCreate(&e));
     CU(sd->d_tw.ensure(kFft));
     CU(sd->d_hperm.ensure(static_cast<size_t>(sd->K) * kFft));
     DevBuf<float2> d_td;
@@ -285,7 +290,7 @@ int do_start(b200sync_sd* sd) {
     return 0;
 }
 
-constexpr long long kOfflineChunkBlocks = 8192;  // ~14.4 M samples per chunk: zpow chunk stays in L2
+constexpr long long kOfflineChunkBlocks = 8192;  // ~14.4 M samples per correlator launch when chasing H2D copies
 constexpr long long kStreamStepBlocks = 4096;    // max blocks per streaming step
 
 // slide a device window down so that it starts at absolute index `keep_from`
@@ -349,6 +354,8 @@ void b200sync_sd_destroy(b200sync_sd* sd) {
         cudaStreamSynchronize(sd->stream);
         cudaStreamDestroy(sd->stream);
     }
+    for (auto& e : sd->ev)
+        if (e) cudaEventDestroy(e);
     delete sd;
 }
 
@@ -495,31 +502,44 @@ static int detect_resident(b200sync_sd* sd, const float2* d_in, size_t n, float2
     const long long nb_total = (static_cast<long long>(n) - F) / S + 1;
     const long long P = nb_total * S;
     CU(sd->d_zoff.ensure(static_cast<size_t>(P) + 64));
-    const long long chunk_range = kOfflineChunkBlocks * S + T + 2;
-    CU(sd->d_ws.ensure(peak_workspace_bytes_sms(chunk_range, sd->T, sd->num_sms)));
+    const long long hi_total = std::max(0LL, P - T - 1);
+    CU(sd->d_ws.ensure(peak_workspace_bytes_sms(hi_total + 1, sd->T, sd->num_sms)));
     if (int rc = ensure_det(sd, static_cast<size_t>(P / (T + 1) + 2))) return rc;
     if (int rc = reset_state(sd, st)) return rc;
     if (d_out_delayed) {
         const size_t zeros = std::min<size_t>(sd->delay, n);
         CU(cudaMemsetAsync(d_out_delayed, 0, zeros * sizeof(float2), st));
     }
-    long long lo = 0;
+    // correlator in chunks (so it can chase H2D copies); the peak stage runs ONCE over the
+    // whole decided range: its sequential table scan costs per launch, not per sample
+    sd->ev_valid = false;
+    CU(cudaEventRecord(sd->ev[0], st));
     for (long long b0 = 0; b0 < nb_total; b0 += kOfflineChunkBlocks) {
-        const long long nb = std::min(kOfflineChunkBlocks, nb_total - b0);
+        const long long nb = chunk_ready ? std::min(kOfflineChunkBlocks, nb_total - b0) : nb_total;
         if (chunk_ready) {
             // wait until the H2D copy covering the last sample of this chunk has landed
             const long long last_sample = (b0 + nb - 1) * S + F - 1;
             CU(cudaStreamWaitEvent(st, chunk_ready[last_sample / chunk_samples], 0));
         }
-        long long hi = (b0 + nb) * S - T - 1;
-        if (hi < lo) hi = lo;
-        if (int rc = run_chunk(sd, d_in, 0, sd->d_zoff.p, 0, b0, nb, lo, hi, d_out_delayed, st)) return rc;
-        lo = hi;
+        if (int rc = run_chunk(sd, d_in, 0, sd->d_zoff.p, 0, b0, nb, 0, 0, d_out_delayed, st)) return rc;
+        if (!chunk_ready) break;
     }
+    CU(cudaEventRecord(sd->ev[1], st));
+    if (hi_total > 0) {
+        CU(launch_peak_phase1(sd->d_zoff.p, 0, P, 0, hi_total, sd->T, sd->power_threshold, sd->d_ws.p,
+                              sd->d_ws.cap, nullptr, sd->num_sms, st));
+        CU(launch_peak_phase2(0, hi_total, sd->T, sd->d_ws.p, sd->d_ws.cap, -1, sd->d_state.p,
+                              sd->d_det_idx.p, (unsigned)sd->d_det_idx.cap, sd->num_sms, st));
+        g_launches += 4;
+    }
+    CU(cudaEventRecord(sd->ev[2], st));
     sd->metric_n = static_cast<size_t>(P);
     sd->metric_ptr = sd->d_zoff.p;
     sd->metric_base = 0;
     if (int rc = collect_records(sd, d_in, 0, sd->d_zoff.p, 0, st, sd->h_recs)) return rc;
+    CU(cudaEventRecord(sd->ev[3], st));
+    CU(cudaEventSynchronize(sd->ev[3]));
+    sd->ev_valid = true;
     // only what the reference block would have tagged: output index < items published
     size_t cnt = 0;
     for (const auto& r : sd->h_recs) {
@@ -587,6 +607,19 @@ int b200sync_sd_detect_host(b200sync_sd* sd, const float* in, size_t n, b200sync
     for (size_t i = 0; i < made; ++i) cudaEventDestroy(ev[i]);
     cudaStreamDestroy(cs);
     return rc;
+}
+
+int b200sync_sd_last_timings(const b200sync_sd* sd, float* correlate_ms, float* peaks_ms, float* refine_ms) {
+    if (!sd) return fail(B200SYNC_EINVAL, "null context");
+    if (!sd->ev_valid) return fail(B200SYNC_EINVAL, "no offline call has completed yet");
+    float a = 0, b = 0, c = 0;
+    CU(cudaEventElapsedTime(&a, sd->ev[0], sd->ev[1]));
+    CU(cudaEventElapsedTime(&b, sd->ev[1], sd->ev[2]));
+    CU(cudaEventElapsedTime(&c, sd->ev[2], sd->ev[3]));
+    if (correlate_ms) *correlate_ms = a;
+    if (peaks_ms) *peaks_ms = b;
+    if (refine_ms) *refine_ms = c;
+    return 0;
 }
 
 int b200sync_sd_copy_metric(const b200sync_sd* sd, float* zpow, size_t n) {

@@ -111,7 +111,9 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
 // PM/syncword_detection.hpp:326-342 with exactly the arithmetic of correlate_kernel.
 // One group per detection, grid-stride over the device-side detection count.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kGroupThreads)
+constexpr int kRefineThreads = kGroupThreads + 32;  // 4 FFT warps + 1 warp for the sequential noise sum
+
+__global__ void __launch_bounds__(kRefineThreads)
 refine_kernel(const float2* __restrict__ in, long long in_base, const float* __restrict__ zpow,
               long long z_base, const float2* __restrict__ hperm, int K, int S, int min_freq_bin,
               const float2* __restrict__ tw_g, const unsigned long long* __restrict__ det_idx,
@@ -125,6 +127,7 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
     load_twiddles(tw_s, tw_g);
     __syncthreads();
     const int tid = threadIdx.x;
+    const bool fft_warp = tid < kGroupThreads;
     unsigned int n = *det_count;
     if (n > det_cap) n = det_cap;
     for (unsigned int d = blockIdx.x; d < n; d += gridDim.x) {
@@ -133,32 +136,43 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
         const int kk = (int)(p - b * S);
         const int m = (kFft - kk) & (kFft - 1);
         const long long s0 = b * (long long)S;
-        const float2* src = in + (s0 - in_base);
-        float2 v[16], xs[16];
+        float2 xs[16];
+        if (fft_warp) {
+            const float2* src = in + (s0 - in_base);
+            float2 v[16];
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) v[n1] = __ldcs(src + 128 * n1 + tid);
-        fft_a(v, xs, tw_s, xb, tid, 1);
-        // noise power, sequential float sum over k = F/4 .. 3F/4-1 in index order (:257-265)
+            for (int n1 = 0; n1 < 16; ++n1) v[n1] = __ldcs(src + 128 * n1 + tid);
+            fft_a(v, xs, tw_s, xb, tid, 1);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) xpow[(tid + 128 * (j >> 3)) + 256 * (j & 7)] = norm2(xs[j]);
-        __syncthreads();
-        if (tid == 0) {
-            float acc = 0.0f;
-            for (int f = kFft / 4; f < 3 * kFft / 4; ++f) acc = __fadd_rn(acc, xpow[f]);
-            noise_s = __fdiv_rn(acc, __fmul_rn((float)(kFft / 2), (float)kFft));
+            for (int j = 0; j < 16; ++j) xpow[(tid + 128 * (j >> 3)) + 256 * (j & 7)] = norm2(xs[j]);
         }
-        for (int k = 0; k < K; ++k) {
-            const float2* h = hperm + (size_t)k * 16 * kGroupThreads + tid;
-            float2 y[16], c[16];
+        __syncthreads();
+        if (fft_warp) {
+            for (int k = 0; k < K; ++k) {
+                const float2* h = hperm + (size_t)k * 16 * kGroupThreads + tid;
+                float2 y[16], c[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) y[j] = cmul(xs[j], __ldg(h + j * kGroupThreads));
-            fft_b(y, c, tw_s, xb, tid, 1);
-            if (tid == (m & 127)) {
-                float2 val = c[0];
+                for (int j = 0; j < 16; ++j) y[j] = cmul(xs[j], __ldg(h + j * kGroupThreads));
+                fft_b(y, c, tw_s, xb, tid, 1);
+                if (tid == (m & 127)) {
+                    float2 val = c[0];
 #pragma unroll
-                for (int m1 = 1; m1 < 16; ++m1) val = ((m >> 7) == m1) ? c[m1] : val;
-                corr_s[k] = val;
+                    for (int m1 = 1; m1 < 16; ++m1) val = ((m >> 7) == m1) ? c[m1] : val;
+                    corr_s[k] = val;
+                }
             }
+        } else if (tid == kGroupThreads) {
+            // noise power: sequential float sum over k = F/4 .. 3F/4-1 in index order (:257-265),
+            // overlapped with the hypothesis FFTs of the other four warps
+            float acc = 0.0f;
+            for (int f = kFft / 4; f < 3 * kFft / 4; f += 16) {
+                float t[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) t[u] = xpow[f + u];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) acc = __fadd_rn(acc, t[u]);
+            }
+            noise_s = __fdiv_rn(acc, __fmul_rn((float)(kFft / 2), (float)kFft));
         }
         __syncthreads();
         if (tid == 0) {
@@ -228,7 +242,7 @@ cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_
     int grid = num_sms * 4;
     if ((unsigned)grid > det_cap) grid = (int)det_cap;
     if (grid < 1) grid = 1;
-    refine_kernel<<<grid, kGroupThreads, 0, st>>>(d_in, in_base, d_zpow, z_base, d_hperm, K, S,
+    refine_kernel<<<grid, kRefineThreads, 0, st>>>(d_in, in_base, d_zpow, z_base, d_hperm, K, S,
                                                   min_freq_bin, d_tw, d_det_idx, d_det_count, det_cap,
                                                   d_recs);
     return cudaGetLastError();

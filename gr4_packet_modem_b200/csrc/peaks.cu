@@ -252,8 +252,26 @@ chain_scan_kernel(const uint16_t* __restrict__ tables, long long nseg, int T, in
     int cur = t < Fr ? t : 0;
     for (long long base = 0; base < nseg; base += kScanBatch) {
         const int nb = (int)min((long long)kScanBatch, nseg - base);
-        const int total = nb * Fr;
-        for (int i = t; i < total; i += kScanThreads) tab[i] = tables[base * Fr + i];
+        const int total = nb * Fr;  // uint16 entries, contiguous in global memory
+        {
+            // stage the batch with 16-byte loads (the workspace areas are 256-byte aligned
+            // but base*Fr entries may start at any even/odd entry: peel to alignment)
+            const uint16_t* src = tables + base * Fr;
+            const int head = (int)(((16 - ((size_t)src & 15)) & 15) / 2);
+            const int h = head < total ? head : total;
+            if (t < h) tab[t] = src[t];
+            const int nvec = (total - h) / 8;
+            const uint4* vsrc = reinterpret_cast<const uint4*>(src + h);
+            for (int i = t; i < nvec; i += kScanThreads) {
+                const uint4 v = vsrc[i];
+                uint16_t* d = tab + h + 8 * i;  // smem side may be misaligned: store halves
+                d[0] = (uint16_t)(v.x & 0xffff); d[1] = (uint16_t)(v.x >> 16);
+                d[2] = (uint16_t)(v.y & 0xffff); d[3] = (uint16_t)(v.y >> 16);
+                d[4] = (uint16_t)(v.z & 0xffff); d[5] = (uint16_t)(v.z >> 16);
+                d[6] = (uint16_t)(v.w & 0xffff); d[7] = (uint16_t)(v.w >> 16);
+            }
+            for (int i = h + 8 * nvec + t; i < total; i += kScanThreads) tab[i] = src[i];
+        }
         __syncthreads();
         if (t < Fr) {
             for (int s = 0; s < nb; ++s) {

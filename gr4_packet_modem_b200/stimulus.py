@@ -66,14 +66,25 @@ def packet_capture(n_samples: int, seed: int = 1, esn0_db: float = 20.0, cfo: fl
     return x, np.array([s for s in starts if s + 297 <= n_samples], dtype=np.int64)
 
 
+def _hash32_torch(idx, salt: int):
+    """32-bit mixing hash of an int64 index tensor (pure function of index and salt)."""
+    lo = idx & 0xFFFFFFFF
+    hi = (idx >> 32) & 0xFFFFFFFF
+    h = (lo * 2654435761 + hi * 40503 + salt) & 0xFFFFFFFF
+    h = ((h ^ (h >> 16)) * 2246822507) & 0xFFFFFFFF
+    h = ((h ^ (h >> 13)) * 3266489909) & 0xFFFFFFFF
+    return h ^ (h >> 16)
+
+
 def packet_capture_torch(n_samples: int, device, seed: int = 1, esn0_db: float = 20.0, cfo: float = 0.005,
-                         payload_bytes: int = 1500, sps: int = 4, chunk: int = 1 << 24):
-    """Device-side generator for large captures: returns a torch.complex64 tensor of n_samples
-    on `device`.  Same frame structure and statistics as packet_capture()."""
+                         payload_bytes: int = 1500, sps: int = 4, chunk: int = 1 << 24, start: int = 0):
+    """Device-side generator for large captures: samples [start, start + n_samples) of an endless
+    stream, as a torch.complex64 tensor on `device`.  Every sample is a pure function of
+    (seed, absolute index) — symbols and noise come from integer hashes — so any segment
+    (e.g. one GPU's time shard plus halo) can be generated independently and is consistent
+    with its neighbours.  Same frame structure and statistics as packet_capture()."""
     import torch
 
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
     taps = torch.tensor(tx_rrc_taps(sps), dtype=torch.float32, device=device)
     ntaps = taps.numel()
     frame_len = 64 + 128 + (payload_bytes + 4) * 4
@@ -82,20 +93,17 @@ def packet_capture_torch(n_samples: int, device, seed: int = 1, esn0_db: float =
     n0 = TX_POWER * sps * 10.0 ** (-0.1 * esn0_db)
     hist = (ntaps + sps - 1) // sps  # symbols of filter memory
     kernel = taps.flip(0).view(1, 1, -1)
-    for s0 in range(0, n_samples, chunk):
-        m = min(chunk, n_samples - s0)
+    for c0 in range(0, n_samples, chunk):
+        m = min(chunk, n_samples - c0)
+        s0 = start + c0
         sym0 = s0 // sps - hist
         nsym = m // sps + hist + 2
-        idx = torch.arange(sym0, sym0 + nsym, device=device)
-        # symbols are a pure function of (seed, symbol index): chunking does not change the capture
-        h = (idx * 2654435761 + seed * 40503) & 0xFFFFFFFF
-        h = ((h ^ (h >> 15)) * 2246822519) & 0xFFFFFFFF
-        h = ((h ^ (h >> 13)) * 3266489917) & 0xFFFFFFFF
-        h = h ^ (h >> 16)
+        idx = torch.arange(sym0, sym0 + nsym, device=device, dtype=torch.int64)
+        h = _hash32_torch(idx.clamp(min=0), seed * 7919 + 17)
         re = 1.0 - 2.0 * (h & 1).to(torch.float32)
         im = 1.0 - 2.0 * ((h >> 1) & 1).to(torch.float32)
-        inframe = torch.remainder(idx, frame_len)
-        is_sw = (inframe < 64) & (idx >= 0)
+        inframe = torch.remainder(idx.clamp(min=0), frame_len)
+        is_sw = inframe < 64
         re = torch.where(is_sw, sw[inframe.clamp(max=63)], re * (1.0 / math.sqrt(2.0)))
         im = torch.where(is_sw, torch.zeros_like(im), im * (1.0 / math.sqrt(2.0)))
         valid = (idx >= 0).to(torch.float32)
@@ -103,13 +111,21 @@ def packet_capture_torch(n_samples: int, device, seed: int = 1, esn0_db: float =
         up = torch.zeros(2, 1, nsym * sps, dtype=torch.float32, device=device)
         up[0, 0, ::sps] = re
         up[1, 0, ::sps] = im
+        del re, im, h, inframe, is_sw, valid, idx
         up = torch.nn.functional.pad(up, (ntaps - 1, 0))
         y = torch.nn.functional.conv1d(up, kernel)  # causal FIR: y[n] = sum_k taps[k] up[n-k]
+        del up
         off = s0 - sym0 * sps
         sig = torch.complex(y[0, 0, off:off + m], y[1, 0, off:off + m])
-        n = torch.arange(s0, s0 + m, device=device, dtype=torch.float64)
-        ph = torch.remainder(n * cfo, 2.0 * math.pi).to(torch.float32)
+        del y
+        n = torch.arange(s0, s0 + m, device=device, dtype=torch.int64)
+        ph = torch.remainder(n.to(torch.float64) * cfo, 2.0 * math.pi).to(torch.float32)
         sig = sig * torch.complex(torch.cos(ph), torch.sin(ph))
-        noise = torch.randn(m, 2, generator=g, device=device, dtype=torch.float32) * math.sqrt(n0 / 2.0)
-        out[s0:s0 + m] = sig + torch.view_as_complex(noise)
+        del ph
+        u1 = (_hash32_torch(n, seed * 104729 + 1).to(torch.float32) + 1.0) * (1.0 / 4294967296.0)
+        u2 = _hash32_torch(n, seed * 1299709 + 2).to(torch.float32) * (2.0 * math.pi / 4294967296.0)
+        del n
+        r = torch.sqrt(-2.0 * torch.log(u1.clamp(min=1e-12))) * math.sqrt(n0 / 2.0)
+        out[c0:c0 + m] = sig + torch.complex(r * torch.cos(u2), r * torch.sin(u2))
+        del sig, u1, u2, r
     return out

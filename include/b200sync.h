@@ -148,6 +148,11 @@ int b200sync_sd_shard_phase2(b200sync_sd* sd, uint32_t entry_offset, b200sync_de
 int b200sync_sd_records_to_tags(const b200sync_sd* sd, const b200sync_detection_record* recs, size_t n,
                                 b200sync_sd_tag* tags);
 
+/* Device time (CUDA events recorded on the caller's stream) of the stages of the last
+ * detect_device / detect_host call: correlator launches, peak stage, refine + record copy.
+ * With detect_host the correlator figure includes waiting for the H2D copies it chases. */
+int b200sync_sd_last_timings(const b200sync_sd* sd, float* correlate_ms, float* peaks_ms, float* refine_ms);
+
 /* Debug/verification tap: copy the per-sample winning correlation power of the last
  * detect_device/detect_host call (zpow[0..n)) to host memory. */
 int b200sync_sd_copy_metric(const b200sync_sd* sd, float* zpow, size_t n);
