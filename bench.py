@@ -44,23 +44,23 @@ def flop_per_sample(K: int, S: int = 1752) -> float:
 class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.rows, self._halt = index, [], threading.Event()
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
                                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
                 self.rows.append([c.strip() for c in o.stdout.strip().split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self) -> dict:
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
