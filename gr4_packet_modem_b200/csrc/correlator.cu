@@ -17,7 +17,7 @@
 namespace b200sync {
 
 __device__ __forceinline__ void load_twiddles(float2* tw_s, const float2* __restrict__ tw_g) {
-    for (int i = threadIdx.x; i < kFft; i += blockDim.x) tw_s[i] = tw_g[i];
+    for (int i = threadIdx.x; i < kTwTotal; i += blockDim.x) tw_s[i] = tw_g[i];
 }
 
 // ---------------------------------------------------------------------------------
@@ -27,8 +27,9 @@ __device__ __forceinline__ void load_twiddles(float2* tw_s, const float2* __rest
 __global__ void __launch_bounds__(kGroupThreads)
 template_spectra_kernel(const float2* __restrict__ td /*[K][2048] zero padded*/,
                         float2* __restrict__ hperm, const float2* __restrict__ tw_g) {
-    __shared__ float2 tw_s[kFft];
-    __shared__ float2 xb[kXchgFloat2];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* tw_s = reinterpret_cast<float2*>(smem_raw);
+    float2* xb = tw_s + kTwTotal;
     load_twiddles(tw_s, tw_g);
     __syncthreads();
     const int tid = threadIdx.x;
@@ -56,7 +57,7 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
     const int g = threadIdx.x >> 7;
     const int tid = threadIdx.x & 127;
-    float2* xb = tw_s + kFft + g * kXchgFloat2;
+    float2* xb = tw_s + kTwTotal + g * kXchgFloat2;
     load_twiddles(tw_s, tw_g);
     __syncthreads();
     const int ngroups = blockDim.x >> 7;
@@ -119,10 +120,11 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
               const float2* __restrict__ tw_g, const unsigned long long* __restrict__ det_idx,
               const unsigned int* __restrict__ det_count, unsigned int det_cap,
               DetectionRecord* __restrict__ recs) {
-    __shared__ float2 tw_s[kFft];
-    __shared__ float2 xb[kXchgFloat2];
-    __shared__ float xpow[kFft];
-    __shared__ float2 corr_s[kMaxHyp];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* tw_s = reinterpret_cast<float2*>(smem_raw);
+    float2* xb = tw_s + kTwTotal;
+    float2* corr_s = xb + kXchgFloat2;
+    float* xpow = reinterpret_cast<float*>(corr_s + kMaxHyp + 1);
     __shared__ float noise_s;
     load_twiddles(tw_s, tw_g);
     __syncthreads();
@@ -206,12 +208,16 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
 // ---------------------------------------------------------------------------------
 cudaError_t launch_template_spectra(const float2* d_td, float2* d_hperm, int K, const float2* d_tw,
                                     cudaStream_t st) {
-    template_spectra_kernel<<<K, kGroupThreads, 0, st>>>(d_td, d_hperm, d_tw);
+    const size_t smem = sizeof(float2) * (size_t)(kTwTotal + kXchgFloat2);
+    cudaError_t e = cudaFuncSetAttribute(template_spectra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    template_spectra_kernel<<<K, kGroupThreads, smem, st>>>(d_td, d_hperm, d_tw);
     return cudaGetLastError();
 }
 
 size_t correlate_smem_bytes(int groups) {
-    return sizeof(float2) * (size_t)(kFft + groups * kXchgFloat2);
+    return sizeof(float2) * (size_t)(kTwTotal + groups * kXchgFloat2);
 }
 
 cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpow, long long z_base,
@@ -242,7 +248,10 @@ cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_
     int grid = num_sms * 4;
     if ((unsigned)grid > det_cap) grid = (int)det_cap;
     if (grid < 1) grid = 1;
-    refine_kernel<<<grid, kRefineThreads, 0, st>>>(d_in, in_base, d_zpow, z_base, d_hperm, K, S,
+    const size_t smem = sizeof(float2) * (size_t)(kTwTotal + kXchgFloat2 + kMaxHyp + 1) + sizeof(float) * kFft;
+    cudaError_t e = cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    refine_kernel<<<grid, kRefineThreads, smem, st>>>(d_in, in_base, d_zpow, z_base, d_hperm, K, S,
                                                   min_freq_bin, d_tw, d_det_idx, d_det_count, det_cap,
                                                   d_recs);
     return cudaGetLastError();
