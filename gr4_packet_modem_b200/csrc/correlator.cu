@@ -93,7 +93,7 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
 #pragma unroll
             for (int m1 = 0; m1 < 16; ++m1) {
                 const float p = norm2(c[m1]);  // :307
-                best[m1] = (p > best[m1]) ? p : best[m1];  // strict >, first hypothesis wins ties (:308)
+                best[m1] = fmaxf(best[m1], p);  // == the strict '>' update of :308 for the power itself
             }
         }
         // time reversal: lag kk lives at index (F - kk) mod F (:300)

@@ -1,0 +1,66 @@
+"""CPU tests (no GPU): the C-ABI library loads, exports every symbol include/b200sync.h declares,
+and fails loudly (no CPU fallback) when no Blackwell device is usable."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def native():
+    import __graft_entry__ as ge
+
+    if not os.path.exists(os.path.join(ROOT, "gr4_packet_modem_b200", "libb200sync.so")):
+        ge.build()
+    from gr4_packet_modem_b200 import _native
+
+    return _native
+
+
+def declared_functions():
+    hdr = open(os.path.join(ROOT, "include", "b200sync.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200sync_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(native):
+    lib = ctypes.CDLL(native.LIB_PATH)
+    names = declared_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/b200sync.h but not exported"
+    assert lib.b200sync_abi_version() == 1
+
+
+def test_struct_layouts_match_header(native):
+    assert ctypes.sizeof(native.DetectionRecord) == 48
+    assert ctypes.sizeof(native.SyncwordTag) == 40
+
+
+def test_no_cpu_fallback(native):
+    """Without a CUDA device create() must fail with an error, never compute on the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from gr4_packet_modem_b200 import SyncwordDetection
+    from gr4_packet_modem_b200.blocks import B200SyncError
+    from gr4_packet_modem_b200.firdes import BPSK, SYNCWORD, unit_energy_rrc
+
+    with pytest.raises(B200SyncError):
+        SyncwordDetection(unit_energy_rrc(), SYNCWORD, BPSK, -4, 4)
+
+
+def test_product_does_not_reference_oracle():
+    """The product path must not import, link or call anything under oracle/."""
+    pkg = os.path.join(ROOT, "gr4_packet_modem_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")) or f == "Makefile":
+                txt = open(os.path.join(d, f), errors="ignore").read()
+                for line in txt.splitlines():
+                    code = line.split("//")[0].split("#")[0] if not f.endswith(".py") else line.split("#")[0]
+                    assert "pyoracle" not in code and "liboracle" not in code and "oracle/" not in code, (f, line)

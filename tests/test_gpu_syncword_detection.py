@@ -177,3 +177,29 @@ def test_settings_errors(rx_params):
         _gpu(rx_params, min_freq_bin=2, max_freq_bin=1)
     with pytest.raises(B200SyncError, match="fft_size too small"):
         _gpu(dict(rx_params, syncword=np.zeros(600, np.uint8)))
+
+
+@pytest.mark.parametrize("T", [0, 1, 5, 31, 32, 33, 100, 500, 1023])
+def test_time_threshold_sweep_bit_exact(oracle, rx_params, T):
+    """Both flags kernels (generic T < 32, group-scan T >= 32) and the chain kernels for every
+    piece length, against the oracle's sequential state machine, on a noisy capture with many
+    marginal threshold decisions."""
+    from gr4_packet_modem_b200.stimulus import packet_capture
+
+    x, _ = packet_capture(1 << 18, seed=9, esn0_db=2.0, cfo=0.02, payload_bytes=60)
+    sd = _gpu(rx_params, min_freq_bin=-1, max_freq_bin=1, power_threshold=4.0, time_threshold=T)
+    consumed, recs, tags = sd.detect_host(x)
+    o = oracle.SyncwordDetection(**rx_params, min_freq_bin=-1, max_freq_bin=1, power_threshold=4.0,
+                                 time_threshold=T, fft_kind=oracle.FFT_MIRROR)
+    oc, _, otags = o.run(x, chunk=1 << 18, )
+    assert consumed == oc
+    assert tags["index"].tolist() == [t.index for t in otags]
+    if T >= 31:  # tiny windows of a 4x-oversampled correlation never pass the threshold test
+        assert len(tags) > 10
+    # and streaming in odd chunks
+    sd.start()
+    c2, _, t2 = sd.run(x, chunk=7001)
+    o2 = oracle.SyncwordDetection(**rx_params, min_freq_bin=-1, max_freq_bin=1, power_threshold=4.0,
+                                  time_threshold=T, fft_kind=oracle.FFT_MIRROR)
+    oc2, _, ot2 = o2.run(x, chunk=7001)
+    assert c2 == oc2 and [i for _, i, _ in t2] == [t.index for t in ot2]
