@@ -41,33 +41,48 @@ def flop_per_sample(K: int, S: int = 1752) -> float:
     return ((1 + K) * 112640 + 9 * K * 2048 + 3 * 1024) / S
 
 
-class ClockSampler(threading.Thread):
-    def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+class ClockSampler:
+    """Streams `nvidia-smi -lms 100` for the duration of the timed region (B200_PROFILING.md clocks line)."""
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        while not self._halt.is_set():
-            try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                self.rows.append([c.strip() for c in o.stdout.strip().split(",")])
-            except Exception:
-                pass
-            self._halt.wait(0.2)
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self) -> dict:
-        self._halt.set()
-        self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        rows = []
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            rows = [[c.strip() for c in l.split(",")] for l in out.strip().splitlines()]
+        ok = [r for r in rows if len(r) >= 7]
+
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:
+                return None
+        sm = [num(r[0]) for r in ok if num(r[0]) is not None]
+        mx = [num(r[1]) for r in ok if num(r[1]) is not None]
+        pw = [num(r[2]) for r in ok if num(r[2]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        reasons = sorted({names[i] for r in ok for i in range(4) if r[3 + i] == "Active"})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm)}
 
 
 def rx_settings(bins: int):
@@ -139,7 +154,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=30, help="log2 samples per GPU")
@@ -253,7 +268,7 @@ def main():
         step_host()
         barrier()
         t0 = time.perf_counter()
-        reps = max(1, min(args.steps, 3))
+        reps = 3
         for _ in range(reps):
             c_h, nd_h = step_host()
         barrier()
