@@ -55,6 +55,19 @@ class SyncwordTag(C.Structure):
     ]
 
 
+class FeConfig(C.Structure):
+    _fields_ = [
+        ("rate", C.c_float),
+        ("taps", C.c_void_p),
+        ("n_taps", C.c_uint32),
+        ("filter_size", C.c_uint32),
+        ("phase_incr", C.c_float),
+        ("enable_resampler", C.c_uint32),
+        ("enable_rotator", C.c_uint32),
+        ("device", C.c_int32),
+    ]
+
+
 _lib = None
 
 
@@ -85,6 +98,16 @@ def lib():
     L.b200sync_sd_copy_metric.argtypes = [vp, vp, sz]
     pf = C.POINTER(C.c_float)
     L.b200sync_sd_last_timings.argtypes = [vp, pf, pf, pf]
+    L.b200sync_fe_create.argtypes = [C.POINTER(FeConfig), C.POINTER(vp)]
+    L.b200sync_fe_destroy.argtypes = [vp]
+    L.b200sync_fe_start.argtypes = [vp]
+    L.b200sync_fe_last_error.restype = C.c_char_p
+    L.b200sync_fe_max_output.argtypes = [vp, sz]
+    L.b200sync_fe_max_output.restype = sz
+    L.b200sync_fe_process.argtypes = [vp, vp, sz, vp, sz, psz, psz]
+    L.b200sync_fe_process_device.argtypes = [vp, vp, sz, vp, sz, vp, psz, psz]
+    for name in ("b200sync_fe_create", "b200sync_fe_start", "b200sync_fe_process", "b200sync_fe_process_device"):
+        getattr(L, name).restype = C.c_int
     for name in ("b200sync_sd_create", "b200sync_sd_start", "b200sync_sd_info", "b200sync_sd_process",
                  "b200sync_sd_detect_device", "b200sync_sd_detect_host", "b200sync_sd_shard_phase1",
                  "b200sync_sd_shard_phase2", "b200sync_sd_records_to_tags", "b200sync_sd_copy_metric",
@@ -101,4 +124,10 @@ class B200SyncError(RuntimeError):
 def check(rc: int) -> int:
     if rc < 0:
         raise B200SyncError(f"libb200sync error {rc}: {lib().b200sync_last_error().decode()}")
+    return rc
+
+
+def check_fe(rc: int) -> int:
+    if rc < 0:
+        raise B200SyncError(f"libb200sync error {rc}: {lib().b200sync_fe_last_error().decode()}")
     return rc

@@ -210,4 +210,86 @@ class SyncwordDetection:
         return z
 
 
-__all__ = ["SyncwordDetection", "DetectionRecord", "SyncwordTag", "B200SyncError", "RECORD_DTYPE", "TAG_DTYPE"]
+class FrontEnd:
+    """PfbArbResampler<c64,c64,float,float> followed by Rotator<float>, fused in one kernel
+    (PM/pfb_arb_resampler.hpp, PM/rotator.hpp; wiring apps/packet_transceiver.cpp:71-75).
+    Settings carry the reference names: rate, taps, filter_size, phase_incr."""
+
+    def __init__(self, rate: float = 1.0, taps=None, filter_size: int = 32, phase_incr: float = 0.0,
+                 enable_resampler: bool = True, enable_rotator: bool = True, device: int = 0):
+        self.rate = float(np.float32(rate))
+        self.taps = np.ascontiguousarray(taps if taps is not None else np.zeros(0), dtype=np.float32)
+        self.filter_size = int(filter_size)
+        self.phase_incr = float(np.float32(phase_incr))
+        self.enable_resampler, self.enable_rotator = bool(enable_resampler), bool(enable_rotator)
+        self.device = int(device)
+        self._h = C.c_void_p()
+        self.start()
+
+    def start(self) -> None:
+        """settingsChanged() + start() of both blocks; raises where the reference throws
+        ("filter_size cannot be 0", PM/pfb_arb_resampler.hpp:70-72)."""
+        from ._native import FeConfig, check_fe
+
+        L = _native.lib()
+        self._destroy()
+        cfg = FeConfig(self.rate, self.taps.ctypes.data if self.taps.size else None, self.taps.size,
+                       self.filter_size, self.phase_incr, int(self.enable_resampler), int(self.enable_rotator),
+                       self.device)
+        h = C.c_void_p()
+        check_fe(L.b200sync_fe_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+
+    def _destroy(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _native.lib().b200sync_fe_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    def max_output(self, n_in: int) -> int:
+        return int(_native.lib().b200sync_fe_max_output(self._h, n_in))
+
+    def process_bulk(self, in_span, max_out: int | None = None):
+        """processBulk(inSpan, outSpan) with host spans -> (consumed, produced items)."""
+        from ._native import check_fe
+
+        x = np.ascontiguousarray(in_span, dtype=np.complex64)
+        if max_out is None:
+            max_out = self.max_output(x.size)
+        out = np.empty(max_out, np.complex64)
+        nc, npd = C.c_size_t(0), C.c_size_t(0)
+        check_fe(_native.lib().b200sync_fe_process(self._h, x.ctypes.data, x.size, out.ctypes.data, max_out,
+                                                   C.byref(nc), C.byref(npd)))
+        return nc.value, out[:npd.value]
+
+    def process_device(self, d_in_ptr: int, n_in: int, d_out_ptr: int, max_out: int, stream_ptr: int = 0):
+        from ._native import check_fe
+
+        nc, npd = C.c_size_t(0), C.c_size_t(0)
+        check_fe(_native.lib().b200sync_fe_process_device(self._h, C.c_void_p(d_in_ptr), n_in, C.c_void_p(d_out_ptr),
+                                                          max_out, C.c_void_p(stream_ptr or None), C.byref(nc),
+                                                          C.byref(npd)))
+        return nc.value, npd.value
+
+
+class PfbArbResampler(FrontEnd):
+    """gr::packet_modem::PfbArbResampler<c64, c64, float, float> alone (PM/pfb_arb_resampler.hpp)."""
+
+    def __init__(self, rate: float, taps, filter_size: int = 32, device: int = 0):
+        super().__init__(rate=rate, taps=taps, filter_size=filter_size, enable_rotator=False, device=device)
+
+
+class Rotator(FrontEnd):
+    """gr::packet_modem::Rotator<float> alone (PM/rotator.hpp)."""
+
+    def __init__(self, phase_incr: float, device: int = 0):
+        super().__init__(phase_incr=phase_incr, enable_resampler=False, device=device)
+
+
+__all__ = ["SyncwordDetection", "DetectionRecord", "SyncwordTag", "B200SyncError", "RECORD_DTYPE", "TAG_DTYPE",
+           "FrontEnd", "PfbArbResampler", "Rotator"]

@@ -157,6 +157,44 @@ int b200sync_sd_last_timings(const b200sync_sd* sd, float* correlate_ms, float* 
  * detect_device/detect_host call (zpow[0..n)) to host memory. */
 int b200sync_sd_copy_metric(const b200sync_sd* sd, float* zpow, size_t n);
 
+/* ------------------------------------------------------------------------------
+ * Front end: PfbArbResampler + Rotator fused     PM/pfb_arb_resampler.hpp, PM/rotator.hpp
+ * (the SFO / CFO conditioning stage in front of SyncwordDetection,
+ *  apps/packet_transceiver.cpp:71-75).  Either stage can be disabled, which gives the two
+ *  reference blocks individually.
+ * ------------------------------------------------------------------------------ */
+typedef struct b200sync_fe_config {
+    float rate;                /* PfbArbResampler::rate, TRate = float (PM/pfb_arb_resampler.hpp:63)  */
+    const float* taps;         /* PfbArbResampler::taps (prototype filter)            (:64)           */
+    uint32_t n_taps;
+    uint32_t filter_size;      /* PfbArbResampler::filter_size, default 32            (:65)           */
+    float phase_incr;          /* Rotator::phase_incr in rad/sample                   (PM/rotator.hpp:42) */
+    uint32_t enable_resampler; /* 0: bypass the resampler (Rotator block alone)                       */
+    uint32_t enable_rotator;   /* 0: bypass the rotator (PfbArbResampler block alone)                 */
+    int32_t device;
+} b200sync_fe_config;
+
+typedef struct b200sync_fe b200sync_fe;
+
+/* settingsChanged() of both blocks + start(): polyphase split, derivative filter, decim/filt
+ * rates (PM/pfb_arb_resampler.hpp:67-120), _exp_incr (PM/rotator.hpp:44-48); state reset. */
+int b200sync_fe_create(const b200sync_fe_config* cfg, b200sync_fe** out);
+void b200sync_fe_destroy(b200sync_fe* fe);
+int b200sync_fe_start(b200sync_fe* fe);
+const char* b200sync_fe_last_error(void);
+/* Upper bound on the outputs n_in further inputs can produce (buffer sizing for Async ports). */
+size_t b200sync_fe_max_output(const b200sync_fe* fe, size_t n_in);
+
+/* processBulk(inSpan, outSpan) of the resampler (PM/pfb_arb_resampler.hpp:122-182) followed by
+ * Rotator::processOne on every produced item; streaming state (filter history, output phase)
+ * lives behind the handle.  Consumes all n_in items unless the output span fills up first.
+ * Host spans: */
+int b200sync_fe_process(b200sync_fe* fe, const float* in, size_t n_in, float* out, size_t max_out,
+                        size_t* n_consumed, size_t* n_produced);
+/* Device spans, asynchronous on cuda_stream (the counts are computed on the host up front). */
+int b200sync_fe_process_device(b200sync_fe* fe, const void* d_in, size_t n_in, void* d_out, size_t max_out,
+                               void* cuda_stream, size_t* n_consumed, size_t* n_produced);
+
 #ifdef __cplusplus
 }
 #endif
