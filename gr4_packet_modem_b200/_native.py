@@ -55,6 +55,30 @@ class SyncwordTag(C.Structure):
     ]
 
 
+class StreamTag(C.Structure):
+    _fields_ = [
+        ("index", C.c_uint64),
+        ("has_syncword", C.c_uint32),
+        ("other", C.c_uint32),
+        ("sw", SyncwordTag),
+    ]
+
+
+class SfConfig(C.Structure):
+    _fields_ = [
+        ("samples_per_symbol", C.c_uint32),
+        ("taps", C.c_void_p),
+        ("n_taps", C.c_uint32),
+        ("num_arms", C.c_uint32),
+        ("delay", C.c_uint32),
+        ("device", C.c_int32),
+    ]
+
+
+class SdfHeader(C.Structure):
+    _fields_ = [("invalid_header", C.c_uint32), ("packet_length", C.c_uint64)]
+
+
 class FeConfig(C.Structure):
     _fields_ = [
         ("rate", C.c_float),
@@ -106,6 +130,20 @@ def lib():
     L.b200sync_fe_max_output.restype = sz
     L.b200sync_fe_process.argtypes = [vp, vp, sz, vp, sz, psz, psz]
     L.b200sync_fe_process_device.argtypes = [vp, vp, sz, vp, sz, vp, psz, psz]
+    L.b200sync_sf_create.argtypes = [C.POINTER(SfConfig), C.POINTER(vp)]
+    L.b200sync_sf_destroy.argtypes = [vp]
+    L.b200sync_sf_start.argtypes = [vp]
+    L.b200sync_sf_last_error.restype = C.c_char_p
+    L.b200sync_sf_process.argtypes = [vp, vp, sz, vp, sz, vp, sz, psz, psz, vp, sz, psz]
+    L.b200sync_sf_process_device.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, psz, psz, vp, sz, psz]
+    L.b200sync_sdf_create.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+    L.b200sync_sdf_destroy.argtypes = [vp]
+    L.b200sync_sdf_start.argtypes = [vp]
+    pi = C.POINTER(C.c_int)
+    L.b200sync_sdf_process.argtypes = [vp, vp, sz, vp, sz, vp, vp, sz, psz, psz, psz, vp, pi, pi]
+    for name in ("b200sync_sf_create", "b200sync_sf_start", "b200sync_sf_process", "b200sync_sf_process_device",
+                 "b200sync_sdf_create", "b200sync_sdf_start", "b200sync_sdf_process"):
+        getattr(L, name).restype = C.c_int
     for name in ("b200sync_fe_create", "b200sync_fe_start", "b200sync_fe_process", "b200sync_fe_process_device"):
         getattr(L, name).restype = C.c_int
     for name in ("b200sync_sd_create", "b200sync_sd_start", "b200sync_sd_info", "b200sync_sd_process",
@@ -124,6 +162,12 @@ class B200SyncError(RuntimeError):
 def check(rc: int) -> int:
     if rc < 0:
         raise B200SyncError(f"libb200sync error {rc}: {lib().b200sync_last_error().decode()}")
+    return rc
+
+
+def check_sf(rc: int) -> int:
+    if rc < 0:
+        raise B200SyncError(f"libb200sync error {rc}: {lib().b200sync_sf_last_error().decode()}")
     return rc
 
 

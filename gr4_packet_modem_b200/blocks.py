@@ -277,6 +277,113 @@ class FrontEnd:
         return nc.value, npd.value
 
 
+STREAM_TAG_DTYPE = np.dtype([("index", "<u8"), ("has_syncword", "<u4"), ("other", "<u4"), ("sw", TAG_DTYPE)])
+assert STREAM_TAG_DTYPE.itemsize == C.sizeof(_native.StreamTag)
+
+
+def stream_tags_from_detection(tags: np.ndarray) -> np.ndarray:
+    """SyncwordDetection output tags (absolute output indices) as a stream-tag array."""
+    st = np.zeros(tags.size, STREAM_TAG_DTYPE)
+    st["index"] = tags["index"]
+    st["has_syncword"] = 1
+    st["sw"] = tags
+    return st
+
+
+class SymbolFilter:
+    """gr::packet_modem::SymbolFilter<c64, c64, float> on the GPU (PM/symbol_filter.hpp).
+    Settings: samples_per_symbol, taps, num_arms, delay (:53-59)."""
+
+    def __init__(self, taps, num_arms: int, samples_per_symbol: int = 4, delay: int = 0, device: int = 0):
+        self.taps = np.ascontiguousarray(taps, dtype=np.float32)
+        self.num_arms, self.samples_per_symbol, self.delay = int(num_arms), int(samples_per_symbol), int(delay)
+        self.device = int(device)
+        self._h = C.c_void_p()
+        self.start()
+
+    def start(self) -> None:
+        from ._native import SfConfig, check_sf
+
+        self._destroy()
+        cfg = SfConfig(self.samples_per_symbol, self.taps.ctypes.data if self.taps.size else None, self.taps.size,
+                       self.num_arms, self.delay, self.device)
+        h = C.c_void_p()
+        check_sf(_native.lib().b200sync_sf_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+
+    def _destroy(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _native.lib().b200sync_sf_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    def process_bulk(self, in_span, in_tags: np.ndarray | None = None):
+        """processBulk over a host span carrying `in_tags` (STREAM_TAG_DTYPE, indices relative to the
+        span).  Returns (consumed, symbols, out_tags) with out_tags indices relative to the symbols."""
+        from ._native import check_sf
+
+        x = np.ascontiguousarray(in_span, dtype=np.complex64)
+        it = np.ascontiguousarray(in_tags if in_tags is not None else np.zeros(0, STREAM_TAG_DTYPE), STREAM_TAG_DTYPE)
+        max_out = x.size // max(self.samples_per_symbol, 1) + it.size + 2
+        out = np.empty(max_out, np.complex64)
+        ot = np.zeros(it.size + 64, STREAM_TAG_DTYPE)
+        nc, npd, nt = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+        check_sf(_native.lib().b200sync_sf_process(self._h, x.ctypes.data, x.size, it.ctypes.data if it.size else None,
+                                                   it.size, out.ctypes.data, max_out, C.byref(nc), C.byref(npd),
+                                                   ot.ctypes.data, ot.size, C.byref(nt)))
+        return nc.value, out[:npd.value], ot[:nt.value].copy()
+
+
+class SyncwordDetectionFilter:
+    """gr::packet_modem::SyncwordDetectionFilter (PM/syncword_detection_filter.hpp): host control logic
+    behind the C ABI."""
+
+    def __init__(self, samples_per_symbol: int = 4, syncword_size: int = 64, header_size: int = 128):
+        h = C.c_void_p()
+        check(_native.lib().b200sync_sdf_create(samples_per_symbol, syncword_size, header_size, C.byref(h)))
+        self._h = h
+        check(_native.lib().b200sync_sdf_start(self._h))
+
+    def __del__(self):
+        try:
+            if self._h.value:
+                _native.lib().b200sync_sdf_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def process_bulk(self, in_span, n_out: int | None = None, tag: np.void | None = None, header=None,
+                     n_ignored: int = 0):
+        """header: None | ("parsed", packet_length) | ("invalid",).  Returns
+        (consumed, out, forwarded_tag_or_None, header_consumed, ignored_consumed, in_packet)."""
+        from ._native import SdfHeader, StreamTag, check_sf
+
+        x = np.ascontiguousarray(in_span, dtype=np.complex64)
+        n_out = x.size if n_out is None else n_out
+        out = np.zeros(n_out, np.complex64)
+        hdr = None
+        if header is not None:
+            hdr = SdfHeader(1, 0) if header[0] == "invalid" else SdfHeader(0, int(header[1]))
+        tin = None
+        if tag is not None:
+            tin = StreamTag.from_buffer_copy(np.asarray(tag, STREAM_TAG_DTYPE).tobytes())
+        tout = StreamTag()
+        nc, hu, iu = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+        fwd, inpkt = C.c_int(0), C.c_int(0)
+        check_sf(_native.lib().b200sync_sdf_process(self._h, x.ctypes.data, x.size, out.ctypes.data, n_out,
+                                                    C.byref(tin) if tin is not None else None,
+                                                    C.byref(hdr) if hdr is not None else None, n_ignored,
+                                                    C.byref(nc), C.byref(hu), C.byref(iu), C.byref(tout),
+                                                    C.byref(fwd), C.byref(inpkt)))
+        t = np.frombuffer(bytes(tout), STREAM_TAG_DTYPE)[0] if fwd.value else None
+        return nc.value, out[:nc.value], t, hu.value, iu.value, bool(inpkt.value)
+
+
 class PfbArbResampler(FrontEnd):
     """gr::packet_modem::PfbArbResampler<c64, c64, float, float> alone (PM/pfb_arb_resampler.hpp)."""
 
@@ -292,4 +399,5 @@ class Rotator(FrontEnd):
 
 
 __all__ = ["SyncwordDetection", "DetectionRecord", "SyncwordTag", "B200SyncError", "RECORD_DTYPE", "TAG_DTYPE",
-           "FrontEnd", "PfbArbResampler", "Rotator"]
+           "FrontEnd", "PfbArbResampler", "Rotator", "SymbolFilter", "SyncwordDetectionFilter",
+           "STREAM_TAG_DTYPE", "stream_tags_from_detection"]

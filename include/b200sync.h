@@ -195,6 +195,75 @@ int b200sync_fe_process(b200sync_fe* fe, const float* in, size_t n_in, float* ou
 int b200sync_fe_process_device(b200sync_fe* fe, const void* d_in, size_t n_in, void* d_out, size_t max_out,
                                void* cuda_stream, size_t* n_consumed, size_t* n_produced);
 
+/* ------------------------------------------------------------------------------
+ * Stream tags crossing SyncwordDetectionFilter and SymbolFilter.  A GR4 tag is a property_map;
+ * the hot path only reads the syncword_* keys (PM/syncword_detection.hpp:106-114), every other
+ * key travels as an opaque id.
+ * ------------------------------------------------------------------------------ */
+typedef struct b200sync_stream_tag {
+    uint64_t index;         /* item index relative to the span of the call it is passed to / returned from */
+    uint32_t has_syncword;  /* the tag carries the syncword_* keys in `sw`                                */
+    uint32_t other;         /* != 0: opaque id of non-syncword keys carried by the same tag               */
+    b200sync_sd_tag sw;     /* syncword fields (sw.index unused)                                          */
+} b200sync_stream_tag;
+
+/* ------------------------------------------------------------------------------
+ * SymbolFilter<c64, c64, float>                               PM/symbol_filter.hpp
+ * ------------------------------------------------------------------------------ */
+typedef struct b200sync_sf_config {
+    uint32_t samples_per_symbol;  /* PM/symbol_filter.hpp:55 */
+    const float* taps;            /* :56 prototype filter, taps.size() == num_arms * arm length */
+    uint32_t n_taps;
+    uint32_t num_arms;            /* :58 */
+    uint32_t delay;               /* :59 */
+    int32_t device;
+} b200sync_sf_config;
+
+typedef struct b200sync_sf b200sync_sf;
+
+/* settingsChanged() + start() (PM/symbol_filter.hpp:64-110). */
+int b200sync_sf_create(const b200sync_sf_config* cfg, b200sync_sf** out);
+void b200sync_sf_destroy(b200sync_sf* sf);
+int b200sync_sf_start(b200sync_sf* sf);
+const char* b200sync_sf_last_error(void);
+
+/* processBulk (PM/symbol_filter.hpp:112-252) over a span that may carry any number of tags
+ * (sorted by index; the GR4 shell passes at most one, at index 0, because the runtime cuts chunks at
+ * tags).  Consumes all n_in items; produces one item per symbol clock tick; returns the re-indexed
+ * tags (delayed by `delay`, placed on the nearest output symbol, syncword_phase adjusted when
+ * time_est < 0).  B200SYNC_ENOMEM if max_out / max_out_tags are too small (state unchanged). */
+int b200sync_sf_process(b200sync_sf* sf, const float* in, size_t n_in, const b200sync_stream_tag* in_tags,
+                        size_t n_in_tags, float* out, size_t max_out, size_t* n_consumed, size_t* n_produced,
+                        b200sync_stream_tag* out_tags, size_t max_out_tags, size_t* n_out_tags);
+int b200sync_sf_process_device(b200sync_sf* sf, const void* d_in, size_t n_in, const b200sync_stream_tag* in_tags,
+                               size_t n_in_tags, void* d_out, size_t max_out, void* cuda_stream, size_t* n_consumed,
+                               size_t* n_produced, b200sync_stream_tag* out_tags, size_t max_out_tags,
+                               size_t* n_out_tags);
+
+/* ------------------------------------------------------------------------------
+ * SyncwordDetectionFilter<c64>                    PM/syncword_detection_filter.hpp
+ * Control logic only (which syncword tags survive while inside a packet) plus the pass-through
+ * copy of host spans; with device-resident data pass in = out = NULL and only the counts matter.
+ * ------------------------------------------------------------------------------ */
+typedef struct b200sync_sdf_header {   /* one message of the `parsed_header` port (:136-154) */
+    uint32_t invalid_header;           /* meta.contains("invalid_header")                    */
+    uint64_t packet_length;            /* meta.at("packet_length")                           */
+} b200sync_sdf_header;
+
+typedef struct b200sync_sdf b200sync_sdf;
+int b200sync_sdf_create(uint32_t samples_per_symbol, uint32_t syncword_size, uint32_t header_size,
+                        b200sync_sdf** out);
+void b200sync_sdf_destroy(b200sync_sdf* f);
+int b200sync_sdf_start(b200sync_sdf* f);
+/* One processBulk(headerSpan, ignoredSpan, inSpan, outSpan) call (:54-210).
+ *   tag_in      merged input tag on the first item, or NULL
+ *   header      first pending parsed_header message, or NULL; n_ignored pending ignored_syncword messages
+ *   tag_out     receives the tag to publish at output offset 0 when *tag_forwarded is set (:82-107) */
+int b200sync_sdf_process(b200sync_sdf* f, const float* in, size_t n_in, float* out, size_t n_out,
+                         const b200sync_stream_tag* tag_in, const b200sync_sdf_header* header, size_t n_ignored,
+                         size_t* n_consumed, size_t* header_consumed, size_t* ignored_consumed,
+                         b200sync_stream_tag* tag_out, int* tag_forwarded, int* in_packet);
+
 #ifdef __cplusplus
 }
 #endif
