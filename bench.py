@@ -190,14 +190,13 @@ def main():
     lib = _native.lib()
 
     # ---- this rank's time shard of a world*n_per-sample capture (shard + halo blocks) ----
+    from gr4_packet_modem_b200.sharding import gather_entry_offset, plan_shards
+
     total_n = n_per * world
-    total_blocks = (total_n - FFT) // S + 1
-    fb = rank * total_blocks // world
-    nbk = (rank + 1) * total_blocks // world - fb
-    halo = (TAU + S) // S
-    cb0, cb1 = max(0, fb - halo), min(total_blocks, fb + nbk + halo)
-    seg0 = cb0 * S
-    seg_n = (cb1 - 1) * S + FFT - seg0 if world > 1 else n_per
+    shard = plan_shards(total_n, world, FFT, S, TAU)[rank]
+    total_blocks, fb, nbk = shard.total_blocks, shard.first_block, shard.n_blocks
+    seg0 = shard.first_sample
+    seg_n = shard.n_samples if world > 1 else n_per
     x = packet_capture_torch(seg_n, dev, seed=1, esn0_db=20.0, cfo=0.005, start=seg0)
     torch.cuda.synchronize()
     max_recs = seg_n // (TAU + 1) + 2
@@ -207,12 +206,8 @@ def main():
             c, recs, _ = sd.detect_device(x.data_ptr(), n_per, stream)
             return c, len(recs)
         table = sd.shard_phase1(x.data_ptr(), seg0, seg_n, fb, nbk, total_blocks, stream)
-        t = torch.from_numpy(table.astype(np.int32)).to(dev)
-        allt = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(allt, t)  # T+1 small integers per rank: the only exchange of the path
-        j = 0
-        for r in range(rank):
-            j = int(allt[r][j].item())
+        # T+1 small integers per rank: the only exchange of the path
+        j = gather_entry_offset(table, rank, world, device=dev)
         recs, _ = sd.shard_phase2(j, max_recs)
         return nbk * S, len(recs)
 

@@ -203,3 +203,34 @@ def test_time_threshold_sweep_bit_exact(oracle, rx_params, T):
                                   time_threshold=T, fft_kind=oracle.FFT_MIRROR)
     oc2, _, ot2 = o2.run(x, chunk=7001)
     assert c2 == oc2 and [i for _, i, _ in t2] == [t.index for t in ot2]
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_time_sharded_equals_single_run(rx_params, world):
+    """SURVEY §8e on one GPU: the capture cut into `world` time shards (own context each, halo blocks,
+    chain tables composed on the host) gives exactly the records of the single-context run."""
+    import torch
+
+    from gr4_packet_modem_b200.sharding import entry_offsets, plan_shards
+    from gr4_packet_modem_b200.stimulus import packet_capture
+
+    n = 1 << 21
+    x, _ = packet_capture(n, seed=31, esn0_db=4.0, cfo=0.01, payload_bytes=80)
+    kw = dict(min_freq_bin=-2, max_freq_bin=2, power_threshold=7.0)
+    ref_c, ref_recs, _ = _gpu(rx_params, **kw).detect_host(x)
+    shards = plan_shards(n, world, 2048, 1752, 768)
+    ctxs, tables, bufs = [], [], []
+    for s in shards:
+        sd = _gpu(rx_params, **kw)
+        seg = torch.from_numpy(x[s.first_sample:s.first_sample + s.n_samples].copy()).cuda()
+        tables.append(sd.shard_phase1(seg.data_ptr(), s.first_sample, s.n_samples, s.first_block, s.n_blocks,
+                                      s.total_blocks))
+        ctxs.append(sd)
+        bufs.append(seg)
+    got = []
+    for sd, j in zip(ctxs, entry_offsets(tables)):
+        recs, _ = sd.shard_phase2(j, n // 769 + 2)
+        got.append(recs)
+    got = np.concatenate(got)
+    assert len(got) == len(ref_recs) > 20
+    assert np.array_equal(got.view(np.uint8), ref_recs.view(np.uint8))
