@@ -19,6 +19,7 @@
 #include <new>
 #include <numbers>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "b200sync_internal.h"
@@ -84,6 +85,7 @@ struct b200sync_sd {
     DevBuf<DetectionRecord> d_recs;
     DevBuf<unsigned char> d_ws;
     std::vector<DetectionRecord> h_recs;
+    PeakState* h_state = nullptr;  // pinned
     // streaming (process): staging windows with absolute origins
     cudaStream_t stream = nullptr;
     DevBuf<float2> d_x, d_xtmp;
@@ -136,40 +138,35 @@ int run_chunk(b200sync_sd* sd, const float2* d_in, long long in_base, float* d_z
               cudaStream_t st) {
     CU(launch_correlate(d_in, in_base, d_z, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, b0, nb,
                         sd->d_tw.p, d_out_delayed, 0, (int)sd->delay, sd->num_sms, st));
-    if (nb > 0) g_launches += 1;
     if (hi > lo) {
         const long long z_end = (b0 + nb) * (long long)sd->S;
         CU(launch_peak_phase1(d_z, z_base, z_end, lo, hi, sd->T, sd->power_threshold, sd->d_ws.p,
                               sd->d_ws.cap, nullptr, sd->num_sms, st));
         CU(launch_peak_phase2(lo, hi, sd->T, sd->d_ws.p, sd->d_ws.cap, -1, sd->d_state.p,
                               sd->d_det_idx.p, (unsigned)sd->d_det_idx.cap, sd->num_sms, st));
-        g_launches += 4;
     }
     return 0;
 }
 
-// refine the device-side detection list into host records (sorted by index)
+// refine the device-side detection list (already sorted by index, peaks.cu det_gather_kernel)
+// into host records.  The refine launch sizes itself from the device-side count, so the host
+// synchronises once to learn the count and once for the records.
 int collect_records(b200sync_sd* sd, const float2* d_in, long long in_base, const float* d_z,
                     long long z_base, cudaStream_t st, std::vector<DetectionRecord>& out) {
-    PeakState hs{};
-    CU(cudaMemcpyAsync(&hs, sd->d_state.p, sizeof(PeakState), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    out.clear();
-    if (hs.det_count == 0) return 0;
-    if (hs.det_count > sd->d_det_idx.cap)
-        return fail(B200SYNC_ENOMEM, "internal detection list overflow");
-    const unsigned n = hs.det_count;
     CU(launch_refine(d_in, in_base, d_z, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->min_bin,
-                     sd->d_tw.p, sd->d_det_idx.p, &sd->d_state.p->det_count, n, sd->d_recs.p,
-                     sd->num_sms, st));
-    g_launches += 1;
-    out.resize(n);
-    CU(cudaMemcpyAsync(out.data(), sd->d_recs.p, sizeof(DetectionRecord) * n, cudaMemcpyDeviceToHost, st));
+                     sd->d_tw.p, sd->d_det_idx.p, &sd->d_state.p->det_count, (unsigned)sd->d_det_idx.cap,
+                     sd->d_recs.p, sd->num_sms, st));
+    CU(cudaMemcpyAsync(sd->h_state, sd->d_state.p, sizeof(PeakState), cudaMemcpyDeviceToHost, st));
     // the list has been drained
     CU(cudaMemsetAsync(&sd->d_state.p->det_count, 0, sizeof(unsigned int), st));
     CU(cudaStreamSynchronize(st));
-    std::sort(out.begin(), out.end(),
-              [](const DetectionRecord& a, const DetectionRecord& b) { return a.index < b.index; });
+    out.clear();
+    const unsigned n = sd->h_state->det_count;
+    if (n == 0) return 0;
+    if (n > sd->d_det_idx.cap) return fail(B200SYNC_ENOMEM, "internal detection list overflow");
+    out.resize(n);
+    CU(cudaMemcpyAsync(out.data(), sd->d_recs.p, sizeof(DetectionRecord) * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -281,6 +278,7 @@ int do_start(b200sync_sd* sd) {
     if (!sd->stream) CU(cudaStreamCreateWithFlags(&sd->stream, cudaStreamNonBlocking));
     for (auto& e : sd->ev)
         if (!e) CU(cudaEventCreate(&e));
+    if (!sd->h_state) CU(cudaMallocHost(&sd->h_state, sizeof(PeakState)));
     CU(sd->d_tw.ensure(kTwTotalHost));
     CU(sd->d_hperm.ensure(static_cast<size_t>(sd->K) * kFft));
     DevBuf<float2> d_td;
@@ -288,7 +286,6 @@ int do_start(b200sync_sd* sd) {
     CU(cudaMemcpyAsync(d_td.p, td.data(), td.size() * sizeof(float2), cudaMemcpyHostToDevice, sd->stream));
     CU(cudaMemcpyAsync(sd->d_tw.p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, sd->stream));
     CU(launch_template_spectra(d_td.p, sd->d_hperm.p, (int)sd->K, sd->d_tw.p, sd->stream));
-    g_launches += 1;
     // streaming state (:191-201)
     if (int rc = reset_state(sd, sd->stream)) return rc;
     CU(cudaStreamSynchronize(sd->stream));
@@ -322,6 +319,10 @@ int slide_window(DevBuf<T>& buf, DevBuf<T>& tmp, long long& base, long long end,
 }
 
 }  // namespace
+
+namespace b200sync {
+void count_launch(int n) { g_launches += static_cast<uint64_t>(n); }
+}  // namespace b200sync
 
 extern "C" {
 
@@ -368,6 +369,7 @@ void b200sync_sd_destroy(b200sync_sd* sd) {
     }
     for (auto& e : sd->ev)
         if (e) cudaEventDestroy(e);
+    if (sd->h_state) cudaFreeHost(sd->h_state);
     delete sd;
 }
 
@@ -390,7 +392,22 @@ int b200sync_sd_info(const b200sync_sd* sd, uint32_t* syncword_samples, uint32_t
 int b200sync_sd_records_to_tags(const b200sync_sd* sd, const b200sync_detection_record* recs, size_t n,
                                 b200sync_sd_tag* tags) {
     if (!sd || (!recs && n) || (!tags && n)) return fail(B200SYNC_EINVAL, "null argument");
-    for (size_t i = 0; i < n; ++i) tags[i] = make_tag(sd, recs[i]);
+    // output_tag() is per-record host arithmetic (atan2f, log10f, double divides): spread large
+    // batches over the host cores
+    const size_t kPerThread = 4096;
+    size_t nthreads = std::min<size_t>((n + kPerThread - 1) / kPerThread,
+                                       std::max(1u, std::thread::hardware_concurrency()));
+    if (nthreads <= 1) {
+        for (size_t i = 0; i < n; ++i) tags[i] = make_tag(sd, recs[i]);
+        return 0;
+    }
+    std::vector<std::thread> pool;
+    pool.reserve(nthreads);
+    for (size_t t = 0; t < nthreads; ++t) {
+        const size_t i0 = n * t / nthreads, i1 = n * (t + 1) / nthreads;
+        pool.emplace_back([=] { for (size_t i = i0; i < i1; ++i) tags[i] = make_tag(sd, recs[i]); });
+    }
+    for (auto& th : pool) th.join();
     return 0;
 }
 
@@ -542,7 +559,6 @@ static int detect_resident(b200sync_sd* sd, const float2* d_in, size_t n, float2
                               sd->d_ws.cap, nullptr, sd->num_sms, st));
         CU(launch_peak_phase2(0, hi_total, sd->T, sd->d_ws.p, sd->d_ws.cap, -1, sd->d_state.p,
                               sd->d_det_idx.p, (unsigned)sd->d_det_idx.cap, sd->num_sms, st));
-        g_launches += 4;
     }
     CU(cudaEventRecord(sd->ev[2], st));
     sd->metric_n = static_cast<size_t>(P);
@@ -671,11 +687,9 @@ int b200sync_sd_shard_phase1(b200sync_sd* sd, const void* d_in, uint64_t first_s
     CU(sd->d_table.ensure(static_cast<size_t>(T) + 1));
     CU(launch_correlate(static_cast<const float2*>(d_in), in_base, sd->d_zoff.p, z_base, sd->d_hperm.p,
                         (int)sd->K, (int)sd->S, cb0, cb1 - cb0, sd->d_tw.p, nullptr, 0, 0, sd->num_sms, st));
-    g_launches += 1;
     if (hi > lo) {
         CU(launch_peak_phase1(sd->d_zoff.p, z_base, cb1 * S, lo, hi, sd->T, sd->power_threshold, sd->d_ws.p,
                               sd->d_ws.cap, sd->d_table.p, sd->num_sms, st));
-        g_launches += 3;
         CU(cudaMemcpyAsync(table, sd->d_table.p, sizeof(uint16_t) * (T + 1), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     } else {
@@ -707,7 +721,6 @@ int b200sync_sd_shard_phase2(b200sync_sd* sd, uint32_t entry_offset, b200sync_de
     if (sh.hi > sh.lo) {
         CU(launch_peak_phase2(sh.lo, sh.hi, sd->T, sd->d_ws.p, sd->d_ws.cap, static_cast<int>(entry_offset),
                               sd->d_state.p, sd->d_det_idx.p, (unsigned)sd->d_det_idx.cap, sd->num_sms, sh.st));
-        g_launches += 2;
     }
     if (int rc = collect_records(sd, sh.d_in, sh.in_base, sd->d_zoff.p, sh.z_base, sh.st, sd->h_recs)) return rc;
     size_t cnt = 0;

@@ -24,6 +24,9 @@ struct PeakState {
     unsigned int _pad;
 };
 
+// api.cu: every kernel launch site calls this (b200sync_launch_count of the C ABI)
+void count_launch(int n = 1);
+
 // correlator.cu
 cudaError_t launch_template_spectra(const float2* d_td, float2* d_hperm, int K, const float2* d_tw,
                                     cudaStream_t st);

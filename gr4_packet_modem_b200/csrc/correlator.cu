@@ -126,12 +126,13 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
     float2* corr_s = xb + kXchgFloat2;
     float* xpow = reinterpret_cast<float*>(corr_s + kMaxHyp + 1);
     __shared__ float noise_s;
+    unsigned int n = *det_count;
+    if (n > det_cap) n = det_cap;
+    if (blockIdx.x >= n) return;  // the grid is sized for the worst case; idle CTAs leave at once
     load_twiddles(tw_s, tw_g);
     __syncthreads();
     const int tid = threadIdx.x;
     const bool fft_warp = tid < kGroupThreads;
-    unsigned int n = *det_count;
-    if (n > det_cap) n = det_cap;
     for (unsigned int d = blockIdx.x; d < n; d += gridDim.x) {
         const long long p = (long long)det_idx[d];
         const long long b = p / S;
@@ -213,6 +214,7 @@ cudaError_t launch_template_spectra(const float2* d_td, float2* d_hperm, int K, 
                                          (int)smem);
     if (e != cudaSuccess) return e;
     template_spectra_kernel<<<K, kGroupThreads, smem, st>>>(d_td, d_hperm, d_tw);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -238,6 +240,7 @@ cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpo
     int grid = (int)(want < num_sms ? want : num_sms);
     correlate_kernel<<<grid, kCorrThreads, smem, st>>>(d_in, in_base, d_zpow, z_base, d_hperm, K, S, b0,
                                                         nb, d_tw, d_out_delayed, out_base, delay);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -254,6 +257,7 @@ cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_
     refine_kernel<<<grid, kRefineThreads, smem, st>>>(d_in, in_base, d_zpow, z_base, d_hperm, K, S,
                                                   min_freq_bin, d_tw, d_det_idx, d_det_count, det_cap,
                                                   d_recs);
+    count_launch();
     return cudaGetLastError();
 }
 

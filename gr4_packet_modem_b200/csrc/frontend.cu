@@ -374,12 +374,14 @@ int fe_run(b200sync_fe* fe, const float2* d_in, size_t n_in, float2* d_out, size
         FCU(cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = static_cast<unsigned>((n_out + kFeTileOut - 1) / kFeTileOut);
         frontend_kernel<<<grid, kFeThreads, smem, st>>>(P, fe->d_taps);
+        count_launch();
         FCU(cudaGetLastError());
     }
     if (fe->do_resample && consumed > 0) {
         const int nxt = fe->hist_cur ^ 1;
         fe_update_hist_kernel<<<(fe->arm + 127) / 128, 128, 0, st>>>(d_in, static_cast<long long>(consumed),
                                                                      fe->d_hist[fe->hist_cur], fe->d_hist[nxt], fe->arm);
+        count_launch();
         FCU(cudaGetLastError());
         fe->hist_cur = nxt;
     }

@@ -22,6 +22,8 @@
 //                       real chain, and the whole-range table (multi-GPU stitching)
 //   chain_emit_kernel   each warp re-walks its segment from its now-known entry
 //                       state and appends examined&&passing peaks to the list
+#include <climits>
+
 #include "b200sync_internal.h"
 
 namespace b200sync {
@@ -29,6 +31,7 @@ namespace b200sync {
 constexpr int kFlagsTile = 4096;    // peaks decided per CTA
 constexpr int kFlagsThreads = 512;
 constexpr int kScanThreads = 1024;  // >= T+1
+constexpr int kPlanTile = 8192;     // == kFastTile (a multiple of kFlagsTile)
 
 struct PeakPlan {
     long long range;   // hi - lo
@@ -36,15 +39,16 @@ struct PeakPlan {
     long long nfr;     // pieces of T+1 samples
     int M;             // pieces per segment
     long long nseg;
-    size_t off_cand, off_pass, off_tables, off_jin, off_flag, total;
+    size_t off_cand, off_pass, off_tables, off_jin, off_flag, off_slots, off_segcnt, off_segoff, total;
 };
 
 static PeakPlan make_plan(long long range, int T, int num_sms) {
     PeakPlan p{};
     const long long Fr = T + 1;
     p.range = range;
-    // every flags tile writes all of its kFlagsTile/32 words; +2 zero words of padding
-    p.nwords = ((range + kFlagsTile - 1) / kFlagsTile) * (kFlagsTile / 32) + 2;
+    // every flags tile writes all of its words (the larger tile of the two flags kernels bounds
+    // both); +2 zero words of padding
+    p.nwords = ((range + kPlanTile - 1) / kPlanTile) * (kPlanTile / 32) + 2;
     p.nfr = (range + Fr - 1) / Fr;
     long long M = (p.nfr + (long long)num_sms * 32 - 1) / ((long long)num_sms * 32);
     if (M < 4) M = 4;
@@ -57,6 +61,9 @@ static PeakPlan make_plan(long long range, int T, int num_sms) {
     p.off_tables = take(sizeof(uint16_t) * (size_t)p.nseg * Fr);
     p.off_jin = take(sizeof(uint16_t) * (size_t)p.nseg);
     p.off_flag = take(sizeof(uint32_t) * (size_t)p.nseg);
+    p.off_slots = take(sizeof(unsigned long long) * (size_t)p.nseg * (size_t)p.M);  // <= one detection per piece
+    p.off_segcnt = take(sizeof(uint32_t) * (size_t)p.nseg);
+    p.off_segoff = take(sizeof(uint32_t) * (size_t)(p.nseg + 1));
     p.total = o;
     return p;
 }
@@ -73,6 +80,9 @@ size_t peak_workspace_bytes_sms(long long max_range, int T, int num_sms) {
     total += (sizeof(uint16_t) * (size_t)nseg_ub * Fr + 255) & ~size_t(255);
     total += (sizeof(uint16_t) * (size_t)nseg_ub + 255) & ~size_t(255);
     total += (sizeof(uint32_t) * (size_t)nseg_ub + 255) & ~size_t(255);
+    // detection slots: nseg * M <= nfr + M, both monotone in the range
+    total += (sizeof(unsigned long long) * (size_t)(p.nfr + p.M + 4) + 255) & ~size_t(255);
+    total += 2 * ((sizeof(uint32_t) * (size_t)(nseg_ub + 1) + 255) & ~size_t(255));
     return total + 1024;
 }
 
@@ -176,136 +186,206 @@ peak_flags_generic_kernel(const float* __restrict__ zpow, long long z_base, long
 
 
 // ---------------------------------------------------------------------------------
-// Fast flags kernel for T >= 32.  The tile's zpow window is staged in shared memory with a
-// 33-word stride per 32-sample group, so one THREAD can run a sequential prefix / suffix max
-// over a whole group with no bank conflicts (lane g reads word 33 g + e: bank (g + e) mod 32).
-// The forward window (p, p+T] = [a, b] then decomposes into
-//     suffix-in-group(a)  |  q whole groups  |  prefix-in-group(b),   q in {m0-1, m0}, m0 = (T-1)/32
-// and the whole-group part is a per-group sliding maximum over the group maxima.
-// ~6 instructions per sample instead of ~45 for the warp-shuffle scans of the generic kernel.
+// Fast flags kernel for T >= 32: no per-sample scans, 4 samples per lane.
+//
+// The tile's zpow window is staged once in shared memory (128-bit loads/stores) together with
+// the maximum and minimum of every aligned 32-sample group.  For a sample p of group G the
+// forward window (p, p+T] is
+//     rest of group G after p  |  q whole groups G+1..G+q  |  a remainder of <= 62 samples,
+// q = (T-31)/32.  Almost every sample is smaller than the maximum M_G of the q whole groups and
+// is rejected by ONE compare; only a group that holds a sample >= M_G (about one in q+1)
+// computes the two partial maxima, with warp-shuffle scans.  The threshold test of a candidate
+// (count of window samples below zpow[p]/thr, :273-279) consults the group extrema first: a group
+// entirely below or entirely not below the threshold is settled by one lane, only groups that
+// straddle it are counted sample by sample (128 samples per warp step).  That bounds the cost on
+// degenerate inputs (constant capture: every sample is a candidate) as well.
+//
+// Ordering is done on the int32 bit patterns of zpow, which is the float ordering because zpow is
+// a squared magnitude (>= +0; not NaN for finite input).
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ int padi(int i) { return i + (i >> 5); }
+constexpr int kFastTile = 8192;   // peaks decided per CTA
+constexpr int kFastThreads = 512;
 
-__global__ void __launch_bounds__(kFlagsThreads)
+__device__ __forceinline__ int warp_incl_scan_max(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v = max(v, t);
+    }
+    return v;
+}
+
+struct FastGeom {
+    int Tpad, ng, nrow;
+};
+__host__ __device__ inline FastGeom fast_geom(int T) {
+    FastGeom g;
+    g.Tpad = (T + 31) & ~31;                          // window origin is group aligned with the tile
+    const int n = g.Tpad + kFastTile + T + 1;         // window elements that can be referenced
+    g.ng = (n + 31) >> 5;
+    g.nrow = (g.ng + 4 + 3) >> 2;                     // rows of 128 samples, >= 4 groups of slack
+    return g;
+}
+
+__global__ void __launch_bounds__(kFastThreads)
 peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_end, long long lo,
                   long long hi, int T, float thr, uint32_t* __restrict__ cand_bits,
                   uint32_t* __restrict__ pass_bits) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = kFlagsTile + 2 * T;
-    const int ng = (n + 31) >> 5;          // groups of 32 (the last may be partial: padded with 0)
-    const int npad = ng * 33;
-    float* z = reinterpret_cast<float*>(smem_raw);
-    float* pre = z + npad;                 // prefix max within group, inclusive
-    float* suf = pre + npad;               // suffix max within group, inclusive
-    float* gmax = suf + npad;              // [ng + 64] group maxima, -inf beyond ng
-    float* gmid = gmax + ng + 64;          // [ng] max of gmax[g+1 .. g+m0-1]
-    uint32_t* passw = reinterpret_cast<uint32_t*>(gmid + ng);
-    unsigned short* cand_list = reinterpret_cast<unsigned short*>(passw + kFlagsTile / 32);
-    __shared__ int ncand;
+    const FastGeom geo = fast_geom(T);
+    const int Tpad = geo.Tpad, nrow = geo.nrow;
+    int* z = reinterpret_cast<int*>(smem_raw);             // [nrow * 128] bit patterns of zpow
+    int* gmax = z + nrow * 128;                            // [nrow * 4]
+    int* gmin = gmax + nrow * 4;                           // [nrow * 4]
+    int* gM = gmin + nrow * 4;                             // [kFastTile / 32] max of the q whole groups
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kFlagsThreads / 32;
-    const long long tile_lo = lo + (long long)blockIdx.x * kFlagsTile;
-    const float NEG = -__int_as_float(0x7f800000);
-    {
-        // stage the window: all global loads issued before the first shared store
-        // (n <= 4096 + 2*1023 -> at most 13 rounds of 512 threads)
-        constexpr int kRounds = (kFlagsTile + 2 * kMaxTimeThreshold + 31 + kFlagsThreads - 1) / kFlagsThreads;
-        const long long q0 = tile_lo - T;                       // absolute index of window element 0
-        const long long lo_ok = q0 < 0 ? -q0 : 0;               // first element with q >= 0
-        const long long hi_ok = min((long long)n, z_end - q0);  // first element with q >= z_end (or n)
-        const float* src = zpow + (q0 - z_base);
-        float v[kRounds];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kFastThreads / 32;
+    const long long tile_lo = lo + (long long)blockIdx.x * kFastTile;
+    const long long q0 = tile_lo - Tpad;                   // absolute index of window element 0
+    const int* src = reinterpret_cast<const int*>(zpow) + (q0 - z_base);
+    const int lo_ok = q0 < 0 ? (int)(-q0) : 0;             // first element inside the stream
+    const long long hi_ll = z_end - q0;                    // first element not yet known
+    const int hi_ok = hi_ll < (long long)(nrow * 128) ? (int)hi_ll : nrow * 128;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    // ---- stage rows of 128 samples; out-of-stream / not-yet-known samples read as 0 (the
+    //      zero-initialised HistoryBuffer before the stream start)
+    for (int r0 = warp; r0 < nrow; r0 += 2 * kWarps) {
+        int4 v[2];
 #pragma unroll
-        for (int r = 0; r < kRounds; ++r) {
-            const int i = tid + r * kFlagsThreads;
-            v[r] = (i >= lo_ok && i < hi_ok) ? src[i] : 0.0f;
-        }
-#pragma unroll
-        for (int r = 0; r < kRounds; ++r) {
-            const int i = tid + r * kFlagsThreads;
-            if (i < ng * 32) z[padi(i)] = v[r];
-        }
-    }
-    if (tid < kFlagsTile / 32) passw[tid] = 0u;
-    if (tid == 0) ncand = 0;
-    for (int g = ng + tid; g < ng + 64; g += kFlagsThreads) gmax[g] = NEG;
-    __syncthreads();
-    // per-group sequential scans: threads [0, ng) do prefixes, threads [ng, 2 ng) do suffixes
-    for (int w = tid; w < 2 * ng; w += kFlagsThreads) {
-        if (w < ng) {
-            const int base = w * 33;
-            float run = NEG;
-#pragma unroll 8
-            for (int e = 0; e < 32; ++e) {
-                run = fmaxf(run, z[base + e]);
-                pre[base + e] = run;
+        for (int u = 0; u < 2; ++u) {
+            const int r = r0 + u * kWarps;
+            const int e0 = r * 128 + 4 * lane;
+            v[u] = make_int4(0, 0, 0, 0);
+            if (r < nrow) {
+                if (vec_ok && e0 >= lo_ok && e0 + 3 < hi_ok) {
+                    v[u] = __ldg(reinterpret_cast<const int4*>(src + e0));
+                } else {
+                    if (e0 + 0 >= lo_ok && e0 + 0 < hi_ok) v[u].x = __ldg(src + e0 + 0);
+                    if (e0 + 1 >= lo_ok && e0 + 1 < hi_ok) v[u].y = __ldg(src + e0 + 1);
+                    if (e0 + 2 >= lo_ok && e0 + 2 < hi_ok) v[u].z = __ldg(src + e0 + 2);
+                    if (e0 + 3 >= lo_ok && e0 + 3 < hi_ok) v[u].w = __ldg(src + e0 + 3);
+                }
             }
-            gmax[w] = run;
-        } else {
-            const int base = (w - ng) * 33;
-            float run = NEG;
-#pragma unroll 8
-            for (int e = 31; e >= 0; --e) {
-                run = fmaxf(run, z[base + e]);
-                suf[base + e] = run;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int r = r0 + u * kWarps;
+            if (r < nrow) {
+                *reinterpret_cast<int4*>(z + r * 128 + 4 * lane) = v[u];
+                int mx = max(max(v[u].x, v[u].y), max(v[u].z, v[u].w));
+                int mn = min(min(v[u].x, v[u].y), min(v[u].z, v[u].w));
+#pragma unroll
+                for (int dd = 1; dd < 8; dd <<= 1) {   // 8 lanes hold one 32-sample group
+                    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, dd));
+                    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, dd));
+                }
+                if ((lane & 7) == 0) {
+                    gmax[r * 4 + (lane >> 3)] = mx;
+                    gmin[r * 4 + (lane >> 3)] = mn;
+                }
             }
         }
     }
     __syncthreads();
-    const int m0 = (T - 1) >> 5;
-    for (int g = tid; g < ng; g += kFlagsThreads) {
-        float m = NEG;
-        for (int k = 1; k < m0; ++k) m = fmaxf(m, gmax[g + k]);
-        gmid[g] = m;
+    const int q = (T - 31) >> 5;         // whole groups inside every forward window of a group
+    const int d = T - 32 * q - 32;       // remainder reaches element (lane + d) of group G+q+1, d in [-1, 30]
+    const int G0 = Tpad >> 5;
+    if (tid < kFastTile / 32) {
+        int m = INT_MIN;
+        for (int k = 1; k <= q; ++k) m = max(m, gmax[G0 + tid + k]);
+        gM[tid] = m;
     }
     __syncthreads();
 
-    {
-        // candidate flags.  All per-sample indices advance by constants between rounds
-        // (kFlagsThreads is a multiple of 32), so they are strength-reduced by hand.
-        const long long rem = hi - tile_lo;
-        const int nvalid = rem < (long long)kFlagsTile ? (int)rem : kFlagsTile;  // p < hi
-        const int a0 = T + 1 + tid, b0 = a0 + T - 1;
-        int ga = a0 >> 5;
-        const int dg = (b0 >> 5) - ga;           // gb - ga: the same in every round
-        const bool whole = (dg == 0);            // [a, b] is exactly one whole group
-        const bool extra = (m0 >= 1) && (dg - 1 == m0);
-        int pa = padi(a0), pb = padi(b0), pz = padi(a0 - 1);
-        uint32_t* cw = cand_bits + (tile_lo - lo) / 32 + warp;
-        constexpr int kStep = kFlagsThreads + kFlagsThreads / 32;  // padded-index stride per round
+    const long long rem_ll = hi - tile_lo;
+    const int nvalid = rem_ll < (long long)kFastTile ? (int)rem_ll : kFastTile;  // p < hi
+    const int tv_need = 2 * T + 1;
+    uint32_t* cw = cand_bits + (tile_lo - lo) / 32;
+    uint32_t* pw = pass_bits + (tile_lo - lo) / 32;
+    const int4* z4 = reinterpret_cast<const int4*>(z + Tpad);
+    for (int it = warp; it < kFastTile / 128; it += kWarps) {
+        // 128 samples per step: lane holds 4 consecutive samples of tile group 4*it + (lane >> 3)
+        const int4 v = z4[it * 32 + lane];
+        const int Mq = gM[4 * it + (lane >> 3)];
+        const bool poss = !(Mq > v.x) || !(Mq > v.y) || !(Mq > v.z) || !(Mq > v.w);
+        const uint32_t pb = __ballot_sync(0xffffffffu, poss);
+        uint32_t cand_out = 0u, pass_out = 0u;   // lane j (< 4) keeps the words of group 4*it + j
+        for (int j = 0; j < 4; ++j) {
+            if (((pb >> (8 * j)) & 0xffu) == 0u) continue;   // warp-uniform
+            const int w = 4 * it + j;
+            const int G = G0 + w;
+            const int zi = z[32 * G + lane];
+            const int M = gM[w];
+            const bool valid = (32 * w + lane) < nvalid;
+            // exclusive suffix maximum inside the group
+            int s = zi;
 #pragma unroll
-        for (int r = 0; r < kFlagsTile / kFlagsThreads; ++r) {
-            const int tp = tid + r * kFlagsThreads;
-            float fwd = suf[pa];
-            if (!whole) {
-                fwd = fmaxf(fmaxf(fwd, pre[pb]), gmid[ga]);
-                if (extra) fwd = fmaxf(fwd, gmax[ga + m0]);
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const int t = __shfl_down_sync(0xffffffffu, s, dd);
+                if (lane + dd < 32) s = max(s, t);
             }
-            const bool cand = (tp < nvalid) && !(fwd > z[pz]);
-            const uint32_t w = __ballot_sync(0xffffffffu, cand);
-            if (lane == 0) cw[r * (kFlagsThreads / 32)] = w;
-            if (cand) cand_list[atomicAdd(&ncand, 1)] = (unsigned short)tp;
-            pa += kStep; pb += kStep; pz += kStep; ga += kFlagsThreads / 32;
-        }
-    }
-    __syncthreads();
-
-    // threshold test for every candidate: count history items below best/thr (:273-279)
-    const int nc = ncand;
-    for (int ci = warp; ci < nc; ci += nwarps) {
-        const int tp = cand_list[ci];
-        const int i = T + tp;
-        const float tv = __fdiv_rn(z[padi(i)], thr);
-        int cnt = 0;
-        if (tv > 0.0f) {  // zpow >= 0: nothing is below a non-positive threshold
-            for (int u = i - T + lane; u <= i + T; u += 32) cnt += (z[padi(u)] < tv) ? 1 : 0;
-        }
+            s = __shfl_down_sync(0xffffffffu, s, 1);
+            if (lane == 31) s = INT_MIN;
+            // remainder: elements 0..e of group G+q+1 (continuing into G+q+2), e = lane + d
+            const int A = G + q + 1;
+            const int pa = warp_incl_scan_max(z[32 * A + lane], lane);
+            const int pbm = warp_incl_scan_max(z[32 * A + 32 + lane], lane);
+            const int e = lane + d;
+            const int ra = __shfl_sync(0xffffffffu, pa, e & 31);
+            const int rb = __shfl_sync(0xffffffffu, pbm, e & 31);
+            const int ga = __shfl_sync(0xffffffffu, pa, 31);
+            const int rem = e < 0 ? INT_MIN : (e < 32 ? ra : max(ga, rb));
+            const int fwd = max(max(s, M), rem);
+            const uint32_t candw = __ballot_sync(0xffffffffu, valid && !(fwd > zi));
+            uint32_t passw = 0u;
+            // threshold test of every candidate of this group (:273-279)
+            uint32_t todo = candw;
+            while (todo) {
+                const int c = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const float zc = __int_as_float(__shfl_sync(0xffffffffu, zi, c));
+                const float tvf = __fdiv_rn(zc, thr);
+                if (!(tvf > 0.0f)) continue;        // zpow >= 0: nothing is below a non-positive threshold
+                const int tv = __float_as_int(tvf);
+                const int ic = 32 * G + c;
+                const int w_lo = ic - T, w_hi = ic + T;
+                const int g_first = w_lo >> 5, g_last = w_hi >> 5;   // at most 65 groups
+                int cnt = 0;
+                uint32_t need[3];
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-        if (lane == 0 && 2 * cnt >= 2 * T + 1) atomicOr(&passw[tp >> 5], 1u << (tp & 31));
+                for (int r = 0; r < 3; ++r) {
+                    const int gi = g_first + 32 * r + lane;
+                    bool nd = false;
+                    if (gi <= g_last) {
+                        if (gmax[gi] < tv) cnt += min(32 * gi + 31, w_hi) - max(32 * gi, w_lo) + 1;
+                        else if (gmin[gi] < tv) nd = true;
+                    }
+                    need[r] = __ballot_sync(0xffffffffu, nd);
+                }
+                const int nchunk = ((g_last - g_first) >> 2) + 1;   // 4 groups = 128 samples per step
+                for (int ch = 0; ch < nchunk; ++ch) {
+                    const uint32_t word = (ch >> 3) == 0 ? need[0] : ((ch >> 3) == 1 ? need[1] : need[2]);
+                    const uint32_t nib = (word >> (4 * (ch & 7))) & 0xfu;
+                    if (nib == 0u) continue;                        // warp-uniform
+                    const int idx0 = 32 * (g_first + 4 * ch) + 4 * lane;
+                    const int4 x = *reinterpret_cast<const int4*>(z + idx0);
+                    if ((nib >> (lane >> 3)) & 1u) {
+                        const unsigned span = 2u * (unsigned)T;
+                        const int o = idx0 - w_lo;
+                        cnt += ((unsigned)(o + 0) <= span && x.x < tv) ? 1 : 0;
+                        cnt += ((unsigned)(o + 1) <= span && x.y < tv) ? 1 : 0;
+                        cnt += ((unsigned)(o + 2) <= span && x.z < tv) ? 1 : 0;
+                        cnt += ((unsigned)(o + 3) <= span && x.w < tv) ? 1 : 0;
+                    }
+                }
+                cnt = __reduce_add_sync(0xffffffffu, cnt);
+                if (2 * cnt >= tv_need) passw |= 1u << c;
+            }
+            if (lane == j) { cand_out = candw; pass_out = passw; }
+        }
+        if (lane < 4) { cw[4 * it + lane] = cand_out; pw[4 * it + lane] = pass_out; }
     }
-    __syncthreads();
-    if (tid < kFlagsTile / 32) pass_bits[(tile_lo - lo) / 32 + tid] = passw[tid];
 }
 
 // bits [fstart + 32*lane, +32) of a piece of length L starting at bit fstart
@@ -476,41 +556,105 @@ chain_scan_kernel(const uint16_t* __restrict__ tables, const uint32_t* __restric
 }
 
 // ---------------------------------------------------------------------------------
+// Each warp re-walks its segment from the now-known entry state.  A piece examines at most one
+// candidate, so segment `seg` owns M slots; detections land there in increasing order and
+// det_offsets/det_gather compact the slots into one SORTED list (no host-side sort).
 __global__ void __launch_bounds__(128)
 chain_emit_kernel(const uint32_t* __restrict__ cand_bits, const uint32_t* __restrict__ pass_bits,
                   long long range, int T, int M, long long nfr, long long nseg,
-                  const uint16_t* __restrict__ seg_jin, long long lo, unsigned long long* __restrict__ det_idx,
-                  unsigned int det_cap, PeakState* __restrict__ state) {
+                  const uint16_t* __restrict__ seg_jin, long long lo, unsigned long long* __restrict__ slots,
+                  uint32_t* __restrict__ seg_count) {
     const int lane = threadIdx.x & 31;
     const long long seg = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (seg >= nseg) return;
     const int Fr = T + 1;
     int j = seg_jin[seg];
+    unsigned int cnt = 0;
+    const long long f0 = seg * (long long)M;
     const long long f_end = min(nfr, (seg + 1) * (long long)M);
-    for (long long f = seg * (long long)M; f < f_end; ++f) {
+    int L = (int)min((long long)Fr, range - f0 * Fr);
+    uint32_t w = piece_word(cand_bits, f0 * Fr, L, lane);
+    for (long long f = f0; f < f_end; ++f) {
         const long long fstart = f * Fr;
-        const int L = (int)min((long long)Fr, range - fstart);
-        uint32_t w = piece_word(cand_bits, fstart, L, lane);
+        const int Lc = L;
+        uint32_t wc = w;
+        if (f + 1 < f_end) {  // prefetch the next piece: the walk itself is a chain of dependent shuffles
+            L = (int)min((long long)Fr, range - (fstart + Fr));
+            w = piece_word(cand_bits, fstart + Fr, L, lane);
+        }
         const int off = 32 * lane;
-        if (off + 31 < j) w = 0u;
-        else if (off < j) w &= 0xffffffffu << (j - off);
-        const uint32_t m = __ballot_sync(0xffffffffu, w != 0u);
-        if (j < L && m != 0u) {
+        if (off + 31 < j) wc = 0u;
+        else if (off < j) wc &= 0xffffffffu << (j - off);
+        const uint32_t m = __ballot_sync(0xffffffffu, wc != 0u);
+        if (j < Lc && m != 0u) {
             const int l0 = __ffs(m) - 1;
-            const uint32_t ww = __shfl_sync(0xffffffffu, w, l0);
+            const uint32_t ww = __shfl_sync(0xffffffffu, wc, l0);
             const int a = 32 * l0 + __ffs(ww) - 1;
-            if (lane == 0) {
-                const long long bit = fstart + a;
-                if ((pass_bits[bit >> 5] >> (bit & 31)) & 1u) {
-                    const unsigned int slot = atomicAdd(&state->det_count, 1u);
-                    if (slot < det_cap) det_idx[slot] = (unsigned long long)(lo + bit);
-                }
+            const long long bit = fstart + a;
+            if ((__ldg(pass_bits + (bit >> 5)) >> (bit & 31)) & 1u) {  // warp-uniform
+                if (lane == 0) slots[seg * (long long)M + cnt] = (unsigned long long)(lo + bit);
+                ++cnt;
             }
-            j = a + Fr - L;
+            j = a + Fr - Lc;
         } else {
-            j = (j >= L) ? (j - L) : 0;
+            j = (j >= Lc) ? (j - Lc) : 0;
         }
     }
+    if (lane == 0) seg_count[seg] = cnt;
+}
+
+// exclusive scan of the per-segment detection counts (one CTA; nseg <= 32 * num_sms + 1)
+__global__ void __launch_bounds__(1024)
+det_offsets_kernel(const uint32_t* __restrict__ seg_count, int nseg, uint32_t* __restrict__ seg_off,
+                   PeakState* __restrict__ state) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry_s;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) carry_s = 0u;
+    __syncthreads();
+    for (int base = 0; base < nseg; base += 1024) {
+        const int i = base + t;
+        const uint32_t v = i < nseg ? seg_count[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) warp_tot[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t wt = warp_tot[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, wt, d);
+                if (lane >= d) wt += y;
+            }
+            warp_tot[lane] = wt;  // inclusive
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        const uint32_t before = carry + (warp ? warp_tot[warp - 1] : 0u) + (x - v);
+        if (i < nseg) seg_off[i] = before;
+        __syncthreads();
+        if (t == 1023) carry_s = carry + warp_tot[31];
+        __syncthreads();
+    }
+    if (t == 0) {
+        seg_off[nseg] = carry_s;
+        state->det_count = carry_s;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+det_gather_kernel(const unsigned long long* __restrict__ slots, const uint32_t* __restrict__ seg_off, int M,
+                  long long nseg, unsigned long long* __restrict__ det_idx, unsigned int det_cap) {
+    const int lane = threadIdx.x & 31;
+    const long long seg = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (seg >= nseg) return;
+    const uint32_t o = seg_off[seg], n = seg_off[seg + 1] - o;
+    for (uint32_t i = lane; i < n; i += 32)
+        if (o + i < det_cap) det_idx[o + i] = slots[seg * (long long)M + i];
 }
 
 // ---------------------------------------------------------------------------------
@@ -530,9 +674,11 @@ cudaError_t launch_peak_phase1(const float* d_zpow, long long z_base, long long 
     uint32_t* pass = reinterpret_cast<uint32_t*>(ws + pl.off_pass);
     uint16_t* tables = reinterpret_cast<uint16_t*>(ws + pl.off_tables);
     cudaError_t e;
-    const long long ntiles = (range + kFlagsTile - 1) / kFlagsTile;
+    const bool fast = T >= 32;
+    const int tile = fast ? kFastTile : kFlagsTile;
+    const long long ntiles = (range + tile - 1) / tile;
     // zero the padding words past the last tile (tiles write every word they own)
-    const long long written = ntiles * (kFlagsTile / 32);
+    const long long written = ntiles * (tile / 32);
     if (written < pl.nwords) {
         e = cudaMemsetAsync(cand + written, 0, sizeof(uint32_t) * (pl.nwords - written), st);
         if (e != cudaSuccess) return e;
@@ -540,27 +686,29 @@ cudaError_t launch_peak_phase1(const float* d_zpow, long long z_base, long long 
         if (e != cudaSuccess) return e;
     }
     uint32_t* segflag = reinterpret_cast<uint32_t*>(ws + pl.off_flag);
-    const int n = kFlagsTile + 2 * T;
-    if (T >= 32) {
-        const int ng = (n + 31) / 32;
-        const size_t smem = sizeof(float) * (3 * (size_t)ng * 33 + (ng + 64) + ng) +
-                            sizeof(uint32_t) * (kFlagsTile / 32) + sizeof(unsigned short) * kFlagsTile;
+    if (fast) {
+        const FastGeom geo = fast_geom(T);
+        const size_t smem = sizeof(int) * ((size_t)geo.nrow * 128 + 2 * (size_t)geo.nrow * 4 + kFastTile / 32);
         e = set_smem_attr((const void*)peak_flags_kernel, smem);
         if (e != cudaSuccess) return e;
-        peak_flags_kernel<<<(unsigned)ntiles, kFlagsThreads, smem, st>>>(d_zpow, z_base, z_end, lo, hi, T,
-                                                                        power_threshold, cand, pass);
+        peak_flags_kernel<<<(unsigned)ntiles, kFastThreads, smem, st>>>(d_zpow, z_base, z_end, lo, hi, T,
+                                                                       power_threshold, cand, pass);
+        count_launch();
     } else {
+        const int n = kFlagsTile + 2 * T;
         const size_t smem = sizeof(float) * 3 * n + sizeof(uint32_t) * (kFlagsTile / 32) +
                             sizeof(unsigned short) * kFlagsTile;
         e = set_smem_attr((const void*)peak_flags_generic_kernel, smem);
         if (e != cudaSuccess) return e;
         peak_flags_generic_kernel<<<(unsigned)ntiles, kFlagsThreads, smem, st>>>(d_zpow, z_base, z_end, lo, hi,
                                                                                 T, power_threshold, cand, pass);
+        count_launch();
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     chain_tables_kernel<<<(unsigned)((pl.nseg + 3) / 4), 128, 0, st>>>(cand, range, T, pl.M, pl.nfr,
                                                                        pl.nseg, tables, segflag);
+    count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (d_range_table != nullptr) {
@@ -569,6 +717,7 @@ cudaError_t launch_peak_phase1(const float* d_zpow, long long z_base, long long 
         if (e != cudaSuccess) return e;
         chain_scan_kernel<<<1, kScanThreads, ssm, st>>>(tables, segflag, pl.nseg, T, 0, -1, nullptr, lo, hi,
                                                         nullptr, d_range_table);
+        count_launch();
         e = cudaGetLastError();
     }
     return e;
@@ -592,11 +741,24 @@ cudaError_t launch_peak_phase2(long long lo, long long hi, int T, void* d_ws, si
     if (e != cudaSuccess) return e;
     chain_scan_kernel<<<1, kScanThreads, ssm, st>>>(tables, segflag, pl.nseg, T, 1, j_in, d_state, lo, hi, jin,
                                                     nullptr);
+    count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    unsigned long long* slots = reinterpret_cast<unsigned long long*>(ws + pl.off_slots);
+    uint32_t* segcnt = reinterpret_cast<uint32_t*>(ws + pl.off_segcnt);
+    uint32_t* segoff = reinterpret_cast<uint32_t*>(ws + pl.off_segoff);
     chain_emit_kernel<<<(unsigned)((pl.nseg + 3) / 4), 128, 0, st>>>(cand, pass, range, T, pl.M, pl.nfr,
-                                                                     pl.nseg, jin, lo, d_det_idx, det_cap,
-                                                                     d_state);
+                                                                     pl.nseg, jin, lo, slots, segcnt);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    det_offsets_kernel<<<1, 1024, 0, st>>>(segcnt, (int)pl.nseg, segoff, d_state);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    det_gather_kernel<<<(unsigned)((pl.nseg + 3) / 4), 128, 0, st>>>(slots, segoff, pl.M, pl.nseg, d_det_idx,
+                                                                    det_cap);
+    count_launch();
     return cudaGetLastError();
 }
 

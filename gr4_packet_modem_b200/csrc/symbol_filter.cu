@@ -379,6 +379,7 @@ int sf_run(b200sync_sf* sf, const float2* d_in, size_t n_in, const b200sync_stre
         SCU(cudaFuncSetAttribute(symbol_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = static_cast<unsigned>((n_out + kSfThreads - 1) / kSfThreads);
         symbol_filter_kernel<<<grid, kSfThreads, smem, st>>>(P, sf->d_taps);
+        count_launch();
         SCU(cudaGetLastError());
         // the pageable `prod` vector must outlive the async copy
         SCU(cudaStreamSynchronize(st));
@@ -388,6 +389,7 @@ int sf_run(b200sync_sf* sf, const float2* d_in, size_t n_in, const b200sync_stre
         sf_update_hist_kernel<<<(sf->hist_len + 127) / 128, 128, 0, st>>>(d_in, static_cast<long long>(n_in),
                                                                          sf->d_hist[sf->hist_cur], sf->d_hist[nxt],
                                                                          sf->hist_len);
+        count_launch();
         SCU(cudaGetLastError());
         sf->hist_cur = nxt;
     }
