@@ -85,7 +85,11 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
 #pragma unroll
         for (int m1 = 0; m1 < 16; ++m1) best[m1] = -1.0f;  // :303
         for (int k = 0; k < K; ++k) {
+#ifdef B200_WHATIF_H0
+            const float2* h = hperm + tid;
+#else
             const float2* h = hperm + (size_t)k * 16 * kGroupThreads + tid;
+#endif
             float2 y[16], c[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) y[j] = cmul(xs[j], __ldg(h + j * kGroupThreads));  // :247-249
