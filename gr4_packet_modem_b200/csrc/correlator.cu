@@ -114,9 +114,28 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
 // ---------------------------------------------------------------------------------
 // Refine: recompute, for each detected sample p, the HistoryItem fields of
 // PM/syncword_detection.hpp:326-342 with exactly the arithmetic of correlate_kernel.
-// One group per detection, grid-stride over the device-side detection count.
+// One CTA per detection at a time, grid-stride over the device-side detection count.
+//
+// Only ONE output sample of each hypothesis' FFT B is needed (index m = (F - lag) mod F), so the
+// transform is pruned to the cone of that output, using the same butterflies in the same order
+// (bit-identical to the full transform):
+//   pass B1  all 256 DFT-8 columns are needed, but only output m3 of each  -> 256 values
+//   pass B2  only the 16 threads (m3, f1 = 0..15), only output m2          ->  16 values
+//   pass B3  only thread (m2, m3), only output m1                          ->   1 value
+// B1 runs on the 128 FFT threads for kRefineChunk hypotheses back to back; B2 and B3 of the whole
+// chunk then run side by side (16 resp. 1 thread per hypothesis): about 1/3 of the arithmetic and
+// 1/8 of the shared-memory traffic of full transforms, and two short tails per chunk instead of K.
 // ---------------------------------------------------------------------------------
 constexpr int kRefineThreads = kGroupThreads + 32;  // 4 FFT warps + 1 warp for the sequential noise sum
+constexpr int kRefineChunk = kRefineThreads / 16;   // hypotheses whose B2 passes fit side by side (10)
+
+template <int N>
+__device__ __forceinline__ float2 pick(const float2 (&v)[N], int idx) {
+    float2 r = v[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) r = (idx == i) ? v[i] : r;
+    return r;
+}
 
 __global__ void __launch_bounds__(kRefineThreads)
 refine_kernel(const float2* __restrict__ in, long long in_base, const float* __restrict__ zpow,
@@ -127,8 +146,10 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
     float2* xb = tw_s + kTwTotal;
-    float2* corr_s = xb + kXchgFloat2;
-    float* xpow = reinterpret_cast<float*>(corr_s + kMaxHyp + 1);
+    float2* b1out = xb + kXchgFloat2;                      // [kRefineChunk][256]
+    float2* b2out = b1out + kRefineChunk * 256;            // [kRefineChunk][16]
+    float2* corr_s = b2out + kRefineChunk * 16;            // [kMaxHyp + 1]
+    float* xpow = reinterpret_cast<float*>(corr_s + kMaxHyp + 1);  // [2048]
     __shared__ float noise_s;
     unsigned int n = *det_count;
     if (n > det_cap) n = det_cap;
@@ -141,7 +162,8 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
         const long long p = (long long)det_idx[d];
         const long long b = p / S;
         const int kk = (int)(p - b * S);
-        const int m = (kFft - kk) & (kFft - 1);
+        const int m = (kFft - kk) & (kFft - 1);            // output index of FFT B, m = 128 m1 + 8 m2 + m3
+        const int m1 = m >> 7, m2 = (m >> 3) & 15, m3 = m & 7;
         const long long s0 = b * (long long)S;
         float2 xs[16];
         if (fft_warp) {
@@ -154,32 +176,67 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
             for (int j = 0; j < 16; ++j) xpow[(tid + 128 * (j >> 3)) + 256 * (j & 7)] = norm2(xs[j]);
         }
         __syncthreads();
-        if (fft_warp) {
-            for (int k = 0; k < K; ++k) {
-                const float2* h = hperm + (size_t)k * 16 * kGroupThreads + tid;
-                float2 y[16], c[16];
+        for (int c0 = 0; c0 < K; c0 += kRefineChunk) {
+            const int nk = min(kRefineChunk, K - c0);
+            if (fft_warp) {
+                // pass B1 of every hypothesis of the chunk: column p keeps only its output m3
+                for (int kq = 0; kq < nk; ++kq) {
+                    const float2* h = hperm + (size_t)(c0 + kq) * 16 * kGroupThreads + tid;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) y[j] = cmul(xs[j], __ldg(h + j * kGroupThreads));
-                fft_b(y, c, tw_s, xb, tid, 1);
-                if (tid == (m & 127)) {
-                    float2 val = c[0];
+                    for (int pi = 0; pi < 2; ++pi) {
+                        float2 w[8];
 #pragma unroll
-                    for (int m1 = 1; m1 < 16; ++m1) val = ((m >> 7) == m1) ? c[m1] : val;
-                    corr_s[k] = val;
+                        for (int dd = 0; dd < 8; ++dd)
+                            w[dd] = cmul(xs[pi * 8 + dd], __ldg(h + (pi * 8 + dd) * kGroupThreads));
+                        dft8(w);
+                        float2 val = w[0];  // output m3 sits at w[bitrev3(m3)]
+#pragma unroll
+                        for (int q = 1; q < 8; ++q) val = (m3 == q) ? w[bitrev3(q)] : val;
+                        const int pp = tid + 128 * pi;
+                        if (m3 != 0) val = cmul(val, tw_s[kTwB1 + m3 * 256 + pp]);
+                        b1out[kq * 256 + pp] = val;
+                    }
                 }
-            }
-        } else if (tid == kGroupThreads) {
-            // noise power: sequential float sum over k = F/4 .. 3F/4-1 in index order (:257-265),
-            // overlapped with the hypothesis FFTs of the other four warps
-            float acc = 0.0f;
-            for (int f = kFft / 4; f < 3 * kFft / 4; f += 16) {
-                float t[16];
+            } else if (c0 == 0 && tid == kGroupThreads) {
+                // noise power: sequential float sum over k = F/4 .. 3F/4-1 in index order (:257-265),
+                // overlapped with the first chunk's B1 passes of the other four warps
+                float acc = 0.0f;
+                for (int f = kFft / 4; f < 3 * kFft / 4; f += 16) {
+                    float t[16];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) t[u] = xpow[f + u];
+                    for (int u = 0; u < 16; ++u) t[u] = xpow[f + u];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) acc = __fadd_rn(acc, t[u]);
+                    for (int u = 0; u < 16; ++u) acc = __fadd_rn(acc, t[u]);
+                }
+                noise_s = __fdiv_rn(acc, __fmul_rn((float)(kFft / 2), (float)kFft));
             }
-            noise_s = __fdiv_rn(acc, __fmul_rn((float)(kFft / 2), (float)kFft));
+            __syncthreads();
+            // pass B2: thread (kq, f1) transforms over f2 and keeps output m2
+            if (tid < 16 * nk) {
+                const int kq = tid >> 4, f1 = tid & 15;
+                float2 c[16];
+#pragma unroll
+                for (int f2 = 0; f2 < 16; ++f2) c[f2] = b1out[kq * 256 + f1 + 16 * f2];
+                dft16(c);
+                float2 val = c[0];
+#pragma unroll
+                for (int q = 1; q < 16; ++q) val = (m2 == q) ? c[bitrev4(q)] : val;
+                if (m2 != 0) val = cmul(val, tw_s[kTwB2 + m2 * 16 + f1]);
+                b2out[kq * 16 + f1] = val;
+            }
+            __syncthreads();
+            // pass B3: one thread per hypothesis transforms over f1 and keeps output m1
+            if (tid < nk) {
+                float2 y[16];
+#pragma unroll
+                for (int f1 = 0; f1 < 16; ++f1) y[f1] = b2out[tid * 16 + f1];
+                dft16(y);
+                float2 val = y[0];
+#pragma unroll
+                for (int q = 1; q < 16; ++q) val = (m1 == q) ? y[bitrev4(q)] : val;
+                corr_s[c0 + tid] = val;
+            }
+            // (b1out / b2out are rewritten only after the next chunk's first barrier)
         }
         __syncthreads();
         if (tid == 0) {
@@ -255,7 +312,8 @@ cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_
     int grid = num_sms * 4;
     if ((unsigned)grid > det_cap) grid = (int)det_cap;
     if (grid < 1) grid = 1;
-    const size_t smem = sizeof(float2) * (size_t)(kTwTotal + kXchgFloat2 + kMaxHyp + 1) + sizeof(float) * kFft;
+    const size_t smem = sizeof(float2) * (size_t)(kTwTotal + kXchgFloat2 + kRefineChunk * (256 + 16) + kMaxHyp + 1) +
+                        sizeof(float) * kFft;
     cudaError_t e = cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     refine_kernel<<<grid, kRefineThreads, smem, st>>>(d_in, in_base, d_zpow, z_base, d_hperm, K, S,
