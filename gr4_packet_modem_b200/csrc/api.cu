@@ -117,7 +117,7 @@ struct b200sync_sd {
 
 namespace {
 
-constexpr int kTwTotalHost = 256 + 2048 + 2048 + 256;  // == kTwTotal of fft2048.cuh
+constexpr int kTwTotalHost = 256 + 2048;  // == kTwTotal of fft2048.cuh
 
 int reset_state(b200sync_sd* sd, cudaStream_t st) {
     CU(sd->d_state.ensure(1));
@@ -254,21 +254,17 @@ int do_start(b200sync_sd* sd) {
         }
     }
     // twiddle table Wt[j] = exp(-2 pi i j / 2048) in float (fft2048.cuh arithmetic contract),
-    // re-ordered into the four conflict-free per-pass tables the kernels index
+    // re-ordered into the two conflict-free tables the kernels index
     std::vector<float2> wt(kFft);
     for (int j = 0; j < kFft; ++j) {
         const double a = 2.0 * std::numbers::pi * static_cast<double>(j) / static_cast<double>(kFft);
         wt[j] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(-std::sin(a)));
     }
     std::vector<float2> tw(kTwTotalHost);
-    for (int k1 = 0; k1 < 16; ++k1)
-        for (int n2 = 0; n2 < 16; ++n2) tw[0 + k1 * 16 + n2] = wt[8 * n2 * k1];
-    for (int k2 = 0; k2 < 16; ++k2)
-        for (int t = 0; t < 128; ++t) tw[256 + k2 * 128 + t] = wt[(t >> 4) * ((t & 15) + 16 * k2)];
-    for (int m3 = 0; m3 < 8; ++m3)
-        for (int p = 0; p < 256; ++p) tw[256 + 2048 + m3 * 256 + p] = wt[p * m3];
     for (int m2 = 0; m2 < 16; ++m2)
-        for (int f1 = 0; f1 < 16; ++f1) tw[256 + 4096 + m2 * 16 + f1] = wt[8 * f1 * m2];
+        for (int f1 = 0; f1 < 16; ++f1) tw[m2 * 16 + f1] = wt[8 * f1 * m2];
+    for (int m3 = 0; m3 < 8; ++m3)
+        for (int p = 0; p < 256; ++p) tw[256 + m3 * 256 + p] = wt[p * m3];
     CU(cudaSetDevice(sd->device));
     cudaDeviceProp prop{};
     CU(cudaGetDeviceProperties(&prop, sd->device));

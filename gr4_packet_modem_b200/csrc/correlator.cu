@@ -193,7 +193,7 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
 #pragma unroll
                         for (int q = 1; q < 8; ++q) val = (m3 == q) ? w[bitrev3(q)] : val;
                         const int pp = tid + 128 * pi;
-                        if (m3 != 0) val = cmul(val, tw_s[kTwB1 + m3 * 256 + pp]);
+                        if (m3 != 0) val = cmul(val, tw_s[kTwL + m3 * 256 + pp]);
                         b1out[kq * 256 + pp] = val;
                     }
                 }
@@ -221,7 +221,7 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
                 float2 val = c[0];
 #pragma unroll
                 for (int q = 1; q < 16; ++q) val = (m2 == q) ? c[bitrev4(q)] : val;
-                if (m2 != 0) val = cmul(val, tw_s[kTwB2 + m2 * 16 + f1]);
+                if (m2 != 0) val = cmul(val, tw_s[kTwS + m2 * 16 + f1]);
                 b2out[kq * 16 + f1] = val;
             }
             __syncthreads();

@@ -39,17 +39,17 @@
 
 namespace b200sync {
 
-// Per-pass twiddle tables.  Every entry is an entry of the one table Wt[j] of the arithmetic
-// contract; they are only re-ordered so that, for each unrolled pass iteration, the 32 lanes
-// of a warp read consecutive float2 (or a 4/16-address broadcast): no shared-memory bank
-// conflicts.  (The first version indexed Wt directly: tw[8*f1*m2] puts 16 lanes on one bank;
-// ncu showed 63% of all shared wavefronts were load conflicts — profiles/r1_correlate_v1.md.)
-//   twA1[k1*16 + n2]   = Wt[8*n2*k1]                 (256)
-//   twA2[k2*128 + tid] = Wt[n3*(k1 + 16*k2)]         (2048)  tid = n3*16 + k1
-//   twB1[m3*256 + p]   = Wt[p*m3]                    (2048)
-//   twB2[m2*16 + f1]   = Wt[8*f1*m2]                 (256)
-constexpr int kTwA1 = 0, kTwA2 = 256, kTwB1 = 256 + 2048, kTwB2 = 256 + 4096;
-constexpr int kTwTotal = 256 + 2048 + 2048 + 256;  // 4608 float2 = 36864 B
+// Twiddle tables.  Every entry is an entry of the one table Wt[j] of the arithmetic contract; they
+// are only re-ordered so that, for each unrolled pass iteration, every half-warp of a 64-bit
+// shared-memory load reads 16 consecutive float2 (or a broadcast): no bank conflicts.  (The first
+// version indexed Wt directly: tw[8*f1*m2] puts 16 lanes on one bank; ncu showed 63% of all shared
+// wavefronts were load conflicts — profiles/r1_ncu_summary.md.)
+//   twS[a*16 + b]  = Wt[8*a*b]   (256)    pass B2: a = m2, b = f1;   pass A1: a = k1, b = n2
+//   twL[a*256 + p] = Wt[a*p]     (2048)   pass B1: a = m3, p;        pass A2: a = n3, p = k1 + 16 k2
+// The forward and the inverse-as-forward transform need the same two sets of factors, so they
+// share the tables (18 KiB of shared memory instead of 36: the rest is L1 for the template spectra).
+constexpr int kTwS = 0, kTwL = 256;
+constexpr int kTwTotal = 256 + 2048;  // 2304 float2 = 18432 B
 
 constexpr int kXchgStrideA = 129;   // exchange layout 1: (a*129 + tid)
 constexpr int kXchgStrideP = 9;     // exchange layout 2: (p*9 + d)
@@ -162,7 +162,7 @@ __device__ __forceinline__ void fft_a(float2 (&v)[16], float2 (&xs)[16], const f
 #pragma unroll
         for (int k1 = 0; k1 < 16; ++k1) {
             float2 val = v[bitrev4(k1)];
-            if (k1 != 0) val = cmul(val, tw[kTwA1 + k1 * 16 + n2]);
+            if (k1 != 0) val = cmul(val, tw[kTwS + k1 * 16 + n2]);
             xb[k1 * kXchgStrideA + tid] = val;
         }
     }
@@ -176,7 +176,7 @@ __device__ __forceinline__ void fft_a(float2 (&v)[16], float2 (&xs)[16], const f
 #pragma unroll
     for (int k2 = 0; k2 < 16; ++k2) {
         float2 val = v[bitrev4(k2)];
-        val = cmul(val, tw[kTwA2 + k2 * 128 + tid]);
+        val = cmul(val, tw[kTwL + n3 * 256 + k1 + 16 * k2]);
         xb[(k1 + 16 * k2) * kXchgStrideP + n3] = val;
     }
     group_sync(bar_id);
@@ -209,7 +209,7 @@ __device__ __forceinline__ void fft_b(float2 (&y)[16], float2 (&c)[16], const fl
 #pragma unroll
         for (int m3 = 0; m3 < 8; ++m3) {
             float2 val = w[bitrev3(m3)];
-            if (m3 != 0) val = cmul(val, tw[kTwB1 + m3 * 256 + p]);
+            if (m3 != 0) val = cmul(val, tw[kTwL + m3 * 256 + p]);
             xb[p * kXchgStrideP + m3] = val;
         }
     }
@@ -223,7 +223,7 @@ __device__ __forceinline__ void fft_b(float2 (&y)[16], float2 (&c)[16], const fl
 #pragma unroll
     for (int m2 = 0; m2 < 16; ++m2) {
         float2 val = c[bitrev4(m2)];
-        if (m2 != 0) val = cmul(val, tw[kTwB2 + m2 * 16 + f1]);
+        if (m2 != 0) val = cmul(val, tw[kTwS + m2 * 16 + f1]);
         xb[f1 * kXchgStrideA + m2 * 8 + m3] = val;
     }
     group_sync(bar_id);
