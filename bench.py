@@ -85,6 +85,28 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm)}
 
 
+def workload_config(log2n: int, K: int) -> dict:
+    """The `config` object of the JSON line: the same for the B200 arm and the reference arm."""
+    return {"workload": f"BASELINE configs[1]: syncword detection over a 2^{log2n}-sample synthetic cf32 "
+                        f"capture per GPU, K={K} hypotheses, QPSK 4 sps RRC, Es/N0 20 dB, CFO 0.005 rad/sample",
+            "samples_per_gpu": 1 << log2n, "fft_size": FFT, "time_threshold": TAU, "power_threshold": 9.5,
+            "l2": "inputs (8 B/sample resident capture) larger than L2; no flush needed",
+            "sharding": "contiguous time shards + 1-block halo; (T+1)-entry chain table all_gather only"}
+
+
+def measured_traffic(log2n: int, K: int, kernel: str = "correlate_kernel"):
+    """DRAM bytes (read + write) of one launch from the committed `ncu --set full` capture, or None
+    when no capture of this configuration is committed (profiles/r1_traffic_2p30.json)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic_2p30.json")))
+        if t["log2n"] != log2n or t["K"] != K:
+            return None
+        k = t["kernels"][kernel]
+        return k["dram_read_bytes"] + k["dram_write_bytes"]
+    except Exception:
+        return None
+
+
 def rx_settings(bins: int):
     from gr4_packet_modem_b200.firdes import BPSK, SYNCWORD, unit_energy_rrc
 
@@ -140,10 +162,10 @@ def run_reference(args):
         "value": rate, "unit": "Msps", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"syncword detection, K={K} hypotheses, QPSK 4 sps RRC, Es/N0 20 dB, CFO 0.005",
-                   "fft_size": FFT, "time_threshold": TAU, "power_threshold": 9.5},
+        "config": workload_config(args.log2n, K),
         "cpu_baseline": {"value": rate, "unit": "Msps", "cores": threads, "kind": "port",
-                         "sample": f"{threads} independent streams x 2^21 samples per step (oracle port of "
+                         "sample": f"bounded sample of the workload: {threads} independent streams x 2^21 samples "
+                                   "of the same signal model per step, one per host thread (oracle port of "
                                    "PM/syncword_detection.hpp, radix-2 FFT in place of FFTW; the reference itself "
                                    "is unbuildable here, DESIGN.md §7)"},
         "e2e": {"value": rate, "unit": "Msps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -295,10 +317,13 @@ def main():
         rm = statistics.mean(d["refine_ms"] for d in corr_ms)
         ach = consumed * BYTES_PER_SAMPLE / (cm * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "correlate_kernel", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": None,
+                    "frac": ach / hbm_peak, "traffic": measured_traffic(args.log2n, K),
+                    "algorithmic_bytes_per_launch": consumed * BYTES_PER_SAMPLE,
                     "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6650 GB/s",
-                    "note": f"K={K} is FP32/shared-memory bound, not HBM bound (SURVEY §8d): "
-                            f"{flop_per_sample(K):.0f} nominal flop/sample"}
+                    "note": f"K={K} is FP32-issue / shared-memory bound, not HBM bound (SURVEY §8d): "
+                            f"{flop_per_sample(K):.0f} nominal flop/sample; ncu (profiles/r1_ncu_summary_v4.md): "
+                            "LSU data pipe 83%, FMA pipe 57%, DRAM 8%; traffic = input (with the 17% block "
+                            "overlap re-read) + the 4 B/sample intermediate zpow"}
         extra = {"stage_ms": {"correlate": cm, "peaks": pm, "refine_and_copy": rm},
                  "fp32": {"achieved_tflops": consumed * flop_per_sample(K) / (cm * 1e-3) / 1e12,
                           "nominal_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12}}
@@ -316,11 +341,7 @@ def main():
         "metric": "complex Msps (cf32) through RX sync (SyncwordDetection)", "value": value, "unit": "Msps",
         "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[1]: syncword detection over a 2^{args.log2n}-sample synthetic cf32 "
-                               f"capture per GPU, K={K} hypotheses, QPSK 4 sps RRC, Es/N0 20 dB, CFO 0.005 rad/sample",
-                   "samples_per_gpu": n_per, "fft_size": FFT, "time_threshold": TAU, "power_threshold": 9.5,
-                   "l2": "inputs (8 B/sample resident capture) larger than L2; no flush needed",
-                   "sharding": "contiguous time shards + 1-block halo; (T+1)-entry chain table all_gather only"},
+        "config": workload_config(args.log2n, K),
         "detections_per_step": ndet, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
         "roofline": roofline, "cpu_baseline": cpu,
     }
