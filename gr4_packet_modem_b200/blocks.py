@@ -31,6 +31,14 @@ TAG_DTYPE = np.dtype([("index", "<u8"), ("syncword_freq", "<f8"), ("syncword_amp
 assert RECORD_DTYPE.itemsize == C.sizeof(DetectionRecord) and TAG_DTYPE.itemsize == C.sizeof(SyncwordTag)
 
 
+_RAW = np.dtype((np.void, RECORD_DTYPE.itemsize))
+
+
+def _copy_records(buf: np.ndarray, n: int) -> np.ndarray:
+    """Copy of the first n records as one memcpy (numpy copies structured arrays field by field)."""
+    return buf.view(_RAW)[:n].copy().view(RECORD_DTYPE)
+
+
 def _tag_dict(t: SyncwordTag) -> dict:
     """The property_map published by output_tag (PM/syncword_detection.hpp:106-114)."""
     return {
@@ -160,7 +168,7 @@ class SyncwordDetection:
         check(L.b200sync_sd_detect_device(self._h, C.c_void_p(d_in_ptr), n, C.c_void_p(d_out_ptr or None),
                                           C.c_void_p(stream_ptr or None), recs.ctypes.data, max_recs, C.byref(nr),
                                           C.byref(nc)))
-        r = recs[:nr.value].copy()
+        r = _copy_records(recs, nr.value)
         return nc.value, r, self.records_to_tags(r)
 
     def detect_host(self, x, max_recs: int = 0):
@@ -177,7 +185,7 @@ class SyncwordDetection:
         nr, nc = C.c_size_t(0), C.c_size_t(0)
         check(L.b200sync_sd_detect_host(self._h, C.c_void_p(ptr), n, recs.ctypes.data, max_recs, C.byref(nr),
                                         C.byref(nc)))
-        r = recs[:nr.value].copy()
+        r = _copy_records(recs, nr.value)
         return nc.value, r, self.records_to_tags(r)
 
     def shard_phase1(self, d_in_ptr: int, first_sample_abs: int, n_in: int, first_block: int, n_blocks: int,
@@ -194,7 +202,7 @@ class SyncwordDetection:
         recs = self._rec_buffer(max(max_recs, 1))
         nr = C.c_size_t(0)
         check(L.b200sync_sd_shard_phase2(self._h, entry_offset, recs.ctypes.data, max_recs, C.byref(nr)))
-        r = recs[:nr.value].copy()
+        r = _copy_records(recs, nr.value)
         return r, self.records_to_tags(r)
 
     def last_timings(self) -> dict:

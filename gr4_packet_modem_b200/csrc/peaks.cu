@@ -238,6 +238,9 @@ peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_
     int* gmax = z + nrow * 128;                            // [nrow * 4]
     int* gmin = gmax + nrow * 4;                           // [nrow * 4]
     int* gM = gmin + nrow * 4;                             // [kFastTile / 32] max of the q whole groups
+    uint32_t* passw = reinterpret_cast<uint32_t*>(gM + kFastTile / 32);          // [kFastTile / 32]
+    int* ncand_s = reinterpret_cast<int*>(passw + kFastTile / 32);
+    unsigned short* cand_list = reinterpret_cast<unsigned short*>(ncand_s + 1);  // [kFastTile] worst case
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kFastThreads / 32;
@@ -296,6 +299,7 @@ peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_
         for (int k = 1; k <= q; ++k) m = max(m, gmax[G0 + tid + k]);
         gM[tid] = m;
     }
+    if (tid == 0) *ncand_s = 0;
     __syncthreads();
 
     const long long rem_ll = hi - tile_lo;
@@ -304,88 +308,107 @@ peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_
     uint32_t* cw = cand_bits + (tile_lo - lo) / 32;
     uint32_t* pw = pass_bits + (tile_lo - lo) / 32;
     const int4* z4 = reinterpret_cast<const int4*>(z + Tpad);
+    // ---- candidates: written to the bitmap and queued for the threshold test
     for (int it = warp; it < kFastTile / 128; it += kWarps) {
         // 128 samples per step: lane holds 4 consecutive samples of tile group 4*it + (lane >> 3)
         const int4 v = z4[it * 32 + lane];
         const int Mq = gM[4 * it + (lane >> 3)];
         const bool poss = !(Mq > v.x) || !(Mq > v.y) || !(Mq > v.z) || !(Mq > v.w);
         const uint32_t pb = __ballot_sync(0xffffffffu, poss);
-        uint32_t cand_out = 0u, pass_out = 0u;   // lane j (< 4) keeps the words of group 4*it + j
-        for (int j = 0; j < 4; ++j) {
-            if (((pb >> (8 * j)) & 0xffu) == 0u) continue;   // warp-uniform
-            const int w = 4 * it + j;
-            const int G = G0 + w;
-            const int zi = z[32 * G + lane];
-            const int M = gM[w];
-            const bool valid = (32 * w + lane) < nvalid;
-            // exclusive suffix maximum inside the group
-            int s = zi;
+        uint32_t cand_out = 0u;                  // lane j (< 4) keeps the word of group 4*it + j
+        if (pb != 0u) {                          // rare: about one group in q+1 holds a possible candidate
+            for (int j = 0; j < 4; ++j) {
+                if (((pb >> (8 * j)) & 0xffu) == 0u) continue;   // warp-uniform
+                const int w = 4 * it + j;
+                const int G = G0 + w;
+                const int zi = z[32 * G + lane];
+                const int M = gM[w];
+                const bool valid = (32 * w + lane) < nvalid;
+                // exclusive suffix maximum inside the group
+                int s = zi;
 #pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) {
-                const int t = __shfl_down_sync(0xffffffffu, s, dd);
-                if (lane + dd < 32) s = max(s, t);
-            }
-            s = __shfl_down_sync(0xffffffffu, s, 1);
-            if (lane == 31) s = INT_MIN;
-            // remainder: elements 0..e of group G+q+1 (continuing into G+q+2), e = lane + d
-            const int A = G + q + 1;
-            const int pa = warp_incl_scan_max(z[32 * A + lane], lane);
-            const int pbm = warp_incl_scan_max(z[32 * A + 32 + lane], lane);
-            const int e = lane + d;
-            const int ra = __shfl_sync(0xffffffffu, pa, e & 31);
-            const int rb = __shfl_sync(0xffffffffu, pbm, e & 31);
-            const int ga = __shfl_sync(0xffffffffu, pa, 31);
-            const int rem = e < 0 ? INT_MIN : (e < 32 ? ra : max(ga, rb));
-            const int fwd = max(max(s, M), rem);
-            const uint32_t candw = __ballot_sync(0xffffffffu, valid && !(fwd > zi));
-            uint32_t passw = 0u;
-            // threshold test of every candidate of this group (:273-279)
-            uint32_t todo = candw;
-            while (todo) {
-                const int c = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const float zc = __int_as_float(__shfl_sync(0xffffffffu, zi, c));
-                const float tvf = __fdiv_rn(zc, thr);
-                if (!(tvf > 0.0f)) continue;        // zpow >= 0: nothing is below a non-positive threshold
-                const int tv = __float_as_int(tvf);
-                const int ic = 32 * G + c;
-                const int w_lo = ic - T, w_hi = ic + T;
-                const int g_first = w_lo >> 5, g_last = w_hi >> 5;   // at most 65 groups
-                int cnt = 0;
-                uint32_t need[3];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    const int gi = g_first + 32 * r + lane;
-                    bool nd = false;
-                    if (gi <= g_last) {
-                        if (gmax[gi] < tv) cnt += min(32 * gi + 31, w_hi) - max(32 * gi, w_lo) + 1;
-                        else if (gmin[gi] < tv) nd = true;
-                    }
-                    need[r] = __ballot_sync(0xffffffffu, nd);
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const int t = __shfl_down_sync(0xffffffffu, s, dd);
+                    if (lane + dd < 32) s = max(s, t);
                 }
-                const int nchunk = ((g_last - g_first) >> 2) + 1;   // 4 groups = 128 samples per step
-                for (int ch = 0; ch < nchunk; ++ch) {
-                    const uint32_t word = (ch >> 3) == 0 ? need[0] : ((ch >> 3) == 1 ? need[1] : need[2]);
-                    const uint32_t nib = (word >> (4 * (ch & 7))) & 0xfu;
-                    if (nib == 0u) continue;                        // warp-uniform
-                    const int idx0 = 32 * (g_first + 4 * ch) + 4 * lane;
-                    const int4 x = *reinterpret_cast<const int4*>(z + idx0);
-                    if ((nib >> (lane >> 3)) & 1u) {
-                        const unsigned span = 2u * (unsigned)T;
-                        const int o = idx0 - w_lo;
-                        cnt += ((unsigned)(o + 0) <= span && x.x < tv) ? 1 : 0;
-                        cnt += ((unsigned)(o + 1) <= span && x.y < tv) ? 1 : 0;
-                        cnt += ((unsigned)(o + 2) <= span && x.z < tv) ? 1 : 0;
-                        cnt += ((unsigned)(o + 3) <= span && x.w < tv) ? 1 : 0;
-                    }
+                s = __shfl_down_sync(0xffffffffu, s, 1);
+                if (lane == 31) s = INT_MIN;
+                // remainder: elements 0..e of group G+q+1 (continuing into G+q+2), e = lane + d
+                const int A = G + q + 1;
+                const int pa = warp_incl_scan_max(z[32 * A + lane], lane);
+                const int pbm = warp_incl_scan_max(z[32 * A + 32 + lane], lane);
+                const int e = lane + d;
+                const int ra = __shfl_sync(0xffffffffu, pa, e & 31);
+                const int rb = __shfl_sync(0xffffffffu, pbm, e & 31);
+                const int ga = __shfl_sync(0xffffffffu, pa, 31);
+                const int rem = e < 0 ? INT_MIN : (e < 32 ? ra : max(ga, rb));
+                const int fwd = max(max(s, M), rem);
+                const bool cand = valid && !(fwd > zi);
+                const uint32_t candw = __ballot_sync(0xffffffffu, cand);
+                if (candw != 0u) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(ncand_s, __popc(candw));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (cand) cand_list[base + __popc(candw & ((1u << lane) - 1u))] = (unsigned short)(32 * w + lane);
                 }
-                cnt = __reduce_add_sync(0xffffffffu, cnt);
-                if (2 * cnt >= tv_need) passw |= 1u << c;
+                if (lane == j) cand_out = candw;
             }
-            if (lane == j) { cand_out = candw; pass_out = passw; }
         }
-        if (lane < 4) { cw[4 * it + lane] = cand_out; pw[4 * it + lane] = pass_out; }
+        if (lane < 4) {
+            cw[4 * it + lane] = cand_out;
+            passw[4 * it + lane] = 0u;
+        }
     }
+    __syncthreads();
+    // ---- threshold test of every candidate (:273-279), spread over all warps of the CTA
+    const int ncand = *ncand_s;
+    for (int ci = warp; ci < ncand; ci += kWarps) {
+        const int tp = cand_list[ci];
+        const int ic = Tpad + tp;
+        const float tvf = __fdiv_rn(__int_as_float(z[ic]), thr);
+        if (!(tvf > 0.0f)) continue;        // zpow >= 0: nothing is below a non-positive threshold
+        const int tv = __float_as_int(tvf);
+        const int w_lo = ic - T, w_hi = ic + T;
+        const int g_first = w_lo >> 5, g_last = w_hi >> 5;   // at most 65 groups
+        int cnt = 0;
+        uint32_t need[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int gi = g_first + 32 * r + lane;
+            bool nd = false;
+            if (gi <= g_last) {
+                if (gmax[gi] < tv) cnt += min(32 * gi + 31, w_hi) - max(32 * gi, w_lo) + 1;
+                else if (gmin[gi] < tv) nd = true;
+            }
+            need[r] = __ballot_sync(0xffffffffu, nd);
+        }
+        const int nchunk = ((g_last - g_first) >> 2) + 1;   // 4 groups = 128 samples per step
+        const unsigned span = 2u * (unsigned)T;
+        const int* zc0 = z + 32 * g_first + 4 * lane;
+        const int o0 = 32 * g_first + 4 * lane - w_lo;      // window offset of this lane's first sample
+        const uint32_t mybit = 1u << (lane >> 3);
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const uint32_t word = (ch >> 3) == 0 ? need[0] : ((ch >> 3) == 1 ? need[1] : need[2]);
+            const uint32_t nib = (word >> (4 * (ch & 7))) & 0xfu;
+            if (nib == 0u) continue;                        // warp-uniform
+            const int4 x = *reinterpret_cast<const int4*>(zc0 + 128 * ch);
+            const int cbase = 32 * g_first + 128 * ch - w_lo;   // window offset of the chunk's first sample
+            if (nib == 0xfu && cbase >= 0 && (unsigned)(cbase + 127) <= span) {
+                // interior chunk, all four groups straddle the threshold: no masks needed
+                cnt += (x.x < tv) + (x.y < tv) + (x.z < tv) + (x.w < tv);
+            } else if (nib & mybit) {
+                const int o = o0 + 128 * ch;
+                cnt += ((unsigned)(o + 0) <= span && x.x < tv) ? 1 : 0;
+                cnt += ((unsigned)(o + 1) <= span && x.y < tv) ? 1 : 0;
+                cnt += ((unsigned)(o + 2) <= span && x.z < tv) ? 1 : 0;
+                cnt += ((unsigned)(o + 3) <= span && x.w < tv) ? 1 : 0;
+            }
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0 && 2 * cnt >= tv_need) atomicOr(&passw[tp >> 5], 1u << (tp & 31));
+    }
+    __syncthreads();
+    if (tid < kFastTile / 32) pw[tid] = passw[tid];
 }
 
 // bits [fstart + 32*lane, +32) of a piece of length L starting at bit fstart
@@ -688,7 +711,8 @@ cudaError_t launch_peak_phase1(const float* d_zpow, long long z_base, long long 
     uint32_t* segflag = reinterpret_cast<uint32_t*>(ws + pl.off_flag);
     if (fast) {
         const FastGeom geo = fast_geom(T);
-        const size_t smem = sizeof(int) * ((size_t)geo.nrow * 128 + 2 * (size_t)geo.nrow * 4 + kFastTile / 32);
+        const size_t smem = sizeof(int) * ((size_t)geo.nrow * 128 + 2 * (size_t)geo.nrow * 4 + 2 * (kFastTile / 32) + 1) +
+                            sizeof(unsigned short) * kFastTile;
         e = set_smem_attr((const void*)peak_flags_kernel, smem);
         if (e != cudaSuccess) return e;
         peak_flags_kernel<<<(unsigned)ntiles, kFastThreads, smem, st>>>(d_zpow, z_base, z_end, lo, hi, T,
