@@ -85,11 +85,12 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm)}
 
 
-def workload_config(log2n: int, K: int) -> dict:
+def workload_config(log2n: int, K: int, esn0: float = 20.0, thr: float = 9.5) -> dict:
     """The `config` object of the JSON line: the same for the B200 arm and the reference arm."""
-    return {"workload": f"BASELINE configs[1]: syncword detection over a 2^{log2n}-sample synthetic cf32 "
-                        f"capture per GPU, K={K} hypotheses, QPSK 4 sps RRC, Es/N0 20 dB, CFO 0.005 rad/sample",
-            "samples_per_gpu": 1 << log2n, "fft_size": FFT, "time_threshold": TAU, "power_threshold": 9.5,
+    which = "configs[1]" if (K == 9 and esn0 == 20.0) else "configs[3] (low-SNR / wide-CFO search)" if K > 9 else "configs[1] variant"
+    return {"workload": f"BASELINE {which}: syncword detection over a 2^{log2n}-sample synthetic cf32 "
+                        f"capture per GPU, K={K} hypotheses, QPSK 4 sps RRC, Es/N0 {esn0:g} dB, CFO 0.005 rad/sample",
+            "samples_per_gpu": 1 << log2n, "fft_size": FFT, "time_threshold": TAU, "power_threshold": thr,
             "l2": "inputs (8 B/sample resident capture) larger than L2; no flush needed",
             "sharding": "contiguous time shards + 1-block halo; (T+1)-entry chain table all_gather only"}
 
@@ -107,14 +108,15 @@ def measured_traffic(log2n: int, K: int, kernel: str = "correlate_kernel"):
         return None
 
 
-def rx_settings(bins: int):
+def rx_settings(bins: int, thr: float = 9.5):
     from gr4_packet_modem_b200.firdes import BPSK, SYNCWORD, unit_energy_rrc
 
     return dict(rrc_taps=unit_energy_rrc(), syncword=SYNCWORD, constellation=BPSK, min_freq_bin=-bins,
-                max_freq_bin=bins, time_threshold=TAU, power_threshold=9.5)
+                max_freq_bin=bins, time_threshold=TAU, power_threshold=thr)
 
 
-def cpu_reference_rate(bins: int, samples_per_thread: int, threads: int, steps: int, warmup: int):
+def cpu_reference_rate(bins: int, samples_per_thread: int, threads: int, steps: int, warmup: int,
+                       esn0: float = 20.0, thr: float = 9.5):
     """The reference's CPU algorithm (oracle port, independent radix-2 FFT): `threads` independent
     streams, one per host thread (one GR4 block instance runs on one worker thread).  Returns
     (aggregate Msps, seconds per step)."""
@@ -122,9 +124,9 @@ def cpu_reference_rate(bins: int, samples_per_thread: int, threads: int, steps: 
     from oracle import pyoracle as po
 
     po.build(ref=False)
-    x, _ = packet_capture(samples_per_thread, seed=1, esn0_db=20.0, cfo=0.005)
-    s = rx_settings(bins)
-    sds = [po.SyncwordDetection(s["rrc_taps"], s["syncword"], s["constellation"], -bins, bins, TAU, 9.5,
+    x, _ = packet_capture(samples_per_thread, seed=1, esn0_db=esn0, cfo=0.005)
+    s = rx_settings(bins, thr)
+    sds = [po.SyncwordDetection(s["rrc_taps"], s["syncword"], s["constellation"], -bins, bins, TAU, thr,
                                 fft_kind=po.FFT_RADIX2) for _ in range(threads)]
     consumed = [0] * threads
 
@@ -155,20 +157,192 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     per_thread = 1 << 21
-    rate, sec = cpu_reference_rate(args.bins, per_thread, threads, max(args.steps, 1), max(args.warmup, 1))
+    rate, sec = cpu_reference_rate(args.bins, per_thread, threads, max(args.steps, 1), max(args.warmup, 1),
+                                   args.esn0, args.thr)
     K = 2 * args.bins + 1
     line = {
         "impl": "reference", "metric": "complex Msps (cf32) through RX sync (SyncwordDetection)",
         "value": rate, "unit": "Msps", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.log2n, K),
+        "config": workload_config(args.log2n, K, args.esn0, args.thr),
         "cpu_baseline": {"value": rate, "unit": "Msps", "cores": threads, "kind": "port",
                          "sample": f"bounded sample of the workload: {threads} independent streams x 2^21 samples "
                                    "of the same signal model per step, one per host thread (oracle port of "
                                    "PM/syncword_detection.hpp, radix-2 FFT in place of FFTW; the reference itself "
                                    "is unbuildable here, DESIGN.md §7)"},
         "e2e": {"value": rate, "unit": "Msps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def hbm_roofline(kernel: str, alg_bytes: float, ms: float, peaks: dict, note: str) -> dict:
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = alg_bytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms,
+            "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6650 GB/s", "note": note}
+
+
+def run_chain(args):
+    """BASELINE configs[2]: raw stream -> fused [PfbArbResampler(1 + 1.2 ppm) + Rotator(0.005)] ->
+    SyncwordDetection (block contract: delayed pass-through + tags) -> SymbolFilter, all device-resident.
+    One step = the three stages over the whole capture; stage times by CUDA events on the launching
+    stream."""
+    import torch
+
+    from gr4_packet_modem_b200 import FrontEnd, SymbolFilter, SyncwordDetection, _native
+    from gr4_packet_modem_b200.blocks import stream_tags_from_detection
+    from gr4_packet_modem_b200.firdes import lowpass_prototype_taps, pfb_matched_filter_taps
+    from gr4_packet_modem_b200.stimulus import packet_capture_torch
+
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("--workload chain is a single-GPU workload")
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    n = 1 << args.log2n
+    K = 2 * args.bins + 1
+    W = max(args.warmup, 3)
+    lib = _native.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    raw = packet_capture_torch(n, dev, seed=1, esn0_db=args.esn0, cfo=0.0)
+    rate = float(np.float32(1.0) + np.float32(1e-6) * np.float32(1.2))
+    fe_taps = lowpass_prototype_taps(32, 40)
+    sf_taps = pfb_matched_filter_taps()
+    sd = SyncwordDetection(**rx_settings(args.bins, args.thr), device=0)
+    probe = FrontEnd(rate=rate, taps=fe_taps, phase_incr=0.005)
+    n_y = probe.max_output(n)
+    del probe
+    y = torch.empty(n_y, dtype=torch.complex64, device=dev)        # conditioned stream
+    dl = torch.empty(n_y, dtype=torch.complex64, device=dev)       # SyncwordDetection's delayed output
+    sym = torch.empty(n_y // 4 + 1024, dtype=torch.complex64, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def step(timed=None):
+        fe = FrontEnd(rate=rate, taps=fe_taps, phase_incr=0.005)   # start(): fresh streaming state per pass
+        sf = SymbolFilter(sf_taps, 32, 4, delay=44)
+        ev[0].record()
+        c_in, n_out = fe.process_device(raw.data_ptr(), n, y.data_ptr(), n_y, stream)
+        ev[1].record()
+        consumed, recs, tags = sd.detect_device(y.data_ptr(), n_out, stream, d_out_ptr=dl.data_ptr())
+        ev[2].record()
+        st = stream_tags_from_detection(tags)
+        c_sf, n_sym, otags = sf.process_device(dl.data_ptr(), consumed, sym.data_ptr(), sym.numel(), st, stream)
+        ev[3].record()
+        torch.cuda.synchronize()
+        if timed is not None:
+            timed.append((ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])))
+        return c_in, n_out, consumed, len(recs), n_sym, len(otags)
+
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    launches0 = lib.b200sync_launch_count()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    timed = []
+    e0.record()
+    for _ in range(args.steps):
+        c_in, n_out, consumed, ndet, n_sym, ntags = step(timed)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = lib.b200sync_launch_count() - launches0
+    ms_per_step = e0.elapsed_time(e1) / args.steps
+    fe_ms = statistics.mean(t[0] for t in timed)
+    sd_ms = statistics.mean(t[1] for t in timed)
+    sf_ms = statistics.mean(t[2] for t in timed)
+    peaks = load_peaks()
+    line = {
+        "metric": "complex Msps (cf32) through RX sync (fused front end + SyncwordDetection + SymbolFilter)",
+        "value": c_in / (ms_per_step * 1e-3) / 1e6, "unit": "Msps", "n_gpus": 1, "steps": args.steps, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[2]: fused RX front end (PfbArbResampler 1+1.2ppm + Rotator 0.005) -> "
+                               f"SyncwordDetection K={K} (block contract, delayed output) -> SymbolFilter 32x44 over a "
+                               f"2^{args.log2n}-sample synthetic cf32 capture on 1 B200, Es/N0 {args.esn0:g} dB",
+                   "samples_per_gpu": n, "l2": "streams (8 B/sample) far larger than L2; no flush needed"},
+        "detections_per_step": ndet, "symbols_per_step": n_sym, "symbol_tags_per_step": ntags, "clocks": clocks,
+        "gpu_launches": int(launches), "e2e": None,
+        "stage_ms": {"frontend": fe_ms, "syncword_detection": sd_ms, "symbol_filter_incl_host_plan": sf_ms},
+        "roofline": hbm_roofline("frontend_kernel", 16.0 * n_out, fe_ms, peaks,
+                                 "16 B/sample (8 in + 8 out); 2 x 40 taps x 2 x (mul, add) = 320 separately rounded "
+                                 "FP32 instructions per output (bit-exact std::inner_product order): FP32-issue bound"),
+        "roofline_symbol_filter": hbm_roofline("symbol_filter_kernel", 10.0 * consumed, sf_ms, peaks,
+                                               "10 B/sample (8 in + 8/4 out); stage time includes the host replay of "
+                                               "the tag state machine and the segment upload"),
+    }
+    print(json.dumps(line))
+
+
+def run_channels(args):
+    """BASELINE configs[4], channel mode: 64 independent channels x 2^24 samples in one call."""
+    import torch
+
+    from gr4_packet_modem_b200 import SyncwordDetection, _native
+    from gr4_packet_modem_b200.stimulus import packet_capture_torch
+
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("--workload channels is a single-GPU workload")
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    C_, n = args.channels, 1 << args.log2n
+    K = 2 * args.bins + 1
+    W = max(args.warmup, 3)
+    lib = _native.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    x = torch.empty(C_ * n, dtype=torch.complex64, device=dev)
+    for c in range(C_):
+        x[c * n:(c + 1) * n] = packet_capture_torch(n, dev, seed=100 + c, esn0_db=args.esn0, cfo=0.005)
+    sd = SyncwordDetection(**rx_settings(args.bins, args.thr), device=0)
+    for _ in range(W):
+        consumed, per = sd.detect_channels_device(x.data_ptr(), C_, n, n, stream)
+    torch.cuda.synchronize()
+    launches0 = lib.b200sync_launch_count()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        consumed, per = sd.detect_channels_device(x.data_ptr(), C_, n, n, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = lib.b200sync_launch_count() - launches0
+    ms_per_step = e0.elapsed_time(e1) / args.steps
+    # single-stream runs of the same channels, one after the other, for comparison
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    same = True
+    for c in range(C_):
+        _, r, _ = sd.detect_device(x.data_ptr() + 8 * c * n, n, stream)
+        same = same and np.array_equal(r.view(np.uint8), per[c].view(np.uint8))
+    t1.record()
+    torch.cuda.synchronize()
+    peaks = load_peaks()
+    line = {
+        "metric": "complex Msps (cf32) through RX sync (SyncwordDetection, batched channels)",
+        "value": C_ * consumed / (ms_per_step * 1e-3) / 1e6, "unit": "Msps", "n_gpus": 1, "steps": args.steps,
+        "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[4] channel mode: {C_} independent channels x 2^{args.log2n} samples, "
+                               f"K={K}, one b200sync_sd_detect_channels_device call per step on 1 B200",
+                   "channels": C_, "samples_per_channel": n,
+                   "l2": "capture (8 B/sample x channels) far larger than L2; no flush needed"},
+        "detections_per_step": int(sum(len(p) for p in per)), "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": None,
+        "sequential_single_stream_ms": t0.elapsed_time(t1), "batched_equals_single_stream": bool(same),
+        "roofline": hbm_roofline("correlate_kernel (whole step)", 8.0 * C_ * consumed, ms_per_step, peaks,
+                                 "whole-step figure; K>=3 is FP32/shared-memory bound (see the detect workload)"),
     }
     print(json.dumps(line))
 
@@ -183,9 +357,21 @@ def main():
     ap.add_argument("--bins", type=int, default=4, help="min/max_freq_bin = -/+bins (K = 2*bins+1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
+    ap.add_argument("--workload", default="detect", choices=["detect", "chain", "channels"],
+                    help="detect: BASELINE configs[1] (default, the metric's configuration; --bins 16 --esn0 0 gives "
+                         "configs[3]); chain: configs[2]; channels: configs[4] channel mode")
+    ap.add_argument("--esn0", type=float, default=20.0, help="Es/N0 of the synthetic capture in dB")
+    ap.add_argument("--thr", type=float, default=9.5, help="power_threshold")
+    ap.add_argument("--channels", type=int, default=64)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "chain":
+        return run_chain(args)
+    if args.workload == "channels":
+        if args.log2n == 30:
+            args.log2n = 24
+        return run_channels(args)
 
     import torch
     import torch.distributed as dist
@@ -206,7 +392,7 @@ def main():
     K = 2 * args.bins + 1
     n_per = 1 << args.log2n
     S = FFT - 297 + 1
-    sd = SyncwordDetection(**rx_settings(args.bins), device=local)
+    sd = SyncwordDetection(**rx_settings(args.bins, args.thr), device=local)
     assert sd.stride == S
     stream = torch.cuda.current_stream().cuda_stream
     lib = _native.lib()
@@ -219,7 +405,7 @@ def main():
     total_blocks, fb, nbk = shard.total_blocks, shard.first_block, shard.n_blocks
     seg0 = shard.first_sample
     seg_n = shard.n_samples if world > 1 else n_per
-    x = packet_capture_torch(seg_n, dev, seed=1, esn0_db=20.0, cfo=0.005, start=seg0)
+    x = packet_capture_torch(seg_n, dev, seed=1, esn0_db=args.esn0, cfo=0.005, start=seg0)
     torch.cuda.synchronize()
     max_recs = seg_n // (TAU + 1) + 2
 
@@ -331,8 +517,8 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu:
         th = os.cpu_count() or 1
-        r1, _ = cpu_reference_rate(args.bins, 1 << 22, 1, 1, 1)
-        rN, _ = cpu_reference_rate(args.bins, 1 << 22, th, 1, 1)
+        r1, _ = cpu_reference_rate(args.bins, 1 << 22, 1, 1, 1, args.esn0, args.thr)
+        rN, _ = cpu_reference_rate(args.bins, 1 << 22, th, 1, 1, args.esn0, args.thr)
         cpu = {"value": rN, "unit": "Msps", "cores": th, "kind": "port", "single_core_msps": r1,
                "sample": f"{th} independent streams x 2^22 samples of the same signal model (oracle port, "
                          "radix-2 FFT in place of FFTW)"}
@@ -341,7 +527,7 @@ def main():
         "metric": "complex Msps (cf32) through RX sync (SyncwordDetection)", "value": value, "unit": "Msps",
         "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.log2n, K),
+        "config": workload_config(args.log2n, K, args.esn0, args.thr),
         "detections_per_step": ndet, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
         "roofline": roofline, "cpu_baseline": cpu,
     }

@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200sync.so")
+# B200SYNC_LIB: development override used by scripts/variants.sh to time alternative builds of the same ABI
+LIB_PATH = os.environ.get("B200SYNC_LIB") or os.path.join(_HERE, "libb200sync.so")
 
 
 class SdConfig(C.Structure):
@@ -116,6 +117,7 @@ def lib():
     L.b200sync_sd_process.argtypes = [vp, vp, sz, vp, psz, vp, sz, psz]
     L.b200sync_sd_detect_device.argtypes = [vp, vp, sz, vp, vp, vp, sz, psz, psz]
     L.b200sync_sd_detect_host.argtypes = [vp, vp, sz, vp, sz, psz, psz]
+    L.b200sync_sd_detect_channels_device.argtypes = [vp, vp, sz, sz, sz, vp, vp, sz, vp, psz]
     L.b200sync_sd_shard_phase1.argtypes = [vp, vp, C.c_uint64, sz, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, sz]
     L.b200sync_sd_shard_phase2.argtypes = [vp, C.c_uint32, vp, sz, psz]
     L.b200sync_sd_records_to_tags.argtypes = [vp, vp, sz, vp]
@@ -147,7 +149,8 @@ def lib():
     for name in ("b200sync_fe_create", "b200sync_fe_start", "b200sync_fe_process", "b200sync_fe_process_device"):
         getattr(L, name).restype = C.c_int
     for name in ("b200sync_sd_create", "b200sync_sd_start", "b200sync_sd_info", "b200sync_sd_process",
-                 "b200sync_sd_detect_device", "b200sync_sd_detect_host", "b200sync_sd_shard_phase1",
+                 "b200sync_sd_detect_device", "b200sync_sd_detect_host", "b200sync_sd_detect_channels_device",
+                 "b200sync_sd_shard_phase1",
                  "b200sync_sd_shard_phase2", "b200sync_sd_records_to_tags", "b200sync_sd_copy_metric",
                  "b200sync_sd_last_timings"):
         getattr(L, name).restype = C.c_int

@@ -188,6 +188,25 @@ class SyncwordDetection:
         r = _copy_records(recs, nr.value)
         return nc.value, r, self.records_to_tags(r)
 
+    def detect_channels_device(self, d_in_ptr: int, n_channels: int, n: int, channel_stride: int = 0,
+                               stream_ptr: int = 0, max_recs: int = 0):
+        """Batched channel mode (b200sync_sd_detect_channels_device): n_channels independent streams of n
+        samples, channel c at d_in_ptr + 8 * c * channel_stride.  Returns (consumed_per_channel,
+        [records of channel 0, records of channel 1, ...])."""
+        L = _native.lib()
+        stride = channel_stride or n
+        if max_recs <= 0:
+            max_recs = n // (self.time_threshold + 1) + 2
+        recs = self._rec_buffer(max_recs * n_channels)
+        counts = np.zeros(n_channels, np.uintp)
+        nc = C.c_size_t(0)
+        check(L.b200sync_sd_detect_channels_device(self._h, C.c_void_p(d_in_ptr), stride, n_channels, n,
+                                                   C.c_void_p(stream_ptr or None), recs.ctypes.data, max_recs,
+                                                   counts.ctypes.data, C.byref(nc)))
+        raw = recs.view(_RAW)
+        out = [raw[c * max_recs:c * max_recs + int(counts[c])].copy().view(RECORD_DTYPE) for c in range(n_channels)]
+        return nc.value, out
+
     def shard_phase1(self, d_in_ptr: int, first_sample_abs: int, n_in: int, first_block: int, n_blocks: int,
                      total_blocks: int, stream_ptr: int = 0) -> np.ndarray:
         L = _native.lib()
@@ -345,6 +364,22 @@ class SymbolFilter:
                                                    it.size, out.ctypes.data, max_out, C.byref(nc), C.byref(npd),
                                                    ot.ctypes.data, ot.size, C.byref(nt)))
         return nc.value, out[:npd.value], ot[:nt.value].copy()
+
+
+    def process_device(self, d_in_ptr: int, n_in: int, d_out_ptr: int, max_out: int, in_tags: np.ndarray | None = None,
+                       stream_ptr: int = 0):
+        """processBulk with device spans (b200sync_sf_process_device) -> (consumed, produced, out_tags)."""
+        from ._native import check_sf
+
+        it = np.ascontiguousarray(in_tags if in_tags is not None else np.zeros(0, STREAM_TAG_DTYPE), STREAM_TAG_DTYPE)
+        ot = np.zeros(it.size + 64, STREAM_TAG_DTYPE)
+        nc, npd, nt = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+        check_sf(_native.lib().b200sync_sf_process_device(self._h, C.c_void_p(d_in_ptr), n_in,
+                                                          it.ctypes.data if it.size else None, it.size,
+                                                          C.c_void_p(d_out_ptr), max_out, C.c_void_p(stream_ptr or None),
+                                                          C.byref(nc), C.byref(npd), ot.ctypes.data, ot.size,
+                                                          C.byref(nt)))
+        return nc.value, npd.value, ot[:nt.value]
 
 
 class SyncwordDetectionFilter:

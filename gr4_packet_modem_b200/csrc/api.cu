@@ -105,6 +105,21 @@ struct b200sync_sd {
     // device-side stage timing of the last offline call (CUDA events on the caller's stream)
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     bool ev_valid = false;
+    // batched channel mode: a few lanes (stream + private metric / workspace / detection list) so
+    // that the short serial kernels of one channel overlap the correlator of the next
+    struct Lane {
+        cudaStream_t st = nullptr;
+        DevBuf<float> z;
+        DevBuf<unsigned char> ws;
+        DevBuf<unsigned long long> det_idx;
+    };
+    static constexpr int kLanes = 3;
+    Lane lanes[kLanes];
+    DevBuf<PeakState> d_chan_state;
+    DevBuf<DetectionRecord> d_chan_recs;
+    PeakState* h_chan_state = nullptr;  // pinned
+    size_t h_chan_cap = 0;
+    cudaEvent_t ev_chan = nullptr;
     // shard
     DevBuf<uint16_t> d_table;
     struct {
@@ -366,6 +381,13 @@ void b200sync_sd_destroy(b200sync_sd* sd) {
     for (auto& e : sd->ev)
         if (e) cudaEventDestroy(e);
     if (sd->h_state) cudaFreeHost(sd->h_state);
+    if (sd->h_chan_state) cudaFreeHost(sd->h_chan_state);
+    if (sd->ev_chan) cudaEventDestroy(sd->ev_chan);
+    for (auto& ln : sd->lanes)
+        if (ln.st) {
+            cudaStreamSynchronize(ln.st);
+            cudaStreamDestroy(ln.st);
+        }
     delete sd;
 }
 
@@ -631,6 +653,101 @@ int b200sync_sd_detect_host(b200sync_sd* sd, const float* in, size_t n, b200sync
     for (size_t i = 0; i < made; ++i) cudaEventDestroy(ev[i]);
     cudaStreamDestroy(cs);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+int b200sync_sd_detect_channels_device(b200sync_sd* sd, const void* d_in, size_t channel_stride,
+                                       size_t n_channels, size_t n, void* cuda_stream,
+                                       b200sync_detection_record* recs, size_t max_recs_per_channel,
+                                       size_t* n_recs, size_t* n_consumed) {
+    if (!sd || !n_recs || !n_consumed || (!d_in && n && n_channels) || (!recs && max_recs_per_channel))
+        return fail(B200SYNC_EINVAL, "null argument");
+    if (n_channels > 1 && channel_stride < n) return fail(B200SYNC_EINVAL, "channel_stride smaller than n");
+    CU(cudaSetDevice(sd->device));
+    cudaStream_t caller = static_cast<cudaStream_t>(cuda_stream);
+    const long long S = sd->S, F = sd->fft_size, T = sd->T;
+    *n_consumed = 0;
+    for (size_t c = 0; c < n_channels; ++c) n_recs[c] = 0;
+    if (n_channels == 0 || n < static_cast<size_t>(F)) return 0;
+    const long long nb_total = (static_cast<long long>(n) - F) / S + 1;
+    const long long P = nb_total * S;
+    const long long hi_total = std::max(0LL, P - T - 1);
+    const size_t cap = std::max<size_t>(64, static_cast<size_t>(P / (T + 1) + 2));
+    const size_t ws_bytes = peak_workspace_bytes_sms(hi_total + 1, sd->T, sd->num_sms);
+    CU(sd->d_chan_state.ensure(n_channels));
+    CU(sd->d_chan_recs.ensure(n_channels * cap));
+    if (sd->h_chan_cap < n_channels) {
+        if (sd->h_chan_state) cudaFreeHost(sd->h_chan_state);
+        sd->h_chan_state = nullptr;
+        sd->h_chan_cap = 0;
+        CU(cudaMallocHost(&sd->h_chan_state, sizeof(PeakState) * n_channels));
+        sd->h_chan_cap = n_channels;
+    }
+    if (!sd->ev_chan) CU(cudaEventCreateWithFlags(&sd->ev_chan, cudaEventDisableTiming));
+    const int nl = static_cast<int>(std::min<size_t>(b200sync_sd::kLanes, n_channels));
+    for (int l = 0; l < nl; ++l) {
+        auto& ln = sd->lanes[l];
+        if (!ln.st) CU(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
+        CU(ln.z.ensure(static_cast<size_t>(P) + 64));
+        CU(ln.ws.ensure(ws_bytes));
+        CU(ln.det_idx.ensure(cap));
+    }
+    // the lanes start after everything already enqueued on the caller's stream (the capture itself)
+    CU(cudaMemsetAsync(sd->d_chan_state.p, 0, sizeof(PeakState) * n_channels, caller));
+    CU(cudaEventRecord(sd->ev_chan, caller));
+    for (int l = 0; l < nl; ++l) CU(cudaStreamWaitEvent(sd->lanes[l].st, sd->ev_chan, 0));
+    const float2* base = static_cast<const float2*>(d_in);
+    for (size_t c = 0; c < n_channels; ++c) {
+        auto& ln = sd->lanes[c % nl];
+        const float2* x = base + c * channel_stride;
+        PeakState* state = sd->d_chan_state.p + c;
+        DetectionRecord* drecs = sd->d_chan_recs.p + c * cap;
+        CU(launch_correlate(x, 0, ln.z.p, 0, sd->d_hperm.p, (int)sd->K, (int)sd->S, 0, nb_total, sd->d_tw.p,
+                            nullptr, 0, (int)sd->delay, sd->num_sms, ln.st));
+        if (hi_total > 0) {
+            CU(launch_peak_phase1(ln.z.p, 0, P, 0, hi_total, sd->T, sd->power_threshold, ln.ws.p, ln.ws.cap,
+                                  nullptr, sd->num_sms, ln.st));
+            CU(launch_peak_phase2(0, hi_total, sd->T, ln.ws.p, ln.ws.cap, -1, state, ln.det_idx.p,
+                                  (unsigned)cap, sd->num_sms, ln.st));
+        }
+        CU(launch_refine(x, 0, ln.z.p, 0, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->min_bin, sd->d_tw.p,
+                         ln.det_idx.p, &state->det_count, (unsigned)cap, drecs, sd->num_sms, ln.st));
+        CU(cudaMemcpyAsync(sd->h_chan_state + c, state, sizeof(PeakState), cudaMemcpyDeviceToHost, ln.st));
+    }
+    for (int l = 0; l < nl; ++l) CU(cudaStreamSynchronize(sd->lanes[l].st));
+    // exact-size record copies, then the reference's "tag already published" filter per channel
+    std::vector<DetectionRecord>& h = sd->h_recs;
+    size_t total = 0;
+    for (size_t c = 0; c < n_channels; ++c) {
+        if (sd->h_chan_state[c].det_count > cap) return fail(B200SYNC_ENOMEM, "internal detection list overflow");
+        total += sd->h_chan_state[c].det_count;
+    }
+    h.resize(total);
+    size_t off = 0;
+    for (size_t c = 0; c < n_channels; ++c) {
+        const size_t cnt = sd->h_chan_state[c].det_count;
+        if (cnt)
+            CU(cudaMemcpyAsync(h.data() + off, sd->d_chan_recs.p + c * cap, sizeof(DetectionRecord) * cnt,
+                               cudaMemcpyDeviceToHost, sd->lanes[0].st));
+        off += cnt;
+    }
+    CU(cudaStreamSynchronize(sd->lanes[0].st));
+    off = 0;
+    for (size_t c = 0; c < n_channels; ++c) {
+        const size_t cnt = sd->h_chan_state[c].det_count;
+        size_t kept = 0;
+        for (size_t i = 0; i < cnt; ++i) {
+            const DetectionRecord& r = h[off + i];
+            if (r.index + sd->delay >= static_cast<uint64_t>(P)) continue;
+            if (kept >= max_recs_per_channel) return fail(B200SYNC_ENOMEM, "record buffer too small");
+            recs[c * max_recs_per_channel + kept++] = r;
+        }
+        n_recs[c] = kept;
+        off += cnt;
+    }
+    *n_consumed = static_cast<size_t>(P);
+    sd->ev_valid = false;
+    return 0;
 }
 
 int b200sync_sd_last_timings(const b200sync_sd* sd, float* correlate_ms, float* peaks_ms, float* refine_ms) {

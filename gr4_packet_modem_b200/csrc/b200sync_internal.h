@@ -10,7 +10,10 @@ namespace b200sync {
 
 constexpr int kFft = 2048;         // the only fft_size the kernels implement (reference default)
 constexpr int kGroupThreads = 128; // threads cooperating on one FFT block
-constexpr int kCorrThreads = 768;  // 4 FFT groups per CTA, 1 persistent CTA per SM
+#ifndef B200_CORR_THREADS
+#define B200_CORR_THREADS 768
+#endif
+constexpr int kCorrThreads = B200_CORR_THREADS;  // 6 FFT groups per CTA, 1 persistent CTA per SM
 constexpr int kMaxHyp = 129;       // max frequency hypotheses (min/max_freq_bin = -/+64)
 constexpr int kMaxTimeThreshold = 1023;  // chain kernels keep one bitmap word per lane
 

@@ -48,6 +48,15 @@ template_spectra_kernel(const float2* __restrict__ td /*[K][2048] zero padded*/,
 // handles blocks gg, gg+G, ... of [b0, b0+nb).  Block b covers absolute samples
 // [b*S, b*S+2048) and produces zpow for [b*S, (b+1)*S).
 // ---------------------------------------------------------------------------------
+#ifndef B200_TWO_XB
+constexpr bool kCorrTwoBuf = false;
+#else
+// one buffer per exchange layout (2 barriers per transform instead of 4) needs 228 KB of shared memory at 6
+// groups: measured SLOWER (6.66 vs 6.17 ms at 2^28, K = 9) because it leaves no L1 for the template spectra
+constexpr bool kCorrTwoBuf = true;
+#endif
+constexpr int kCorrXchg = kCorrTwoBuf ? kXchgFloat2 + kXchgFloat2A : kXchgFloat2;
+
 __global__ void __launch_bounds__(kCorrThreads, 1)
 correlate_kernel(const float2* __restrict__ in, long long in_base, float* __restrict__ zpow,
                  long long z_base, const float2* __restrict__ hperm, int K, int S, long long b0,
@@ -57,7 +66,8 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
     const int g = threadIdx.x >> 7;
     const int tid = threadIdx.x & 127;
-    float2* xb = tw_s + kTwTotal + g * kXchgFloat2;
+    float2* xb = tw_s + kTwTotal + g * kCorrXchg;
+    float2* xb2 = kCorrTwoBuf ? xb + kXchgFloat2 : xb;
     load_twiddles(tw_s, tw_g);
     __syncthreads();
     const int ngroups = blockDim.x >> 7;
@@ -79,7 +89,8 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
                 if (i < S) out_delayed[s0 + i + delay - out_base] = v[n1];
             }
         }
-        fft_a(v, xs, tw_s, xb, tid, bar_id);
+        if constexpr (kCorrTwoBuf) group_sync(bar_id);  // previous block's last reads of xb2 are done
+        fft_a<kCorrTwoBuf>(v, xs, tw_s, xb, tid, bar_id, xb2);
 
         float best[16];
 #pragma unroll
@@ -93,7 +104,7 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
             float2 y[16], c[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) y[j] = cmul(xs[j], __ldg(h + j * kGroupThreads));  // :247-249
-            fft_b(y, c, tw_s, xb, tid, bar_id);                                             // :250-251
+            fft_b<kCorrTwoBuf>(y, c, tw_s, xb, tid, bar_id, xb2);                           // :250-251
 #pragma unroll
             for (int m1 = 0; m1 < 16; ++m1) {
                 const float p = norm2(c[m1]);  // :307
@@ -280,7 +291,7 @@ cudaError_t launch_template_spectra(const float2* d_td, float2* d_hperm, int K, 
 }
 
 size_t correlate_smem_bytes(int groups) {
-    return sizeof(float2) * (size_t)(kTwTotal + groups * kXchgFloat2);
+    return sizeof(float2) * (size_t)(kTwTotal + groups * kCorrXchg);
 }
 
 cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpow, long long z_base,

@@ -54,6 +54,7 @@ constexpr int kTwTotal = 256 + 2048;  // 2304 float2 = 18432 B
 constexpr int kXchgStrideA = 129;   // exchange layout 1: (a*129 + tid)
 constexpr int kXchgStrideP = 9;     // exchange layout 2: (p*9 + d)
 constexpr int kXchgFloat2 = 256 * kXchgStrideP;  // 2304 float2 = 18432 B (>= 16*129 = 2064)
+constexpr int kXchgFloat2A = 16 * kXchgStrideA;  // 2064 float2 = 16512 B: layout 1 alone
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) {
     return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
@@ -153,8 +154,16 @@ __device__ __forceinline__ void group_sync(int bar_id) {
 // ---- FFT A: 2048 samples (registers v[n1] = x[128 n1 + tid]) -> spectrum -------------
 // On return xs[pi*8 + k3] = X[(tid + 128 pi) + 256 k3]   (pi in {0,1}).
 // `tw` are the per-pass twiddle tables (shared memory), `xb` this group's exchange buffer.
+//
+// TWO_BUF: the two exchanges use two separate buffers (xb: layout 2 "p*9+d", xb2: layout 1
+// "a*129+tid"), so a buffer is never rewritten before every thread has passed the barrier that
+// follows its reads: the two "buffer free again" barriers of each transform disappear.  The caller
+// must place one barrier between a transform that read xb2 last (fft_b) and the next fft_a.
+template <bool TWO_BUF = false>
 __device__ __forceinline__ void fft_a(float2 (&v)[16], float2 (&xs)[16], const float2* __restrict__ tw,
-                                      float2* __restrict__ xb, int tid, int bar_id) {
+                                      float2* __restrict__ xb, int tid, int bar_id,
+                                      float2* __restrict__ xb2 = nullptr) {
+    float2* const xa = TWO_BUF ? xb2 : xb;
     // pass A1
     dft16(v);
     {
@@ -163,15 +172,15 @@ __device__ __forceinline__ void fft_a(float2 (&v)[16], float2 (&xs)[16], const f
         for (int k1 = 0; k1 < 16; ++k1) {
             float2 val = v[bitrev4(k1)];
             if (k1 != 0) val = cmul(val, tw[kTwS + k1 * 16 + n2]);
-            xb[k1 * kXchgStrideA + tid] = val;
+            xa[k1 * kXchgStrideA + tid] = val;
         }
     }
     group_sync(bar_id);
     // pass A2
     const int n3 = tid >> 4, k1 = tid & 15;
 #pragma unroll
-    for (int n2 = 0; n2 < 16; ++n2) v[n2] = xb[k1 * kXchgStrideA + n2 * 8 + n3];
-    group_sync(bar_id);
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = xa[k1 * kXchgStrideA + n2 * 8 + n3];
+    if constexpr (!TWO_BUF) group_sync(bar_id);
     dft16(v);
 #pragma unroll
     for (int k2 = 0; k2 < 16; ++k2) {
@@ -196,8 +205,11 @@ __device__ __forceinline__ void fft_a(float2 (&v)[16], float2 (&xs)[16], const f
 
 // ---- FFT B: y[pi*8 + f3] = Y[(tid + 128 pi) + 256 f3] -> c[m1] = C[128 m1 + tid] ------
 // y is destroyed.  The exchange buffer must be free on entry and is free on return.
+template <bool TWO_BUF = false>
 __device__ __forceinline__ void fft_b(float2 (&y)[16], float2 (&c)[16], const float2* __restrict__ tw,
-                                      float2* __restrict__ xb, int tid, int bar_id) {
+                                      float2* __restrict__ xb, int tid, int bar_id,
+                                      float2* __restrict__ xb2 = nullptr) {
+    float2* const xa = TWO_BUF ? xb2 : xb;
     // pass B1
 #pragma unroll
     for (int pi = 0; pi < 2; ++pi) {
@@ -218,19 +230,19 @@ __device__ __forceinline__ void fft_b(float2 (&y)[16], float2 (&c)[16], const fl
     const int m3 = tid >> 4, f1 = tid & 15;
 #pragma unroll
     for (int f2 = 0; f2 < 16; ++f2) c[f2] = xb[(f1 + 16 * f2) * kXchgStrideP + m3];
-    group_sync(bar_id);
+    if constexpr (!TWO_BUF) group_sync(bar_id);
     dft16(c);
 #pragma unroll
     for (int m2 = 0; m2 < 16; ++m2) {
         float2 val = c[bitrev4(m2)];
         if (m2 != 0) val = cmul(val, tw[kTwS + m2 * 16 + f1]);
-        xb[f1 * kXchgStrideA + m2 * 8 + m3] = val;
+        xa[f1 * kXchgStrideA + m2 * 8 + m3] = val;
     }
     group_sync(bar_id);
     // pass B3
 #pragma unroll
-    for (int ff = 0; ff < 16; ++ff) y[ff] = xb[ff * kXchgStrideA + tid];
-    group_sync(bar_id);  // exchange buffer free again
+    for (int ff = 0; ff < 16; ++ff) y[ff] = xa[ff * kXchgStrideA + tid];
+    if constexpr (!TWO_BUF) group_sync(bar_id);  // exchange buffer free again
     dft16(y);
 #pragma unroll
     for (int m1 = 0; m1 < 16; ++m1) c[m1] = y[bitrev4(m1)];

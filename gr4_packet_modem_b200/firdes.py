@@ -52,6 +52,28 @@ def unit_energy_rrc(samples_per_symbol: int = 4, span_symbols: int = 11, alpha: 
     return (rrc / norm).astype(np.float32)
 
 
+def pfb_matched_filter_taps(samples_per_symbol: int = 4, num_arms: int = 32, span_symbols: int = 11,
+                            alpha: float = 0.35) -> np.ndarray:
+    """SymbolFilter's polyphase RRC prototype: num_arms x (sps*span) taps with gain num_arms / ||rrc||
+    (PM/packet_receiver.hpp:96-110; 1408 taps = 32 arms x 44 at the defaults)."""
+    rrc = root_raised_cosine(1.0, float(samples_per_symbol), 1.0, alpha, samples_per_symbol * span_symbols)
+    norm = math.sqrt(float(np.sum(rrc.astype(np.float64) ** 2)))
+    t = root_raised_cosine(num_arms / norm, float(num_arms * samples_per_symbol), 1.0, alpha,
+                           num_arms * samples_per_symbol * span_symbols)
+    return t[:-1]
+
+
+def lowpass_prototype_taps(num_arms: int = 32, taps_per_arm: int = 40) -> np.ndarray:
+    """A num_arms*taps_per_arm-tap low-pass prototype (Blackman-windowed sinc, cutoff 0.5/num_arms, DC gain
+    num_arms) for PfbArbResampler when the caller has no design of its own.  The reference ships a
+    hard-coded 1280-tap remez design (PM/pfb_arb_taps.hpp:13); any prototype of the same shape costs the
+    same on the GPU."""
+    n = num_arms * taps_per_arm
+    k = np.arange(n, dtype=np.float64) - (n - 1) / 2.0
+    h = np.sinc(k / num_arms) * np.blackman(n)
+    return (h * (num_arms / h.sum())).astype(np.float32)
+
+
 # CCSDS 64-bit attached sync marker as used by the reference (PM/packet_receiver.hpp:45-59)
 SYNCWORD = np.array([0, 0, 0, 0, 0, 0, 1, 1, 0, 1, 0, 0, 0, 1, 1, 1, 0, 1, 1, 1, 0, 1, 1, 0, 1, 1, 0, 0, 0, 1, 1, 1,
                      0, 0, 1, 0, 0, 1, 1, 1, 0, 0, 1, 0, 1, 0, 0, 0, 1, 0, 0, 1, 0, 1, 0, 1, 1, 0, 1, 1, 0, 0, 0, 0],

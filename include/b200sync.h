@@ -129,6 +129,20 @@ int b200sync_sd_detect_device(b200sync_sd* sd, const void* d_in, size_t n, void*
 int b200sync_sd_detect_host(b200sync_sd* sd, const float* in, size_t n, b200sync_detection_record* recs,
                             size_t max_recs, size_t* n_recs, size_t* n_consumed);
 
+/* Batched channel mode (BASELINE config 5, SURVEY §8e "channel mode"): n_channels independent
+ * streams of n samples each, channel c at d_in + c * channel_stride complex samples.  Equivalent to
+ * n_channels SyncwordDetection block instances (one per channel of the reference flowgraph), each
+ * running start() + one processBulk over its own stream.  Channels are pipelined over a few CUDA
+ * streams that start after the work already enqueued on cuda_stream; the call returns when all
+ * records are in host memory.
+ *   recs      host array [n_channels * max_recs_per_channel]; channel c's records start at
+ *             recs + c * max_recs_per_channel, their number is n_recs[c]
+ *   n_recs    host array [n_channels];  *n_consumed: items consumed per channel. */
+int b200sync_sd_detect_channels_device(b200sync_sd* sd, const void* d_in, size_t channel_stride,
+                                       size_t n_channels, size_t n, void* cuda_stream,
+                                       b200sync_detection_record* recs, size_t max_recs_per_channel,
+                                       size_t* n_recs, size_t* n_consumed);
+
 /* Time-sharded operation (one context per GPU).  The shard owns FFT
  * blocks [first_block, first_block + n_blocks) of a longer stream; d_in points at absolute
  * sample first_sample_abs and must cover every block the shard computes (one extra block
