@@ -36,6 +36,11 @@ constexpr int kFeThreads = 256;
 constexpr int kFeR = 8;                              // outputs per thread
 constexpr int kFeTileOut = kFeThreads * kFeR;        // 2048 outputs per CTA
 constexpr int kFeTileIn = 2 * kFeTileOut + 128;      // input samples a CTA can stage
+// staged inputs live at skew(i) = i + (i >> 3): thread t's register window starts 8 samples after
+// thread t-1's, so without the skew the 64-bit window loads of a warp would be 16-way bank conflicted
+// (ncu on the unskewed version: 76 % of all shared wavefronts were conflicts)
+constexpr int kFeXinSlots = kFeTileIn + (kFeTileIn >> 3) + 8;
+__device__ __forceinline__ int fe_skew(int i) { return i + (i >> 3); }
 
 struct FeParams {
     const float2* in;        // in[i] is absolute input sample in_base + i
@@ -48,10 +53,10 @@ struct FeParams {
     long long n_out;
     unsigned long long Kf;   // filt_rate in units of 2^-24
     int decim, L0, fs, arm;  // decim_rate, initial _last_filter, filter_size, taps per arm
-    int stride;              // padded arm stride in shared memory
     int do_resample, do_rotate;
     double theta;            // effective rotation per sample
     float amp_eps;           // |incr| - 1
+    float2 wr[kFeR];         // (cos, sin)(r * theta), r = 0..R-1: rotation of output r relative to output 0
 };
 
 __device__ __forceinline__ void timing(const FeParams& P, long long n, long long& c, int& arm, float& acc) {
@@ -64,39 +69,62 @@ __device__ __forceinline__ void timing(const FeParams& P, long long n, long long
     acc = (float)a * (1.0f / 16777216.0f);  // exact: a <= 2^24
 }
 
-__device__ __forceinline__ float2 rotate(const FeParams& P, float2 v, long long n) {
-    // PM/rotator.hpp:56-65 with the recurrence replaced by its closed form
+// (cos, sin) of n * theta, reduced in double (PM/rotator.hpp:56-65 with the recurrence in closed form)
+__device__ __forceinline__ float2 rot_phase(const FeParams& P, long long n) {
     double ph = (double)n * P.theta;
     ph -= 6.283185307179586476925 * rint(ph * 0.15915494309189533577);
     float s, c;
     sincosf((float)ph, &s, &c);
+    return make_float2(c, s);
+}
+// v * e * amplitude(n): the reference renormalises _exp every 512 samples, in between |_exp| drifts as
+// |incr|^(n mod 512) ~ 1 + (n mod 512) * (|incr| - 1)
+__device__ __forceinline__ float2 rot_apply(const FeParams& P, float2 v, float2 e, long long n) {
     const float amp = __fmaf_rn((float)(n & 511), P.amp_eps, 1.0f);
-    c *= amp;
-    s *= amp;
+    const float c = e.x * amp, s = e.y * amp;
     return make_float2(__fsub_rn(__fmul_rn(v.x, c), __fmul_rn(v.y, s)), __fadd_rn(__fmul_rn(v.x, s), __fmul_rn(v.y, c)));
+}
+__device__ __forceinline__ float2 rotate(const FeParams& P, float2 v, long long n) {
+    return rot_apply(P, v, rot_phase(P, n), n);
 }
 
 __global__ void __launch_bounds__(kFeThreads)
-frontend_kernel(const FeParams P, const float* __restrict__ taps_g /*[2][fs][arm]*/) {
+frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (tap, diff tap)*/) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* taps_s = reinterpret_cast<float*>(smem_raw);                 // [fs][stride]
-    float* diff_s = taps_s + P.fs * P.stride;                           // [fs][stride]
-    float2* xin = reinterpret_cast<float2*>(diff_s + P.fs * P.stride);  // [kFeTileIn]
+    float2* td_s = reinterpret_cast<float2*>(smem_raw);   // [fs][arm] (tap, diff tap): one broadcast LDS.64 per tap
+    float2* xin = td_s + P.fs * P.arm;                    // [kFeXinSlots], skewed
     const int tid = threadIdx.x;
     const long long n0 = P.out_base + (long long)blockIdx.x * kFeTileOut;     // first output of this CTA
     const long long n_end = min(P.out_base + P.n_out, n0 + kFeTileOut);
     if (!P.do_resample) {
-        for (long long n = n0 + tid; n < n_end; n += kFeThreads) {
-            float2 v = P.in[n - P.in_base];
-            if (P.do_rotate) v = rotate(P, v, n);
-            P.out[n - P.out_base] = v;
+        // Rotator alone: R consecutive outputs per thread share one sincos
+        const long long nt = n0 + (long long)tid * kFeR;
+        if (nt >= n_end) return;
+        const float2* src = P.in + (nt - P.in_base);
+        float2* dst = P.out + (nt - P.out_base);
+        if (!P.do_rotate) {
+#pragma unroll
+            for (int r = 0; r < kFeR; ++r)
+                if (nt + r < n_end) dst[r] = src[r];
+            return;
+        }
+        const float2 e0 = rot_phase(P, nt);
+#pragma unroll
+        for (int r = 0; r < kFeR; ++r) {
+            if (nt + r < n_end) {
+                const float2 w = P.wr[r];
+                const float2 e = make_float2(e0.x * w.x - e0.y * w.y, e0.x * w.y + e0.y * w.x);
+                dst[r] = rot_apply(P, src[r], e, nt + r);
+            }
         }
         return;
     }
-    for (int i = tid; i < P.fs * P.arm; i += kFeThreads) {
-        const int a = i / P.arm, k = i - a * P.arm;
-        taps_s[a * P.stride + k] = taps_g[i];
-        diff_s[a * P.stride + k] = taps_g[P.fs * P.arm + i];
+    {   // taps: straight 128-bit copy (the global layout is the shared layout)
+        const int n4 = (P.fs * P.arm) >> 1;
+        const float4* g4 = reinterpret_cast<const float4*>(td_g);
+        float4* s4 = reinterpret_cast<float4*>(td_s);
+        for (int i = tid; i < n4; i += kFeThreads) s4[i] = __ldg(g4 + i);
+        if (((P.fs * P.arm) & 1) && tid == 0) td_s[P.fs * P.arm - 1] = td_g[P.fs * P.arm - 1];
     }
     // input span of the tile: [c(n0) - arm - 1, c(n_end-1))
     long long c_first, c_last;
@@ -112,30 +140,48 @@ frontend_kernel(const FeParams P, const float* __restrict__ taps_g /*[2][fs][arm
         const long long h = a - (P.in_base - P.hist_len);
         return h >= 0 ? P.hist[h] : make_float2(0.f, 0.f);
     };
-    if (staged)
-        for (int i = tid; i < span; i += kFeThreads) xin[i] = sample(lo + i);
+    if (staged) {
+        if (lo >= P.in_base) {
+            const float2* src = P.in + (lo - P.in_base);
+            for (int i = tid; i < span; i += kFeThreads) xin[fe_skew(i)] = __ldcs(src + i);
+        } else {
+            for (int i = tid; i < span; i += kFeThreads) xin[fe_skew(i)] = sample(lo + i);
+        }
+    }
     __syncthreads();
 
     const long long nt = n0 + (long long)tid * kFeR;  // this thread's first output
     if (nt >= n_end) return;
-    long long c[kFeR];
-    int arm[kFeR];
+    // timing of the R outputs: one closed-form evaluation, then increments (no further divisions on
+    // the fast path: output r stays on arm0 and one input later iff Lf advanced by exactly r*fs)
+    long long c0;
+    int arm0;
     float acc[kFeR];
+    timing(P, nt, c0, arm0, acc[0]);
+    const unsigned long long tot0 = (unsigned long long)nt * P.Kf;
+    const unsigned long long a0 = tot0 ? ((tot0 - 1) & 0xFFFFFFull) + 1 : 0ull;
+    const unsigned long long wraps0 = (tot0 - a0) >> 24;
+    int dL[kFeR];  // Lf(nt + r) - Lf(nt)
+    dL[0] = 0;
     bool fast = staged && (nt + kFeR <= n_end);
 #pragma unroll
-    for (int r = 0; r < kFeR; ++r) {
-        timing(P, nt + r, c[r], arm[r], acc[r]);
-        if (r > 0) fast = fast && (arm[r] == arm[0]) && (c[r] == c[0] + r);
+    for (int r = 1; r < kFeR; ++r) {
+        const unsigned long long tot = tot0 + (unsigned long long)r * P.Kf;
+        const unsigned long long a = ((tot - 1) & 0xFFFFFFull) + 1;  // tot > 0 for r >= 1 unless Kf == 0
+        const unsigned long long aa = tot ? a : 0ull;
+        const unsigned long long wraps = (tot - aa) >> 24;
+        dL[r] = r * P.decim + (int)(wraps - wraps0);
+        acc[r] = (float)aa * (1.0f / 16777216.0f);
+        fast = fast && (dL[r] == r * P.fs);
     }
     float2 y[kFeR];
     if (fast) {
         // register window: slot of x[c0-1+j] is (j & 7); output r at tap k uses j = r - k
-        const float* tp = taps_s + arm[0] * P.stride;
-        const float* dp = diff_s + arm[0] * P.stride;
-        const float2* xs = xin + (c[0] - 1 - lo);
+        const float2* tp = td_s + arm0 * P.arm;
+        const int b = (int)(c0 - 1 - lo);  // staged index of x[c0-1]
         float2 W[kFeR];
 #pragma unroll
-        for (int j = 0; j < kFeR; ++j) W[j] = xs[j];
+        for (int j = 0; j < kFeR; ++j) W[j] = xin[fe_skew(b + j)];
         float2 af[kFeR], ad[kFeR];
 #pragma unroll
         for (int r = 0; r < kFeR; ++r) af[r] = ad[r] = make_float2(0.f, 0.f);
@@ -143,28 +189,28 @@ frontend_kernel(const FeParams P, const float* __restrict__ taps_g /*[2][fs][arm
         for (; k + kFeR <= P.arm; k += kFeR) {
 #pragma unroll
             for (int kk = 0; kk < kFeR; ++kk) {
-                const float t = tp[k + kk], d = dp[k + kk];
+                const float2 t = tp[k + kk];
 #pragma unroll
                 for (int r = 0; r < kFeR; ++r) {
                     const float2 h = W[(r - kk) & (kFeR - 1)];
-                    af[r].x = __fadd_rn(af[r].x, __fmul_rn(h.x, t));
-                    af[r].y = __fadd_rn(af[r].y, __fmul_rn(h.y, t));
-                    ad[r].x = __fadd_rn(ad[r].x, __fmul_rn(h.x, d));
-                    ad[r].y = __fadd_rn(ad[r].y, __fmul_rn(h.y, d));
+                    af[r].x = __fadd_rn(af[r].x, __fmul_rn(h.x, t.x));
+                    af[r].y = __fadd_rn(af[r].y, __fmul_rn(h.y, t.x));
+                    ad[r].x = __fadd_rn(ad[r].x, __fmul_rn(h.x, t.y));
+                    ad[r].y = __fadd_rn(ad[r].y, __fmul_rn(h.y, t.y));
                 }
                 // x[c0-1-(k+kk+1)] replaces the element leaving the window
-                W[(-(kk + 1)) & (kFeR - 1)] = xs[-(k + kk + 1)];
+                W[(-(kk + 1)) & (kFeR - 1)] = xin[fe_skew(b - (k + kk + 1))];
             }
         }
         for (; k < P.arm; ++k) {  // arm sizes that are not a multiple of R
-            const float t = tp[k], d = dp[k];
+            const float2 t = tp[k];
 #pragma unroll
             for (int r = 0; r < kFeR; ++r) {
-                const float2 h = xs[r - k];
-                af[r].x = __fadd_rn(af[r].x, __fmul_rn(h.x, t));
-                af[r].y = __fadd_rn(af[r].y, __fmul_rn(h.y, t));
-                ad[r].x = __fadd_rn(ad[r].x, __fmul_rn(h.x, d));
-                ad[r].y = __fadd_rn(ad[r].y, __fmul_rn(h.y, d));
+                const float2 h = xin[fe_skew(b + r - k)];
+                af[r].x = __fadd_rn(af[r].x, __fmul_rn(h.x, t.x));
+                af[r].y = __fadd_rn(af[r].y, __fmul_rn(h.y, t.x));
+                ad[r].x = __fadd_rn(ad[r].x, __fmul_rn(h.x, t.y));
+                ad[r].y = __fadd_rn(ad[r].y, __fmul_rn(h.y, t.y));
             }
         }
 #pragma unroll
@@ -172,27 +218,44 @@ frontend_kernel(const FeParams P, const float* __restrict__ taps_g /*[2][fs][arm
             y[r] = make_float2(__fadd_rn(af[r].x, __fmul_rn(acc[r], ad[r].x)),
                                __fadd_rn(af[r].y, __fmul_rn(acc[r], ad[r].y)));
     } else {
+#pragma unroll
         for (int r = 0; r < kFeR; ++r) {
-            if (nt + r >= n_end) break;
-            const float* tp = taps_s + arm[r] * P.stride;
-            const float* dp = diff_s + arm[r] * P.stride;
+            if (nt + r >= n_end) continue;
+            const unsigned q = (unsigned)arm0 + (unsigned)dL[r];
+            const long long cr = c0 + (long long)(q / (unsigned)P.fs);
+            const int armr = (int)(q % (unsigned)P.fs);
+            const float2* tp = td_s + armr * P.arm;
             float2 af = make_float2(0.f, 0.f), ad = make_float2(0.f, 0.f);
             for (int k = 0; k < P.arm; ++k) {
-                const long long a = c[r] - 1 - k;
-                const float2 h = staged ? xin[a - lo] : sample(a);
-                const float t = tp[k], d = dp[k];
-                af.x = __fadd_rn(af.x, __fmul_rn(h.x, t));
-                af.y = __fadd_rn(af.y, __fmul_rn(h.y, t));
-                ad.x = __fadd_rn(ad.x, __fmul_rn(h.x, d));
-                ad.y = __fadd_rn(ad.y, __fmul_rn(h.y, d));
+                const long long a = cr - 1 - k;
+                const float2 h = staged ? xin[fe_skew((int)(a - lo))] : sample(a);
+                const float2 t = tp[k];
+                af.x = __fadd_rn(af.x, __fmul_rn(h.x, t.x));
+                af.y = __fadd_rn(af.y, __fmul_rn(h.y, t.x));
+                ad.x = __fadd_rn(ad.x, __fmul_rn(h.x, t.y));
+                ad.y = __fadd_rn(ad.y, __fmul_rn(h.y, t.y));
             }
             y[r] = make_float2(__fadd_rn(af.x, __fmul_rn(acc[r], ad.x)), __fadd_rn(af.y, __fmul_rn(acc[r], ad.y)));
         }
     }
     float2* dst = P.out + (nt - P.out_base);
+    if (P.do_rotate) {
+        const float2 e0 = rot_phase(P, nt);
 #pragma unroll
-    for (int r = 0; r < kFeR; ++r) {
-        if (nt + r < n_end) dst[r] = P.do_rotate ? rotate(P, y[r], nt + r) : y[r];
+        for (int r = 0; r < kFeR; ++r) {
+            const float2 w = P.wr[r];
+            const float2 e = make_float2(e0.x * w.x - e0.y * w.y, e0.x * w.y + e0.y * w.x);
+            y[r] = rot_apply(P, y[r], e, nt + r);
+        }
+    }
+    if (nt + kFeR <= n_end && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+        for (int r = 0; r < kFeR; r += 2)
+            *reinterpret_cast<float4*>(dst + r) = make_float4(y[r].x, y[r].y, y[r + 1].x, y[r + 1].y);
+    } else {
+#pragma unroll
+        for (int r = 0; r < kFeR; ++r)
+            if (nt + r < n_end) dst[r] = y[r];
     }
 }
 
@@ -306,14 +369,15 @@ int fe_setup(b200sync_fe* fe) {
     if (!fe->stream) FCU(cudaStreamCreateWithFlags(&fe->stream, cudaStreamNonBlocking));
     if (fe->do_resample) {
         // polyphase split with zero padding and the derivative filter (:77-102)
+        // device layout: td[j][k] = (taps[j][k], diff_taps[j][k]) interleaved
         std::vector<float> t(static_cast<size_t>(2) * fe->fs * fe->arm, 0.0f);
         const size_t nt = fe->taps.size();
         for (uint32_t j = 0; j < fe->fs; ++j) {
             int k = 0;
-            for (size_t i = j; i < nt; i += fe->fs) t[static_cast<size_t>(j) * fe->arm + k++] = fe->taps[i];
+            for (size_t i = j; i < nt; i += fe->fs) t[2 * (static_cast<size_t>(j) * fe->arm + k++)] = fe->taps[i];
             k = 0;
             for (size_t i = j; i < nt - 1; i += fe->fs)
-                t[static_cast<size_t>(fe->fs) * fe->arm + static_cast<size_t>(j) * fe->arm + k++] = fe->taps[i + 1] - fe->taps[i];
+                t[2 * (static_cast<size_t>(j) * fe->arm + k++) + 1] = fe->taps[i + 1] - fe->taps[i];
         }
         if (fe->d_taps) cudaFree(fe->d_taps);
         FCU(cudaMalloc(&fe->d_taps, t.size() * sizeof(float)));
@@ -363,17 +427,18 @@ int fe_run(b200sync_fe* fe, const float2* d_in, size_t n_in, float2* d_out, size
         P.L0 = fe->L0;
         P.fs = static_cast<int>(fe->fs);
         P.arm = fe->arm;
-        P.stride = fe->arm + ((fe->arm & 1) ? 0 : 1);  // odd stride: conflict-free across arms
         P.do_resample = fe->do_resample;
         P.do_rotate = fe->do_rotate;
         P.theta = fe->theta;
         P.amp_eps = fe->amp_eps;
+        for (int r = 0; r < kFeR; ++r)
+            P.wr[r] = make_float2(static_cast<float>(std::cos(r * fe->theta)), static_cast<float>(std::sin(r * fe->theta)));
         const size_t smem = fe->do_resample
-                                ? sizeof(float) * 2 * P.fs * P.stride + sizeof(float2) * static_cast<size_t>(kFeTileIn)
+                                ? sizeof(float2) * (static_cast<size_t>(P.fs) * P.arm + static_cast<size_t>(kFeXinSlots))
                                 : 0;
         FCU(cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = static_cast<unsigned>((n_out + kFeTileOut - 1) / kFeTileOut);
-        frontend_kernel<<<grid, kFeThreads, smem, st>>>(P, fe->d_taps);
+        frontend_kernel<<<grid, kFeThreads, smem, st>>>(P, reinterpret_cast<const float2*>(fe->d_taps));
         count_launch();
         FCU(cudaGetLastError());
     }

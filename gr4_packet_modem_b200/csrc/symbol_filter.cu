@@ -20,6 +20,7 @@
 // SyncwordDetectionFilter is pure control logic plus a pass-through copy; it stays on the host
 //  — with device-resident data the copy is a no-op on the same buffer.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <deque>
@@ -132,6 +133,159 @@ symbol_filter_kernel(const SfParams P, const float* __restrict__ taps_g /*[num_a
     P.out[o - P.out_base] = make_float2(__fmul_rn(scale, acc.x), __fmul_rn(scale, acc.y));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast path for the receiver's configuration (samples_per_symbol = SPS, ARM taps per arm; 4 x 44 in
+// PM/packet_receiver.hpp:96-115).  ncu on the generic kernel above showed it latency/ALU bound:
+// three binary searches over the segment list per thread and 2 shared loads per multiply-add.
+//   * sf_tile_seg_kernel finds the segment of every tile's first symbol once (one thread per tile);
+//     threads then walk forward from it (tags are thousands of symbols apart).
+//   * a thread computes R = 4 consecutive symbols: their windows overlap, so every staged sample is
+//     loaded once and used by up to 4 (symbol, tap) pairs; the arm's ARM taps sit in registers.
+//     Per symbol: 14 sample loads instead of 88 shared loads.
+//   * consecutive threads start 4*SPS samples apart; samples are staged at i + (i >> 4) so that the
+//     64-bit window loads of a warp fall on distinct banks.
+// The per-symbol accumulation is still tap 0, 1, 2, ... with a separately rounded multiply and add:
+// bit-exact against std::inner_product (PM/symbol_filter.hpp:208-215).
+// ---------------------------------------------------------------------------------------------
+constexpr int kSfR = 4;
+constexpr int kSfTileOut = kSfThreads * kSfR;  // 1024 symbols per CTA
+__device__ __forceinline__ int sf_skew(int i) { return i + (i >> 4); }
+
+__global__ void sf_tile_seg_kernel(const SfSegment* __restrict__ segs, int n_segs, long long out_base, int tile_out,
+                                   int n_tiles, int* __restrict__ tile_seg) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const long long o = out_base + (long long)t * tile_out;
+    int lo = 0, hi = n_segs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (segs[mid].out_start <= o) lo = mid; else hi = mid - 1;
+    }
+    tile_seg[t] = lo;
+}
+
+template <int SPS, int ARM>
+__global__ void __launch_bounds__(kSfThreads)
+symbol_filter_fast_kernel(const SfParams P, const float* __restrict__ taps_g /*[num_arms][ARM]*/,
+                          const int* __restrict__ tile_seg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* taps_s = reinterpret_cast<float*>(smem_raw);                        // [num_arms][stride]
+    float2* xs = reinterpret_cast<float2*>(taps_s + P.num_arms * P.stride);    // skewed staging
+    __shared__ long long span_s[2];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < P.num_arms * ARM; i += kSfThreads) {
+        const int a = i / ARM, k = i - a * ARM;
+        taps_s[a * P.stride + k] = __ldg(taps_g + i);
+    }
+    const long long o0 = P.out_base + (long long)blockIdx.x * kSfTileOut;
+    const long long o_end = min(P.out_base + P.n_out, o0 + kSfTileOut);
+    const long long o = o0 + (long long)tid * kSfR;     // this thread's first symbol
+    // segment of symbol o: walk forward from the tile's first segment
+    int sg = tile_seg[blockIdx.x];
+    auto in_index = [&](const SfSegment& sgm, long long oo) -> long long {
+        const int d0 = (SPS - sgm.phase0) % SPS;
+        return sgm.in_start + d0 + (oo - sgm.out_start) * SPS;
+    };
+    SfSegment cur = P.segs[sg];
+    if (tid == 0) span_s[0] = in_index(cur, o0);
+    long long next_start = (sg + 1 < P.n_segs) ? P.segs[sg + 1].out_start : LLONG_MAX;
+    const long long o_clamped = o < o_end ? o : o_end - 1;   // idle tail threads follow the last symbol
+    while (next_start <= o_clamped) {
+        ++sg;
+        cur = P.segs[sg];
+        next_start = (sg + 1 < P.n_segs) ? P.segs[sg + 1].out_start : LLONG_MAX;
+    }
+    // the thread that owns the tile's last symbol publishes the end of the input span
+    if (o <= o_end - 1 && o_end - 1 < o + kSfR) {
+        int s2 = sg;
+        SfSegment c2 = cur;
+        long long nx = next_start;
+        while (nx <= o_end - 1) {
+            ++s2;
+            c2 = P.segs[s2];
+            nx = (s2 + 1 < P.n_segs) ? P.segs[s2 + 1].out_start : LLONG_MAX;
+        }
+        span_s[1] = in_index(c2, o_end - 1);
+    }
+    __syncthreads();
+    const long long lo_abs = span_s[0] - (ARM - 1);
+    const long long span_ll = span_s[1] - lo_abs + 1;
+    const bool staged = span_ll <= (long long)P.tile_in;
+    auto sample = [&](long long a) -> float2 {
+        if (a >= P.in_base) return P.in[a - P.in_base];
+        const long long h = a - (P.in_base - P.hist_len);
+        return h >= 0 ? P.hist[h] : make_float2(0.f, 0.f);
+    };
+    if (staged) {
+        const int span = (int)span_ll;
+        if (lo_abs >= P.in_base) {
+            const float2* src = P.in + (lo_abs - P.in_base);
+            for (int i = tid; i < span; i += kSfThreads) xs[sf_skew(i)] = __ldcs(src + i);
+        } else {
+            for (int i = tid; i < span; i += kSfThreads) xs[sf_skew(i)] = sample(lo_abs + i);
+        }
+    }
+    __syncthreads();
+    if (o >= o_end) return;
+    float2* dst = P.out + (o - P.out_base);
+    const bool fast = staged && (o + kSfR <= o_end) && (o + kSfR - 1 < next_start);
+    if (fast) {
+        const float* tp = taps_s + cur.arm * P.stride;
+        float t[ARM];
+#pragma unroll
+        for (int k = 0; k < ARM; ++k) t[k] = tp[k];
+        const int b = (int)(in_index(cur, o) - lo_abs);   // staged index of symbol o's newest sample
+        float2 acc[kSfR];
+#pragma unroll
+        for (int r = 0; r < kSfR; ++r) acc[r] = make_float2(0.f, 0.f);
+        // samples from newest to oldest: symbol r meets tap k = r*SPS - j, i.e. taps in increasing order
+#pragma unroll
+        for (int j = (kSfR - 1) * SPS; j > -ARM; --j) {
+            const float2 h = xs[sf_skew(b + j)];
+#pragma unroll
+            for (int r = 0; r < kSfR; ++r) {
+                const int k = r * SPS - j;
+                if (k >= 0 && k < ARM) {
+                    acc[r].x = __fadd_rn(acc[r].x, __fmul_rn(t[k], h.x));
+                    acc[r].y = __fadd_rn(acc[r].y, __fmul_rn(t[k], h.y));
+                }
+            }
+        }
+        const float sc = cur.scale;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+            for (int r = 0; r < kSfR; r += 2)
+                *reinterpret_cast<float4*>(dst + r) =
+                    make_float4(__fmul_rn(sc, acc[r].x), __fmul_rn(sc, acc[r].y), __fmul_rn(sc, acc[r + 1].x),
+                                __fmul_rn(sc, acc[r + 1].y));
+        } else {
+#pragma unroll
+            for (int r = 0; r < kSfR; ++r) dst[r] = make_float2(__fmul_rn(sc, acc[r].x), __fmul_rn(sc, acc[r].y));
+        }
+        return;
+    }
+    // symbols next to a tag (segment change inside the thread's group), tile tails, unstaged tiles
+    for (int r = 0; r < kSfR; ++r) {
+        const long long oo = o + r;
+        if (oo >= o_end) break;
+        while (next_start <= oo) {
+            ++sg;
+            cur = P.segs[sg];
+            next_start = (sg + 1 < P.n_segs) ? P.segs[sg + 1].out_start : LLONG_MAX;
+        }
+        const long long in_idx = in_index(cur, oo);
+        const float* tp = taps_s + cur.arm * P.stride;
+        float2 acc = make_float2(0.f, 0.f);
+        for (int k = 0; k < ARM; ++k) {
+            const float2 h = staged ? xs[sf_skew((int)(in_idx - k - lo_abs))] : sample(in_idx - k);
+            const float tk = tp[k];
+            acc.x = __fadd_rn(acc.x, __fmul_rn(tk, h.x));
+            acc.y = __fadd_rn(acc.y, __fmul_rn(tk, h.y));
+        }
+        dst[r] = make_float2(__fmul_rn(cur.scale, acc.x), __fmul_rn(cur.scale, acc.y));
+    }
+}
+
 __global__ void sf_update_hist_kernel(const float2* __restrict__ in, long long n_consumed,
                                       const float2* __restrict__ hist_old, float2* __restrict__ hist_new, int hist_len) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,6 +335,8 @@ struct b200sync_sf {
     int hist_cur = 0, hist_len = 0;
     SfSegment* d_segs = nullptr;
     size_t segs_cap = 0;
+    int* d_tile_seg = nullptr;
+    size_t tile_seg_cap = 0;
     float2* d_in = nullptr;
     float2* d_out = nullptr;
     size_t in_cap = 0, out_cap = 0;
@@ -373,14 +529,37 @@ int sf_run(b200sync_sf* sf, const float2* d_in, size_t n_in, const b200sync_stre
         P.num_arms = static_cast<int>(sf->num_arms);
         P.arm_size = sf->arm_size;
         P.stride = sf->arm_size + ((sf->arm_size & 1) ? 0 : 1);
-        P.tile_in = kSfThreads * P.sps + P.arm_size + 4 * P.sps + 8;
-        const size_t smem = sizeof(float) * P.num_arms * P.stride +
-                            sizeof(float2) * static_cast<size_t>(P.sps) * (P.tile_in / P.sps + 2);
-        SCU(cudaFuncSetAttribute(symbol_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const unsigned grid = static_cast<unsigned>((n_out + kSfThreads - 1) / kSfThreads);
-        symbol_filter_kernel<<<grid, kSfThreads, smem, st>>>(P, sf->d_taps);
-        count_launch();
-        SCU(cudaGetLastError());
+        if (P.sps == 4 && P.arm_size == 44) {
+            // the receiver's configuration: register-blocked kernel
+            const int n_tiles = static_cast<int>((n_out + kSfTileOut - 1) / kSfTileOut);
+            if (sf->tile_seg_cap < static_cast<size_t>(n_tiles)) {
+                if (sf->d_tile_seg) cudaFree(sf->d_tile_seg);
+                sf->d_tile_seg = nullptr;
+                SCU(cudaMalloc(&sf->d_tile_seg, (static_cast<size_t>(n_tiles) + 64) * sizeof(int)));
+                sf->tile_seg_cap = static_cast<size_t>(n_tiles) + 64;
+            }
+            sf_tile_seg_kernel<<<(n_tiles + 255) / 256, 256, 0, st>>>(sf->d_segs, P.n_segs, P.out_base, kSfTileOut,
+                                                                      n_tiles, sf->d_tile_seg);
+            count_launch();
+            SCU(cudaGetLastError());
+            P.tile_in = kSfTileOut * P.sps + P.arm_size + 64;  // slack: every tag may add or drop one sample
+            const int slots = P.tile_in + (P.tile_in >> 4) + 8;
+            const size_t smem = sizeof(float) * P.num_arms * P.stride + sizeof(float2) * static_cast<size_t>(slots);
+            auto kern = symbol_filter_fast_kernel<4, 44>;
+            SCU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<n_tiles, kSfThreads, smem, st>>>(P, sf->d_taps, sf->d_tile_seg);
+            count_launch();
+            SCU(cudaGetLastError());
+        } else {
+            P.tile_in = kSfThreads * P.sps + P.arm_size + 4 * P.sps + 8;
+            const size_t smem = sizeof(float) * P.num_arms * P.stride +
+                                sizeof(float2) * static_cast<size_t>(P.sps) * (P.tile_in / P.sps + 2);
+            SCU(cudaFuncSetAttribute(symbol_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const unsigned grid = static_cast<unsigned>((n_out + kSfThreads - 1) / kSfThreads);
+            symbol_filter_kernel<<<grid, kSfThreads, smem, st>>>(P, sf->d_taps);
+            count_launch();
+            SCU(cudaGetLastError());
+        }
         // the pageable `prod` vector must outlive the async copy
         SCU(cudaStreamSynchronize(st));
     }
@@ -449,6 +628,7 @@ void b200sync_sf_destroy(b200sync_sf* sf) {
     for (auto& h : sf->d_hist)
         if (h) cudaFree(h);
     if (sf->d_segs) cudaFree(sf->d_segs);
+    if (sf->d_tile_seg) cudaFree(sf->d_tile_seg);
     if (sf->d_in) cudaFree(sf->d_in);
     if (sf->d_out) cudaFree(sf->d_out);
     delete sf;
