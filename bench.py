@@ -217,17 +217,17 @@ def run_chain(args):
     fe_taps = lowpass_prototype_taps(32, 40)
     sf_taps = pfb_matched_filter_taps()
     sd = SyncwordDetection(**rx_settings(args.bins, args.thr), device=0)
-    probe = FrontEnd(rate=rate, taps=fe_taps, phase_incr=0.005)
-    n_y = probe.max_output(n)
-    del probe
+    fe = FrontEnd(rate=rate, taps=fe_taps, phase_incr=0.005)
+    sf = SymbolFilter(sf_taps, 32, 4, delay=44)
+    n_y = fe.max_output(n)
     y = torch.empty(n_y, dtype=torch.complex64, device=dev)        # conditioned stream
     dl = torch.empty(n_y, dtype=torch.complex64, device=dev)       # SyncwordDetection's delayed output
     sym = torch.empty(n_y // 4 + 1024, dtype=torch.complex64, device=dev)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 
     def step(timed=None):
-        fe = FrontEnd(rate=rate, taps=fe_taps, phase_incr=0.005)   # start(): fresh streaming state per pass
-        sf = SymbolFilter(sf_taps, 32, 4, delay=44)
+        fe.restart()   # start(): fresh streaming state per pass, allocations kept
+        sf.restart()
         ev[0].record()
         c_in, n_out = fe.process_device(raw.data_ptr(), n, y.data_ptr(), n_y, stream)
         ev[1].record()

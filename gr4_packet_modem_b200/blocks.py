@@ -278,6 +278,12 @@ class FrontEnd:
         except Exception:
             pass
 
+    def restart(self) -> None:
+        """start() on the live context: streaming state reset, device allocations kept (b200sync_fe_start)."""
+        from ._native import check_fe
+
+        check_fe(_native.lib().b200sync_fe_start(self._h))
+
     def max_output(self, n_in: int) -> int:
         return int(_native.lib().b200sync_fe_max_output(self._h, n_in))
 
@@ -365,6 +371,12 @@ class SymbolFilter:
                                                    ot.ctypes.data, ot.size, C.byref(nt)))
         return nc.value, out[:npd.value], ot[:nt.value].copy()
 
+
+    def restart(self) -> None:
+        """start() on the live context: state reset, device allocations kept (b200sync_sf_start)."""
+        from ._native import check_sf
+
+        check_sf(_native.lib().b200sync_sf_start(self._h))
 
     def process_device(self, d_in_ptr: int, n_in: int, d_out_ptr: int, max_out: int, in_tags: np.ndarray | None = None,
                        stream_ptr: int = 0):

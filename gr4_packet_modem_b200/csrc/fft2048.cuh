@@ -56,16 +56,36 @@ constexpr int kXchgStrideP = 9;     // exchange layout 2: (p*9 + d)
 constexpr int kXchgFloat2 = 256 * kXchgStrideP;  // 2304 float2 = 18432 B (>= 16*129 = 2064)
 constexpr int kXchgFloat2A = 16 * kXchgStrideA;  // 2064 float2 = 16512 B: layout 1 alone
 
+// Blackwell packed FP32x2 (FADD2 / FMUL2 / FFMA2), -DB200_PACKED_FP32: one instruction per complex
+// add instead of two, each half rounded exactly like the scalar op (sm_100_rt.h), so the arithmetic
+// contract is unchanged.  Measured FP32 throughput is the same 128 op/clk/SM (scripts/ubench_f32x2.cu);
+// only issue slots are saved, and in this kernel the register-pair constraints cost more (extra MOVs,
+// 120 B of spills at 80 registers) than they save: 6.32 ms packed vs 6.19 ms scalar at 2^28, K = 9.
+// The scalar form is therefore the default.
+#ifdef B200_PACKED_FP32
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+// a * w for a COMPILE-TIME constant w: the swizzled constant (-w.y, w.x) is free, a.x / a.y are
+// broadcast operands:  p = a.y * (-w.y, w.x);  r = a.x * (w.x, w.y) + p   == cmul(a, w) bit for bit
+__device__ __forceinline__ float2 cmul_const(float2 a, float2 w) {
+    const float2 p = __fmul2_rn(make_float2(a.y, a.y), make_float2(-w.y, w.x));
+    return __ffma2_rn(make_float2(a.x, a.x), w, p);
+}
+#else
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) {
     return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
 }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) {
     return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y));
 }
+#endif
 __device__ __forceinline__ float2 cmul(float2 a, float2 w) {
     return make_float2(__fmaf_rn(a.x, w.x, -__fmul_rn(a.y, w.y)),
                        __fmaf_rn(a.x, w.y, __fmul_rn(a.y, w.x)));
 }
+#ifndef B200_PACKED_FP32
+__device__ __forceinline__ float2 cmul_const(float2 a, float2 w) { return cmul(a, w); }
+#endif
 __device__ __forceinline__ float norm2(float2 z) { return __fmaf_rn(z.y, z.y, __fmul_rn(z.x, z.x)); }
 // (x,y) * -i
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
@@ -89,13 +109,13 @@ __device__ __forceinline__ float2 mul_w8_3(float2 a) {
 template <int E>
 __device__ __forceinline__ float2 mul_w16(float2 a) {
     if constexpr (E == 0) return a;
-    else if constexpr (E == 1) return cmul(a, make_float2(B200_COS_PI_8, -B200_SIN_PI_8));
+    else if constexpr (E == 1) return cmul_const(a, make_float2(B200_COS_PI_8, -B200_SIN_PI_8));
     else if constexpr (E == 2) return mul_w8_1(a);
-    else if constexpr (E == 3) return cmul(a, make_float2(B200_SIN_PI_8, -B200_COS_PI_8));
+    else if constexpr (E == 3) return cmul_const(a, make_float2(B200_SIN_PI_8, -B200_COS_PI_8));
     else if constexpr (E == 4) return mul_mi(a);
-    else if constexpr (E == 5) return cmul(a, make_float2(-B200_SIN_PI_8, -B200_COS_PI_8));
+    else if constexpr (E == 5) return cmul_const(a, make_float2(-B200_SIN_PI_8, -B200_COS_PI_8));
     else if constexpr (E == 6) return mul_w8_3(a);
-    else return cmul(a, make_float2(-B200_COS_PI_8, -B200_SIN_PI_8));
+    else return cmul_const(a, make_float2(-B200_COS_PI_8, -B200_SIN_PI_8));
 }
 
 template <int HALF, int STEP, int I>

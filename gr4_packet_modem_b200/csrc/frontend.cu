@@ -88,7 +88,7 @@ __device__ __forceinline__ float2 rotate(const FeParams& P, float2 v, long long 
     return rot_apply(P, v, rot_phase(P, n), n);
 }
 
-__global__ void __launch_bounds__(kFeThreads)
+__global__ void __launch_bounds__(kFeThreads, 4)
 frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (tap, diff tap)*/) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* td_s = reinterpret_cast<float2*>(smem_raw);   // [fs][arm] (tap, diff tap): one broadcast LDS.64 per tap
@@ -193,10 +193,12 @@ frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (t
 #pragma unroll
                 for (int r = 0; r < kFeR; ++r) {
                     const float2 h = W[(r - kk) & (kFeR - 1)];
-                    af[r].x = __fadd_rn(af[r].x, __fmul_rn(h.x, t.x));
-                    af[r].y = __fadd_rn(af[r].y, __fmul_rn(h.y, t.x));
-                    ad[r].x = __fadd_rn(ad[r].x, __fmul_rn(h.x, t.y));
-                    ad[r].y = __fadd_rn(ad[r].y, __fmul_rn(h.y, t.y));
+                    // scalar multiplies + one packed FP32x2 add per (re, im) pair: 3 issue slots instead of 4,
+                    // each half rounded like the multiply-then-add of std::inner_product.  (A packed
+                    // multiply as well would be 2 slots, but ptxas 12.9 contracts mul.rn.f32x2 +
+                    // add.rn.f32x2 into FFMA2 even with --fmad=false, which changes the rounding.)
+                    af[r] = __fadd2_rn(af[r], make_float2(__fmul_rn(h.x, t.x), __fmul_rn(h.y, t.x)));
+                    ad[r] = __fadd2_rn(ad[r], make_float2(__fmul_rn(h.x, t.y), __fmul_rn(h.y, t.y)));
                 }
                 // x[c0-1-(k+kk+1)] replaces the element leaving the window
                 W[(-(kk + 1)) & (kFeR - 1)] = xin[fe_skew(b - (k + kk + 1))];
@@ -207,16 +209,13 @@ frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (t
 #pragma unroll
             for (int r = 0; r < kFeR; ++r) {
                 const float2 h = xin[fe_skew(b + r - k)];
-                af[r].x = __fadd_rn(af[r].x, __fmul_rn(h.x, t.x));
-                af[r].y = __fadd_rn(af[r].y, __fmul_rn(h.y, t.x));
-                ad[r].x = __fadd_rn(ad[r].x, __fmul_rn(h.x, t.y));
-                ad[r].y = __fadd_rn(ad[r].y, __fmul_rn(h.y, t.y));
+                af[r] = __fadd2_rn(af[r], make_float2(__fmul_rn(h.x, t.x), __fmul_rn(h.y, t.x)));
+                ad[r] = __fadd2_rn(ad[r], make_float2(__fmul_rn(h.x, t.y), __fmul_rn(h.y, t.y)));
             }
         }
 #pragma unroll
         for (int r = 0; r < kFeR; ++r)
-            y[r] = make_float2(__fadd_rn(af[r].x, __fmul_rn(acc[r], ad[r].x)),
-                               __fadd_rn(af[r].y, __fmul_rn(acc[r], ad[r].y)));
+            y[r] = __fadd2_rn(af[r], make_float2(__fmul_rn(acc[r], ad[r].x), __fmul_rn(acc[r], ad[r].y)));
     } else {
 #pragma unroll
         for (int r = 0; r < kFeR; ++r) {
@@ -300,8 +299,9 @@ struct b200sync_fe {
     // state
     unsigned long long abs_in = 0, abs_out = 0;
     float* d_taps = nullptr;
+    size_t taps_cap = 0;
     float2* d_hist[2] = { nullptr, nullptr };
-    int hist_cur = 0;
+    int hist_cur = 0, hist_cap = 0;
     float2* d_in = nullptr;
     float2* d_out = nullptr;
     size_t in_cap = 0, out_cap = 0;
@@ -379,16 +379,26 @@ int fe_setup(b200sync_fe* fe) {
             for (size_t i = j; i < nt - 1; i += fe->fs)
                 t[2 * (static_cast<size_t>(j) * fe->arm + k++) + 1] = fe->taps[i + 1] - fe->taps[i];
         }
-        if (fe->d_taps) cudaFree(fe->d_taps);
-        FCU(cudaMalloc(&fe->d_taps, t.size() * sizeof(float)));
+        // start() on a live context reuses its allocations (cudaFree is a device-wide synchronisation)
+        if (fe->taps_cap < t.size()) {
+            if (fe->d_taps) cudaFree(fe->d_taps);
+            fe->d_taps = nullptr;
+            fe->taps_cap = 0;
+            FCU(cudaMalloc(&fe->d_taps, t.size() * sizeof(float)));
+            fe->taps_cap = t.size();
+        }
         FCU(cudaMemcpy(fe->d_taps, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     const int hl = fe->arm > 0 ? fe->arm : 1;
     for (auto& h : fe->d_hist) {
-        if (h) cudaFree(h);
-        FCU(cudaMalloc(&h, hl * sizeof(float2)));
+        if (fe->hist_cap < hl) {
+            if (h) cudaFree(h);
+            h = nullptr;
+            FCU(cudaMalloc(&h, hl * sizeof(float2)));
+        }
         FCU(cudaMemset(h, 0, hl * sizeof(float2)));
     }
+    if (fe->hist_cap < hl) fe->hist_cap = hl;
     fe->hist_cur = 0;
     fe->abs_in = fe->abs_out = 0;
     return 0;

@@ -245,10 +245,8 @@ symbol_filter_fast_kernel(const SfParams P, const float* __restrict__ taps_g /*[
 #pragma unroll
             for (int r = 0; r < kSfR; ++r) {
                 const int k = r * SPS - j;
-                if (k >= 0 && k < ARM) {
-                    acc[r].x = __fadd_rn(acc[r].x, __fmul_rn(t[k], h.x));
-                    acc[r].y = __fadd_rn(acc[r].y, __fmul_rn(t[k], h.y));
-                }
+                if (k >= 0 && k < ARM)  // two scalar multiplies + one packed FP32x2 add (see frontend.cu on FFMA2)
+                    acc[r] = __fadd2_rn(acc[r], make_float2(__fmul_rn(t[k], h.x), __fmul_rn(t[k], h.y)));
             }
         }
         const float sc = cur.scale;
@@ -331,8 +329,9 @@ struct b200sync_sf {
     unsigned long long abs_in = 0, abs_out = 0;
     // device
     float* d_taps = nullptr;
+    size_t taps_cap = 0;
     float2* d_hist[2] = { nullptr, nullptr };
-    int hist_cur = 0, hist_len = 0;
+    int hist_cur = 0, hist_len = 0, hist_cap = 0;
     SfSegment* d_segs = nullptr;
     size_t segs_cap = 0;
     int* d_tile_seg = nullptr;
@@ -358,15 +357,25 @@ int sf_setup(b200sync_sf* sf) {
     std::vector<float> t(sf->taps.size());
     for (uint32_t j = 0; j < sf->num_arms; ++j)  // polyphase split :84-90
         for (int k = 0; k < sf->arm_size; ++k) t[static_cast<size_t>(j) * sf->arm_size + k] = sf->taps[j + static_cast<size_t>(k) * sf->num_arms];
-    if (sf->d_taps) cudaFree(sf->d_taps);
-    SCU(cudaMalloc(&sf->d_taps, t.size() * sizeof(float)));
+    // start() on a live context reuses its allocations (cudaFree is a device-wide synchronisation)
+    if (sf->taps_cap < t.size()) {
+        if (sf->d_taps) cudaFree(sf->d_taps);
+        sf->d_taps = nullptr;
+        sf->taps_cap = 0;
+        SCU(cudaMalloc(&sf->d_taps, t.size() * sizeof(float)));
+        sf->taps_cap = t.size();
+    }
     SCU(cudaMemcpy(sf->d_taps, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
     sf->hist_len = sf->arm_size;
     for (auto& h : sf->d_hist) {
-        if (h) cudaFree(h);
-        SCU(cudaMalloc(&h, sf->hist_len * sizeof(float2)));
+        if (sf->hist_cap < sf->hist_len) {
+            if (h) cudaFree(h);
+            h = nullptr;
+            SCU(cudaMalloc(&h, sf->hist_len * sizeof(float2)));
+        }
         SCU(cudaMemset(h, 0, sf->hist_len * sizeof(float2)));
     }
+    if (sf->hist_cap < sf->hist_len) sf->hist_cap = sf->hist_len;
     sf->hist_cur = 0;
     sf->clock_phase = 0;  // start() :110
     sf->pfb_arm = 0;
