@@ -14,6 +14,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <map>
+#include <optional>
 #include <span>
 #include <stdexcept>
 #include <string>
@@ -90,5 +91,27 @@ template <typename T>
 struct PortInShim {
     std::size_t min_samples = 1;
 };
+
+
+// what gr::Block<Derived> gives a block for input tags (GR/Block.hpp:616-618): the runtime merges the
+// tags of the chunk's first sample into _mergedInputTag before calling processBulk
+template <typename Derived>
+struct BlockShim {
+    std::string name = "b200";
+    Tag _mergedInputTag{ 0, {} };
+    bool input_tags_present() const { return !_mergedInputTag.map.empty(); }
+    const Tag& mergedInputTag() const { return _mergedInputTag; }
+    // test driver side: what the runtime does before / after a processBulk call
+    void offer_input_tag(const property_map& m) { _mergedInputTag = Tag{ 0, m }; }
+    void clear_input_tag() { _mergedInputTag.map.clear(); }
+};
+
+// gr::Message stand-in: only the `data` member the hot-path blocks read
+// (PM/syncword_detection_filter.hpp:137 `headerSpan[0].data.value()`)
+struct Message {
+    std::optional<property_map> data;
+};
+
+struct Async {};
 
 } // namespace gr

@@ -22,16 +22,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/b200sync.h"
-
-#if __has_include(<gnuradio-4.0/Block.hpp>)
-#include <gnuradio-4.0/Block.hpp>
-#include <gnuradio-4.0/reflection.hpp>
-#define B200SYNC_HAVE_GR4 1
-#else
-#include "gr4_compat.hpp"
-#define B200SYNC_HAVE_GR4 0
-#endif
+#include "b200_shell_common.hpp"  // the C ABI + real GR4 headers when present, gr4_compat.hpp otherwise
 
 namespace gr::packet_modem {
 

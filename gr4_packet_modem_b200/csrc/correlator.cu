@@ -320,13 +320,21 @@ cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_
                           const float2* d_hperm, int K, int S, int min_freq_bin, const float2* d_tw,
                           const unsigned long long* d_det_idx, const unsigned int* d_det_count,
                           unsigned int det_cap, DetectionRecord* d_recs, int num_sms, cudaStream_t st) {
-    int grid = num_sms * 4;
-    if ((unsigned)grid > det_cap) grid = (int)det_cap;
-    if (grid < 1) grid = 1;
     const size_t smem = sizeof(float2) * (size_t)(kTwTotal + kXchgFloat2 + kRefineChunk * (256 + 16) + kMaxHyp + 1) +
                         sizeof(float) * kFft;
     cudaError_t e = cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    // exactly one resident wave (shared memory allows 3 CTAs per SM): a grid of 4 per SM ran a second,
+    // one-third-full wave that took as long as the first
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, refine_kernel, kRefineThreads, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+    }
+    int grid = num_sms * per_sm;
+    if ((unsigned)grid > det_cap) grid = (int)det_cap;
+    if (grid < 1) grid = 1;
     refine_kernel<<<grid, kRefineThreads, smem, st>>>(d_in, in_base, d_zpow, z_base, d_hperm, K, S,
                                                   min_freq_bin, d_tw, d_det_idx, d_det_count, det_cap,
                                                   d_recs);

@@ -84,8 +84,21 @@ __device__ __forceinline__ float2 rot_apply(const FeParams& P, float2 v, float2 
     const float c = e.x * amp, s = e.y * amp;
     return make_float2(__fsub_rn(__fmul_rn(v.x, c), __fmul_rn(v.y, s)), __fadd_rn(__fmul_rn(v.x, s), __fmul_rn(v.y, c)));
 }
-__device__ __forceinline__ float2 rotate(const FeParams& P, float2 v, long long n) {
-    return rot_apply(P, v, rot_phase(P, n), n);
+// Rotation factors of outputs nt .. nt+R-1.  One sincos per ABSOLUTE group of R outputs (n - n mod R),
+// the others by a table rotation: the factor of output n is a function of n alone, so the stream does
+// not depend on how it was cut into calls (streaming == offline == fused, bit for bit).  nt mod R is
+// uniform over the CTA; it is 0 for every CTA of an aligned (offline) call.
+__device__ __forceinline__ void rot_factors(const FeParams& P, long long nt, float2 (&e)[kFeR]) {
+    const int d = (int)(nt & (kFeR - 1));
+    const float2 ea = rot_phase(P, nt - d);
+    float2 eb = ea;
+    if (d != 0) eb = rot_phase(P, nt - d + kFeR);
+#pragma unroll
+    for (int r = 0; r < kFeR; ++r) {
+        const float2 b = (d + r < kFeR) ? ea : eb;
+        const float2 w = P.wr[(d + r) & (kFeR - 1)];
+        e[r] = make_float2(__fmaf_rn(b.x, w.x, -__fmul_rn(b.y, w.y)), __fmaf_rn(b.x, w.y, __fmul_rn(b.y, w.x)));
+    }
 }
 
 __global__ void __launch_bounds__(kFeThreads, 4)
@@ -108,15 +121,11 @@ frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (t
                 if (nt + r < n_end) dst[r] = src[r];
             return;
         }
-        const float2 e0 = rot_phase(P, nt);
+        float2 e[kFeR];
+        rot_factors(P, nt, e);
 #pragma unroll
-        for (int r = 0; r < kFeR; ++r) {
-            if (nt + r < n_end) {
-                const float2 w = P.wr[r];
-                const float2 e = make_float2(e0.x * w.x - e0.y * w.y, e0.x * w.y + e0.y * w.x);
-                dst[r] = rot_apply(P, src[r], e, nt + r);
-            }
-        }
+        for (int r = 0; r < kFeR; ++r)
+            if (nt + r < n_end) dst[r] = rot_apply(P, src[r], e[r], nt + r);
         return;
     }
     {   // taps: straight 128-bit copy (the global layout is the shared layout)
@@ -239,13 +248,10 @@ frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (t
     }
     float2* dst = P.out + (nt - P.out_base);
     if (P.do_rotate) {
-        const float2 e0 = rot_phase(P, nt);
+        float2 e[kFeR];
+        rot_factors(P, nt, e);
 #pragma unroll
-        for (int r = 0; r < kFeR; ++r) {
-            const float2 w = P.wr[r];
-            const float2 e = make_float2(e0.x * w.x - e0.y * w.y, e0.x * w.y + e0.y * w.x);
-            y[r] = rot_apply(P, y[r], e, nt + r);
-        }
+        for (int r = 0; r < kFeR; ++r) y[r] = rot_apply(P, y[r], e[r], nt + r);
     }
     if (nt + kFeR <= n_end && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
@@ -481,8 +487,9 @@ int b200sync_fe_create(const b200sync_fe_config* cfg, b200sync_fe** out) {
     fe->rate = cfg->rate;
     fe->phase_incr = cfg->phase_incr;
     if (cfg->taps && cfg->n_taps) fe->taps.assign(cfg->taps, cfg->taps + cfg->n_taps);
-    fe->fs = cfg->filter_size ? cfg->filter_size : 32;
     fe->do_resample = cfg->enable_resampler != 0;
+    // 0 is an error for the resampler, as in the reference (:70-72); the rotator alone has no filter
+    fe->fs = (cfg->filter_size || fe->do_resample) ? cfg->filter_size : 32;
     fe->do_rotate = cfg->enable_rotator != 0;
     fe->device = cfg->device;
     const int rc = fe_setup(fe);

@@ -63,7 +63,9 @@ def test_reference_qa_assertions_streaming(oracle, rx_params, freq_error):
         assert abs(m["syncword_time_est"]) < 0.05
 
 
-@pytest.mark.parametrize("esn0_db,thr,bins", [(20.0, 9.5, 4), (0.0, 9.5, 4), (3.0, 6.0, 1), (20.0, 9.5, 0)])
+@pytest.mark.parametrize("esn0_db,thr,bins", [(20.0, 9.5, 4), (0.0, 9.5, 4), (3.0, 6.0, 1), (20.0, 9.5, 0),
+                                              # BASELINE configs[3]: Es/N0 0 dB, K = 17 / 33, threshold sweep ends
+                                              (0.0, 6.0, 8), (0.0, 20.0, 8), (0.0, 12.0, 16)])
 def test_offline_bit_exact_vs_mirror_oracle(oracle, rx_params, esn0_db, thr, bins):
     """Whole pipeline bit-for-bit: metric, detection set, raw records, estimates."""
     from gr4_packet_modem_b200.stimulus import packet_capture
