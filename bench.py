@@ -218,7 +218,8 @@ def run_chain(args):
     sf_taps = pfb_matched_filter_taps()
     sd = SyncwordDetection(**rx_settings(args.bins, args.thr), device=0)
     fe = FrontEnd(rate=rate, taps=fe_taps, phase_incr=0.005)
-    sf = SymbolFilter(sf_taps, 32, 4, delay=44)
+    # PM/packet_receiver.hpp:94-115: CoarseFrequencyCorrection(delay 26) -> SymbolFilter(delay 44), fused
+    sf = SymbolFilter(sf_taps, 32, 4, delay=44, fused_cfc_delay=None if args.no_cfc else 26)
     n_y = fe.max_output(n)
     y = torch.empty(n_y, dtype=torch.complex64, device=dev)        # conditioned stream
     dl = torch.empty(n_y, dtype=torch.complex64, device=dev)       # SyncwordDetection's delayed output
@@ -262,12 +263,15 @@ def run_chain(args):
     sf_ms = statistics.mean(t[2] for t in timed)
     peaks = load_peaks()
     line = {
-        "metric": "complex Msps (cf32) through RX sync (fused front end + SyncwordDetection + SymbolFilter)",
+        "metric": "complex Msps (cf32) through RX sync (fused front end + SyncwordDetection + "
+                  + ("" if args.no_cfc else "CoarseFrequencyCorrection + ") + "SymbolFilter)",
         "value": c_in / (ms_per_step * 1e-3) / 1e6, "unit": "Msps", "n_gpus": 1, "steps": args.steps, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"BASELINE configs[2]: fused RX front end (PfbArbResampler 1+1.2ppm + Rotator 0.005) -> "
-                               f"SyncwordDetection K={K} (block contract, delayed output) -> SymbolFilter 32x44 over a "
+                               f"SyncwordDetection K={K} (block contract, delayed output) -> "
+                               + ("" if args.no_cfc else "CoarseFrequencyCorrection(delay 26) fused into ") +
+                               f"SymbolFilter 32x44 over a "
                                f"2^{args.log2n}-sample synthetic cf32 capture on 1 B200, Es/N0 {args.esn0:g} dB",
                    "samples_per_gpu": n, "l2": "streams (8 B/sample) far larger than L2; no flush needed"},
         "detections_per_step": ndet, "symbols_per_step": n_sym, "symbol_tags_per_step": ntags, "clocks": clocks,
@@ -363,6 +367,7 @@ def main():
     ap.add_argument("--esn0", type=float, default=20.0, help="Es/N0 of the synthetic capture in dB")
     ap.add_argument("--thr", type=float, default=9.5, help="power_threshold")
     ap.add_argument("--channels", type=int, default=64)
+    ap.add_argument("--no-cfc", action="store_true", help="chain workload: leave CoarseFrequencyCorrection out")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -138,6 +138,16 @@ def lib():
     L.b200sync_sf_last_error.restype = C.c_char_p
     L.b200sync_sf_process.argtypes = [vp, vp, sz, vp, sz, vp, sz, psz, psz, vp, sz, psz]
     L.b200sync_sf_process_device.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, psz, psz, vp, sz, psz]
+    L.b200sync_sf_fuse_cfc.argtypes = [vp, C.c_int, C.c_uint32]
+    L.b200sync_sf_fuse_cfc.restype = C.c_int
+    L.b200sync_cfc_create.argtypes = [C.c_uint32, C.c_int32, C.POINTER(vp)]
+    L.b200sync_cfc_destroy.argtypes = [vp]
+    L.b200sync_cfc_start.argtypes = [vp]
+    L.b200sync_cfc_last_error.restype = C.c_char_p
+    L.b200sync_cfc_process.argtypes = [vp, vp, sz, vp, sz, vp]
+    L.b200sync_cfc_process_device.argtypes = [vp, vp, sz, vp, sz, vp, vp]
+    for name in ("b200sync_cfc_create", "b200sync_cfc_start", "b200sync_cfc_process", "b200sync_cfc_process_device"):
+        getattr(L, name).restype = C.c_int
     L.b200sync_sdf_create.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
     L.b200sync_sdf_destroy.argtypes = [vp]
     L.b200sync_sdf_start.argtypes = [vp]
@@ -165,6 +175,12 @@ class B200SyncError(RuntimeError):
 def check(rc: int) -> int:
     if rc < 0:
         raise B200SyncError(f"libb200sync error {rc}: {lib().b200sync_last_error().decode()}")
+    return rc
+
+
+def check_cfc(rc: int) -> int:
+    if rc < 0:
+        raise B200SyncError(f"libb200sync error {rc}: {lib().b200sync_cfc_last_error().decode()}")
     return rc
 
 

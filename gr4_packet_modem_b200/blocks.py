@@ -327,10 +327,14 @@ class SymbolFilter:
     """gr::packet_modem::SymbolFilter<c64, c64, float> on the GPU (PM/symbol_filter.hpp).
     Settings: samples_per_symbol, taps, num_arms, delay (:53-59)."""
 
-    def __init__(self, taps, num_arms: int, samples_per_symbol: int = 4, delay: int = 0, device: int = 0):
+    def __init__(self, taps, num_arms: int, samples_per_symbol: int = 4, delay: int = 0, device: int = 0,
+                 fused_cfc_delay: int | None = None):
+        """fused_cfc_delay: when not None, a CoarseFrequencyCorrection{delay = fused_cfc_delay} runs as the
+        filter's load stage (b200sync_sf_fuse_cfc): the input span is then the CFC block's input."""
         self.taps = np.ascontiguousarray(taps, dtype=np.float32)
         self.num_arms, self.samples_per_symbol, self.delay = int(num_arms), int(samples_per_symbol), int(delay)
         self.device = int(device)
+        self.fused_cfc_delay = fused_cfc_delay
         self._h = C.c_void_p()
         self.start()
 
@@ -343,6 +347,8 @@ class SymbolFilter:
         h = C.c_void_p()
         check_sf(_native.lib().b200sync_sf_create(C.byref(cfg), C.byref(h)))
         self._h = h
+        if self.fused_cfc_delay is not None:
+            check_sf(_native.lib().b200sync_sf_fuse_cfc(self._h, 1, int(self.fused_cfc_delay)))
 
     def _destroy(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -392,6 +398,56 @@ class SymbolFilter:
                                                           C.byref(nc), C.byref(npd), ot.ctypes.data, ot.size,
                                                           C.byref(nt)))
         return nc.value, npd.value, ot[:nt.value]
+
+
+class CoarseFrequencyCorrection:
+    """gr::packet_modem::CoarseFrequencyCorrection<float> on the GPU (PM/coarse_frequency_correction.hpp).
+    Setting: delay (:44).  Tags are forwarded unchanged (default tag policy), so only samples come back."""
+
+    def __init__(self, delay: int = 0, device: int = 0):
+        from ._native import check_cfc
+
+        self.delay, self.device = int(delay), int(device)
+        self._h = C.c_void_p()
+        h = C.c_void_p()
+        check_cfc(_native.lib().b200sync_cfc_create(self.delay, self.device, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                _native.lib().b200sync_cfc_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def start(self) -> None:
+        from ._native import check_cfc
+
+        check_cfc(_native.lib().b200sync_cfc_start(self._h))
+
+    restart = start
+
+    def process_bulk(self, in_span, in_tags: np.ndarray | None = None) -> np.ndarray:
+        """processBulk over a host span carrying `in_tags` (STREAM_TAG_DTYPE, indices relative to the span)."""
+        from ._native import check_cfc
+
+        x = np.ascontiguousarray(in_span, dtype=np.complex64)
+        it = np.ascontiguousarray(in_tags if in_tags is not None else np.zeros(0, STREAM_TAG_DTYPE), STREAM_TAG_DTYPE)
+        out = np.empty_like(x)
+        check_cfc(_native.lib().b200sync_cfc_process(self._h, x.ctypes.data if x.size else None, x.size,
+                                                     it.ctypes.data if it.size else None, it.size,
+                                                     out.ctypes.data if x.size else None))
+        return out
+
+    def process_device(self, d_in_ptr: int, n: int, d_out_ptr: int, in_tags: np.ndarray | None = None,
+                       stream_ptr: int = 0) -> None:
+        from ._native import check_cfc
+
+        it = np.ascontiguousarray(in_tags if in_tags is not None else np.zeros(0, STREAM_TAG_DTYPE), STREAM_TAG_DTYPE)
+        check_cfc(_native.lib().b200sync_cfc_process_device(self._h, C.c_void_p(d_in_ptr), n,
+                                                            it.ctypes.data if it.size else None, it.size,
+                                                            C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr or None)))
 
 
 class SyncwordDetectionFilter:

@@ -36,6 +36,8 @@ class SymbolFilterB200
         cfg.device = device;
         // "samples_per_symbol cannot be zero" / "num_arms cannot be zero" (:67-72) come back as the text
         if (b200sync_sf_create(&cfg, &_ctx) != 0) throw gr::exception(b200sync_sf_last_error());
+        if (fused_cfc_delay >= 0 && b200sync_sf_fuse_cfc(_ctx, 1, static_cast<uint32_t>(fused_cfc_delay)) != 0)
+            throw gr::exception(b200sync_sf_last_error());
     }
 
 public:
@@ -52,6 +54,9 @@ public:
     size_t num_arms = 1;
     size_t delay = 0;
     int device = 0;  // extra: CUDA device ordinal
+    // extra: >= 0 absorbs the CoarseFrequencyCorrection{delay = fused_cfc_delay} block that precedes this one
+    // in the receiver (PM/packet_receiver.hpp:94-95, 195-202) into the filter's load stage
+    int fused_cfc_delay = -1;
 
     SymbolFilterB200() = default;
     SymbolFilterB200(const SymbolFilterB200&) = delete;
@@ -69,6 +74,8 @@ public:
     {
         if (!_ctx) configure();
         else if (b200sync_sf_start(_ctx) != 0) throw gr::exception(b200sync_sf_last_error());
+        else if (fused_cfc_delay >= 0 && b200sync_sf_fuse_cfc(_ctx, 1, static_cast<uint32_t>(fused_cfc_delay)) != 0)
+            throw gr::exception(b200sync_sf_last_error());
         _tags.clear();
     }
 
@@ -117,5 +124,6 @@ public:
 }  // namespace gr::packet_modem
 
 #if B200SYNC_HAVE_GR4
-ENABLE_REFLECTION(gr::packet_modem::SymbolFilterB200, in, out, samples_per_symbol, taps, num_arms, delay, device);
+ENABLE_REFLECTION(gr::packet_modem::SymbolFilterB200, in, out, samples_per_symbol, taps, num_arms, delay, device,
+                  fused_cfc_delay);
 #endif

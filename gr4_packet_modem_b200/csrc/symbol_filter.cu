@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "b200sync_internal.h"
+#include "cfc.cuh"
 
 namespace b200sync {
 
@@ -42,6 +43,7 @@ struct SfSegment {
 };
 
 constexpr int kSfThreads = 256;
+constexpr int kSfThreadsC = kSfThreads;
 
 struct SfParams {
     const float2* in;
@@ -55,7 +57,26 @@ struct SfParams {
     int n_segs;
     int sps, num_arms, arm_size, stride;
     int tile_in;         // staged input samples per CTA
+    const CfcSegment* cfc;  // fused CoarseFrequencyCorrection load stage (cfc.cuh); n_cfc = 0: off
+    int n_cfc;
 };
+
+// Fused CoarseFrequencyCorrection: rotate the staged samples in place.  Thread t owns a run of
+// consecutive staged samples so that one sincosf serves 8 of them (cfc.cuh); IDX maps a staged index to
+// its shared-memory slot.  Samples before the stream start (zeros) are left alone.
+template <typename IDX>
+__device__ __forceinline__ void sf_cfc_inplace(const SfParams& P, float2* xs, long long lo_abs, int span, IDX idx) {
+    const int per = (span + kSfThreadsC - 1) / kSfThreadsC;
+    const int i0 = threadIdx.x * per;
+    const int i1 = min(span, i0 + per);
+    CfcCursor c;
+    for (int i = i0; i < i1; ++i) {
+        const long long n = lo_abs + i;
+        if (n < 0) continue;
+        float2* slot = xs + idx(i);
+        *slot = cfc_apply(P.cfc, P.n_cfc, c, n, *slot);
+    }
+}
 
 __global__ void __launch_bounds__(kSfThreads)
 symbol_filter_kernel(const SfParams P, const float* __restrict__ taps_g /*[num_arms][arm_size]*/) {
@@ -102,8 +123,18 @@ symbol_filter_kernel(const SfParams P, const float* __restrict__ taps_g /*[num_a
             const int ph = i % P.sps, m = i / P.sps;
             xs[ph * ph_stride + m] = sample(lo_abs + i);
         }
+        if (P.n_cfc > 0) {
+            __syncthreads();
+            const int sps = P.sps;
+            sf_cfc_inplace(P, xs, lo_abs, span, [=](int i) { return (i % sps) * ph_stride + i / sps; });
+        }
     }
     __syncthreads();
+    CfcCursor cfc_cur;  // unstaged tiles only
+    auto sample_c = [&](long long a) -> float2 {
+        const float2 v = sample(a);
+        return (P.n_cfc > 0 && a >= 0) ? cfc_apply(P.cfc, P.n_cfc, cfc_cur, a, v) : v;
+    };
     const long long o = o0 + tid;
     if (o >= o_end) return;
     long long in_idx;
@@ -124,7 +155,7 @@ symbol_filter_kernel(const SfParams P, const float* __restrict__ taps_g /*[num_a
         }
     } else {
         for (int k = 0; k < P.arm_size; ++k) {
-            const float2 h = sample(in_idx - k);
+            const float2 h = sample_c(in_idx - k);
             const float t = tp[k];
             acc.x = __fadd_rn(acc.x, __fmul_rn(t, h.x));
             acc.y = __fadd_rn(acc.y, __fmul_rn(t, h.y));
@@ -164,7 +195,7 @@ __global__ void sf_tile_seg_kernel(const SfSegment* __restrict__ segs, int n_seg
     tile_seg[t] = lo;
 }
 
-template <int SPS, int ARM>
+template <int SPS, int ARM, bool CFC>
 __global__ void __launch_bounds__(kSfThreads)
 symbol_filter_fast_kernel(const SfParams P, const float* __restrict__ taps_g /*[num_arms][ARM]*/,
                           const int* __restrict__ tile_seg) {
@@ -224,8 +255,17 @@ symbol_filter_fast_kernel(const SfParams P, const float* __restrict__ taps_g /*[
         } else {
             for (int i = tid; i < span; i += kSfThreads) xs[sf_skew(i)] = sample(lo_abs + i);
         }
+        if constexpr (CFC) {
+            __syncthreads();
+            sf_cfc_inplace(P, xs, lo_abs, span, [](int i) { return sf_skew(i); });
+        }
     }
     __syncthreads();
+    CfcCursor cfc_cur;  // unstaged tiles only
+    auto sample_c = [&](long long a) -> float2 {
+        const float2 v = sample(a);
+        return (CFC && a >= 0) ? cfc_apply(P.cfc, P.n_cfc, cfc_cur, a, v) : v;
+    };
     if (o >= o_end) return;
     float2* dst = P.out + (o - P.out_base);
     const bool fast = staged && (o + kSfR <= o_end) && (o + kSfR - 1 < next_start);
@@ -275,7 +315,7 @@ symbol_filter_fast_kernel(const SfParams P, const float* __restrict__ taps_g /*[
         const float* tp = taps_s + cur.arm * P.stride;
         float2 acc = make_float2(0.f, 0.f);
         for (int k = 0; k < ARM; ++k) {
-            const float2 h = staged ? xs[sf_skew((int)(in_idx - k - lo_abs))] : sample(in_idx - k);
+            const float2 h = staged ? xs[sf_skew((int)(in_idx - k - lo_abs))] : sample_c(in_idx - k);
             const float tk = tp[k];
             acc.x = __fadd_rn(acc.x, __fmul_rn(tk, h.x));
             acc.y = __fadd_rn(acc.y, __fmul_rn(tk, h.y));
@@ -340,6 +380,13 @@ struct b200sync_sf {
     float2* d_out = nullptr;
     size_t in_cap = 0, out_cap = 0;
     cudaStream_t stream = nullptr;
+    // fused CoarseFrequencyCorrection in front of the filter (b200sync_sf_fuse_cfc)
+    bool cfc_on = false;
+    uint32_t cfc_delay = 0;
+    CfcPlanner cfc;
+    std::vector<CfcSegment> cfc_live;
+    CfcSegment* d_cfc = nullptr;
+    size_t cfc_cap = 0;
 };
 
 namespace {
@@ -382,6 +429,7 @@ int sf_setup(b200sync_sf* sf) {
     sf->scale = 1.0f;
     sf->pending.clear();
     sf->abs_in = sf->abs_out = 0;
+    sf->cfc.reset(sf->cfc_delay);
     return 0;
 }
 
@@ -538,6 +586,23 @@ int sf_run(b200sync_sf* sf, const float2* d_in, size_t n_in, const b200sync_stre
         P.num_arms = static_cast<int>(sf->num_arms);
         P.arm_size = sf->arm_size;
         P.stride = sf->arm_size + ((sf->arm_size & 1) ? 0 : 1);
+        if (sf->cfc_on) {
+            // the frequency correction sees the same tags, before the filter does (PM/packet_receiver.hpp:195-202)
+            const long long back = static_cast<long long>(sf->abs_in) - sf->hist_len;
+            sf->cfc.advance(n_in, in_tags, n_in_tags);
+            sf->cfc.live_segments(back, sf->cfc_live);
+            if (sf->cfc_cap < sf->cfc_live.size()) {
+                if (sf->d_cfc) cudaFree(sf->d_cfc);
+                sf->d_cfc = nullptr;
+                sf->cfc_cap = 0;
+                SCU(cudaMalloc(&sf->d_cfc, (sf->cfc_live.size() + 64) * sizeof(CfcSegment)));
+                sf->cfc_cap = sf->cfc_live.size() + 64;
+            }
+            SCU(cudaMemcpyAsync(sf->d_cfc, sf->cfc_live.data(), sf->cfc_live.size() * sizeof(CfcSegment),
+                                cudaMemcpyHostToDevice, st));
+            P.cfc = sf->d_cfc;
+            P.n_cfc = static_cast<int>(sf->cfc_live.size());
+        }
         if (P.sps == 4 && P.arm_size == 44) {
             // the receiver's configuration: register-blocked kernel
             const int n_tiles = static_cast<int>((n_out + kSfTileOut - 1) / kSfTileOut);
@@ -554,7 +619,7 @@ int sf_run(b200sync_sf* sf, const float2* d_in, size_t n_in, const b200sync_stre
             P.tile_in = kSfTileOut * P.sps + P.arm_size + 64;  // slack: every tag may add or drop one sample
             const int slots = P.tile_in + (P.tile_in >> 4) + 8;
             const size_t smem = sizeof(float) * P.num_arms * P.stride + sizeof(float2) * static_cast<size_t>(slots);
-            auto kern = symbol_filter_fast_kernel<4, 44>;
+            auto kern = sf->cfc_on ? symbol_filter_fast_kernel<4, 44, true> : symbol_filter_fast_kernel<4, 44, false>;
             SCU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<n_tiles, kSfThreads, smem, st>>>(P, sf->d_taps, sf->d_tile_seg);
             count_launch();
@@ -583,6 +648,10 @@ int sf_run(b200sync_sf* sf, const float2* d_in, size_t n_in, const b200sync_stre
     }
     sf->abs_in += n_in;
     sf->abs_out += n_out;
+    if (sf->cfc_on) {
+        if (n_out == 0) sf->cfc.advance(n_in, in_tags, n_in_tags);  // no kernel ran, the tags still count
+        sf->cfc.prune(static_cast<long long>(sf->abs_in) - sf->hist_len);
+    }
     *n_consumed = n_in;
     *n_produced = static_cast<size_t>(n_out);
     for (size_t i = 0; i < otags.size(); ++i) out_tags[i] = otags[i];
@@ -638,6 +707,7 @@ void b200sync_sf_destroy(b200sync_sf* sf) {
         if (h) cudaFree(h);
     if (sf->d_segs) cudaFree(sf->d_segs);
     if (sf->d_tile_seg) cudaFree(sf->d_tile_seg);
+    if (sf->d_cfc) cudaFree(sf->d_cfc);
     if (sf->d_in) cudaFree(sf->d_in);
     if (sf->d_out) cudaFree(sf->d_out);
     delete sf;
@@ -646,6 +716,15 @@ void b200sync_sf_destroy(b200sync_sf* sf) {
 int b200sync_sf_start(b200sync_sf* sf) {
     if (!sf) return sf_fail(B200SYNC_EINVAL, "null context");
     return sf_setup(sf);
+}
+
+int b200sync_sf_fuse_cfc(b200sync_sf* sf, int enable, uint32_t cfc_delay) {
+    if (!sf) return sf_fail(B200SYNC_EINVAL, "null context");
+    if (sf->abs_in != 0) return sf_fail(B200SYNC_EINVAL, "fuse_cfc must be called before the first process call (or start())");
+    sf->cfc_on = enable != 0;
+    sf->cfc_delay = cfc_delay;
+    sf->cfc.reset(cfc_delay);
+    return 0;
 }
 
 int b200sync_sf_process_device(b200sync_sf* sf, const void* d_in, size_t n_in, const b200sync_stream_tag* in_tags,

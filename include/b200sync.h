@@ -254,6 +254,34 @@ int b200sync_sf_process_device(b200sync_sf* sf, const void* d_in, size_t n_in, c
                                size_t* n_produced, b200sync_stream_tag* out_tags, size_t max_out_tags,
                                size_t* n_out_tags);
 
+/* Fuses a CoarseFrequencyCorrection block (below) into the filter's load stage: the span handed to
+ * b200sync_sf_process* is then the INPUT of CoarseFrequencyCorrection{delay = cfc_delay} and the
+ * output is that of the SymbolFilter behind it (PM/packet_receiver.hpp:94-115, 195-202) — one pass
+ * over the samples instead of two, bit-identical to running the two contexts back to back.  Call
+ * after create()/start() and before the first process call. */
+int b200sync_sf_fuse_cfc(b200sync_sf* sf, int enable, uint32_t cfc_delay);
+
+/* ------------------------------------------------------------------------------
+ * CoarseFrequencyCorrection<float>            PM/coarse_frequency_correction.hpp
+ * (sits between SyncwordDetectionFilter and SymbolFilter)
+ * ------------------------------------------------------------------------------ */
+typedef struct b200sync_cfc b200sync_cfc;
+/* emplaceBlock<CoarseFrequencyCorrection<>>({{"delay", delay}}) (:44, 100-103). */
+int b200sync_cfc_create(uint32_t delay, int32_t device, b200sync_cfc** out);
+void b200sync_cfc_destroy(b200sync_cfc* c);
+/* back to the initial state: unit rotator, no pending frequency (:40-47) */
+int b200sync_cfc_start(b200sync_cfc* c);
+const char* b200sync_cfc_last_error(void);
+/* processBulk (:67-98) over a span carrying any number of tags (sorted by index; only tags with
+ * has_syncword, i.e. a "syncword_freq" key, act: `delay` samples after such a tag the rotator is
+ * reset to phase -freq*delay and frequency -freq; a newer tag arriving first replaces it).  Tags are
+ * forwarded unchanged by the block's default tag policy, so none are returned.  in == out is
+ * allowed for device spans. */
+int b200sync_cfc_process(b200sync_cfc* c, const float* in, size_t n, const b200sync_stream_tag* in_tags,
+                         size_t n_in_tags, float* out);
+int b200sync_cfc_process_device(b200sync_cfc* c, const void* d_in, size_t n, const b200sync_stream_tag* in_tags,
+                                size_t n_in_tags, void* d_out, void* cuda_stream);
+
 /* ------------------------------------------------------------------------------
  * SyncwordDetectionFilter<c64>                    PM/syncword_detection_filter.hpp
  * Control logic only (which syncword tags survive while inside a packet) plus the pass-through

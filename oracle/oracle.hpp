@@ -435,6 +435,47 @@ public:
 };
 
 // ----------------------------------------------------------------------------
+// CoarseFrequencyCorrection<float> — PM/coarse_frequency_correction.hpp:40-98
+// (sits between SyncwordDetectionFilter and SymbolFilter,
+//  PM/packet_receiver.hpp:94-95, 195-202.)  processBulk() takes one chunk whose
+// FIRST sample may carry a tag with a "syncword_freq" key (has_freq / freq).
+// ----------------------------------------------------------------------------
+class CoarseFrequencyCorrection
+{
+public:
+    size_t delay = 0;
+    c64 _exp{ 1.0f, 0.0f };
+    c64 _exp_incr{ 1.0f, 0.0f };
+    unsigned _counter = 0;
+    float _next_freq = 0.0f;
+    std::ptrdiff_t _next_freq_delay = 0;
+
+    void set_freq(float freq) // :50-59
+    {
+        _exp = { std::cos(freq * static_cast<float>(delay)), -std::sin(freq * static_cast<float>(delay)) };
+        _exp_incr = { std::cos(freq), -std::sin(freq) };
+        _counter = 0;
+    }
+    void processBulk(const c64* in, size_t n, c64* out, bool has_freq, double freq) // :67-98
+    {
+        if (has_freq) { // pmtv::cast<float>(tag.map.at("syncword_freq")): the tag holds a double
+            _next_freq = static_cast<float>(freq);
+            _next_freq_delay = static_cast<std::ptrdiff_t>(delay);
+        }
+        for (size_t j = 0; j < n; ++j) {
+            if (_next_freq_delay == 0) set_freq(_next_freq);
+            out[j] = cmul_plain(in[j], _exp);
+            _exp = cmul_plain(_exp, _exp_incr);
+            if ((++_counter % 512) == 0) {
+                const float m = std::hypot(_exp.real(), _exp.imag());
+                _exp = c64(_exp.real() / m, _exp.imag() / m);
+            }
+            if (_next_freq_delay >= 0) --_next_freq_delay;
+        }
+    }
+};
+
+// ----------------------------------------------------------------------------
 // PfbArbResampler<c64, c64, float, TRate> — PM/pfb_arb_resampler.hpp:67-182
 // ----------------------------------------------------------------------------
 template <typename TRate>

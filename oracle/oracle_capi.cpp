@@ -111,6 +111,21 @@ void orc_rotator(float phase_incr, const float* in, size_t n, float* out)
     for (size_t k = 0; k < n; ++k) o[k] = r.processOne(i[k]);
 }
 
+// ---- CoarseFrequencyCorrection ----
+void* orc_cfc_create(size_t delay)
+{
+    auto c = std::make_unique<CoarseFrequencyCorrection>();
+    c->delay = delay;
+    return c.release();
+}
+void orc_cfc_destroy(void* h) { delete static_cast<CoarseFrequencyCorrection*>(h); }
+// one chunk; has_freq != 0: the chunk's first sample carries a tag with syncword_freq = freq
+void orc_cfc_process(void* h, const float* in, size_t n, float* out, int has_freq, double freq)
+{
+    static_cast<CoarseFrequencyCorrection*>(h)->processBulk(reinterpret_cast<const c64*>(in), n,
+                                                            reinterpret_cast<c64*>(out), has_freq != 0, freq);
+}
+
 // ---- PfbArbResampler ----
 struct ResamplerBox {
     bool dbl;

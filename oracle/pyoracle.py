@@ -96,6 +96,10 @@ def lib():
         L.orc_sd_template.restype = C.c_int
         L.orc_sd_template.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.orc_rotator.argtypes = [C.c_float, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.orc_cfc_create.restype = C.c_void_p
+        L.orc_cfc_create.argtypes = [C.c_size_t]
+        L.orc_cfc_destroy.argtypes = [C.c_void_p]
+        L.orc_cfc_process.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_double]
         L.orc_resampler_create.restype = C.c_void_p
         L.orc_resampler_create.argtypes = [C.c_double, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t]
         L.orc_resampler_destroy.argtypes = [C.c_void_p]
@@ -248,6 +252,38 @@ def rotator(x, phase_incr) -> np.ndarray:
     out = np.empty_like(x)
     lib().orc_rotator(phase_incr, x.ctypes.data, x.size, out.ctypes.data)
     return out
+
+
+class CoarseFrequencyCorrection:
+    """Restated CoarseFrequencyCorrection<float> (PM/coarse_frequency_correction.hpp)."""
+
+    def __init__(self, delay=0):
+        self._h = lib().orc_cfc_create(delay)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_cfc_destroy(self._h)
+            self._h = None
+
+    def process_bulk(self, x, freq=None):
+        """One chunk; `freq` is the syncword_freq of the tag on its first sample (None: no tag)."""
+        x = _c64(x)
+        out = np.empty_like(x)
+        lib().orc_cfc_process(self._h, x.ctypes.data, x.size, out.ctypes.data, int(freq is not None),
+                              float(freq if freq is not None else 0.0))
+        return out
+
+    def run(self, x, tags):
+        """Whole stream with (index, syncword_freq) tags: the runtime cuts chunks so that every tag sits
+        on the first sample of a chunk (GR/Block.hpp:1501-1508)."""
+        x = _c64(x)
+        out = np.empty_like(x)
+        cuts = [0] + [int(i) for i, _ in tags] + [x.size]
+        freqs = [None] + [f for _, f in tags]
+        for a, b, f in zip(cuts[:-1], cuts[1:], freqs):
+            if b > a or f is not None:
+                out[a:b] = self.process_bulk(x[a:b], f)
+        return out
 
 
 class PfbArbResampler:

@@ -1,5 +1,6 @@
 // Drives the C++ block shells of the whole RX synchronisation chain the way the GR4 runtime does:
-//   PfbArbResamplerB200 -> RotatorB200 -> SyncwordDetectionB200 -> SyncwordDetectionFilterB200 -> SymbolFilterB200
+//   PfbArbResamplerB200 -> RotatorB200 -> SyncwordDetectionB200 -> SyncwordDetectionFilterB200
+//     -> CoarseFrequencyCorrectionB200 -> SymbolFilterB200
 // Each stage is offered bounded chunks that start at tags (GR/Block.hpp:1501-1508), its consume()/publish()
 // calls are honoured, and the tags it publishes are carried to the next stage with absolute indices.
 // A stand-in for the header parser answers every forwarded syncword with a parsed_header message.
@@ -16,6 +17,7 @@
 #include <span>
 #include <vector>
 
+#include "../../gr4_packet_modem_b200/blocks/coarse_frequency_correction_b200.hpp"
 #include "../../gr4_packet_modem_b200/blocks/pfb_arb_resampler_b200.hpp"
 #include "../../gr4_packet_modem_b200/blocks/symbol_filter_b200.hpp"
 #include "../../gr4_packet_modem_b200/blocks/syncword_detection_b200.hpp"
@@ -113,8 +115,8 @@ int main(int argc, char** argv)
     const size_t chunk = static_cast<size_t>(std::atoll(argv[8]));
     const std::string prefix = argv[9];
     const gr::property_map none;
-    TagList no_tags, t_sd, t_sdf, t_sf, t_unused;
-    std::vector<c64> y, z, d, f, sym;
+    TagList no_tags, t_sd, t_sdf, t_cfc, t_sf, t_unused;
+    std::vector<c64> y, z, d, f, g, sym;
 
     // error text of the reference comes through (PM/pfb_arb_resampler.hpp:70-72)
     {
@@ -187,6 +189,15 @@ int main(int argc, char** argv)
     });
     print_tags("syncword_detection_filter", t_sdf);
 
+    // PM/packet_receiver.hpp:94-95: delay = (rrc_taps.size() - 1) / 2 + samples_per_symbol
+    gr::packet_modem::CoarseFrequencyCorrectionB200 freq_correction;
+    freq_correction.delay = (rrc.size() - 1) / 2 + 4;
+    freq_correction.settingsChanged(none, none);
+    freq_correction.start();
+    run_stage("coarse_frequency_correction", freq_correction, f, t_sdf, chunk, 1, g, t_cfc,
+              [&](auto& i, auto& o) { return freq_correction.processBulk(i, o); });
+    print_tags("coarse_frequency_correction", t_cfc);
+
     gr::packet_modem::SymbolFilterB200 symbol_filter;
     symbol_filter.taps = sf_taps;
     symbol_filter.num_arms = 32;
@@ -194,14 +205,35 @@ int main(int argc, char** argv)
     symbol_filter.delay = rrc.size() - 1;  // PM/packet_receiver.hpp:115
     symbol_filter.settingsChanged(none, none);
     symbol_filter.start();
-    run_stage("symbol_filter", symbol_filter, f, t_sdf, chunk, 1, sym, t_sf,
+    run_stage("symbol_filter", symbol_filter, g, t_cfc, chunk, 1, sym, t_sf,
               [&](auto& i, auto& o) { return symbol_filter.processBulk(i, o); });
     print_tags("symbol_filter", t_sf);
+
+    // SymbolFilter with the frequency correction fused into its load stage, fed the filter's output
+    // directly, must give the pair's symbols exactly
+    {
+        gr::packet_modem::SymbolFilterB200 fused;
+        fused.taps = sf_taps;
+        fused.num_arms = 32;
+        fused.samples_per_symbol = 4;
+        fused.delay = rrc.size() - 1;
+        fused.fused_cfc_delay = static_cast<int>((rrc.size() - 1) / 2 + 4);
+        fused.settingsChanged(none, none);
+        fused.start();
+        std::vector<c64> symf;
+        TagList t_f;
+        run_stage("fused_cfc_symbol_filter", fused, f, t_sdf, chunk, 1, symf, t_f,
+                  [&](auto& i, auto& o) { return fused.processBulk(i, o); });
+        std::printf("fused_cfc_equals_pair %d\n",
+                    symf.size() == sym.size() && t_f.size() == t_sf.size() &&
+                            std::memcmp(symf.data(), sym.data(), sym.size() * sizeof(c64)) == 0 ? 1 : 0);
+    }
 
     dump(prefix + "_resampled.cf32", y);
     dump(prefix + "_rotated.cf32", z);
     dump(prefix + "_delayed.cf32", d);
     dump(prefix + "_filtered.cf32", f);
+    dump(prefix + "_corrected.cf32", g);
     dump(prefix + "_symbols.cf32", sym);
     return 0;
 }

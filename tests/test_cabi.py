@@ -52,6 +52,10 @@ def test_no_cpu_fallback(native):
 
     with pytest.raises(B200SyncError):
         SyncwordDetection(unit_energy_rrc(), SYNCWORD, BPSK, -4, 4)
+    from gr4_packet_modem_b200 import CoarseFrequencyCorrection
+
+    with pytest.raises(B200SyncError):
+        CoarseFrequencyCorrection(26)
 
 
 def test_product_does_not_reference_oracle():

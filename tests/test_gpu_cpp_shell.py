@@ -60,11 +60,13 @@ def _build(tmp_path, src, name):
 
 
 def test_cpp_rx_chain_shells(oracle, rx_params, tmp_path):
-    """The five block shells chained the way packet_receiver.hpp wires them (resampler -> rotator ->
-    SyncwordDetection -> SyncwordDetectionFilter -> SymbolFilter), driven from C++ with GR4-style chunks:
+    """The six block shells chained the way packet_receiver.hpp wires them (resampler -> rotator ->
+    SyncwordDetection -> SyncwordDetectionFilter -> CoarseFrequencyCorrection -> SymbolFilter), driven from
+    C++ with GR4-style chunks:
     every stage's stream and tags against the oracle's restated blocks (bit-exact except behind the
     rotator, whose parity is a tolerance) and against the Python mirrors (bit-exact everywhere)."""
-    from gr4_packet_modem_b200 import FrontEnd, SyncwordDetection
+    from gr4_packet_modem_b200 import CoarseFrequencyCorrection, FrontEnd, SyncwordDetection
+    from gr4_packet_modem_b200.blocks import STREAM_TAG_DTYPE
     from gr4_packet_modem_b200.firdes import lowpass_prototype_taps, pfb_matched_filter_taps
     from gr4_packet_modem_b200.stimulus import packet_capture
 
@@ -84,8 +86,9 @@ def test_cpp_rx_chain_shells(oracle, rx_params, tmp_path):
     lines = r.stdout.strip().splitlines()
     assert lines[0] == "error filter_size cannot be 0"  # PM/pfb_arb_resampler.hpp:70-72
     assert "fused_equals_pair 1" in lines
+    assert "fused_cfc_equals_pair 1" in lines
     load = lambda s: np.fromfile(prefix + f"_{s}.cf32", np.complex64)  # noqa: E731
-    y, z, d, f, sym = (load(s) for s in ("resampled", "rotated", "delayed", "filtered", "symbols"))
+    y, z, d, f, g, sym = (load(s) for s in ("resampled", "rotated", "delayed", "filtered", "corrected", "symbols"))
 
     def tags_of(stage):
         out = []
@@ -128,6 +131,22 @@ def test_cpp_rx_chain_shells(oracle, rx_params, tmp_path):
             until = i + block
     assert [i for i, _ in t_sdf] == expect and 5 < len(expect) <= len(t_sd)
     assert all(len(kv) == 7 for _, kv in t_sdf)
+
+    # CoarseFrequencyCorrection (delay 26): tags forwarded unchanged; the Python mirror exactly (the C++ shell
+    # sees one tag per chunk, the mirror all of them in one span), the oracle's recurrence within tolerance
+    t_cfc = tags_of("coarse_frequency_correction")
+    assert t_cfc == t_sdf and g.size == f.size
+    cfc_delay = (rrc.size - 1) // 2 + 4
+    it = np.zeros(len(t_sdf), STREAM_TAG_DTYPE)
+    it["index"] = [i for i, _ in t_sdf]
+    it["has_syncword"] = 1
+    it["sw"]["syncword_freq"] = [float(kv["syncword_freq"]) for _, kv in t_sdf]
+    gp = CoarseFrequencyCorrection(cfc_delay).process_bulk(f, it)
+    assert np.array_equal(g.view(np.uint32), gp.view(np.uint32))
+    og = oracle.CoarseFrequencyCorrection(cfc_delay).run(f, [(i, float(kv["syncword_freq"])) for i, kv in t_sdf])
+    assert np.linalg.norm(g - og) / np.linalg.norm(og) < 1e-5
+    assert not np.array_equal(g, f)
+    f = g  # what SymbolFilter was fed
 
     # SymbolFilter: the oracle block driven by the same tags, chunks cut at tags (GR/Block.hpp:1501-1508)
     osf = oracle.SymbolFilter(sf_taps, 32, 4, delay=rrc.size - 1)

@@ -249,3 +249,35 @@ def test_rotator_reference_qa(oracle):
         if p >= np.pi:
             p -= 2 * np.pi
     assert np.max(np.abs(y - (np.cos(ph) + 1j * np.sin(ph)))) < 5e-4
+
+
+# ---------------------------------------------------------------- CoarseFrequencyCorrection
+def test_coarse_frequency_correction_restatement(oracle):
+    """PM/coarse_frequency_correction.hpp:67-98 (the reference has no QA for this block; the assertions
+    follow its documentation :23-36 and test/qa_rotator.cpp's tolerance): untouched before the first
+    reset; `delay` samples after a syncword_freq tag the signal is rotated by -freq with phase
+    -freq*delay at the reset sample; a newer tag within `delay` samples replaces the pending reset."""
+    n = 20000
+    x = np.ones(n, np.complex64)
+    for delay in (0, 26):
+        y = oracle.CoarseFrequencyCorrection(delay).run(x, [(1000, 0.01), (9000, -0.03), (9010, 0.02)])
+        k = np.arange(n)
+        ph = np.zeros(n)
+        a = 1000 + delay
+        # third tag: within `delay` of the second only when delay > 10
+        if delay > 10:
+            b = 9010 + delay
+            ph[a:b] = -np.float32(0.01) * (k[a:b] - 1000.0)
+            ph[b:] = -np.float32(0.02) * (k[b:] - 9010.0)
+        else:
+            b, c = 9000 + delay, 9010 + delay
+            ph[a:b] = -np.float32(0.01) * (k[a:b] - 1000.0)
+            ph[b:c] = np.float32(0.03) * (k[b:c] - 9000.0)
+            ph[c:] = -np.float32(0.02) * (k[c:] - 9010.0)
+        assert np.array_equal(y[:a], x[:a])
+        assert np.max(np.abs(y - np.exp(1j * ph))) < 5e-4
+    # a tag exactly `delay` samples after its predecessor is examined before the sample loop of its chunk
+    # (:73-79), so the reset that was due on that very sample never happens
+    y = oracle.CoarseFrequencyCorrection(26).run(x, [(100, 0.01), (126, 0.02)])
+    assert np.array_equal(y[:152], x[:152])
+    assert abs(np.angle(y[153] * np.conj(y[152])) + 0.02) < 1e-6
