@@ -13,19 +13,15 @@
 namespace b200sync {
 
 // ---- host planner ----------------------------------------------------------------------------
-CfcSegment CfcPlanner::make_segment(long long start, float freq, uint32_t delay) {
+CfcSeed CfcPlanner::make_segment(long long start, float freq, uint32_t delay) {
     // set_freq(), :50-59 — all in float, like the reference
     const float a = freq * static_cast<float>(delay);
-    const float e_re = std::cos(a), e_im = -std::sin(a);
-    const float i_re = std::cos(freq), i_im = -std::sin(freq);
-    CfcSegment s{};
+    CfcSeed s{};
     s.start = start;
-    s.phase0 = std::atan2(static_cast<double>(e_im), static_cast<double>(e_re));
-    s.theta = std::atan2(static_cast<double>(i_im), static_cast<double>(i_re));
-    s.amp0_eps = static_cast<float>(std::hypot(static_cast<double>(e_re), static_cast<double>(e_im)) - 1.0);
-    s.amp_eps = static_cast<float>(std::hypot(static_cast<double>(i_re), static_cast<double>(i_im)) - 1.0);
-    for (int r = 0; r < kCfcGroup; ++r)
-        s.w[r] = make_float2(static_cast<float>(std::cos(r * s.theta)), static_cast<float>(std::sin(r * s.theta)));
+    s.e_re = std::cos(a);
+    s.e_im = -std::sin(a);
+    s.i_re = std::cos(freq);
+    s.i_im = -std::sin(freq);
     return s;
 }
 
@@ -60,16 +56,59 @@ void CfcPlanner::advance(size_t n, const b200sync_stream_tag* tags, size_t n_tag
     abs_pos_ = end;
 }
 
-void CfcPlanner::live_segments(long long from_abs, std::vector<CfcSegment>& out) const {
+void CfcPlanner::live_segments(long long from_abs, std::vector<CfcSeed>& out) const {
     out.clear();
     size_t first = 0;
     for (size_t i = 0; i < segs_.size(); ++i)
         if (segs_[i].start <= from_abs) first = i;
-    for (size_t i = first; i < segs_.size(); ++i) out.push_back(segs_[i]);
+    out.assign(segs_.begin() + static_cast<std::ptrdiff_t>(first), segs_.end());
 }
 
 void CfcPlanner::prune(long long from_abs) {
     while (segs_.size() > 1 && segs_[1].start <= from_abs) segs_.pop_front();
+}
+
+// ---- seeds -> segments ---------------------------------------------------------------------------
+__global__ void cfc_expand_kernel(const CfcSeed* __restrict__ seeds, CfcSegment* __restrict__ segs, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const CfcSeed sd = seeds[i];
+    CfcSegment s;
+    s.start = sd.start;
+    s.phase0 = atan2((double)sd.e_im, (double)sd.e_re);
+    s.theta = atan2((double)sd.i_im, (double)sd.i_re);
+    s.amp0_eps = (float)(hypot((double)sd.e_re, (double)sd.e_im) - 1.0);
+    s.amp_eps = (float)(hypot((double)sd.i_re, (double)sd.i_im) - 1.0);
+#pragma unroll
+    for (int r = 0; r < kCfcGroup; ++r) {
+        double sn, cs;
+        sincos(r * s.theta, &sn, &cs);
+        s.w[r] = make_float2((float)cs, (float)sn);
+    }
+    segs[i] = s;
+}
+
+cudaError_t cfc_upload_segments(const std::vector<CfcSeed>& seeds, CfcSeed** d_seeds, CfcSegment** d_segs, size_t* cap,
+                                cudaStream_t st) {
+    if (*cap < seeds.size()) {
+        if (*d_seeds) cudaFree(*d_seeds);
+        if (*d_segs) cudaFree(*d_segs);
+        *d_seeds = nullptr;
+        *d_segs = nullptr;
+        *cap = 0;
+        const size_t want = seeds.size() + seeds.size() / 2 + 64;
+        cudaError_t e = cudaMalloc(d_seeds, want * sizeof(CfcSeed));
+        if (e != cudaSuccess) return e;
+        e = cudaMalloc(d_segs, want * sizeof(CfcSegment));
+        if (e != cudaSuccess) return e;
+        *cap = want;
+    }
+    cudaError_t e = cudaMemcpyAsync(*d_seeds, seeds.data(), seeds.size() * sizeof(CfcSeed), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    const int n = static_cast<int>(seeds.size());
+    cfc_expand_kernel<<<(n + 127) / 128, 128, 0, st>>>(*d_seeds, *d_segs, n);
+    count_launch();
+    return cudaGetLastError();
 }
 
 // ---- stand-alone kernel ------------------------------------------------------------------------
@@ -128,13 +167,14 @@ struct b200sync_cfc {
     uint32_t delay = 0;
     int device = 0;
     CfcPlanner plan;
+    CfcSeed* d_seeds = nullptr;
     CfcSegment* d_segs = nullptr;
     size_t segs_cap = 0;
     float2* d_in = nullptr;
     float2* d_out = nullptr;
     size_t buf_cap = 0;
     cudaStream_t stream = nullptr;
-    std::vector<CfcSegment> live;
+    std::vector<CfcSeed> live;
 };
 
 namespace {
@@ -147,14 +187,7 @@ int cfc_run(b200sync_cfc* c, const float2* d_in, size_t n, const b200sync_stream
     const long long abs0 = c->plan.abs_pos();
     c->plan.advance(n, tags, n_tags);
     c->plan.live_segments(abs0, c->live);
-    if (c->segs_cap < c->live.size()) {
-        if (c->d_segs) cudaFree(c->d_segs);
-        c->d_segs = nullptr;
-        c->segs_cap = 0;
-        CCU(cudaMalloc(&c->d_segs, (c->live.size() + 64) * sizeof(CfcSegment)));
-        c->segs_cap = c->live.size() + 64;
-    }
-    CCU(cudaMemcpyAsync(c->d_segs, c->live.data(), c->live.size() * sizeof(CfcSegment), cudaMemcpyHostToDevice, st));
+    CCU(cfc_upload_segments(c->live, &c->d_seeds, &c->d_segs, &c->segs_cap, st));
     const unsigned grid = static_cast<unsigned>((n + kCfcTile - 1) / kCfcTile);
     cfc_kernel<<<grid, kCfcThreads, 0, st>>>(d_in, d_out, static_cast<long long>(n), abs0, c->d_segs,
                                              static_cast<int>(c->live.size()));
@@ -196,6 +229,7 @@ void b200sync_cfc_destroy(b200sync_cfc* c) {
         cudaStreamDestroy(c->stream);
     }
     if (c->d_segs) cudaFree(c->d_segs);
+    if (c->d_seeds) cudaFree(c->d_seeds);
     if (c->d_in) cudaFree(c->d_in);
     if (c->d_out) cudaFree(c->d_out);
     delete c;

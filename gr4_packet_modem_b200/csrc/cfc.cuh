@@ -34,6 +34,15 @@ struct CfcSegment {
     float2 w[kCfcGroup]; // (cos, sin)(r * theta)
 };
 
+// What the host knows about a segment: where it starts and the four float values set_freq() computes
+// (:53-57, host libm like the reference).  cfc_expand_kernel derives the CfcSegment fields from it on
+// the device (double atan2 / hypot / cos / sin), so the per-tag host cost is four float libm calls.
+struct CfcSeed {
+    long long start;
+    float e_re, e_im;  // _exp at the reset
+    float i_re, i_im;  // _exp_incr
+};
+
 // Host side: replays the tag logic of processBulk (:73-79, 81-83, 94-96) and keeps the segments a
 // later call may still need (the SymbolFilter history reaches `keep_back` samples behind a call).
 class CfcPlanner {
@@ -43,19 +52,24 @@ public:
     // start inside [abs_pos, abs_pos + n) and advances abs_pos.
     void advance(size_t n, const b200sync_stream_tag* tags, size_t n_tags);
     // segments covering [abs_pos_before_call - keep_back, now): call after advance()
-    void live_segments(long long from_abs, std::vector<CfcSegment>& out) const;
+    void live_segments(long long from_abs, std::vector<CfcSeed>& out) const;
     void prune(long long from_abs);
     long long abs_pos() const { return abs_pos_; }
 
 private:
-    static CfcSegment make_segment(long long start, float freq, uint32_t delay);
+    static CfcSeed make_segment(long long start, float freq, uint32_t delay);
     uint32_t delay_ = 0;
     long long abs_pos_ = 0;
     bool pending_ = false;
     float pending_freq_ = 0.0f;
     long long pending_at_ = 0;
-    std::deque<CfcSegment> segs_;
+    std::deque<CfcSeed> segs_;
 };
+
+// seeds (host memory) -> segments in d_segs (capacity grown as needed), asynchronous on st.  The caller
+// keeps `seeds` alive until the stream has been synchronised.
+cudaError_t cfc_upload_segments(const std::vector<CfcSeed>& seeds, CfcSeed** d_seeds, CfcSegment** d_segs, size_t* cap,
+                                cudaStream_t st);
 
 #ifdef __CUDACC__
 // Walks forward from segment index `sg` to the segment of absolute sample n (segments sorted by start).
@@ -81,6 +95,25 @@ struct CfcCursor {
     float amp0_eps = 0.f, amp_eps = 0.f;
 };
 
+// (cos, sin) of the phase at the group base g = m - m mod 8 of a segment
+__device__ __forceinline__ float2 cfc_group_base(double theta, double phase0, long long g) {
+    double ph = fma((double)g, theta, phase0);
+    ph -= 6.283185307179586476925 * rint(ph * 0.15915494309189533577);
+    float s, co;
+    sincosf((float)ph, &s, &co);
+    return make_float2(co, s);
+}
+// v * ebase * w[m mod 8] * |exp|(m): every path that applies the correction goes through this function
+__device__ __forceinline__ float2 cfc_rotate(float2 ebase, float2 w, long long m, float amp0_eps, float amp_eps, float2 v) {
+    const float2 e = make_float2(__fmaf_rn(ebase.x, w.x, -__fmul_rn(ebase.y, w.y)),
+                                 __fmaf_rn(ebase.x, w.y, __fmul_rn(ebase.y, w.x)));
+    float amp = __fmaf_rn((float)(m & 511), amp_eps, 1.0f);
+    if (m < 512) amp = __fmaf_rn(amp, amp0_eps, amp);
+    const float cr = __fmul_rn(e.x, amp), si = __fmul_rn(e.y, amp);
+    return make_float2(__fsub_rn(__fmul_rn(v.x, cr), __fmul_rn(v.y, si)),
+                       __fadd_rn(__fmul_rn(v.x, si), __fmul_rn(v.y, cr)));
+}
+
 __device__ __forceinline__ float2 cfc_apply(const CfcSegment* __restrict__ segs, int n_segs, CfcCursor& c,
                                             long long n, float2 v) {
     if (c.sg < 0 || n >= c.seg_next || n < c.seg_start) {
@@ -94,21 +127,10 @@ __device__ __forceinline__ float2 cfc_apply(const CfcSegment* __restrict__ segs,
     const long long m = n - c.seg_start;
     const long long g = m & ~(long long)(kCfcGroup - 1);
     if (g != c.gbase) {
-        double ph = fma((double)g, segs[c.sg].theta, segs[c.sg].phase0);
-        ph -= 6.283185307179586476925 * rint(ph * 0.15915494309189533577);
-        float s, co;
-        sincosf((float)ph, &s, &co);
-        c.ebase = make_float2(co, s);
+        c.ebase = cfc_group_base(segs[c.sg].theta, segs[c.sg].phase0, g);
         c.gbase = g;
     }
-    const float2 w = segs[c.sg].w[(int)(m & (kCfcGroup - 1))];
-    const float2 e = make_float2(__fmaf_rn(c.ebase.x, w.x, -__fmul_rn(c.ebase.y, w.y)),
-                                 __fmaf_rn(c.ebase.x, w.y, __fmul_rn(c.ebase.y, w.x)));
-    float amp = __fmaf_rn((float)(m & 511), c.amp_eps, 1.0f);
-    if (m < 512) amp = __fmaf_rn(amp, c.amp0_eps, amp);
-    const float cr = __fmul_rn(e.x, amp), si = __fmul_rn(e.y, amp);
-    return make_float2(__fsub_rn(__fmul_rn(v.x, cr), __fmul_rn(v.y, si)),
-                       __fadd_rn(__fmul_rn(v.x, si), __fmul_rn(v.y, cr)));
+    return cfc_rotate(c.ebase, segs[c.sg].w[(int)(m & (kCfcGroup - 1))], m, c.amp0_eps, c.amp_eps, v);
 }
 #endif
 

@@ -202,6 +202,7 @@ symbol_filter_fast_kernel(const SfParams P, const float* __restrict__ taps_g /*[
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* taps_s = reinterpret_cast<float*>(smem_raw);                        // [num_arms][stride]
     float2* xs = reinterpret_cast<float2*>(taps_s + P.num_arms * P.stride);    // skewed staging
+    [[maybe_unused]] float2* ebase_s = xs + (P.tile_in + (P.tile_in >> 4) + 8);  // CFC: one factor per 8 samples
     __shared__ long long span_s[2];
     const int tid = threadIdx.x;
     for (int i = tid; i < P.num_arms * ARM; i += kSfThreads) {
@@ -249,15 +250,44 @@ symbol_filter_fast_kernel(const SfParams P, const float* __restrict__ taps_g /*[
     };
     if (staged) {
         const int span = (int)span_ll;
-        if (lo_abs >= P.in_base) {
-            const float2* src = P.in + (lo_abs - P.in_base);
-            for (int i = tid; i < span; i += kSfThreads) xs[sf_skew(i)] = __ldcs(src + i);
-        } else {
-            for (int i = tid; i < span; i += kSfThreads) xs[sf_skew(i)] = sample(lo_abs + i);
-        }
+        bool rotated = false;
         if constexpr (CFC) {
-            __syncthreads();
-            sf_cfc_inplace(P, xs, lo_abs, span, [](int i) { return sf_skew(i); });
+            // Fused CoarseFrequencyCorrection, common case: the whole tile lies in ONE correction segment
+            // (resets are a packet apart).  One sincosf per group of 8 samples goes to shared memory, then
+            // every sample is rotated on its way from global to shared memory — no second pass.  A thread's
+            // samples are kSfThreads apart, so its position in the group (m mod 8) never changes.
+            const int sgc = cfc_search(P.cfc, P.n_cfc, lo_abs);   // same address in every thread: broadcast
+            const long long c_start = P.cfc[sgc].start;
+            const long long c_next = (sgc + 1 < P.n_cfc) ? P.cfc[sgc + 1].start : LLONG_MAX;
+            if (lo_abs >= c_start && lo_abs + span <= c_next && lo_abs >= P.in_base) {
+                rotated = true;
+                const double theta = P.cfc[sgc].theta, phase0 = P.cfc[sgc].phase0;
+                const float a0 = P.cfc[sgc].amp0_eps, a1 = P.cfc[sgc].amp_eps;
+                const long long m_lo = lo_abs - c_start;
+                const long long g_first = m_lo & ~(long long)(kCfcGroup - 1);
+                const int n_groups = (int)((m_lo + span - 1 - g_first) >> 3) + 1;
+                for (int k = tid; k < n_groups; k += kSfThreads)
+                    ebase_s[k] = cfc_group_base(theta, phase0, g_first + (long long)k * kCfcGroup);
+                __syncthreads();
+                const float2 w = P.cfc[sgc].w[(int)((m_lo + tid) & (kCfcGroup - 1))];
+                const float2* src = P.in + (lo_abs - P.in_base);
+                for (int i = tid; i < span; i += kSfThreads) {
+                    const long long m = m_lo + i;
+                    xs[sf_skew(i)] = cfc_rotate(ebase_s[(int)((m - g_first) >> 3)], w, m, a0, a1, __ldcs(src + i));
+                }
+            }
+        }
+        if (!rotated) {
+            if (lo_abs >= P.in_base) {
+                const float2* src = P.in + (lo_abs - P.in_base);
+                for (int i = tid; i < span; i += kSfThreads) xs[sf_skew(i)] = __ldcs(src + i);
+            } else {
+                for (int i = tid; i < span; i += kSfThreads) xs[sf_skew(i)] = sample(lo_abs + i);
+            }
+            if constexpr (CFC) {  // a reset inside the tile, or history samples: rotate in place
+                __syncthreads();
+                sf_cfc_inplace(P, xs, lo_abs, span, [](int i) { return sf_skew(i); });
+            }
         }
     }
     __syncthreads();
@@ -384,7 +414,8 @@ struct b200sync_sf {
     bool cfc_on = false;
     uint32_t cfc_delay = 0;
     CfcPlanner cfc;
-    std::vector<CfcSegment> cfc_live;
+    std::vector<CfcSeed> cfc_live;
+    CfcSeed* d_cfc_seeds = nullptr;
     CfcSegment* d_cfc = nullptr;
     size_t cfc_cap = 0;
 };
@@ -544,6 +575,8 @@ int sf_run(b200sync_sf* sf, const float2* d_in, size_t n_in, const b200sync_stre
     if (n_in == 0) return 0;
     std::vector<SfSegment> segs;
     std::vector<b200sync_stream_tag> otags;
+    segs.reserve(2 * n_in_tags + 2);
+    otags.reserve(n_in_tags + sf->pending.size());
     unsigned long long n_out = 0;
     // keep the state so a failing call leaves the block untouched
     const int cp = sf->clock_phase, arm = sf->pfb_arm;
@@ -591,15 +624,7 @@ int sf_run(b200sync_sf* sf, const float2* d_in, size_t n_in, const b200sync_stre
             const long long back = static_cast<long long>(sf->abs_in) - sf->hist_len;
             sf->cfc.advance(n_in, in_tags, n_in_tags);
             sf->cfc.live_segments(back, sf->cfc_live);
-            if (sf->cfc_cap < sf->cfc_live.size()) {
-                if (sf->d_cfc) cudaFree(sf->d_cfc);
-                sf->d_cfc = nullptr;
-                sf->cfc_cap = 0;
-                SCU(cudaMalloc(&sf->d_cfc, (sf->cfc_live.size() + 64) * sizeof(CfcSegment)));
-                sf->cfc_cap = sf->cfc_live.size() + 64;
-            }
-            SCU(cudaMemcpyAsync(sf->d_cfc, sf->cfc_live.data(), sf->cfc_live.size() * sizeof(CfcSegment),
-                                cudaMemcpyHostToDevice, st));
+            SCU(cfc_upload_segments(sf->cfc_live, &sf->d_cfc_seeds, &sf->d_cfc, &sf->cfc_cap, st));
             P.cfc = sf->d_cfc;
             P.n_cfc = static_cast<int>(sf->cfc_live.size());
         }
@@ -618,7 +643,8 @@ int sf_run(b200sync_sf* sf, const float2* d_in, size_t n_in, const b200sync_stre
             SCU(cudaGetLastError());
             P.tile_in = kSfTileOut * P.sps + P.arm_size + 64;  // slack: every tag may add or drop one sample
             const int slots = P.tile_in + (P.tile_in >> 4) + 8;
-            const size_t smem = sizeof(float) * P.num_arms * P.stride + sizeof(float2) * static_cast<size_t>(slots);
+            const size_t smem = sizeof(float) * P.num_arms * P.stride + sizeof(float2) * static_cast<size_t>(slots) +
+                                (sf->cfc_on ? sizeof(float2) * static_cast<size_t>(P.tile_in / kCfcGroup + 4) : 0);
             auto kern = sf->cfc_on ? symbol_filter_fast_kernel<4, 44, true> : symbol_filter_fast_kernel<4, 44, false>;
             SCU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<n_tiles, kSfThreads, smem, st>>>(P, sf->d_taps, sf->d_tile_seg);
@@ -708,6 +734,7 @@ void b200sync_sf_destroy(b200sync_sf* sf) {
     if (sf->d_segs) cudaFree(sf->d_segs);
     if (sf->d_tile_seg) cudaFree(sf->d_tile_seg);
     if (sf->d_cfc) cudaFree(sf->d_cfc);
+    if (sf->d_cfc_seeds) cudaFree(sf->d_cfc_seeds);
     if (sf->d_in) cudaFree(sf->d_in);
     if (sf->d_out) cudaFree(sf->d_out);
     delete sf;
