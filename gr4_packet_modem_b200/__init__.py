@@ -7,4 +7,4 @@ built library raises.
 """
 from .firdes import root_raised_cosine  # noqa: F401
 from .blocks import (SyncwordDetection, DetectionRecord, SyncwordTag, FrontEnd, PfbArbResampler,  # noqa: F401
-                     Rotator, SymbolFilter, SyncwordDetectionFilter, CoarseFrequencyCorrection)
+                     Rotator, SymbolFilter, SyncwordDetectionFilter, CoarseFrequencyCorrection, SyncwordWipeoff, CostasLoop)

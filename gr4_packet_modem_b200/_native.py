@@ -76,6 +76,10 @@ class SfConfig(C.Structure):
     ]
 
 
+class ClConfig(C.Structure):
+    _fields_ = [("loop_bandwidth", C.c_double), ("constellation", C.c_uint32), ("device", C.c_int32)]
+
+
 class SdfHeader(C.Structure):
     _fields_ = [("invalid_header", C.c_uint32), ("packet_length", C.c_uint64)]
 
@@ -148,6 +152,24 @@ def lib():
     L.b200sync_cfc_process_device.argtypes = [vp, vp, sz, vp, sz, vp, vp]
     for name in ("b200sync_cfc_create", "b200sync_cfc_start", "b200sync_cfc_process", "b200sync_cfc_process_device"):
         getattr(L, name).restype = C.c_int
+    L.b200sync_wo_create.argtypes = [vp, C.c_uint32, C.c_int32, C.POINTER(vp)]
+    L.b200sync_wo_destroy.argtypes = [vp]
+    L.b200sync_wo_start.argtypes = [vp]
+    L.b200sync_wo_process.argtypes = [vp, vp, sz, vp, sz, vp]
+    L.b200sync_wo_process_device.argtypes = [vp, vp, sz, vp, sz, vp, vp]
+    L.b200sync_cl_create.argtypes = [C.POINTER(ClConfig), C.POINTER(vp)]
+    L.b200sync_cl_destroy.argtypes = [vp]
+    L.b200sync_cl_start.argtypes = [vp]
+    L.b200sync_cl_last_error.restype = C.c_char_p
+    L.b200sync_cl_info.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.b200sync_cl_process.argtypes = [vp, vp, sz, vp, sz, vp]
+    L.b200sync_cl_process_device.argtypes = [vp, vp, sz, vp, sz, vp, vp]
+    L.b200sync_cl_fuse_wipeoff.argtypes = [vp, vp, C.c_uint32]
+    L.b200sync_cl_state.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    for name in ("b200sync_wo_create", "b200sync_wo_start", "b200sync_wo_process", "b200sync_wo_process_device",
+                 "b200sync_cl_create", "b200sync_cl_start", "b200sync_cl_info", "b200sync_cl_process",
+                 "b200sync_cl_process_device", "b200sync_cl_fuse_wipeoff", "b200sync_cl_state"):
+        getattr(L, name).restype = C.c_int
     L.b200sync_sdf_create.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
     L.b200sync_sdf_destroy.argtypes = [vp]
     L.b200sync_sdf_start.argtypes = [vp]
@@ -193,4 +215,10 @@ def check_sf(rc: int) -> int:
 def check_fe(rc: int) -> int:
     if rc < 0:
         raise B200SyncError(f"libb200sync error {rc}: {lib().b200sync_fe_last_error().decode()}")
+    return rc
+
+
+def check_cl(rc: int) -> int:
+    if rc < 0:
+        raise B200SyncError(f"libb200sync error {rc}: {lib().b200sync_cl_last_error().decode()}")
     return rc

@@ -450,6 +450,136 @@ class CoarseFrequencyCorrection:
                                                             C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr or None)))
 
 
+def _tags_arg(in_tags):
+    it = np.ascontiguousarray(in_tags if in_tags is not None else np.zeros(0, STREAM_TAG_DTYPE), STREAM_TAG_DTYPE)
+    return it, (it.ctypes.data if it.size else None), it.size
+
+
+class SyncwordWipeoff:
+    """gr::packet_modem::SyncwordWipeoff<c64, float> on the GPU (PM/syncword_wipeoff.hpp).  Setting: syncword
+    (:36).  Tags are forwarded unchanged (default tag policy), so only items come back."""
+
+    def __init__(self, syncword, device: int = 0):
+        from ._native import check_cl
+
+        self.syncword = np.ascontiguousarray(syncword, dtype=np.float32)
+        h = C.c_void_p()
+        self._h = C.c_void_p()
+        check_cl(_native.lib().b200sync_wo_create(self.syncword.ctypes.data if self.syncword.size else None,
+                                                  self.syncword.size, int(device), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                _native.lib().b200sync_wo_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def start(self) -> None:
+        from ._native import check_cl
+
+        check_cl(_native.lib().b200sync_wo_start(self._h))
+
+    def process_bulk(self, in_span, in_tags: np.ndarray | None = None) -> np.ndarray:
+        """processBulk over a host span carrying `in_tags` (STREAM_TAG_DTYPE, indices relative to the span)."""
+        from ._native import check_cl
+
+        x = np.ascontiguousarray(in_span, dtype=np.complex64)
+        _it, tp, nt = _tags_arg(in_tags)
+        out = np.empty_like(x)
+        check_cl(_native.lib().b200sync_wo_process(self._h, x.ctypes.data if x.size else None, x.size, tp, nt,
+                                                   out.ctypes.data if x.size else None))
+        return out
+
+    def process_device(self, d_in_ptr: int, n: int, d_out_ptr: int, in_tags: np.ndarray | None = None,
+                       stream_ptr: int = 0) -> None:
+        from ._native import check_cl
+
+        _it, tp, nt = _tags_arg(in_tags)
+        check_cl(_native.lib().b200sync_wo_process_device(self._h, C.c_void_p(d_in_ptr), n, tp, nt,
+                                                          C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr or None)))
+
+
+class CostasLoop:
+    """gr::packet_modem::CostasLoop<float, float> on the GPU (PM/costas_loop.hpp).  Settings: loop_bandwidth
+    (:52), constellation "PILOT" | "BPSK" | "QPSK", case-insensitive (:53-54, 63-65).  Tags are forwarded
+    unchanged (default tag policy), so only items come back."""
+
+    CONSTELLATIONS = {"PILOT": 0, "BPSK": 1, "QPSK": 2}
+
+    def __init__(self, loop_bandwidth: float = 0.01, constellation: str = "BPSK", device: int = 0):
+        from ._native import ClConfig, B200SyncError, check_cl
+
+        key = str(constellation).upper()
+        if key not in self.CONSTELLATIONS:  # magic_enum::enum_cast(...).value() throws in the reference
+            raise B200SyncError(f"unknown constellation {constellation!r}")
+        self.loop_bandwidth, self.constellation = float(loop_bandwidth), key
+        cfg = ClConfig(self.loop_bandwidth, self.CONSTELLATIONS[key], int(device))
+        h = C.c_void_p()
+        self._h = C.c_void_p()
+        check_cl(_native.lib().b200sync_cl_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                _native.lib().b200sync_cl_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def start(self) -> None:
+        from ._native import check_cl
+
+        check_cl(_native.lib().b200sync_cl_start(self._h))
+
+    def fuse_wipeoff(self, syncword) -> None:
+        """Put a SyncwordWipeoff{syncword} in front of the loop, inside the same kernel."""
+        from ._native import check_cl
+
+        sw = np.ascontiguousarray(syncword if syncword is not None else [], dtype=np.float32)
+        check_cl(_native.lib().b200sync_cl_fuse_wipeoff(self._h, sw.ctypes.data if sw.size else None, sw.size))
+
+    @property
+    def coefficients(self):
+        """(_k1, _k2)"""
+        from ._native import check_cl
+
+        k1, k2 = C.c_float(), C.c_float()
+        check_cl(_native.lib().b200sync_cl_info(self._h, C.byref(k1), C.byref(k2)))
+        return k1.value, k2.value
+
+    @property
+    def state(self):
+        """(_phase, _freq) after the last processed item"""
+        from ._native import check_cl
+
+        ph, fr = C.c_float(), C.c_float()
+        check_cl(_native.lib().b200sync_cl_state(self._h, C.byref(ph), C.byref(fr)))
+        return ph.value, fr.value
+
+    def process_bulk(self, in_span, in_tags: np.ndarray | None = None) -> np.ndarray:
+        """processBulk over a host span carrying `in_tags` (STREAM_TAG_DTYPE, indices relative to the span)."""
+        from ._native import check_cl
+
+        x = np.ascontiguousarray(in_span, dtype=np.complex64)
+        _it, tp, nt = _tags_arg(in_tags)
+        out = np.empty_like(x)
+        check_cl(_native.lib().b200sync_cl_process(self._h, x.ctypes.data if x.size else None, x.size, tp, nt,
+                                                   out.ctypes.data if x.size else None))
+        return out
+
+    def process_device(self, d_in_ptr: int, n: int, d_out_ptr: int, in_tags: np.ndarray | None = None,
+                       stream_ptr: int = 0) -> None:
+        from ._native import check_cl
+
+        _it, tp, nt = _tags_arg(in_tags)
+        check_cl(_native.lib().b200sync_cl_process_device(self._h, C.c_void_p(d_in_ptr), n, tp, nt,
+                                                          C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr or None)))
+
+
 class SyncwordDetectionFilter:
     """gr::packet_modem::SyncwordDetectionFilter (PM/syncword_detection_filter.hpp): host control logic
     behind the C ABI."""

@@ -56,6 +56,16 @@ constexpr bool kCorrTwoBuf = false;
 constexpr bool kCorrTwoBuf = true;
 #endif
 constexpr int kCorrXchg = kCorrTwoBuf ? kXchgFloat2 + kXchgFloat2A : kXchgFloat2;
+#ifdef B200_REG_B1
+constexpr bool kRegB1 = true;
+#else
+constexpr bool kRegB1 = false;
+#endif
+#ifdef B200_REG_B2
+constexpr bool kRegB2 = true;
+#else
+constexpr bool kRegB2 = false;
+#endif
 
 __global__ void __launch_bounds__(kCorrThreads, 1)
 correlate_kernel(const float2* __restrict__ in, long long in_base, float* __restrict__ zpow,
@@ -73,6 +83,10 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
     const int ngroups = blockDim.x >> 7;
     const long long gstride = (long long)gridDim.x * ngroups;
     const int bar_id = 1 + g;
+
+    float2 t1[14], t2[15];
+    if constexpr (kRegB1) load_b1_twiddles(t1, tw_s, tid);
+    if constexpr (kRegB2) load_b2_twiddles(t2, tw_s, tid);
 
     for (long long blk = (long long)blockIdx.x * ngroups + g; blk < nb; blk += gstride) {
         const long long s0 = (b0 + blk) * (long long)S;  // absolute first sample of the block
@@ -104,7 +118,7 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
             float2 y[16], c[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) y[j] = cmul(xs[j], __ldg(h + j * kGroupThreads));  // :247-249
-            fft_b<kCorrTwoBuf>(y, c, tw_s, xb, tid, bar_id, xb2);                           // :250-251
+            fft_b<kCorrTwoBuf, kRegB1, kRegB2>(y, c, tw_s, xb, tid, bar_id, xb2, t1, t2);   // :250-251
 #pragma unroll
             for (int m1 = 0; m1 < 16; ++m1) {
                 const float p = norm2(c[m1]);  // :307

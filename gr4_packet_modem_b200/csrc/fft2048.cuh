@@ -225,10 +225,27 @@ __device__ __forceinline__ void fft_a(float2 (&v)[16], float2 (&xs)[16], const f
 
 // ---- FFT B: y[pi*8 + f3] = Y[(tid + 128 pi) + 256 f3] -> c[m1] = C[128 m1 + tid] ------
 // y is destroyed.  The exchange buffer must be free on entry and is free on return.
-template <bool TWO_BUF = false>
+//
+// REG_B1 / REG_B2: the inter-pass factors of pass B1 / B2 depend only on the thread, not on the
+// hypothesis, so a caller that runs many transforms back to back (correlate_kernel: K per block) can
+// hold them in registers (load_b1_twiddles / load_b2_twiddles) instead of re-reading shared memory
+// K times.  Same table entries, same multiplies: bit-identical.
+__device__ __forceinline__ void load_b1_twiddles(float2 (&t1)[14], const float2* __restrict__ tw, int tid) {
+#pragma unroll
+    for (int pi = 0; pi < 2; ++pi)
+#pragma unroll
+        for (int m3 = 1; m3 < 8; ++m3) t1[pi * 7 + m3 - 1] = tw[kTwL + m3 * 256 + tid + 128 * pi];
+}
+__device__ __forceinline__ void load_b2_twiddles(float2 (&t2)[15], const float2* __restrict__ tw, int tid) {
+#pragma unroll
+    for (int m2 = 1; m2 < 16; ++m2) t2[m2 - 1] = tw[kTwS + m2 * 16 + (tid & 15)];
+}
+
+template <bool TWO_BUF = false, bool REG_B1 = false, bool REG_B2 = false>
 __device__ __forceinline__ void fft_b(float2 (&y)[16], float2 (&c)[16], const float2* __restrict__ tw,
                                       float2* __restrict__ xb, int tid, int bar_id,
-                                      float2* __restrict__ xb2 = nullptr) {
+                                      float2* __restrict__ xb2 = nullptr, const float2* t1 = nullptr,
+                                      const float2* t2 = nullptr) {
     float2* const xa = TWO_BUF ? xb2 : xb;
     // pass B1
 #pragma unroll
@@ -241,7 +258,7 @@ __device__ __forceinline__ void fft_b(float2 (&y)[16], float2 (&c)[16], const fl
 #pragma unroll
         for (int m3 = 0; m3 < 8; ++m3) {
             float2 val = w[bitrev3(m3)];
-            if (m3 != 0) val = cmul(val, tw[kTwL + m3 * 256 + p]);
+            if (m3 != 0) val = cmul(val, REG_B1 ? t1[pi * 7 + (m3 > 0 ? m3 - 1 : 0)] : tw[kTwL + m3 * 256 + p]);
             xb[p * kXchgStrideP + m3] = val;
         }
     }
@@ -255,7 +272,7 @@ __device__ __forceinline__ void fft_b(float2 (&y)[16], float2 (&c)[16], const fl
 #pragma unroll
     for (int m2 = 0; m2 < 16; ++m2) {
         float2 val = c[bitrev4(m2)];
-        if (m2 != 0) val = cmul(val, tw[kTwS + m2 * 16 + f1]);
+        if (m2 != 0) val = cmul(val, REG_B2 ? t2[m2 > 0 ? m2 - 1 : 0] : tw[kTwS + m2 * 16 + f1]);
         xa[f1 * kXchgStrideA + m2 * 8 + m3] = val;
     }
     group_sync(bar_id);

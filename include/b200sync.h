@@ -283,6 +283,63 @@ int b200sync_cfc_process_device(b200sync_cfc* c, const void* d_in, size_t n, con
                                 size_t n_in_tags, void* d_out, void* cuda_stream);
 
 /* ------------------------------------------------------------------------------
+ * SyncwordWipeoff<c64, float>                               PM/syncword_wipeoff.hpp
+ * CostasLoop<float, float>                                  PM/costas_loop.hpp
+ * (the consumers of the syncword_amplitude / syncword_phase tags behind the
+ *  SymbolFilter, PM/packet_receiver.hpp:117-125, 203-218.)
+ * ------------------------------------------------------------------------------ */
+typedef struct b200sync_wo b200sync_wo;
+/* emplaceBlock<SyncwordWipeoff<>>({{"syncword", syncword}}) (:34-36). */
+int b200sync_wo_create(const float* syncword, uint32_t n_syncword, int32_t device, b200sync_wo** out);
+void b200sync_wo_destroy(b200sync_wo* w);
+/* back to the initial state: not inside a syncword (:27-28) */
+int b200sync_wo_start(b200sync_wo* w);
+/* processBulk (:38-91) over a span carrying any number of tags (sorted by index): a tag with
+ * has_syncword (a "syncword_amplitude" key) that arrives while no syncword is being wiped starts one:
+ * the next syncword.size() items are multiplied by the syncword, everything else is copied.  The state
+ * (_in_syncword, _position) carries over to the next call.  Tags are forwarded unchanged by the block's
+ * default tag policy, so none are returned.  in == out is allowed for device spans. */
+int b200sync_wo_process(b200sync_wo* w, const float* in, size_t n, const b200sync_stream_tag* in_tags,
+                        size_t n_in_tags, float* out);
+int b200sync_wo_process_device(b200sync_wo* w, const void* d_in, size_t n, const b200sync_stream_tag* in_tags,
+                               size_t n_in_tags, void* d_out, void* cuda_stream);
+
+#define B200SYNC_CONSTELLATION_PILOT 0
+#define B200SYNC_CONSTELLATION_BPSK 1
+#define B200SYNC_CONSTELLATION_QPSK 2
+typedef struct b200sync_cl_config {
+    double loop_bandwidth;   /* CostasLoop::loop_bandwidth, default 0.01 (PM/costas_loop.hpp:52) */
+    uint32_t constellation;  /* CostasLoop::constellation, default BPSK  (:53-54)                */
+    int32_t device;
+} b200sync_cl_config;
+typedef struct b200sync_cl b200sync_cl;
+/* emplaceBlock<CostasLoop<>>({settings}) + settingsChanged(): loop coefficients K1, K2 from the cubic
+ * in loop_bandwidth (:56-90). */
+int b200sync_cl_create(const b200sync_cl_config* cfg, b200sync_cl** out);
+void b200sync_cl_destroy(b200sync_cl* c);
+/* back to the initial state: _phase = _freq = 0 (:22-23) */
+int b200sync_cl_start(b200sync_cl* c);
+const char* b200sync_cl_last_error(void);   /* shared by the b200sync_wo_* and b200sync_cl_* calls */
+/* the float coefficients _k1, _k2 (:88-89) */
+int b200sync_cl_info(const b200sync_cl* c, float* k1, float* k2);
+/* processBulk (:94-149) over a span carrying any number of tags (sorted by index): a tag with
+ * has_syncword (a "syncword_phase" key) does set_phase(sw.syncword_phase) before its item (:102-107).
+ * The stretches between such tags are independent and run one GPU thread each; the loop state at the end
+ * of the span stays on the device for the next call.  in == out is allowed for device spans. */
+int b200sync_cl_process(b200sync_cl* c, const float* in, size_t n, const b200sync_stream_tag* in_tags,
+                        size_t n_in_tags, float* out);
+int b200sync_cl_process_device(b200sync_cl* c, const void* d_in, size_t n, const b200sync_stream_tag* in_tags,
+                               size_t n_in_tags, void* d_out, void* cuda_stream);
+/* Fuses a SyncwordWipeoff{syncword} block into the loop's load stage: the span handed to
+ * b200sync_cl_process* is then the INPUT of SyncwordWipeoff and the output that of the CostasLoop behind
+ * it (PM/packet_receiver.hpp:203-218; PayloadMetadataInsert between them passes items through) — one
+ * pass over the symbols instead of two, bit-identical to running the two contexts back to back.
+ * n_syncword = 0 removes the fusion.  Call after create()/start() and before the first process call. */
+int b200sync_cl_fuse_wipeoff(b200sync_cl* c, const float* syncword, uint32_t n_syncword);
+/* the loop state after the last processed item (copied from the device; synchronises) */
+int b200sync_cl_state(b200sync_cl* c, float* phase, float* freq);
+
+/* ------------------------------------------------------------------------------
  * SyncwordDetectionFilter<c64>                    PM/syncword_detection_filter.hpp
  * Control logic only (which syncword tags survive while inside a packet) plus the pass-through
  * copy of host spans; with device-resident data pass in = out = NULL and only the counts matter.

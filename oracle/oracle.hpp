@@ -476,6 +476,139 @@ public:
 };
 
 // ----------------------------------------------------------------------------
+// SyncwordWipeoff<c64, float> — PM/syncword_wipeoff.hpp:38-91.
+// processBulk() takes one chunk whose FIRST sample may carry a tag with a
+// "syncword_amplitude" key (has_tag).
+// ----------------------------------------------------------------------------
+class SyncwordWipeoff
+{
+public:
+    std::vector<float> syncword;
+    bool _in_syncword = false;
+    size_t _position = 0;
+
+    void processBulk(const c64* in, size_t n, c64* out, bool has_tag)
+    {
+        if (!_in_syncword && has_tag) { // :52-61
+            _in_syncword = true;
+            _position = 0;
+        }
+        size_t j = 0;
+        if (_in_syncword) { // :65-75
+            const size_t m = std::min(n, syncword.size() - _position);
+            for (; j < m; ++j) {
+                // std::complex<float> * float scales both parts
+                out[j] = c64(in[j].real() * syncword[_position], in[j].imag() * syncword[_position]);
+                ++_position;
+            }
+            if (_position == syncword.size()) _in_syncword = false;
+        }
+        if (!_in_syncword) { // :77-82
+            for (; j < n; ++j) out[j] = in[j];
+        }
+    }
+};
+
+// ----------------------------------------------------------------------------
+// CostasLoop<float, float> — PM/costas_loop.hpp:56-149.
+// processBulk() takes one chunk whose FIRST sample may carry a tag with a
+// "syncword_phase" key (has_phase / phase).
+//
+// Two trig arithmetics (like the two FFT arithmetics of oracle_fft.hpp):
+//   Libm   — std::cos / std::sin, what the reference calls (:113-114);
+//   Mirror — the GPU's arithmetic contract (csrc/costas.cuh: b200_sincosf), restated here
+//            op for op so that the CUDA kernel can be pinned bit-for-bit.
+// ----------------------------------------------------------------------------
+enum class TrigKind : int { Libm = 0, Mirror = 1 };
+
+inline void mirror_sincosf(float x, float& s, float& c)
+{
+    const float q = std::rint(x * 0.636619772367581343f);
+    float r = std::fmaf(q, -1.5703125f, x);
+    r = std::fmaf(q, -4.837512969970703125e-4f, r);
+    r = std::fmaf(q, -7.54978995489188216e-8f, r);
+    const float z = r * r;
+    float ps = std::fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f);
+    ps = std::fmaf(ps, z, -1.6666654611e-1f);
+    ps = ps * z;
+    const float sr = std::fmaf(ps, r, r);
+    float pc = std::fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f);
+    pc = std::fmaf(pc, z, 4.166664568298827e-2f);
+    pc = pc * (z * z);
+    const float cr = std::fmaf(-0.5f, z, 1.0f) + pc;
+    const int n = static_cast<int>(q) & 3;
+    const float s0 = (n & 1) ? cr : sr;
+    const float c0 = (n & 1) ? sr : cr;
+    s = (n & 2) ? -s0 : s0;
+    c = ((n + 1) & 2) ? -c0 : c0;
+}
+
+class CostasLoop
+{
+public:
+    enum Constellation : int { PILOT = 0, BPSK = 1, QPSK = 2 }; // PM/constellation.hpp
+    double loop_bandwidth = 0.01;
+    Constellation constellation = BPSK;
+    TrigKind trig = TrigKind::Libm;
+    float _phase = 0, _freq = 0, _k1 = 0, _k2 = 0;
+
+    void settingsChanged() // :56-90
+    {
+        double discriminant_gain = 1.0;
+        if (constellation == QPSK) discriminant_gain = std::numbers::sqrt2;
+        const double loop_bandwidth_2 = loop_bandwidth * loop_bandwidth;
+        const double loop_bandwidth_3 = loop_bandwidth_2 * loop_bandwidth;
+        const double loop_bandwidth_4 = loop_bandwidth_2 * loop_bandwidth_2;
+        const double s = std::cbrt(36.0 * loop_bandwidth_2 +
+                                   std::sqrt(3.0) * std::sqrt(432.0 * loop_bandwidth_4 + 848.0 * loop_bandwidth_3 +
+                                                              624.0 * loop_bandwidth_2 + 204.0 * loop_bandwidth + 25.0) +
+                                   36.0 * loop_bandwidth + 9.0);
+        const double z = -(-12.0 * loop_bandwidth - 6.0) / (3.0 * std::cbrt(6.0) * (2.0 * loop_bandwidth + 1.0) * s) +
+                         (std::cbrt(2.0) * s) / (std::cbrt(9.0) * (2.0 * loop_bandwidth + 1.0)) - 1.0;
+        const double k1 = 1.0 - z * z;
+        const double k2 = (1.0 - z) * (1.0 - z);
+        _k1 = static_cast<float>(k1 / discriminant_gain);
+        _k2 = static_cast<float>(k2 / discriminant_gain);
+    }
+
+    void processBulk(const c64* in, size_t n, c64* out, bool has_phase, float phase) // :94-149
+    {
+        if (has_phase) { // set_phase(), :38-45
+            _phase = phase;
+            _freq = 0;
+        }
+        for (size_t j = 0; j < n; ++j) {
+            float sn, cs;
+            if (trig == TrigKind::Libm) {
+                cs = std::cos(_phase);
+                sn = std::sin(_phase);
+            } else {
+                mirror_sincosf(_phase, sn, cs);
+            }
+            const c64 lo{ cs, -sn };
+            const c64 z_out = cmul_plain(in[j], lo);
+            out[j] = z_out;
+            float error = 0;
+            switch (constellation) {
+            case PILOT: error = z_out.imag(); break;
+            case BPSK: error = z_out.real() * z_out.imag(); break;
+            case QPSK:
+                error = (z_out.real() > 0 ? z_out.imag() : -z_out.imag()) +
+                        (z_out.imag() > 0 ? -z_out.real() : z_out.real());
+                break;
+            }
+            _freq += _k2 * error;
+            _phase += _k1 * error + _freq;
+            if (_phase >= std::numbers::pi_v<float>) {
+                _phase -= 2.0f * std::numbers::pi_v<float>;
+            } else if (_phase < -std::numbers::pi_v<float>) {
+                _phase += 2.0f * std::numbers::pi_v<float>;
+            }
+        }
+    }
+};
+
+// ----------------------------------------------------------------------------
 // PfbArbResampler<c64, c64, float, TRate> — PM/pfb_arb_resampler.hpp:67-182
 // ----------------------------------------------------------------------------
 template <typename TRate>

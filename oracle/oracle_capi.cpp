@@ -126,6 +126,51 @@ void orc_cfc_process(void* h, const float* in, size_t n, float* out, int has_fre
                                                             reinterpret_cast<c64*>(out), has_freq != 0, freq);
 }
 
+// ---- SyncwordWipeoff ----
+void* orc_wo_create(const float* syncword, size_t n)
+{
+    auto w = std::make_unique<SyncwordWipeoff>();
+    w->syncword.assign(syncword, syncword + n);
+    return w.release();
+}
+void orc_wo_destroy(void* h) { delete static_cast<SyncwordWipeoff*>(h); }
+// one chunk; has_tag != 0: the chunk's first sample carries a tag with a syncword_amplitude key
+void orc_wo_process(void* h, const float* in, size_t n, float* out, int has_tag)
+{
+    static_cast<SyncwordWipeoff*>(h)->processBulk(reinterpret_cast<const c64*>(in), n, reinterpret_cast<c64*>(out),
+                                                  has_tag != 0);
+}
+
+// ---- CostasLoop ----
+void* orc_cl_create(double loop_bandwidth, int constellation, int trig_kind)
+{
+    auto c = std::make_unique<CostasLoop>();
+    c->loop_bandwidth = loop_bandwidth;
+    c->constellation = static_cast<CostasLoop::Constellation>(constellation);
+    c->trig = static_cast<TrigKind>(trig_kind);
+    c->settingsChanged();
+    return c.release();
+}
+void orc_cl_destroy(void* h) { delete static_cast<CostasLoop*>(h); }
+// one chunk; has_phase != 0: the chunk's first sample carries a tag with syncword_phase = phase
+void orc_cl_process(void* h, const float* in, size_t n, float* out, int has_phase, float phase)
+{
+    static_cast<CostasLoop*>(h)->processBulk(reinterpret_cast<const c64*>(in), n, reinterpret_cast<c64*>(out),
+                                             has_phase != 0, phase);
+}
+void orc_cl_state(void* h, float* phase, float* freq, float* k1, float* k2)
+{
+    auto* c = static_cast<CostasLoop*>(h);
+    *phase = c->_phase;
+    *freq = c->_freq;
+    *k1 = c->_k1;
+    *k2 = c->_k2;
+}
+void orc_mirror_sincosf(const float* x, size_t n, float* s, float* c)
+{
+    for (size_t i = 0; i < n; ++i) mirror_sincosf(x[i], s[i], c[i]);
+}
+
 // ---- PfbArbResampler ----
 struct ResamplerBox {
     bool dbl;

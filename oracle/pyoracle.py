@@ -100,6 +100,17 @@ def lib():
         L.orc_cfc_create.argtypes = [C.c_size_t]
         L.orc_cfc_destroy.argtypes = [C.c_void_p]
         L.orc_cfc_process.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_double]
+        L.orc_wo_create.restype = C.c_void_p
+        L.orc_wo_create.argtypes = [C.c_void_p, C.c_size_t]
+        L.orc_wo_destroy.argtypes = [C.c_void_p]
+        L.orc_wo_process.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+        L.orc_cl_create.restype = C.c_void_p
+        L.orc_cl_create.argtypes = [C.c_double, C.c_int, C.c_int]
+        L.orc_cl_destroy.argtypes = [C.c_void_p]
+        L.orc_cl_process.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_float]
+        pf = C.POINTER(C.c_float)
+        L.orc_cl_state.argtypes = [C.c_void_p, pf, pf, pf, pf]
+        L.orc_mirror_sincosf.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.orc_resampler_create.restype = C.c_void_p
         L.orc_resampler_create.argtypes = [C.c_double, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t]
         L.orc_resampler_destroy.argtypes = [C.c_void_p]
@@ -284,6 +295,84 @@ class CoarseFrequencyCorrection:
             if b > a or f is not None:
                 out[a:b] = self.process_bulk(x[a:b], f)
         return out
+
+
+def _chunked(x, tags, fn):
+    """Whole stream with (index, value) tags: the runtime cuts chunks so that every tag sits on the first
+    sample of a chunk (GR/Block.hpp:1501-1508); fn(chunk, value_or_None) -> out chunk."""
+    x = _c64(x)
+    out = np.empty_like(x)
+    cuts = [0] + [int(i) for i, _ in tags] + [x.size]
+    vals = [None] + [v for _, v in tags]
+    for a, b, v in zip(cuts[:-1], cuts[1:], vals):
+        if b > a:
+            out[a:b] = fn(x[a:b], v)
+    return out
+
+
+class SyncwordWipeoff:
+    """Restated SyncwordWipeoff<c64, float> (PM/syncword_wipeoff.hpp)."""
+
+    def __init__(self, syncword):
+        sw = np.ascontiguousarray(syncword, dtype=np.float32)
+        self._h = lib().orc_wo_create(sw.ctypes.data, sw.size)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_wo_destroy(self._h)
+            self._h = None
+
+    def process_bulk(self, x, has_tag=False):
+        x = _c64(x)
+        out = np.empty_like(x)
+        lib().orc_wo_process(self._h, x.ctypes.data, x.size, out.ctypes.data, int(bool(has_tag)))
+        return out
+
+    def run(self, x, tag_indices):
+        """Whole stream; a syncword_amplitude tag at every index of `tag_indices` (sorted, distinct)."""
+        return _chunked(x, [(i, True) for i in tag_indices], lambda c, v: self.process_bulk(c, v is not None))
+
+
+TRIG_LIBM = 0    # std::cos / std::sin, as the reference
+TRIG_MIRROR = 1  # bit-exact mirror of the GPU's b200_sincosf (csrc/costas.cuh)
+PILOT, BPSK_LOOP, QPSK_LOOP = 0, 1, 2
+
+
+class CostasLoop:
+    """Restated CostasLoop<float, float> (PM/costas_loop.hpp)."""
+
+    def __init__(self, loop_bandwidth=0.01, constellation=BPSK_LOOP, trig=TRIG_LIBM):
+        self._h = lib().orc_cl_create(float(loop_bandwidth), int(constellation), int(trig))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_cl_destroy(self._h)
+            self._h = None
+
+    def process_bulk(self, x, phase=None):
+        """One chunk; `phase` is the syncword_phase of the tag on its first sample (None: no tag)."""
+        x = _c64(x)
+        out = np.empty_like(x)
+        lib().orc_cl_process(self._h, x.ctypes.data, x.size, out.ctypes.data, int(phase is not None),
+                             float(phase if phase is not None else 0.0))
+        return out
+
+    def run(self, x, tags):
+        """Whole stream with (index, syncword_phase) tags (sorted, distinct indices)."""
+        return _chunked(x, list(tags), self.process_bulk)
+
+    def state(self):
+        """(_phase, _freq, _k1, _k2)"""
+        v = [C.c_float() for _ in range(4)]
+        lib().orc_cl_state(self._h, *[C.byref(a) for a in v])
+        return tuple(a.value for a in v)
+
+
+def mirror_sincosf(x):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    s, c = np.empty_like(x), np.empty_like(x)
+    lib().orc_mirror_sincosf(x.ctypes.data, x.size, s.ctypes.data, c.ctypes.data)
+    return s, c
 
 
 class PfbArbResampler:

@@ -281,3 +281,102 @@ def test_coarse_frequency_correction_restatement(oracle):
     y = oracle.CoarseFrequencyCorrection(26).run(x, [(100, 0.01), (126, 0.02)])
     assert np.array_equal(y[:152], x[:152])
     assert abs(np.angle(y[153] * np.conj(y[152])) + 0.02) < 1e-6
+
+
+# ---------------------------------------------------------------- SyncwordWipeoff / CostasLoop (§8(f) rank 2)
+_QA_WIPEOFF_SYNCWORD = [1, 1, 1, 1, 1, 1, -1, -1, 1, -1, 1, 1, 1, -1, -1, -1, 1, -1, -1, -1, 1, -1, -1, 1, -1, -1, 1, 1,
+                        1, -1, -1, -1, 1, 1, -1, 1, 1, -1, -1, -1, 1, 1, -1, 1, -1, 1, 1, 1, -1, 1, 1, -1, 1, -1, 1, -1,
+                        -1, 1, -1, -1, 1, 1, 1, 1]  # test/qa_syncword_wipeoff.cpp:20-25
+
+
+def test_syncword_wipeoff_reference_qa(oracle):
+    """test/qa_syncword_wipeoff.cpp:14-49: a ramp whose syncword stretches (at 10, 100, 250) were multiplied
+    by the syncword comes back as the ramp."""
+    n = 1000
+    expected = np.arange(n).astype(np.complex64)
+    v = expected.copy()
+    sw = np.array(_QA_WIPEOFF_SYNCWORD, np.float32)
+    positions = [10, 100, 250]
+    for p in positions:
+        v[p:p + 64] *= sw
+    got = oracle.SyncwordWipeoff(sw).run(v, positions)
+    assert np.array_equal(got, expected)
+    # a tag that arrives while a syncword is still being wiped is not looked at (:52); the state survives
+    # any chunking (:65-75)
+    w = oracle.SyncwordWipeoff(sw)
+    x = np.ones(300, np.complex64)
+    got = w.run(x, [5, 40, 69, 200])
+    want = x.copy()
+    want[5:69] *= sw
+    want[69:133] *= sw
+    want[200:264] *= sw
+    assert np.array_equal(got, want)
+
+
+def _costas_qa_input(constellation, n, seed):
+    rng = np.random.default_rng(seed)
+    d = rng.integers(0, 4, n)
+    if constellation == 0:
+        v = np.ones(n, np.complex64)
+    elif constellation == 1:
+        v = np.where(d % 2 != 0, -1.0, 1.0).astype(np.complex64)
+    else:
+        a = np.float32(1.0 / np.sqrt(2.0))
+        v = (np.where(d % 2 == 0, a, -a) + 1j * np.where(d // 2 == 0, a, -a)).astype(np.complex64)
+    return v
+
+
+@pytest.mark.parametrize("trig", [0, 1])
+@pytest.mark.parametrize("constellation", [0, 1, 2])
+def test_costas_loop_reference_qa(oracle, constellation, trig):
+    """test/qa_costas_loop.cpp:16-66: PILOT / BPSK / QPSK symbols through Rotator(0.01) and the loop; after
+    1000 symbols every output is within 1e-2 of the transmitted symbol.  Both trig arithmetics."""
+    n = 100000
+    v = _costas_qa_input(constellation, n, 5 + constellation)
+    rot = oracle.rotator(v, 0.01)
+    out = oracle.CostasLoop(0.01, constellation, trig).run(rot, [])
+    w = out[1000:] * np.conj(v[1000:])
+    assert np.max(np.abs(w - 1.0)) < 1e-2
+
+
+def test_costas_loop_coefficients_and_set_phase(oracle):
+    """settingsChanged() (PM/costas_loop.hpp:56-90): K1 = 1 - z^2, K2 = (1 - z)^2 with z the closed-form
+    root for the given B_L*T (evaluated here independently in Python doubles); both grow with the loop
+    bandwidth; QPSK divides by sqrt(2).
+    set_phase() (:38-45, 102-107): a syncword_phase tag sets the NCO phase and zeroes the frequency."""
+    def coeffs(b):
+        s = np.cbrt(36 * b**2 + np.sqrt(3.0) * np.sqrt(432 * b**4 + 848 * b**3 + 624 * b**2 + 204 * b + 25) + 36 * b + 9)
+        z = -(-12 * b - 6) / (3 * np.cbrt(6.0) * (2 * b + 1) * s) + (np.cbrt(2.0) * s) / (np.cbrt(9.0) * (2 * b + 1)) - 1
+        return 1 - z * z, (1 - z) ** 2
+    cl = oracle.CostasLoop(0.01, 1)
+    _, _, k1, k2 = cl.state()
+    w1, w2 = coeffs(0.01)
+    assert k1 == np.float32(w1) and k2 == np.float32(w2)
+    assert 0.02 < k1 < 0.05 and abs((1 - np.sqrt(k2)) ** 2 - (1 - k1)) < 1e-6   # same z in both
+    _, _, h1, h2 = oracle.CostasLoop(0.02, 1).state()
+    assert h1 > k1 and h2 > k2
+    _, _, q1, q2 = oracle.CostasLoop(0.01, 2).state()
+    assert abs(q1 * np.sqrt(2.0) - k1) < 1e-7 and abs(q2 * np.sqrt(2.0) - k2) < 1e-7
+    x = (np.ones(64) * np.exp(1j * 0.7)).astype(np.complex64)
+    out = cl.run(x, [(0, 0.7), (32, -2.0)])
+    assert abs(out[0] - 1.0) < 1e-6                      # derotated by exactly the tag phase
+    assert abs(out[32] - np.exp(1j * 2.7)) < 1e-6        # second tag: phase -2.0, frequency back to 0
+
+
+@pytest.mark.parametrize("constellation", [0, 1, 2])
+def test_costas_loop_trig_arithmetics_agree(oracle, constellation):
+    """The mirror of the GPU's sincos (max abs error < 1.2e-7) against libm inside the loop: the closed loop
+    is contractive, so the two trajectories stay within north_star's filter-output tolerance."""
+    x = np.linspace(-4.0, 4.0, 400001).astype(np.float32)
+    s, c = oracle.mirror_sincosf(x)
+    assert np.max(np.abs(s - np.sin(x.astype(np.float64)))) < 1.2e-7
+    assert np.max(np.abs(c - np.cos(x.astype(np.float64)))) < 1.2e-7
+    n = 50000
+    rng = np.random.default_rng(17)
+    v = _costas_qa_input(constellation, n, 23)
+    noise = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64) * np.float32(0.05)
+    rot = oracle.rotator(v, 0.004) + noise
+    tags = [(0, 0.1), (6208, -1.3), (12416, 3.0), (30000, 0.0)]
+    a = oracle.CostasLoop(0.01, constellation, 0).run(rot, tags)
+    b = oracle.CostasLoop(0.01, constellation, 1).run(rot, tags)
+    assert np.linalg.norm(a - b) / np.linalg.norm(a) < 1e-5
