@@ -198,9 +198,9 @@ def run_chain(args):
     stream."""
     import torch
 
-    from gr4_packet_modem_b200 import FrontEnd, SymbolFilter, SyncwordDetection, _native
+    from gr4_packet_modem_b200 import CostasLoop, FrontEnd, SymbolFilter, SyncwordDetection, _native
     from gr4_packet_modem_b200.blocks import stream_tags_from_detection
-    from gr4_packet_modem_b200.firdes import lowpass_prototype_taps, pfb_matched_filter_taps
+    from gr4_packet_modem_b200.firdes import SYNCWORD, lowpass_prototype_taps, pfb_matched_filter_taps
     from gr4_packet_modem_b200.stimulus import packet_capture_torch
 
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
@@ -224,7 +224,10 @@ def run_chain(args):
     y = torch.empty(n_y, dtype=torch.complex64, device=dev)        # conditioned stream
     dl = torch.empty(n_y, dtype=torch.complex64, device=dev)       # SyncwordDetection's delayed output
     sym = torch.empty(n_y // 4 + 1024, dtype=torch.complex64, device=dev)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    # PM/packet_receiver.hpp:117-125, 203-214: SyncwordWipeoff(bipolar syncword) fused into CostasLoop (defaults)
+    cl = CostasLoop(0.01, "BPSK")
+    cl.fuse_wipeoff(np.where(np.asarray(SYNCWORD) != 0, -1.0, 1.0).astype(np.float32))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
 
     def step(timed=None):
         fe.restart()   # start(): fresh streaming state per pass, allocations kept
@@ -237,9 +240,13 @@ def run_chain(args):
         st = stream_tags_from_detection(tags)
         c_sf, n_sym, otags = sf.process_device(dl.data_ptr(), consumed, sym.data_ptr(), sym.numel(), st, stream)
         ev[3].record()
+        cl.start()
+        cl.process_device(sym.data_ptr(), n_sym, sym.data_ptr(), otags, stream)  # in place
+        ev[4].record()
         torch.cuda.synchronize()
         if timed is not None:
-            timed.append((ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])))
+            timed.append((ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]),
+                          ev[3].elapsed_time(ev[4])))
         return c_in, n_out, consumed, len(recs), n_sym, len(otags)
 
     for _ in range(W):
@@ -261,28 +268,33 @@ def run_chain(args):
     fe_ms = statistics.mean(t[0] for t in timed)
     sd_ms = statistics.mean(t[1] for t in timed)
     sf_ms = statistics.mean(t[2] for t in timed)
+    cl_ms = statistics.mean(t[3] for t in timed)
     peaks = load_peaks()
     line = {
         "metric": "complex Msps (cf32) through RX sync (fused front end + SyncwordDetection + "
-                  + ("" if args.no_cfc else "CoarseFrequencyCorrection + ") + "SymbolFilter)",
+                  + ("" if args.no_cfc else "CoarseFrequencyCorrection + ") + "SymbolFilter + SyncwordWipeoff + CostasLoop)",
         "value": c_in / (ms_per_step * 1e-3) / 1e6, "unit": "Msps", "n_gpus": 1, "steps": args.steps, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"BASELINE configs[2]: fused RX front end (PfbArbResampler 1+1.2ppm + Rotator 0.005) -> "
                                f"SyncwordDetection K={K} (block contract, delayed output) -> "
                                + ("" if args.no_cfc else "CoarseFrequencyCorrection(delay 26) fused into ") +
-                               f"SymbolFilter 32x44 over a "
+                               f"SymbolFilter 32x44 -> SyncwordWipeoff fused into CostasLoop (BPSK, B_L T 0.01) over a "
                                f"2^{args.log2n}-sample synthetic cf32 capture on 1 B200, Es/N0 {args.esn0:g} dB",
                    "samples_per_gpu": n, "l2": "streams (8 B/sample) far larger than L2; no flush needed"},
         "detections_per_step": ndet, "symbols_per_step": n_sym, "symbol_tags_per_step": ntags, "clocks": clocks,
         "gpu_launches": int(launches), "e2e": None,
-        "stage_ms": {"frontend": fe_ms, "syncword_detection": sd_ms, "symbol_filter_incl_host_plan": sf_ms},
+        "stage_ms": {"frontend": fe_ms, "syncword_detection": sd_ms, "symbol_filter_incl_host_plan": sf_ms,
+                     "wipeoff_costas_loop": cl_ms},
         "roofline": hbm_roofline("frontend_kernel", 16.0 * n_out, fe_ms, peaks,
                                  "16 B/sample (8 in + 8 out); 2 x 40 taps x 2 x (mul, add) = 320 separately rounded "
                                  "FP32 instructions per output (bit-exact std::inner_product order): FP32-issue bound"),
         "roofline_symbol_filter": hbm_roofline("symbol_filter_kernel", 10.0 * consumed, sf_ms, peaks,
                                                "10 B/sample (8 in + 8/4 out); stage time includes the host replay of "
                                                "the tag state machine and the segment upload"),
+        "roofline_costas_loop": hbm_roofline("costas_kernel", 16.0 * n_sym, cl_ms, peaks,
+                                             "16 B/symbol (8 in + 8 out), one thread per packet stretch: bound by the "
+                                             "latency of the longest sequential recurrence (one packet), not by HBM"),
     }
     print(json.dumps(line))
 

@@ -55,30 +55,46 @@ costas_kernel(const float2* in, float2* out, const ClSegment* __restrict__ segs,
     }
     float2(*rows)[kClRow] = tile[warp];
     while (__any_sync(kFull, pos < end)) {
-#pragma unroll 4
-        for (int s = 0; s < 32; ++s) {
-            const long long b = __shfl_sync(kFull, pos, s) + lane;
-            const long long e = __shfl_sync(kFull, end, s);
-            const long long w = __shfl_sync(kFull, wipe, s);
-            if (b < e) {
-                float2 x = in[b];
-                if (w != kNoWipe) {  // SyncwordWipeoff: *out_item++ = *in_item++ * syncword[_position++] (:68-70)
-                    const long long d = b - w;
-                    if (d >= 0 && d < n_sync) {
-                        const float sw = __ldg(syncword + d);
-                        x.x = __fmul_rn(x.x, sw);
-                        x.y = __fmul_rn(x.y, sw);
-                    }
-                }
-                rows[s][lane] = x;
+        {
+            // all 32 row loads of the tile are issued before the first one is used (predicated, no branches:
+            // a guarded load inside a branch is not hoisted and every row would expose its own DRAM latency)
+            float2 v[32];
+#pragma unroll
+            for (int s = 0; s < 32; ++s) {
+                const long long b = __shfl_sync(kFull, pos, s) + lane;
+                const long long e = __shfl_sync(kFull, end, s);
+                const float2* src = in + (b < e ? b : 0);
+                v[s] = make_float2(0.0f, 0.0f);
+                if (b < e) v[s] = *src;
+            }
+            // SyncwordWipeoff: *out_item++ = *in_item++ * syncword[_position++] (:68-70); x * 1.0f == x elsewhere
+#pragma unroll
+            for (int s = 0; s < 32; ++s) {
+                const long long b = __shfl_sync(kFull, pos, s) + lane;
+                const long long w = __shfl_sync(kFull, wipe, s);
+                const long long d = b - w;
+                float sw = 1.0f;
+                if (w != kNoWipe && d >= 0 && d < n_sync) sw = __ldg(syncword + d);
+                rows[s][lane] = make_float2(__fmul_rn(v[s].x, sw), __fmul_rn(v[s].y, sw));
             }
         }
         __syncwarp();
         const long long left = end - pos;
         const int cnt = left >= kClTile ? kClTile : (left > 0 ? static_cast<int>(left) : 0);
-        for (int j = 0; j < cnt; ++j) rows[lane][j] = costas_step<CONSTELLATION>(rows[lane][j], st, k1, k2);
+        {
+            // the lane's row lives in registers while the recurrence runs: no shared-memory latency on the
+            // dependent chain phase -> sincos -> error -> phase
+            float2 r[kClTile];
+#pragma unroll
+            for (int j = 0; j < kClTile; ++j) r[j] = rows[lane][j];
+#pragma unroll
+            for (int j = 0; j < kClTile; ++j)
+                if (j < cnt) r[j] = costas_step<CONSTELLATION>(r[j], st, k1, k2);
+#pragma unroll
+            for (int j = 0; j < kClTile; ++j) rows[lane][j] = r[j];
+        }
         __syncwarp();
-#pragma unroll 4
+#pragma unroll 8
         for (int s = 0; s < 32; ++s) {
             const long long b = __shfl_sync(kFull, pos, s) + lane;
             const long long e = __shfl_sync(kFull, end, s);

@@ -9,7 +9,7 @@
 //   * every add / sub / mul below is a separately rounded IEEE binary32 op, in the reference's
 //     evaluation order (std::complex<float> product = (ac - bd, ad + bc), no contraction);
 //   * std::cos / std::sin of the reference (libm, < 1 ulp) are replaced by b200_sincosf below:
-//     Cody-Waite reduction by pi/2 in three fmaf steps, then the classic single-precision minimax
+//     Cody-Waite reduction by pi/2 (quotient by magic-number rounding, three fmaf steps), then the classic single-precision minimax
 //     polynomials on |r| <= pi/4 (max abs error 1.2e-7 on [-4, 4], tests/test_oracle_golden.py).
 //     The libm oracle and the mirror oracle agree to north_star's filter-output tolerance (rel-L2 < 1e-5).
 #pragma once
@@ -20,7 +20,11 @@ namespace b200sync {
 enum ClConstellation : int { kClPilot = 0, kClBpsk = 1, kClQpsk = 2 };
 
 __device__ __forceinline__ void b200_sincosf(float x, float& s, float& c) {
-    const float q = rintf(__fmul_rn(x, 0.636619772367581343f));  // nearest multiple of pi/2
+    // nearest multiple of pi/2 by the add-and-subtract-1.5*2^23 idiom (two FADDs on the FMA pipe instead of
+    // FRND + F2I on the quarter-rate conversion pipe, which sit on the loop's critical path); equal to
+    // rintf() for |x| < 2^22 * pi/2, and the oracle mirrors this very formulation
+    const float qb = __fadd_rn(__fmul_rn(x, 0.636619772367581343f), 12582912.0f);
+    const float q = __fsub_rn(qb, 12582912.0f);
     float r = __fmaf_rn(q, -1.5703125f, x);
     r = __fmaf_rn(q, -4.837512969970703125e-4f, r);
     r = __fmaf_rn(q, -7.54978995489188216e-8f, r);
@@ -33,7 +37,7 @@ __device__ __forceinline__ void b200_sincosf(float x, float& s, float& c) {
     pc = __fmaf_rn(pc, z, 4.166664568298827e-2f);
     pc = __fmul_rn(pc, __fmul_rn(z, z));
     const float cr = __fadd_rn(__fmaf_rn(-0.5f, z, 1.0f), pc);
-    const int n = static_cast<int>(q) & 3;
+    const int n = __float_as_int(qb) & 3;  // 12582912 = 0xC00000 is a multiple of 4: the low mantissa bits are q mod 4
     const float s0 = (n & 1) ? cr : sr;
     const float c0 = (n & 1) ? sr : cr;
     s = (n & 2) ? -s0 : s0;

@@ -523,7 +523,8 @@ enum class TrigKind : int { Libm = 0, Mirror = 1 };
 
 inline void mirror_sincosf(float x, float& s, float& c)
 {
-    const float q = std::rint(x * 0.636619772367581343f);
+    const float qb = x * 0.636619772367581343f + 12582912.0f; // round to nearest even by adding 1.5 * 2^23
+    const float q = qb - 12582912.0f;
     float r = std::fmaf(q, -1.5703125f, x);
     r = std::fmaf(q, -4.837512969970703125e-4f, r);
     r = std::fmaf(q, -7.54978995489188216e-8f, r);
@@ -536,7 +537,7 @@ inline void mirror_sincosf(float x, float& s, float& c)
     pc = std::fmaf(pc, z, 4.166664568298827e-2f);
     pc = pc * (z * z);
     const float cr = std::fmaf(-0.5f, z, 1.0f) + pc;
-    const int n = static_cast<int>(q) & 3;
+    const int n = static_cast<int>(std::bit_cast<uint32_t>(qb) & 3u);
     const float s0 = (n & 1) ? cr : sr;
     const float c0 = (n & 1) ? sr : cr;
     s = (n & 2) ? -s0 : s0;

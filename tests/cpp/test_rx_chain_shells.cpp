@@ -1,6 +1,6 @@
 // Drives the C++ block shells of the whole RX synchronisation chain the way the GR4 runtime does:
 //   PfbArbResamplerB200 -> RotatorB200 -> SyncwordDetectionB200 -> SyncwordDetectionFilterB200
-//     -> CoarseFrequencyCorrectionB200 -> SymbolFilterB200
+//     -> CoarseFrequencyCorrectionB200 -> SymbolFilterB200 -> SyncwordWipeoffB200 -> CostasLoopB200
 // Each stage is offered bounded chunks that start at tags (GR/Block.hpp:1501-1508), its consume()/publish()
 // calls are honoured, and the tags it publishes are carried to the next stage with absolute indices.
 // A stand-in for the header parser answers every forwarded syncword with a parsed_header message.
@@ -18,6 +18,8 @@
 #include <vector>
 
 #include "../../gr4_packet_modem_b200/blocks/coarse_frequency_correction_b200.hpp"
+#include "../../gr4_packet_modem_b200/blocks/costas_loop_b200.hpp"
+#include "../../gr4_packet_modem_b200/blocks/syncword_wipeoff_b200.hpp"
 #include "../../gr4_packet_modem_b200/blocks/pfb_arb_resampler_b200.hpp"
 #include "../../gr4_packet_modem_b200/blocks/symbol_filter_b200.hpp"
 #include "../../gr4_packet_modem_b200/blocks/syncword_detection_b200.hpp"
@@ -228,6 +230,45 @@ int main(int argc, char** argv)
                     symf.size() == sym.size() && t_f.size() == t_sf.size() &&
                             std::memcmp(symf.data(), sym.data(), sym.size() * sizeof(c64)) == 0 ? 1 : 0);
     }
+
+    // PM/packet_receiver.hpp:117-125, 203-214: SymbolFilter -> SyncwordWipeoff(bipolar syncword) ->
+    // [PayloadMetadataInsert: items pass through] -> CostasLoop (defaults)
+    std::vector<float> syncword_bipolar;
+    for (auto bit : detection.syncword) syncword_bipolar.push_back(bit ? -1.0f : 1.0f);
+    std::vector<c64> wiped, locked;
+    TagList t_wo, t_cl;
+    gr::packet_modem::SyncwordWipeoffB200 wipeoff;
+    wipeoff.syncword = syncword_bipolar;
+    wipeoff.settingsChanged(none, none);
+    wipeoff.start();
+    run_stage("syncword_wipeoff", wipeoff, sym, t_sf, chunk, 1, wiped, t_wo,
+              [&](auto& i, auto& o) { return wipeoff.processBulk(i, o); });
+    gr::packet_modem::CostasLoopB200 costas;
+    costas.settingsChanged(none, none);
+    costas.start();
+    run_stage("costas_loop", costas, wiped, t_wo, chunk, 1, locked, t_cl,
+              [&](auto& i, auto& o) { return costas.processBulk(i, o); });
+    {
+        gr::packet_modem::CostasLoopB200 fused;
+        fused.fused_wipeoff_syncword = syncword_bipolar;
+        fused.settingsChanged(none, none);
+        fused.start();
+        std::vector<c64> lf;
+        TagList t_f;
+        run_stage("fused_wipeoff_costas_loop", fused, sym, t_sf, chunk, 1, lf, t_f,
+                  [&](auto& i, auto& o) { return fused.processBulk(i, o); });
+        std::printf("fused_wipeoff_equals_pair %d\n",
+                    lf.size() == locked.size() && t_f.size() == t_cl.size() &&
+                            std::memcmp(lf.data(), locked.data(), locked.size() * sizeof(c64)) == 0 ? 1 : 0);
+        try {
+            gr::packet_modem::CostasLoopB200 bad;
+            bad.constellation = "8PSK";
+            bad.settingsChanged(none, none);
+            std::printf("costas_error none\n");
+        } catch (const gr::exception& e) { std::printf("costas_error %s\n", e.what()); }
+    }
+    dump(prefix + "_wiped.cf32", wiped);
+    dump(prefix + "_locked.cf32", locked);
 
     dump(prefix + "_resampled.cf32", y);
     dump(prefix + "_rotated.cf32", z);

@@ -175,3 +175,27 @@ def test_cpp_rx_chain_shells(oracle, rx_params, tmp_path):
     assert [i for i, _ in t_sf] == [i for i, _ in ot_all] and len(t_sf) >= len(t_sdf) - 1
     for (_, kv), (_, ph) in zip(t_sf, ot_all):
         assert np.float32(float(kv["syncword_phase"])) == np.float32(ph) and len(kv) == 7
+
+    # SyncwordWipeoff + CostasLoop behind the SymbolFilter (PM/packet_receiver.hpp:117-125, 203-214): the
+    # oracle blocks driven by the SymbolFilter's tags, mirror trig bit for bit, libm within tolerance; in a
+    # locked packet the wiped syncword comes out as 64 symbols of one sign on the real axis
+    from gr4_packet_modem_b200.firdes import SYNCWORD
+
+    assert "fused_wipeoff_equals_pair 1" in lines
+    assert any(l.startswith("costas_error unknown constellation") for l in lines)
+    wiped, locked = load("wiped"), load("locked")
+    sw = np.where(np.asarray(SYNCWORD) != 0, -1.0, 1.0).astype(np.float32)
+    idx = [i for i, _ in t_sf]
+    ow = oracle.SyncwordWipeoff(sw).run(sym, idx)
+    assert np.array_equal(wiped.view(np.uint32), ow.view(np.uint32))
+    ptags = [(i, float(kv["syncword_phase"])) for i, kv in t_sf]
+    ol = oracle.CostasLoop(0.01, 1, oracle.TRIG_MIRROR).run(ow, ptags)
+    assert np.array_equal(locked.view(np.uint32), ol.view(np.uint32))
+    ol_ref = oracle.CostasLoop(0.01, 1, oracle.TRIG_LIBM).run(ow, ptags)
+    assert np.linalg.norm(locked - ol_ref) / np.linalg.norm(ol_ref) < 1e-5
+    good = 0
+    for i in idx:
+        s = locked[i + 8:i + 64]
+        if s.size == 56 and np.all(s.real > 0.3) and np.max(np.abs(s.imag)) < 0.6:
+            good += 1
+    assert good >= len(idx) - 2, (good, len(idx))
