@@ -121,6 +121,9 @@ def lib():
     L.b200sync_sd_process.argtypes = [vp, vp, sz, vp, psz, vp, sz, psz]
     L.b200sync_sd_detect_device.argtypes = [vp, vp, sz, vp, vp, vp, sz, psz, psz]
     L.b200sync_sd_detect_host.argtypes = [vp, vp, sz, vp, sz, psz, psz]
+    L.b200sync_sd_detect_file.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_uint64, vp, sz, psz, psz,
+                                          C.POINTER(C.c_uint64)]
+    L.b200sync_sd_detect_file.restype = C.c_int
     L.b200sync_sd_detect_channels_device.argtypes = [vp, vp, sz, sz, sz, vp, vp, sz, vp, psz]
     L.b200sync_sd_shard_phase1.argtypes = [vp, vp, C.c_uint64, sz, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, sz]
     L.b200sync_sd_shard_phase2.argtypes = [vp, C.c_uint32, vp, sz, psz]

@@ -188,6 +188,27 @@ class SyncwordDetection:
         r = _copy_records(recs, nr.value)
         return nc.value, r, self.records_to_tags(r)
 
+    def detect_file(self, filename, first_item: int = 0, max_items: int | None = None, max_recs: int = 0):
+        """Whole raw cf32 capture file — the format FileSource<c64> reads (PM/file_source.hpp) — staged
+        through pinned buffers (b200sync_sd_detect_file).  Returns (consumed, records, tags, items_read)."""
+        import os
+
+        L = _native.lib()
+        path = os.fsencode(filename)
+        limit = (1 << 64) - 1 if max_items is None else int(max_items)
+        if max_recs <= 0:
+            try:
+                items = max(0, os.path.getsize(filename) // 8 - first_item)
+            except OSError:
+                items = 0
+            max_recs = min(items, limit) // (self.time_threshold + 1) + 2
+        recs = self._rec_buffer(max_recs)
+        nr, nc, ni = C.c_size_t(0), C.c_size_t(0), C.c_uint64(0)
+        check(L.b200sync_sd_detect_file(self._h, path, int(first_item), limit, recs.ctypes.data, max_recs,
+                                        C.byref(nr), C.byref(nc), C.byref(ni)))
+        r = _copy_records(recs, nr.value)
+        return nc.value, r, self.records_to_tags(r), ni.value
+
     def detect_channels_device(self, d_in_ptr: int, n_channels: int, n: int, channel_stride: int = 0,
                                stream_ptr: int = 0, max_recs: int = 0):
         """Batched channel mode (b200sync_sd_detect_channels_device): n_channels independent streams of n

@@ -11,6 +11,7 @@
 //   * buffer management and the streaming bookkeeping (_items_consumed, pending tags).
 #include <algorithm>
 #include <atomic>
+#include <cerrno>
 #include <cmath>
 #include <complex>
 #include <cstdio>
@@ -120,6 +121,10 @@ struct b200sync_sd {
     PeakState* h_chan_state = nullptr;  // pinned
     size_t h_chan_cap = 0;
     cudaEvent_t ev_chan = nullptr;
+    // raw capture ingestion (b200sync_sd_detect_file): pinned staging ring + copy stream
+    float2* h_stage = nullptr;
+    cudaEvent_t ev_stage[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
     // shard
     DevBuf<uint16_t> d_table;
     struct {
@@ -383,6 +388,10 @@ void b200sync_sd_destroy(b200sync_sd* sd) {
     if (sd->h_state) cudaFreeHost(sd->h_state);
     if (sd->h_chan_state) cudaFreeHost(sd->h_chan_state);
     if (sd->ev_chan) cudaEventDestroy(sd->ev_chan);
+    if (sd->h_stage) cudaFreeHost(sd->h_stage);
+    for (auto& e : sd->ev_stage)
+        if (e) cudaEventDestroy(e);
+    if (sd->copy_stream) cudaStreamDestroy(sd->copy_stream);
     for (auto& ln : sd->lanes)
         if (ln.st) {
             cudaStreamSynchronize(ln.st);
@@ -538,39 +547,32 @@ int b200sync_sd_process(b200sync_sd* sd, const float* in, size_t n_in, float* ou
 }
 
 // ------------------------------------------------------------------------------------------
-static int detect_resident(b200sync_sd* sd, const float2* d_in, size_t n, float2* d_out_delayed,
-                           cudaStream_t st, cudaEvent_t* chunk_ready, long long chunk_samples,
-                           b200sync_detection_record* recs, size_t max_recs, size_t* n_recs,
-                           size_t* n_consumed) {
+// offline detection = detect_begin + correlator chunks over [0, nb_total) + detect_finish
+static int detect_begin(b200sync_sd* sd, size_t n, float2* d_out_delayed, cudaStream_t st, long long* nb_total,
+                        long long* P) {
     const long long S = sd->S, F = sd->fft_size, T = sd->T;
-    *n_recs = 0;
-    *n_consumed = 0;
-    if (n < static_cast<size_t>(F)) return 0;
-    const long long nb_total = (static_cast<long long>(n) - F) / S + 1;
-    const long long P = nb_total * S;
-    CU(sd->d_zoff.ensure(static_cast<size_t>(P) + 64));
-    const long long hi_total = std::max(0LL, P - T - 1);
+    *nb_total = (static_cast<long long>(n) - F) / S + 1;
+    *P = *nb_total * S;
+    CU(sd->d_zoff.ensure(static_cast<size_t>(*P) + 64));
+    const long long hi_total = std::max(0LL, *P - T - 1);
     CU(sd->d_ws.ensure(peak_workspace_bytes_sms(hi_total + 1, sd->T, sd->num_sms)));
-    if (int rc = ensure_det(sd, static_cast<size_t>(P / (T + 1) + 2))) return rc;
+    if (int rc = ensure_det(sd, static_cast<size_t>(*P / (T + 1) + 2))) return rc;
     if (int rc = reset_state(sd, st)) return rc;
     if (d_out_delayed) {
         const size_t zeros = std::min<size_t>(sd->delay, n);
         CU(cudaMemsetAsync(d_out_delayed, 0, zeros * sizeof(float2), st));
     }
-    // correlator in chunks (so it can chase H2D copies); the peak stage runs ONCE over the
-    // whole decided range: its sequential table scan costs per launch, not per sample
     sd->ev_valid = false;
     CU(cudaEventRecord(sd->ev[0], st));
-    for (long long b0 = 0; b0 < nb_total; b0 += kOfflineChunkBlocks) {
-        const long long nb = chunk_ready ? std::min(kOfflineChunkBlocks, nb_total - b0) : nb_total;
-        if (chunk_ready) {
-            // wait until the H2D copy covering the last sample of this chunk has landed
-            const long long last_sample = (b0 + nb - 1) * S + F - 1;
-            CU(cudaStreamWaitEvent(st, chunk_ready[last_sample / chunk_samples], 0));
-        }
-        if (int rc = run_chunk(sd, d_in, 0, sd->d_zoff.p, 0, b0, nb, 0, 0, d_out_delayed, st)) return rc;
-        if (!chunk_ready) break;
-    }
+    return 0;
+}
+
+// the peak stage runs ONCE over the whole decided range (its sequential table scan costs per launch,
+// not per sample), then refine + records to the host
+static int detect_finish(b200sync_sd* sd, const float2* d_in, long long P, cudaStream_t st,
+                         b200sync_detection_record* recs, size_t max_recs, size_t* n_recs, size_t* n_consumed) {
+    const long long T = sd->T;
+    const long long hi_total = std::max(0LL, P - T - 1);
     CU(cudaEventRecord(sd->ev[1], st));
     if (hi_total > 0) {
         CU(launch_peak_phase1(sd->d_zoff.p, 0, P, 0, hi_total, sd->T, sd->power_threshold, sd->d_ws.p,
@@ -596,6 +598,30 @@ static int detect_resident(b200sync_sd* sd, const float2* d_in, size_t n, float2
     *n_recs = cnt;
     *n_consumed = static_cast<size_t>(P);
     return 0;
+}
+
+static int detect_resident(b200sync_sd* sd, const float2* d_in, size_t n, float2* d_out_delayed,
+                           cudaStream_t st, cudaEvent_t* chunk_ready, long long chunk_samples,
+                           b200sync_detection_record* recs, size_t max_recs, size_t* n_recs,
+                           size_t* n_consumed) {
+    const long long S = sd->S, F = sd->fft_size;
+    *n_recs = 0;
+    *n_consumed = 0;
+    if (n < static_cast<size_t>(F)) return 0;
+    long long nb_total = 0, P = 0;
+    if (int rc = detect_begin(sd, n, d_out_delayed, st, &nb_total, &P)) return rc;
+    // correlator in chunks (so it can chase H2D copies)
+    for (long long b0 = 0; b0 < nb_total; b0 += kOfflineChunkBlocks) {
+        const long long nb = chunk_ready ? std::min(kOfflineChunkBlocks, nb_total - b0) : nb_total;
+        if (chunk_ready) {
+            // wait until the H2D copy covering the last sample of this chunk has landed
+            const long long last_sample = (b0 + nb - 1) * S + F - 1;
+            CU(cudaStreamWaitEvent(st, chunk_ready[last_sample / chunk_samples], 0));
+        }
+        if (int rc = run_chunk(sd, d_in, 0, sd->d_zoff.p, 0, b0, nb, 0, 0, d_out_delayed, st)) return rc;
+        if (!chunk_ready) break;
+    }
+    return detect_finish(sd, d_in, P, st, recs, max_recs, n_recs, n_consumed);
 }
 
 int b200sync_sd_detect_device(b200sync_sd* sd, const void* d_in, size_t n, void* d_out_delayed,
@@ -653,6 +679,78 @@ int b200sync_sd_detect_host(b200sync_sd* sd, const float* in, size_t n, b200sync
     for (size_t i = 0; i < made; ++i) cudaEventDestroy(ev[i]);
     cudaStreamDestroy(cs);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Raw capture ingestion: the on-disk format of FileSource<std::complex<float>>
+// (PM/file_source.hpp:47-53: fread of sizeof(T)-byte items, no header; apps/README.md:15-19 "raw complex64").
+// The file is read piece by piece into a small ring of pinned staging buffers; each piece goes to the
+// device on a copy stream and the correlator chunks it completes are enqueued behind its event, so disk
+// reads, PCIe copies and kernels overlap.  The capture ends up resident in HBM (8 B/sample).
+int b200sync_sd_detect_file(b200sync_sd* sd, const char* filename, uint64_t first_item, uint64_t max_items,
+                            b200sync_detection_record* recs, size_t max_recs, size_t* n_recs,
+                            size_t* n_consumed, uint64_t* n_items_read) {
+    if (!sd || !filename || !n_recs || !n_consumed || (!recs && max_recs))
+        return fail(B200SYNC_EINVAL, "null argument");
+    CU(cudaSetDevice(sd->device));
+    *n_recs = 0;
+    *n_consumed = 0;
+    if (n_items_read) *n_items_read = 0;
+    FILE* f = std::fopen(filename, "rb");  // PM/file_source.hpp:31-37
+    if (!f) return fail(B200SYNC_EINVAL, std::string("error opening file: ") + std::strerror(errno));
+    struct Closer {
+        FILE* f;
+        ~Closer() { std::fclose(f); }
+    } closer{f};
+    if (fseeko(f, 0, SEEK_END) != 0) return fail(B200SYNC_EUNSUPPORTED, "not a seekable file (FIFOs: use b200sync_sd_process)");
+    const uint64_t items_in_file = static_cast<uint64_t>(ftello(f)) / sizeof(float2);  // whole items only, like fread
+    if (first_item > items_in_file) first_item = items_in_file;
+    const size_t n = static_cast<size_t>(std::min<uint64_t>(items_in_file - first_item, max_items));
+    if (fseeko(f, static_cast<off_t>(first_item * sizeof(float2)), SEEK_SET) != 0)
+        return fail(B200SYNC_EINVAL, std::string("seek failed: ") + std::strerror(errno));
+    if (n_items_read) *n_items_read = n;
+    const long long S = sd->S, F = sd->fft_size;
+    if (n < static_cast<size_t>(F)) return 0;
+    CU(sd->d_xoff.ensure(n));
+    constexpr int kSlots = 3;
+    const size_t piece = 4u << 20;  // 4 Mi items = 32 MiB per read / copy
+    if (!sd->h_stage) {
+        CU(cudaMallocHost(&sd->h_stage, kSlots * piece * sizeof(float2)));
+        for (int i = 0; i < kSlots; ++i) CU(cudaEventCreateWithFlags(&sd->ev_stage[i], cudaEventDisableTiming));
+        CU(cudaStreamCreateWithFlags(&sd->copy_stream, cudaStreamNonBlocking));
+    }
+    cudaStream_t st = sd->stream, cs = sd->copy_stream;
+    long long nb_total = 0, P = 0;
+    if (int rc = detect_begin(sd, n, nullptr, st, &nb_total, &P)) return rc;
+    long long b_done = 0;  // correlator blocks already enqueued
+    size_t off = 0;
+    for (size_t i = 0; off < n; ++i) {
+        const int slot = static_cast<int>(i % kSlots);
+        float2* h = sd->h_stage + static_cast<size_t>(slot) * piece;
+        if (i >= kSlots) CU(cudaEventSynchronize(sd->ev_stage[slot]));  // its previous copy has left the buffer
+        const size_t cnt = std::min(piece, n - off);
+        const size_t got = std::fread(h, sizeof(float2), cnt, f);  // PM/file_source.hpp:52
+        if (got != cnt) {
+            cudaStreamSynchronize(cs);
+            cudaStreamSynchronize(st);
+            return fail(B200SYNC_EINVAL, std::string("error reading from file: ") +
+                                             (std::feof(f) ? "file shrank while reading" : std::strerror(errno)));
+        }
+        CU(cudaMemcpyAsync(sd->d_xoff.p + off, h, cnt * sizeof(float2), cudaMemcpyHostToDevice, cs));
+        CU(cudaEventRecord(sd->ev_stage[slot], cs));
+        off += cnt;
+        // blocks whose last sample is now on its way: b * S + F <= off
+        const long long b_ready = std::min(nb_total, (static_cast<long long>(off) - F) / S + 1);
+        if (b_ready > b_done) {
+            CU(cudaStreamWaitEvent(st, sd->ev_stage[slot], 0));
+            for (long long b0 = b_done; b0 < b_ready; b0 += kOfflineChunkBlocks)
+                if (int rc = run_chunk(sd, sd->d_xoff.p, 0, sd->d_zoff.p, 0, b0,
+                                       std::min(kOfflineChunkBlocks, b_ready - b0), 0, 0, nullptr, st))
+                    return rc;
+            b_done = b_ready;
+        }
+    }
+    return detect_finish(sd, sd->d_xoff.p, P, st, recs, max_recs, n_recs, n_consumed);
 }
 
 // ------------------------------------------------------------------------------------------

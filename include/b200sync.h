@@ -129,6 +129,19 @@ int b200sync_sd_detect_device(b200sync_sd* sd, const void* d_in, size_t n, void*
 int b200sync_sd_detect_host(b200sync_sd* sd, const float* in, size_t n, b200sync_detection_record* recs,
                             size_t max_recs, size_t* n_recs, size_t* n_consumed);
 
+/* Raw capture ingestion: the same over a capture FILE in the format
+ * FileSource<std::complex<float>> reads (PM/file_source.hpp:47-53; apps/packet_receiver_file.cpp:29-31;
+ * apps/README.md:15-19): interleaved little-endian float32 I/Q, no header.  Items [first_item,
+ * first_item + max_items) of the file (clipped to its length; a trailing partial item is ignored, like
+ * fread) are read through pinned staging buffers so disk reads, H2D copies and kernels overlap; the
+ * capture stays resident on the device.  Record indices are relative to first_item.  *n_items_read
+ * (optional) receives the number of items taken from the file.  A missing / unreadable file fails with
+ * the reference's message ("error opening file: ...", :33-36); a FIFO is B200SYNC_EUNSUPPORTED (stream
+ * it through b200sync_sd_process instead). */
+int b200sync_sd_detect_file(b200sync_sd* sd, const char* filename, uint64_t first_item, uint64_t max_items,
+                            b200sync_detection_record* recs, size_t max_recs, size_t* n_recs,
+                            size_t* n_consumed, uint64_t* n_items_read);
+
 /* Batched channel mode (BASELINE config 5, SURVEY §8e "channel mode"): n_channels independent
  * streams of n samples each, channel c at d_in + c * channel_stride complex samples.  Equivalent to
  * n_channels SyncwordDetection block instances (one per channel of the reference flowgraph), each

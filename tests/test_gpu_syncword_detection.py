@@ -270,3 +270,42 @@ def test_batched_channels_equal_single_runs(oracle, rx_params, n_channels, strid
     # a second call on the same context (buffers reused) gives the same answer
     _, per2 = sd.detect_channels_device(d.data_ptr(), n_channels, n, stride)
     assert all(np.array_equal(a.view(np.uint8), b.view(np.uint8)) for a, b in zip(per, per2))
+
+
+def test_detect_file_equals_detect_host(oracle, rx_params, tmp_path):
+    """Raw capture ingestion: a cf32 file in FileSource<c64>'s format
+    (PM/file_source.hpp:47-53), larger than the staging ring (3 x 32 MiB) so that slots are reused, gives
+    the records of the same samples handed over in host memory; offsets, a trailing partial item, short
+    and missing files behave like fread / the reference's error."""
+    from gr4_packet_modem_b200 import SyncwordDetection
+    from gr4_packet_modem_b200.blocks import B200SyncError
+    from gr4_packet_modem_b200.stimulus import packet_capture
+
+    n = (1 << 24) + 12345   # 128 MiB + a ragged tail: 5 pieces through 3 slots
+    base, _ = packet_capture(1 << 22, seed=21, esn0_db=12.0, cfo=0.004, payload_bytes=300)
+    x = np.tile(base, n // base.size + 1)[:n]
+    path = tmp_path / "capture.cf32"
+    with open(path, "wb") as f:
+        x.tofile(f)
+        f.write(b"\x01\x02\x03")   # partial trailing item: ignored like fread's item count
+    sd = SyncwordDetection(**rx_params, min_freq_bin=-4, max_freq_bin=4)
+    c0, r0, t0 = sd.detect_host(x)
+    c1, r1, t1, items = sd.detect_file(path)
+    assert items == n and c1 == c0 and len(r1) == len(r0) > 1000
+    assert r1.tobytes() == r0.tobytes() and t1.tobytes() == t0.tobytes()
+    # window of the file: indices relative to first_item
+    first, cnt = 1000003, 3000000
+    c2, r2, _ = sd.detect_host(x[first:first + cnt])
+    c3, r3, _, items = sd.detect_file(path, first_item=first, max_items=cnt)
+    assert items == cnt and c3 == c2 and r3.tobytes() == r2.tobytes()
+    # the mirror oracle on a prefix of the file
+    m = 1 << 20
+    o = oracle.SyncwordDetection(**rx_params, min_freq_bin=-4, max_freq_bin=4, fft_kind=oracle.FFT_MIRROR)
+    oc, _, otags = o.run(x[:m], chunk=1 << 16)
+    c4, r4, t4, _ = sd.detect_file(path, max_items=m)
+    assert c4 == oc and t4["index"].tolist() == [t.index for t in otags]
+    # fewer items than one FFT block: nothing consumed (:215-227); beyond the end: empty
+    assert sd.detect_file(path, max_items=2047)[0] == 0
+    assert sd.detect_file(path, first_item=n + 10)[3] == 0
+    with pytest.raises(B200SyncError, match="error opening file"):
+        sd.detect_file(tmp_path / "missing.cf32")
