@@ -42,14 +42,17 @@ def flop_per_sample(K: int, S: int = 1752) -> float:
 
 
 class ClockSampler:
-    """Streams `nvidia-smi -lms 100` for the duration of the timed region (B200_PROFILING.md clocks line)."""
+    """Streams `nvidia-smi -lms 100` (B200_PROFILING.md clocks line).  Started BEFORE the warm-up so that the
+    tool is already streaming when the timed region begins; every row is stamped on arrival and only rows
+    that arrived inside [mark_begin(), stop()] count.  A timed region shorter than the sampling period can
+    see no row at all: then the rows of the warm-up (same kernels, same load) are used and `window` says so."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.proc = index, None
+        self.index, self.proc, self.rows, self.t_begin, self.thread = index, None, [], None, None
 
     def start(self):
         try:
@@ -58,31 +61,47 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
 
     def stop(self) -> dict:
-        rows = []
+        t_end = time.perf_counter()
         if self.proc is not None:
             self.proc.terminate()
             try:
-                out, _ = self.proc.communicate(timeout=5)
+                self.proc.wait(timeout=5)
             except Exception:
                 self.proc.kill()
-                out = ""
-            rows = [[c.strip() for c in l.split(",")] for l in out.strip().splitlines()]
-        ok = [r for r in rows if len(r) >= 7]
+            if self.thread is not None:
+                self.thread.join(timeout=2)
+        ok = [(t, r) for t, r in self.rows if len(r) >= 7]
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        inside = [r for t, r in ok if t0 <= t <= t_end + 0.15]
+        window = "timed region"
+        if not inside:
+            inside, window = [r for _, r in ok][-5:], "warm-up (timed region shorter than the sampling period)"
 
         def num(v):
             try:
                 return float(v)
             except ValueError:
                 return None
-        sm = [num(r[0]) for r in ok if num(r[0]) is not None]
-        mx = [num(r[1]) for r in ok if num(r[1]) is not None]
-        pw = [num(r[2]) for r in ok if num(r[2]) is not None]
+        sm = [num(r[0]) for r in inside if num(r[0]) is not None]
+        mx = [num(r[1]) for r in inside if num(r[1]) is not None]
+        pw = [num(r[2]) for r in inside if num(r[2]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in ok for i in range(4) if r[3 + i] == "Active"})
+        reasons = sorted({names[i] for r in inside for i in range(4) if r[3 + i] == "Active"})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def workload_config(log2n: int, K: int, esn0: float = 20.0, thr: float = 9.5) -> dict:
@@ -201,7 +220,7 @@ def run_chain(args):
     from gr4_packet_modem_b200 import CostasLoop, FrontEnd, SymbolFilter, SyncwordDetection, _native
     from gr4_packet_modem_b200.blocks import stream_tags_from_detection
     from gr4_packet_modem_b200.firdes import SYNCWORD, lowpass_prototype_taps, pfb_matched_filter_taps
-    from gr4_packet_modem_b200.stimulus import packet_capture_torch
+    from gr4_packet_modem_b200.stimulus import DeviceStimulus
 
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         raise SystemExit("--workload chain is a single-GPU workload")
@@ -212,7 +231,7 @@ def run_chain(args):
     W = max(args.warmup, 3)
     lib = _native.lib()
     stream = torch.cuda.current_stream().cuda_stream
-    raw = packet_capture_torch(n, dev, seed=1, esn0_db=args.esn0, cfo=0.0)
+    raw = DeviceStimulus(seed=1, esn0_db=args.esn0, cfo=0.0).generate(n, dev)  # native generator, csrc/stimulus.cu
     rate = float(np.float32(1.0) + np.float32(1e-6) * np.float32(1.2))
     fe_taps = lowpass_prototype_taps(32, 40)
     sf_taps = pfb_matched_filter_taps()
@@ -249,12 +268,13 @@ def run_chain(args):
                           ev[3].elapsed_time(ev[4])))
         return c_in, n_out, consumed, len(recs), n_sym, len(otags)
 
+    sampler = ClockSampler(0)
+    sampler.start()
     for _ in range(W):
         step()
     torch.cuda.synchronize()
     launches0 = lib.b200sync_launch_count()
-    sampler = ClockSampler(0)
-    sampler.start()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     timed = []
     e0.record()
@@ -304,7 +324,7 @@ def run_channels(args):
     import torch
 
     from gr4_packet_modem_b200 import SyncwordDetection, _native
-    from gr4_packet_modem_b200.stimulus import packet_capture_torch
+    from gr4_packet_modem_b200.stimulus import DeviceStimulus
 
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         raise SystemExit("--workload channels is a single-GPU workload")
@@ -317,14 +337,16 @@ def run_channels(args):
     stream = torch.cuda.current_stream().cuda_stream
     x = torch.empty(C_ * n, dtype=torch.complex64, device=dev)
     for c in range(C_):
-        x[c * n:(c + 1) * n] = packet_capture_torch(n, dev, seed=100 + c, esn0_db=args.esn0, cfo=0.005)
+        DeviceStimulus(seed=100 + c, esn0_db=args.esn0, cfo=0.005).generate_device(x[c * n:].data_ptr(), n, 0, stream)
+    torch.cuda.synchronize()
     sd = SyncwordDetection(**rx_settings(args.bins, args.thr), device=0)
+    sampler = ClockSampler(0)
+    sampler.start()
     for _ in range(W):
         consumed, per = sd.detect_channels_device(x.data_ptr(), C_, n, n, stream)
     torch.cuda.synchronize()
     launches0 = lib.b200sync_launch_count()
-    sampler = ClockSampler(0)
-    sampler.start()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -394,7 +416,7 @@ def main():
     import torch.distributed as dist
 
     from gr4_packet_modem_b200 import SyncwordDetection, _native
-    from gr4_packet_modem_b200.stimulus import packet_capture_torch
+    from gr4_packet_modem_b200.stimulus import DeviceStimulus
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -422,7 +444,9 @@ def main():
     total_blocks, fb, nbk = shard.total_blocks, shard.first_block, shard.n_blocks
     seg0 = shard.first_sample
     seg_n = shard.n_samples if world > 1 else n_per
-    x = packet_capture_torch(seg_n, dev, seed=1, esn0_db=args.esn0, cfo=0.005, start=seg0)
+    # the capture is written into HBM by the native generator (csrc/stimulus.cu): every sample is a function
+    # of (seed, absolute index), so each rank generates exactly its own shard + halo of the same stream
+    x = DeviceStimulus(seed=1, esn0_db=args.esn0, cfo=0.005, device=local).generate(seg_n, dev, seg0)
     torch.cuda.synchronize()
     max_recs = seg_n // (TAU + 1) + 2
 
@@ -441,20 +465,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(W):
         step_device()
     barrier()
     launches0 = lib.b200sync_launch_count()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     consumed = ndet = 0
     corr_ms = []
     for _ in range(args.steps):
         consumed, ndet = step_device()
-        if world == 1:
-            corr_ms.append(sd.last_timings())
+        corr_ms.append(sd.last_timings())
+    shard_samples = consumed  # this rank's samples per step: what ITS correlate launch processed
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -518,17 +543,17 @@ def main():
         cm = statistics.mean(d["correlate_ms"] for d in corr_ms)
         pm = statistics.mean(d["peaks_ms"] for d in corr_ms)
         rm = statistics.mean(d["refine_ms"] for d in corr_ms)
-        ach = consumed * BYTES_PER_SAMPLE / (cm * 1e-3) / 1e9
+        ach = shard_samples * BYTES_PER_SAMPLE / (cm * 1e-3) / 1e9  # rank 0's launch (every rank runs the same shape)
         roofline = {"bound": "hbm", "kernel": "correlate_kernel", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach / hbm_peak, "traffic": measured_traffic(args.log2n, K),
-                    "algorithmic_bytes_per_launch": consumed * BYTES_PER_SAMPLE,
+                    "algorithmic_bytes_per_launch": shard_samples * BYTES_PER_SAMPLE, "ms_per_launch": cm,
                     "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6650 GB/s",
                     "note": f"K={K} is FP32-issue / shared-memory bound, not HBM bound (SURVEY §8d): "
                             f"{flop_per_sample(K):.0f} nominal flop/sample; ncu (profiles/r1_ncu_summary_v4.md): "
                             "LSU data pipe 83%, FMA pipe 57%, DRAM 8%; traffic = input (with the 17% block "
                             "overlap re-read) + the 4 B/sample intermediate zpow"}
         extra = {"stage_ms": {"correlate": cm, "peaks": pm, "refine_and_copy": rm},
-                 "fp32": {"achieved_tflops": consumed * flop_per_sample(K) / (cm * 1e-3) / 1e12,
+                 "fp32": {"achieved_tflops": shard_samples * flop_per_sample(K) / (cm * 1e-3) / 1e12,
                           "nominal_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12}}
 
     cpu = None

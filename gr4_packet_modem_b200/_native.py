@@ -80,6 +80,13 @@ class ClConfig(C.Structure):
     _fields_ = [("loop_bandwidth", C.c_double), ("constellation", C.c_uint32), ("device", C.c_int32)]
 
 
+class StimConfig(C.Structure):
+    _fields_ = [("taps", C.c_void_p), ("n_taps", C.c_uint32), ("interpolation", C.c_uint32),
+                ("syncword_symbols", C.c_void_p), ("n_syncword", C.c_uint32), ("header_symbols", C.c_uint32),
+                ("payload_symbols", C.c_uint32), ("gap_symbols", C.c_uint32), ("phase_incr", C.c_float),
+                ("noise_amplitude", C.c_float), ("seed", C.c_uint64), ("device", C.c_int32)]
+
+
 class SdfHeader(C.Structure):
     _fields_ = [("invalid_header", C.c_uint32), ("packet_length", C.c_uint64)]
 
@@ -173,6 +180,12 @@ def lib():
                  "b200sync_cl_create", "b200sync_cl_start", "b200sync_cl_info", "b200sync_cl_process",
                  "b200sync_cl_process_device", "b200sync_cl_fuse_wipeoff", "b200sync_cl_state"):
         getattr(L, name).restype = C.c_int
+    L.b200sync_stim_create.argtypes = [C.POINTER(StimConfig), C.POINTER(vp)]
+    L.b200sync_stim_create.restype = C.c_int
+    L.b200sync_stim_destroy.argtypes = [vp]
+    L.b200sync_stim_last_error.restype = C.c_char_p
+    L.b200sync_stim_generate_device.argtypes = [vp, C.c_uint64, sz, vp, vp]
+    L.b200sync_stim_generate_device.restype = C.c_int
     L.b200sync_sdf_create.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
     L.b200sync_sdf_destroy.argtypes = [vp]
     L.b200sync_sdf_start.argtypes = [vp]
@@ -224,4 +237,10 @@ def check_fe(rc: int) -> int:
 def check_cl(rc: int) -> int:
     if rc < 0:
         raise B200SyncError(f"libb200sync error {rc}: {lib().b200sync_cl_last_error().decode()}")
+    return rc
+
+
+def check_stim(rc: int) -> int:
+    if rc < 0:
+        raise B200SyncError(f"libb200sync error {rc}: {lib().b200sync_stim_last_error().decode()}")
     return rc

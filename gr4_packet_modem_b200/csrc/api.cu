@@ -896,8 +896,11 @@ int b200sync_sd_shard_phase1(b200sync_sd* sd, const void* d_in, uint64_t first_s
     if (int rc = ensure_det(sd, static_cast<size_t>((hi - lo) / (T + 1) + 2))) return rc;
     if (int rc = reset_state(sd, st)) return rc;
     CU(sd->d_table.ensure(static_cast<size_t>(T) + 1));
+    sd->ev_valid = false;
+    CU(cudaEventRecord(sd->ev[0], st));
     CU(launch_correlate(static_cast<const float2*>(d_in), in_base, sd->d_zoff.p, z_base, sd->d_hperm.p,
                         (int)sd->K, (int)sd->S, cb0, cb1 - cb0, sd->d_tw.p, nullptr, 0, 0, sd->num_sms, st));
+    CU(cudaEventRecord(sd->ev[1], st));
     if (hi > lo) {
         CU(launch_peak_phase1(sd->d_zoff.p, z_base, cb1 * S, lo, hi, sd->T, sd->power_threshold, sd->d_ws.p,
                               sd->d_ws.cap, sd->d_table.p, sd->num_sms, st));
@@ -933,7 +936,13 @@ int b200sync_sd_shard_phase2(b200sync_sd* sd, uint32_t entry_offset, b200sync_de
         CU(launch_peak_phase2(sh.lo, sh.hi, sd->T, sd->d_ws.p, sd->d_ws.cap, static_cast<int>(entry_offset),
                               sd->d_state.p, sd->d_det_idx.p, (unsigned)sd->d_det_idx.cap, sd->num_sms, sh.st));
     }
+    // stage timing of the shard: correlate = ev0..ev1, peaks = phase-1 rest + phase 2 (the wait for the
+    // table exchange in between is host time and not counted: ev[2] closes phase 2 only), refine = ev2..ev3
+    CU(cudaEventRecord(sd->ev[2], sh.st));
     if (int rc = collect_records(sd, sh.d_in, sh.in_base, sd->d_zoff.p, sh.z_base, sh.st, sd->h_recs)) return rc;
+    CU(cudaEventRecord(sd->ev[3], sh.st));
+    CU(cudaEventSynchronize(sd->ev[3]));
+    sd->ev_valid = true;
     size_t cnt = 0;
     for (const auto& r : sd->h_recs) {
         if (r.index + sd->delay >= static_cast<uint64_t>(sh.P_total)) continue;

@@ -129,3 +129,81 @@ def packet_capture_torch(n_samples: int, device, seed: int = 1, esn0_db: float =
         out[c0:c0 + m] = sig + torch.complex(r * torch.cos(u2), r * torch.sin(u2))
         del sig, u1, u2, r
     return out
+
+
+class DeviceStimulus:
+    """The native generator (csrc/stimulus.cu, b200sync_stim_*): frames -> InterpolatingFirFilter ->
+    Rotator -> + gaussian NoiseSource in one kernel that writes the capture into HBM; every sample a pure
+    function of (seed, absolute index).  Same signal model and parameters as packet_capture()."""
+
+    def __init__(self, seed: int = 1, esn0_db: float | None = 20.0, cfo: float = 0.005, payload_bytes: int = 1500,
+                 sps: int = 4, gap_symbols: int = 0, taps=None, device: int = 0):
+        import ctypes as C
+
+        from . import _native
+
+        self.taps = np.ascontiguousarray(tx_rrc_taps(sps) if taps is None else taps, dtype=np.float32)
+        self.sync = np.ascontiguousarray(1.0 - 2.0 * SYNCWORD.astype(np.float32))
+        self.sps, self.seed, self.cfo = int(sps), int(seed), float(np.float32(cfo))
+        self.header_symbols, self.payload_symbols, self.gap_symbols = 128, (payload_bytes + 4) * 4, int(gap_symbols)
+        self.frame_len = self.sync.size + self.header_symbols + self.payload_symbols + self.gap_symbols
+        # NoiseSource amplitude = sqrt(N0), N0 = 0.32 * sps * 10^(-EsN0/10) (apps/packet_transceiver.cpp:48-52)
+        self.noise_amplitude = 0.0 if esn0_db is None else float(np.float32(math.sqrt(TX_POWER * sps * 10.0 ** (-0.1 * esn0_db))))
+        cfg = _native.StimConfig(self.taps.ctypes.data, self.taps.size, self.sps, self.sync.ctypes.data, self.sync.size,
+                                 self.header_symbols, self.payload_symbols, self.gap_symbols, self.cfo,
+                                 self.noise_amplitude, self.seed, int(device))
+        h = C.c_void_p()
+        self._h = C.c_void_p()
+        _native.check_stim(_native.lib().b200sync_stim_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        try:
+            from . import _native
+
+            if getattr(self, "_h", None) is not None and self._h.value:
+                _native.lib().b200sync_stim_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def generate_device(self, d_out_ptr: int, n: int, first_sample: int = 0, stream_ptr: int = 0) -> None:
+        import ctypes as C
+
+        from . import _native
+
+        _native.check_stim(_native.lib().b200sync_stim_generate_device(self._h, int(first_sample), int(n),
+                                                                       C.c_void_p(d_out_ptr),
+                                                                       C.c_void_p(stream_ptr or None)))
+
+    def generate(self, n: int, device, first_sample: int = 0):
+        """torch.complex64 tensor on `device` holding samples [first_sample, first_sample + n)."""
+        import torch
+
+        out = torch.empty(n, dtype=torch.complex64, device=device)
+        self.generate_device(out.data_ptr(), n, first_sample, torch.cuda.current_stream().cuda_stream)
+        return out
+
+    def symbols(self, k0: int, k1: int) -> np.ndarray:
+        """Host restatement of the symbol sequence [k0, k1) (integer hash of the symbol index)."""
+        k = np.arange(k0, k1, dtype=np.int64)
+        f = np.remainder(np.maximum(k, 0), self.frame_len)
+        sd = (self.seed ^ (self.seed >> 32)) & 0xFFFFFFFF
+        h = hash32(np.maximum(k, 0), (sd * 7919 + 17) & 0xFFFFFFFF)
+        a = np.float32(0.70710678118654752440)
+        q = np.where(h & 1, -a, a).astype(np.float32) + 1j * np.where(h & 2, -a, a).astype(np.float32)
+        s = np.where(f < self.sync.size, self.sync[np.minimum(f, self.sync.size - 1)].astype(np.complex64),
+                     q.astype(np.complex64))
+        s = np.where((f >= self.sync.size + self.header_symbols + self.payload_symbols) | (k < 0), 0, s)
+        return s.astype(np.complex64)
+
+
+def hash32(idx: np.ndarray, salt: int) -> np.ndarray:
+    """csrc/stimulus.cu: stim_hash (same mixing function as _hash32_torch)."""
+    idx = np.asarray(idx, dtype=np.int64).astype(np.uint64)
+    lo, hi = idx & np.uint64(0xFFFFFFFF), (idx >> np.uint64(32)) & np.uint64(0xFFFFFFFF)
+    m = np.uint64(0xFFFFFFFF)
+    h = (lo * np.uint64(2654435761) + hi * np.uint64(40503) + np.uint64(salt)) & m
+    h = ((h ^ (h >> np.uint64(16))) * np.uint64(2246822507)) & m
+    h = ((h ^ (h >> np.uint64(13))) * np.uint64(3266489909)) & m
+    return (h ^ (h >> np.uint64(16))).astype(np.uint64)

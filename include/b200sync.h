@@ -353,6 +353,34 @@ int b200sync_cl_fuse_wipeoff(b200sync_cl* c, const float* syncword, uint32_t n_s
 int b200sync_cl_state(b200sync_cl* c, float* phase, float* freq);
 
 /* ------------------------------------------------------------------------------
+ * On-GPU stimulus: frames -> InterpolatingFirFilter -> Rotator -> + NoiseSource,
+ * PM/interpolating_fir_filter.hpp:93-99, PM/rotator.hpp:56-65, PM/noise_source.hpp:74-78, PM/add.hpp
+ * as wired in apps/packet_transceiver.cpp:60-80, 140-165 — one pass that writes a synthetic capture into
+ * device memory.  Every sample is a pure function of (seed, absolute sample index), so time shards can be
+ * generated independently on different GPUs.
+ * ------------------------------------------------------------------------------ */
+typedef struct b200sync_stim_config {
+    const float* taps;              /* InterpolatingFirFilter::taps (TX RRC, PM/packet_transmitter_rrc_taps.hpp) */
+    uint32_t n_taps;
+    uint32_t interpolation;         /* InterpolatingFirFilter::interpolation = samples per symbol               */
+    const float* syncword_symbols;  /* the syncword as real BPSK symbols (+1 / -1), sent first in every frame   */
+    uint32_t n_syncword;
+    uint32_t header_symbols;        /* QPSK symbols after the syncword (128)                                    */
+    uint32_t payload_symbols;       /* QPSK symbols of the payload ((bytes + 4) * 4)                            */
+    uint32_t gap_symbols;           /* zero symbols between frames (0: back-to-back stream mode)                */
+    float phase_incr;               /* Rotator::phase_incr, rad/sample (0: no rotator)                          */
+    float noise_amplitude;          /* NoiseSource::amplitude, "gaussian": E|n|^2 = amplitude^2 (0: no noise)   */
+    uint64_t seed;
+    int32_t device;
+} b200sync_stim_config;
+typedef struct b200sync_stim b200sync_stim;
+int b200sync_stim_create(const b200sync_stim_config* cfg, b200sync_stim** out);
+void b200sync_stim_destroy(b200sync_stim* s);
+const char* b200sync_stim_last_error(void);
+/* Writes samples [first_sample, first_sample + n) of the endless stream to d_out (asynchronous on cuda_stream). */
+int b200sync_stim_generate_device(b200sync_stim* s, uint64_t first_sample, size_t n, void* d_out, void* cuda_stream);
+
+/* ------------------------------------------------------------------------------
  * SyncwordDetectionFilter<c64>                    PM/syncword_detection_filter.hpp
  * Control logic only (which syncword tags survive while inside a packet) plus the pass-through
  * copy of host spans; with device-resident data pass in = out = NULL and only the counts matter.
