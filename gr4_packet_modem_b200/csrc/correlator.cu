@@ -13,6 +13,7 @@
 // refine_kernel for the sparse set of detected peaks only.
 #include "b200sync_internal.h"
 #include "fft2048.cuh"
+#include "tma.cuh"
 
 namespace b200sync {
 
@@ -78,8 +79,13 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
     const int tid = threadIdx.x & 127;
     float2* xb = tw_s + kTwTotal + g * kCorrXchg;
     float2* xb2 = kCorrTwoBuf ? xb + kXchgFloat2 : xb;
-    load_twiddles(tw_s, tw_g);
-    __syncthreads();
+    {   // the 18 KiB twiddle table: one TMA bulk copy per persistent CTA
+        __shared__ __align__(8) unsigned long long tw_bar;
+        if (threadIdx.x == 0) mbar_init(&tw_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) tma_load_1d(tw_s, tw_g, kTwTotal * sizeof(float2), &tw_bar);
+        mbar_wait(&tw_bar, 0);
+    }
     const int ngroups = blockDim.x >> 7;
     const long long gstride = (long long)gridDim.x * ngroups;
     const int bar_id = 1 + g;
@@ -313,14 +319,17 @@ cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpo
                              const float2* d_tw, float2* d_out_delayed, long long out_base, int delay,
                              int num_sms, cudaStream_t st) {
     if (nb <= 0) return cudaSuccess;
-    static bool attr_set = false;
+    // function attributes are per device: one flag per ordinal (a process may hold contexts on several GPUs)
+    static bool attr_set[64] = {};
     const int groups = kCorrThreads / kGroupThreads;
     const size_t smem = correlate_smem_bytes(groups);
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(correlate_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        e = cudaFuncSetAttribute(correlate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     long long want = (nb + groups - 1) / groups;
     int grid = (int)(want < num_sms ? want : num_sms);

@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "b200sync_internal.h"
+#include "tma.cuh"
 
 namespace b200sync {
 
@@ -128,12 +129,17 @@ frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (t
             if (nt + r < n_end) dst[r] = rot_apply(P, src[r], e[r], nt + r);
         return;
     }
-    {   // taps: straight 128-bit copy (the global layout is the shared layout)
-        const int n4 = (P.fs * P.arm) >> 1;
-        const float4* g4 = reinterpret_cast<const float4*>(td_g);
-        float4* s4 = reinterpret_cast<float4*>(td_s);
-        for (int i = tid; i < n4; i += kFeThreads) s4[i] = __ldg(g4 + i);
-        if (((P.fs * P.arm) & 1) && tid == 0) td_s[P.fs * P.arm - 1] = td_g[P.fs * P.arm - 1];
+    // taps: the global layout is the shared layout, so the whole (tap, diff tap) table is ONE bulk copy by
+    // the TMA engine (cp.async.bulk -> UBLKCP) that runs while the threads stage the input samples below
+    __shared__ __align__(8) unsigned long long tap_bar;
+    const uint32_t tap_bytes = (uint32_t)(P.fs * P.arm) * (uint32_t)sizeof(float2);
+    const bool tap_tma = (tap_bytes & 15u) == 0;  // an odd entry count (8 bytes over) takes the plain copy
+    if (tap_tma) {
+        if (tid == 0) mbar_init(&tap_bar, 1);
+        __syncthreads();
+        if (tid == 0) tma_load_1d(td_s, td_g, tap_bytes, &tap_bar);
+    } else {
+        for (int i = tid; i < P.fs * P.arm; i += kFeThreads) td_s[i] = td_g[i];
     }
     // input span of the tile: [c(n0) - arm - 1, c(n_end-1))
     long long c_first, c_last;
@@ -157,6 +163,7 @@ frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (t
             for (int i = tid; i < span; i += kFeThreads) xin[fe_skew(i)] = sample(lo + i);
         }
     }
+    if (tap_tma) mbar_wait(&tap_bar, 0);
     __syncthreads();
 
     const long long nt = n0 + (long long)tid * kFeR;  // this thread's first output
