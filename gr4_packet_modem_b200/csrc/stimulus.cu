@@ -49,9 +49,9 @@ __host__ __device__ __forceinline__ unsigned int stim_hash(long long idx, unsign
 }
 
 // symbol k of the endless frame sequence: BPSK syncword (real), QPSK header + payload, zeros in the gap
-__device__ __forceinline__ float2 stim_symbol(const StimParams& P, const float* __restrict__ sync_s, long long k) {
+// (f = k mod frame_len is passed in: one 64-bit modulo per thread instead of one per symbol)
+__device__ __forceinline__ float2 stim_symbol(const StimParams& P, const float* __restrict__ sync_s, long long k, int f) {
     if (k < 0) return make_float2(0.0f, 0.0f);
-    const int f = (int)(k % P.frame_len);
     if (f < P.n_sync) return make_float2(sync_s[f], 0.0f);
     if (f >= P.n_sync + P.n_hdr_payload) return make_float2(0.0f, 0.0f);
     const unsigned int h = stim_hash(k, P.sym_salt);
@@ -78,9 +78,13 @@ stimulus_kernel(const StimParams P, const float* __restrict__ taps_poly /*[inter
     const long long s_lo = k * P.interp;
     if (s_lo >= P.first + P.n) return;
     float2 sym[kStimMaxArm];  // sym[j] = symbol k - j: the history, newest first (GR/HistoryBuffer.hpp)
+    int f = (int)(k % P.frame_len);  // position of symbol k in its frame; steps back with wrap-around
 #pragma unroll
     for (int j = 0; j < kStimMaxArm; ++j)
-        if (j < P.arm_len) sym[j] = stim_symbol(P, sync_s, k - j);
+        if (j < P.arm_len) {
+            sym[j] = stim_symbol(P, sync_s, k - j, f);
+            f = (f == 0) ? P.frame_len - 1 : f - 1;
+        }
     for (int arm = 0; arm < P.interp; ++arm) {
         const long long n = s_lo + arm;
         if (n < P.first || n >= P.first + P.n) continue;
