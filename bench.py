@@ -320,69 +320,111 @@ def run_chain(args):
 
 
 def run_channels(args):
-    """BASELINE configs[4], channel mode: 64 independent channels x 2^24 samples in one call."""
+    """BASELINE configs[4], channel mode: `--channels` independent channels x 2^log2n samples.  Under torchrun
+    the channels are partitioned over the ranks (channel c on rank c mod world; strong scaling: the total work
+    is fixed), each rank makes one batched call per step; nothing is exchanged on the data path, the records
+    stay with the rank that owns the channel."""
     import torch
+    import torch.distributed as dist
 
     from gr4_packet_modem_b200 import SyncwordDetection, _native
     from gr4_packet_modem_b200.stimulus import DeviceStimulus
 
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        raise SystemExit("--workload channels is a single-GPU workload")
-    torch.cuda.set_device(0)
-    dev = torch.device("cuda", 0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     C_, n = args.channels, 1 << args.log2n
+    mine = list(range(rank, C_, world))   # this rank's channels
+    Cl = len(mine)
     K = 2 * args.bins + 1
     W = max(args.warmup, 3)
     lib = _native.lib()
     stream = torch.cuda.current_stream().cuda_stream
-    x = torch.empty(C_ * n, dtype=torch.complex64, device=dev)
-    for c in range(C_):
-        DeviceStimulus(seed=100 + c, esn0_db=args.esn0, cfo=0.005).generate_device(x[c * n:].data_ptr(), n, 0, stream)
+    x = torch.empty(max(Cl, 1) * n, dtype=torch.complex64, device=dev)
+    for i, c in enumerate(mine):
+        DeviceStimulus(seed=100 + c, esn0_db=args.esn0, cfo=0.005, device=local).generate_device(
+            x[i * n:].data_ptr(), n, 0, stream)
     torch.cuda.synchronize()
-    sd = SyncwordDetection(**rx_settings(args.bins, args.thr), device=0)
-    sampler = ClockSampler(0)
+    sd = SyncwordDetection(**rx_settings(args.bins, args.thr), device=local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        if Cl == 0:
+            return 0, []
+        return sd.detect_channels_device(x.data_ptr(), Cl, n, n, stream)
+
+    sampler = ClockSampler(local)
     sampler.start()
     for _ in range(W):
-        consumed, per = sd.detect_channels_device(x.data_ptr(), C_, n, n, stream)
-    torch.cuda.synchronize()
+        consumed, per = step()
+    barrier()
     launches0 = lib.b200sync_launch_count()
     sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        consumed, per = sd.detect_channels_device(x.data_ptr(), C_, n, n, stream)
+        consumed, per = step()
     e1.record()
-    torch.cuda.synchronize()
+    barrier()
     clocks = sampler.stop()
     launches = lib.b200sync_launch_count() - launches0
-    ms_per_step = e0.elapsed_time(e1) / args.steps
+    ms = e0.elapsed_time(e1)
+    total = Cl * consumed
+    ndet = int(sum(len(p) for p in per))
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        c = torch.tensor([total, ndet], device=dev, dtype=torch.int64)
+        dist.all_reduce(c)
+        total, ndet = int(c[0].item()), int(c[1].item())
+    ms_per_step = ms / args.steps
     # single-stream runs of the same channels, one after the other, for comparison
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     same = True
-    for c in range(C_):
-        _, r, _ = sd.detect_device(x.data_ptr() + 8 * c * n, n, stream)
-        same = same and np.array_equal(r.view(np.uint8), per[c].view(np.uint8))
+    for i in range(Cl):
+        _, r, _ = sd.detect_device(x.data_ptr() + 8 * i * n, n, stream)
+        same = same and np.array_equal(r.view(np.uint8), per[i].view(np.uint8))
     t1.record()
     torch.cuda.synchronize()
+    if world > 1:
+        f = torch.tensor([1 if same else 0], device=dev, dtype=torch.int64)
+        dist.all_reduce(f, op=dist.ReduceOp.MIN)
+        same = bool(f.item())
+    if rank != 0:
+        dist.destroy_process_group()
+        return
     peaks = load_peaks()
     line = {
         "metric": "complex Msps (cf32) through RX sync (SyncwordDetection, batched channels)",
-        "value": C_ * consumed / (ms_per_step * 1e-3) / 1e6, "unit": "Msps", "n_gpus": 1, "steps": args.steps,
-        "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "value": total / (ms_per_step * 1e-3) / 1e6, "unit": "Msps", "n_gpus": world, "steps": args.steps,
+        "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"BASELINE configs[4] channel mode: {C_} independent channels x 2^{args.log2n} samples, "
-                               f"K={K}, one b200sync_sd_detect_channels_device call per step on 1 B200",
+                               f"K={K}, channels partitioned over {world} B200(s), one "
+                               f"b200sync_sd_detect_channels_device call per rank and step",
                    "channels": C_, "samples_per_channel": n,
                    "l2": "capture (8 B/sample x channels) far larger than L2; no flush needed"},
-        "detections_per_step": int(sum(len(p) for p in per)), "clocks": clocks, "gpu_launches": int(launches),
+        "detections_per_step": ndet, "clocks": clocks, "gpu_launches": int(launches),
         "e2e": None,
-        "sequential_single_stream_ms": t0.elapsed_time(t1), "batched_equals_single_stream": bool(same),
-        "roofline": hbm_roofline("correlate_kernel (whole step)", 8.0 * C_ * consumed, ms_per_step, peaks,
+        "sequential_single_stream_ms_rank0": t0.elapsed_time(t1), "batched_equals_single_stream": bool(same),
+        "roofline": hbm_roofline("correlate_kernel (whole step, rank 0)", 8.0 * Cl * consumed, ms_per_step, peaks,
                                  "whole-step figure; K>=3 is FP32/shared-memory bound (see the detect workload)"),
     }
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

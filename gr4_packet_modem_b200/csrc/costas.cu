@@ -37,8 +37,8 @@ constexpr int kClRow = kClTile + 1;  // float2 row stride: lane l, column j -> b
 template <int CONSTELLATION>
 __global__ void __launch_bounds__(kClWarps * 32)
 costas_kernel(const float2* in, float2* out, const ClSegment* __restrict__ segs,
-              int n_segs, float k1, float k2, ClState* __restrict__ state, const float* __restrict__ syncword,
-              int n_sync) {
+              int n_segs, float k1, float k2, const ClState* __restrict__ state_in, ClState* __restrict__ state_out,
+              const float* __restrict__ syncword, int n_sync) {
     __shared__ float2 tile[kClWarps][32][kClRow];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sg = (blockIdx.x * kClWarps + warp) * 32 + lane;
@@ -50,7 +50,7 @@ costas_kernel(const float2* in, float2* out, const ClSegment* __restrict__ segs,
         pos = s.start;
         end = s.end;
         wipe = s.wipe_start;
-        if (s.carry) st = *state;
+        if (s.carry) st = *state_in;
         else st.phase = s.phase0;
     }
     float2(*rows)[kClRow] = tile[warp];
@@ -103,7 +103,9 @@ costas_kernel(const float2* in, float2* out, const ClSegment* __restrict__ segs,
         __syncwarp();
         if (pos < end) pos += kClTile;
     }
-    if (sg == n_segs - 1) *state = st;  // the last stretch of the span hands its state to the next call
+    // the last stretch of the span hands its state to the next call — through the OTHER slot of a two-slot
+    // buffer, so the CTA of the first stretch can never read a value written by this launch
+    if (sg == n_segs - 1) *state_out = st;
 }
 
 // SyncwordWipeoff alone: the pass-through copy is a device-to-device copy issued by the caller; this kernel
@@ -217,7 +219,8 @@ struct b200sync_cl {
     double loop_bandwidth = 0.01;
     float k1 = 0.0f, k2 = 0.0f;
     bool fresh = true;              // no item processed since start(): the state is (0, 0)
-    ClState* d_state = nullptr;
+    ClState* d_state = nullptr;     // two slots, ping-pong per call
+    int state_cur = 0;              // slot holding the state after the last call
     WipeoffPlanner wipe;            // n_sync == 0: no fused SyncwordWipeoff
     float* d_syncword = nullptr;
     ClSegment* d_segs = nullptr;
@@ -298,21 +301,22 @@ int cl_run(b200sync_cl* c, const float2* d_in, size_t n, const b200sync_stream_t
     switch (c->constellation) {
     case B200SYNC_CONSTELLATION_PILOT:
         costas_kernel<kClPilot><<<grid, kClWarps * 32, 0, st>>>(d_in, d_out, c->d_segs, n_segs, c->k1, c->k2,
-                                                                c->d_state, c->d_syncword, n_sync);
+                                                                c->d_state + c->state_cur, c->d_state + (c->state_cur ^ 1), c->d_syncword, n_sync);
         break;
     case B200SYNC_CONSTELLATION_BPSK:
         costas_kernel<kClBpsk><<<grid, kClWarps * 32, 0, st>>>(d_in, d_out, c->d_segs, n_segs, c->k1, c->k2,
-                                                               c->d_state, c->d_syncword, n_sync);
+                                                               c->d_state + c->state_cur, c->d_state + (c->state_cur ^ 1), c->d_syncword, n_sync);
         break;
     default:
         costas_kernel<kClQpsk><<<grid, kClWarps * 32, 0, st>>>(d_in, d_out, c->d_segs, n_segs, c->k1, c->k2,
-                                                               c->d_state, c->d_syncword, n_sync);
+                                                               c->d_state + c->state_cur, c->d_state + (c->state_cur ^ 1), c->d_syncword, n_sync);
         break;
     }
     count_launch();
     LCU(cudaGetLastError());
     LCU(cudaStreamSynchronize(st));  // the pageable segment vector must outlive the async copy
     c->fresh = false;
+    c->state_cur ^= 1;
     return 0;
 }
 
@@ -422,8 +426,8 @@ int b200sync_cl_create(const b200sync_cl_config* cfg, b200sync_cl** out) {
     loop_coefficients(cfg->loop_bandwidth, c->constellation, &c->k1, &c->k2);
     cudaError_t e = cudaSetDevice(cfg->device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_state, sizeof(ClState));
-    if (e == cudaSuccess) e = cudaMemset(c->d_state, 0, sizeof(ClState));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_state, 2 * sizeof(ClState));
+    if (e == cudaSuccess) e = cudaMemset(c->d_state, 0, 2 * sizeof(ClState));
     if (e != cudaSuccess) {
         b200sync_cl_destroy(c);
         return cl_fail(B200SYNC_ECUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(e));
@@ -451,7 +455,8 @@ int b200sync_cl_start(b200sync_cl* c) {
     c->fresh = true;
     c->wipe.reset();
     LCU(cudaSetDevice(c->device));
-    LCU(cudaMemset(c->d_state, 0, sizeof(ClState)));
+    LCU(cudaMemset(c->d_state, 0, 2 * sizeof(ClState)));
+    c->state_cur = 0;
     return 0;
 }
 
@@ -475,7 +480,7 @@ int b200sync_cl_state(b200sync_cl* c, float* phase, float* freq) {
     if (!c) return cl_fail(B200SYNC_EINVAL, "null context");
     LCU(cudaSetDevice(c->device));
     ClState s;
-    LCU(cudaMemcpy(&s, c->d_state, sizeof(s), cudaMemcpyDeviceToHost));
+    LCU(cudaMemcpy(&s, c->d_state + c->state_cur, sizeof(s), cudaMemcpyDeviceToHost));
     if (phase) *phase = s.phase;
     if (freq) *freq = s.freq;
     return 0;
