@@ -127,6 +127,14 @@ def measured_traffic(log2n: int, K: int, kernel: str = "correlate_kernel"):
         return None
 
 
+def measured_fp32_peak():
+    """FP32 FMA peak measured on this pool's B200 (SURVEY §8d asks for a measured figure), or None."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "r1_fp32_peak.json")))["fp32_fma_tflops"])
+    except Exception:
+        return None
+
+
 def rx_settings(bins: int, thr: float = 9.5):
     from gr4_packet_modem_b200.firdes import BPSK, SYNCWORD, unit_energy_rrc
 
@@ -596,7 +604,10 @@ def main():
                             "overlap re-read) + the 4 B/sample intermediate zpow"}
         extra = {"stage_ms": {"correlate": cm, "peaks": pm, "refine_and_copy": rm},
                  "fp32": {"achieved_tflops": shard_samples * flop_per_sample(K) / (cm * 1e-3) / 1e12,
-                          "nominal_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12}}
+                          "nominal_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12,
+                          "measured_peak_tflops": measured_fp32_peak(),
+                          "note": "achieved = nominal flop (5 N log2 N per FFT, SURVEY §8d) / correlate time; measured "
+                                  "peak = FFMA2 microbenchmark, profiles/r1_fp32_peak.json (an FMA = 2 flop)"}}
 
     cpu = None
     if world == 1 and not args.no_cpu:
