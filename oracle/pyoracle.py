@@ -214,7 +214,10 @@ class SyncwordDetection:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().orc_sd_destroy(self._h)
+            try:
+                lib().orc_sd_destroy(self._h)
+            except Exception:  # interpreter shutdown
+                pass
             self._h = None
 
     def process_bulk(self, x, want_output=True, max_tags=1 << 16):
@@ -273,7 +276,10 @@ class CoarseFrequencyCorrection:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().orc_cfc_destroy(self._h)
+            try:
+                lib().orc_cfc_destroy(self._h)
+            except Exception:  # interpreter shutdown
+                pass
             self._h = None
 
     def process_bulk(self, x, freq=None):
@@ -319,7 +325,10 @@ class SyncwordWipeoff:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().orc_wo_destroy(self._h)
+            try:
+                lib().orc_wo_destroy(self._h)
+            except Exception:  # interpreter shutdown
+                pass
             self._h = None
 
     def process_bulk(self, x, has_tag=False):
@@ -346,7 +355,10 @@ class CostasLoop:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().orc_cl_destroy(self._h)
+            try:
+                lib().orc_cl_destroy(self._h)
+            except Exception:  # interpreter shutdown
+                pass
             self._h = None
 
     def process_bulk(self, x, phase=None):
@@ -386,7 +398,10 @@ class PfbArbResampler:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().orc_resampler_destroy(self._h)
+            try:
+                lib().orc_resampler_destroy(self._h)
+            except Exception:  # interpreter shutdown
+                pass
             self._h = None
 
     def process_bulk(self, x, n_out, timing=False):
@@ -416,7 +431,10 @@ class SymbolFilter:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().orc_symfilt_destroy(self._h)
+            try:
+                lib().orc_symfilt_destroy(self._h)
+            except Exception:  # interpreter shutdown
+                pass
             self._h = None
 
     def process_bulk(self, x, n_out, tag: StreamTag | None = None, max_tags=64):
@@ -439,7 +457,10 @@ class SyncwordDetectionFilter:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().orc_sdf_destroy(self._h)
+            try:
+                lib().orc_sdf_destroy(self._h)
+            except Exception:  # interpreter shutdown
+                pass
             self._h = None
 
     def process_bulk(self, x, n_out=None, tag: StreamTag | None = None, header=None, n_ignored=0):
