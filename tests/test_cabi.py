@@ -38,6 +38,9 @@ def test_library_exports_every_declared_symbol(native):
 def test_struct_layouts_match_header(native):
     assert ctypes.sizeof(native.DetectionRecord) == 48
     assert ctypes.sizeof(native.SyncwordTag) == 40
+    assert ctypes.sizeof(native.StreamTag) == 56
+    assert ctypes.sizeof(native.ClConfig) == 16
+    assert ctypes.sizeof(native.StimConfig) == 64
 
 
 def test_no_cpu_fallback(native):
@@ -52,10 +55,17 @@ def test_no_cpu_fallback(native):
 
     with pytest.raises(B200SyncError):
         SyncwordDetection(unit_energy_rrc(), SYNCWORD, BPSK, -4, 4)
-    from gr4_packet_modem_b200 import CoarseFrequencyCorrection
+    from gr4_packet_modem_b200 import CoarseFrequencyCorrection, CostasLoop, SyncwordWipeoff
+    from gr4_packet_modem_b200.stimulus import DeviceStimulus
 
     with pytest.raises(B200SyncError):
         CoarseFrequencyCorrection(26)
+    with pytest.raises(B200SyncError):
+        CostasLoop(0.01, "QPSK")
+    with pytest.raises(B200SyncError):
+        SyncwordWipeoff([1.0, -1.0])
+    with pytest.raises(B200SyncError):
+        DeviceStimulus(seed=1)
 
 
 def test_product_does_not_reference_oracle():
