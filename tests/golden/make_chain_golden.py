@@ -1,0 +1,87 @@
+"""Regenerates tests/golden/sync_chain_golden.npz: a seeded 2^17-sample capture and what the ORACLE's
+restated blocks make of it along the receiver chain (PM/packet_receiver.hpp:76-125, 195-218):
+SyncwordDetection (independent radix-2 FFT arithmetic) -> CoarseFrequencyCorrection -> SymbolFilter ->
+SyncwordWipeoff -> CostasLoop (libm trig = the reference's arithmetic).
+
+The reference itself cannot be built here, so these vectors pin the oracle — and through it
+the GPU path — across rounds: tests/test_oracle_golden.py::test_chain_golden_pins_oracle (CPU) and
+tests/test_gpu_chain_golden.py (GPU).  Run in the build container:  python tests/golden/make_chain_golden.py"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+
+def oracle_chain(po, x, sf_taps, rrc, syncword_bits, bpsk, payload_bytes):
+    """-> dict of the chain's observable outputs for capture x."""
+    o = po.SyncwordDetection(rrc, syncword_bits, bpsk, -4, 4, 768, 9.5, fft_kind=po.FFT_RADIX2)
+    consumed, delayed, tags = o.run(x, chunk=1 << 16, want_output=True)
+    # SyncwordDetectionFilter: the syncword tag that opens a packet closes the gate for the packet's length
+    block = 4 * (128 + 64 - 16 + 4 * (payload_bytes + 4))   # PM/syncword_detection_filter.hpp:141-152
+    kept, until = [], -1
+    for t in tags:
+        if t.index >= until:
+            kept.append(t)
+            until = t.index + block
+    cfc_delay = (rrc.size - 1) // 2 + 4                       # PM/packet_receiver.hpp:94-95
+    corrected = po.CoarseFrequencyCorrection(cfc_delay).run(delayed, [(t.index, t.freq) for t in kept])
+    sf = po.SymbolFilter(sf_taps, 32, 4, delay=rrc.size - 1)
+    by_index = {t.index: t for t in kept}
+    cuts = sorted(by_index)
+    pos, ys, otags, nout = 0, [], [], 0
+    while pos < corrected.size:
+        end = min([c for c in cuts if c > pos] + [corrected.size])
+        tag = None
+        if pos in by_index:
+            t = by_index[pos]
+            tag = po.StreamTag()
+            tag.has_syncword = True
+            tag.amplitude, tag.time_est, tag.phase, tag.freq, tag.other = t.amplitude, t.time_est, t.phase, t.freq, 0
+        c, ysym, ot = sf.process_bulk(corrected[pos:end], end - pos + 2, tag)
+        otags += [(nout + q.index, q.phase) for q in ot]
+        ys.append(ysym)
+        nout += ysym.size
+        pos += c
+    sym = np.concatenate(ys)
+    sw = np.where(np.asarray(syncword_bits) != 0, -1.0, 1.0).astype(np.float32)
+    wiped = po.SyncwordWipeoff(sw).run(sym, [i for i, _ in otags])
+    locked = po.CostasLoop(0.01, 1, po.TRIG_LIBM).run(wiped, otags)
+    return dict(consumed=np.int64(consumed),
+                tag_index=np.array([t.index for t in tags], np.int64),
+                tag_freq=np.array([t.freq for t in tags], np.float64),
+                tag_phase=np.array([t.phase for t in tags], np.float32),
+                tag_time_est=np.array([t.time_est for t in tags], np.float32),
+                tag_amplitude=np.array([t.amplitude for t in tags], np.float32),
+                tag_freq_bin=np.array([t.freq_bin for t in tags], np.int32),
+                kept_index=np.array([t.index for t in kept], np.int64),
+                symbol_tag_index=np.array([i for i, _ in otags], np.int64),
+                symbol_tag_phase=np.array([p for _, p in otags], np.float32),
+                symbols=sym, locked=locked)
+
+
+def settings():
+    from gr4_packet_modem_b200.firdes import BPSK, SYNCWORD, pfb_matched_filter_taps, unit_energy_rrc
+
+    return unit_energy_rrc(), SYNCWORD, BPSK, np.asarray(pfb_matched_filter_taps(), np.float32)
+
+
+def main():
+    from gr4_packet_modem_b200.stimulus import packet_capture
+    from oracle import pyoracle as po
+
+    po.build(ref=False)
+    payload = 200
+    x, starts = packet_capture(1 << 17, seed=2026, esn0_db=8.0, cfo=0.012, payload_bytes=payload, noise_seed=17)
+    rrc, sw, bpsk, sf_taps = settings()
+    out = oracle_chain(po, x, sf_taps, rrc, sw, bpsk, payload)
+    np.savez_compressed(os.path.join(HERE, "sync_chain_golden.npz"), capture=x, true_starts=starts,
+                        payload_bytes=np.int64(payload), **out)
+    print("tags", out["tag_index"].size, "kept", out["kept_index"].size, "symbols", out["symbols"].size)
+
+
+if __name__ == "__main__":
+    main()

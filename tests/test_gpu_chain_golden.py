@@ -1,0 +1,72 @@
+"""The GPU receiver chain against the committed fixture tests/golden/sync_chain_golden.npz (oracle outputs for a
+seeded capture; generator tests/golden/make_chain_golden.py): SyncwordDetection -> [SyncwordDetectionFilter gate]
+-> CoarseFrequencyCorrection -> SymbolFilter -> SyncwordWipeoff -> CostasLoop through the Python mirrors of the
+C ABI, unfused and fused.  Bars (north_star): detection indices and counts exact; |df| < 1e-5 rad/sample,
+|dphi| < 1e-3 rad; filter outputs relative L2 < 1e-5 (the two closed-form NCOs against the reference's float
+recurrences; 1e-4 behind the Costas loop, whose feedback sees those differences)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a.astype(np.complex128) - b.astype(np.complex128)) / np.linalg.norm(b.astype(np.complex128)))
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_gpu_chain_matches_golden(rx_params, fused):
+    from gr4_packet_modem_b200 import (CoarseFrequencyCorrection, CostasLoop, SymbolFilter, SyncwordDetection,
+                                       SyncwordWipeoff)
+    from gr4_packet_modem_b200.blocks import STREAM_TAG_DTYPE
+    from gr4_packet_modem_b200.firdes import SYNCWORD, pfb_matched_filter_taps
+
+    g = np.load(os.path.join(GOLDEN, "sync_chain_golden.npz"))
+    x, payload = g["capture"], int(g["payload_bytes"])
+    rrc = rx_params["rrc_taps"]
+    sd = SyncwordDetection(**rx_params, min_freq_bin=-4, max_freq_bin=4)
+    consumed, delayed, tags = sd.run(x, chunk=1 << 16, want_output=True)
+    assert consumed == int(g["consumed"])
+    assert [t[1] for t in tags] == g["tag_index"].tolist()
+    kv = [t[2] for t in tags]
+    assert [d["syncword_freq_bin"] for d in kv] == g["tag_freq_bin"].tolist()
+    assert np.max(np.abs(np.array([d["syncword_freq"] for d in kv]) - g["tag_freq"])) < 1e-5
+    dphi = np.angle(np.exp(1j * (np.array([d["syncword_phase"] for d in kv], np.float64) - g["tag_phase"])))
+    assert np.max(np.abs(dphi)) < 1e-3
+    assert np.max(np.abs(np.array([d["syncword_time_est"] for d in kv]) - g["tag_time_est"])) < 1e-3
+    assert np.allclose([d["syncword_amplitude"] for d in kv], g["tag_amplitude"], rtol=1e-4)
+    # the gate of SyncwordDetectionFilter (PM/syncword_detection_filter.hpp:141-152)
+    block = 4 * (128 + 64 - 16 + 4 * (payload + 4))
+    kept, until = [], -1
+    for _, idx, d in tags:
+        if idx >= until:
+            kept.append((idx, d))
+            until = idx + block
+    assert [i for i, _ in kept] == g["kept_index"].tolist()
+    it = np.zeros(len(kept), STREAM_TAG_DTYPE)
+    it["index"] = [i for i, _ in kept]
+    it["has_syncword"] = 1
+    for k in ("syncword_freq", "syncword_amplitude", "syncword_phase", "syncword_time_est"):
+        it["sw"][k] = [d[k] for _, d in kept]
+    cfc_delay = (rrc.size - 1) // 2 + 4
+    sf_taps = pfb_matched_filter_taps()
+    if fused:
+        c, sym, ot = SymbolFilter(sf_taps, 32, 4, delay=rrc.size - 1, fused_cfc_delay=cfc_delay).process_bulk(delayed, it)
+    else:
+        corrected = CoarseFrequencyCorrection(cfc_delay).process_bulk(delayed, it)
+        c, sym, ot = SymbolFilter(sf_taps, 32, 4, delay=rrc.size - 1).process_bulk(corrected, it)
+    assert c == delayed.size and sym.size == g["symbols"].size
+    assert ot["index"].tolist() == g["symbol_tag_index"].tolist()
+    assert np.max(np.abs(np.angle(np.exp(1j * (ot["sw"]["syncword_phase"].astype(np.float64) - g["symbol_tag_phase"]))))) < 1e-3
+    assert _rel(sym, g["symbols"]) < 1e-5
+    sw = np.where(np.asarray(SYNCWORD) != 0, -1.0, 1.0).astype(np.float32)
+    if fused:
+        cl = CostasLoop(0.01, "BPSK")
+        cl.fuse_wipeoff(sw)
+        locked = cl.process_bulk(sym, ot)
+    else:
+        locked = CostasLoop(0.01, "BPSK").process_bulk(SyncwordWipeoff(sw).process_bulk(sym, ot), ot)
+    assert _rel(locked, g["locked"]) < 1e-4

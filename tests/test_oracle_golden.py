@@ -380,3 +380,30 @@ def test_costas_loop_trig_arithmetics_agree(oracle, constellation):
     a = oracle.CostasLoop(0.01, constellation, 0).run(rot, tags)
     b = oracle.CostasLoop(0.01, constellation, 1).run(rot, tags)
     assert np.linalg.norm(a - b) / np.linalg.norm(a) < 1e-5
+
+
+# ---------------------------------------------------------------- committed chain fixture
+def test_chain_golden_pins_oracle(oracle):
+    """tests/golden/sync_chain_golden.npz (made by tests/golden/make_chain_golden.py from the oracle) pins the
+    oracle's whole chain — SyncwordDetection -> CoarseFrequencyCorrection -> SymbolFilter -> SyncwordWipeoff ->
+    CostasLoop — across rounds: integer results exactly, floating-point results to 1e-5 (libm may differ in the
+    last place between hosts)."""
+    import importlib.util
+
+    gold = np.load(os.path.join(GOLD, "sync_chain_golden.npz"))
+    spec = importlib.util.spec_from_file_location("make_chain_golden", os.path.join(GOLD, "make_chain_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    rrc, sw, bpsk, sf_taps = m.settings()
+    out = m.oracle_chain(oracle, gold["capture"], sf_taps, rrc, sw, bpsk, int(gold["payload_bytes"]))
+    for k in ("consumed", "tag_index", "tag_freq_bin", "kept_index", "symbol_tag_index"):
+        assert np.array_equal(out[k], gold[k]), k
+    for k in ("tag_freq", "tag_phase", "tag_time_est", "tag_amplitude", "symbol_tag_phase"):
+        assert np.allclose(out[k], gold[k], rtol=1e-5, atol=1e-6), k
+    for k in ("symbols", "locked"):
+        assert out[k].size == gold[k].size and np.linalg.norm(out[k] - gold[k]) / np.linalg.norm(gold[k]) < 1e-5, k
+    # the fixture is a sensible receiver run: every transmitted syncword found at its true sample, carrier
+    # offset estimated, and the Costas loop output sits on the BPSK/QPSK constellation points
+    found = gold["tag_index"] - 1537
+    assert set(found.tolist()) >= set(int(s) for s in gold["true_starts"] if s + 1537 + 297 < int(gold["consumed"]))
+    assert np.all(np.abs(gold["tag_freq"] - 0.012) < 1.5e-3)
