@@ -557,8 +557,11 @@ def main():
             if world == 1:
                 c, recs, _ = sd.detect_host((hx.data_ptr(), n_host))
                 return c, len(recs)
-            x.copy_(hx, non_blocking=True)
-            return step_device()
+            # this rank's shard + halo from pinned host memory: the correlator chases the H2D pieces
+            table = sd.shard_phase1_host((hx.data_ptr(), n_host), seg0, fb, nbk, total_blocks)
+            j = gather_entry_offset(table, rank, world, device=dev)
+            recs, _ = sd.shard_phase2(j, max_recs)
+            return nbk * S, len(recs)
 
         step_host()
         barrier()

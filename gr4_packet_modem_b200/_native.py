@@ -133,6 +133,8 @@ def lib():
     L.b200sync_sd_detect_file.restype = C.c_int
     L.b200sync_sd_detect_channels_device.argtypes = [vp, vp, sz, sz, sz, vp, vp, sz, vp, psz]
     L.b200sync_sd_shard_phase1.argtypes = [vp, vp, C.c_uint64, sz, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, sz]
+    L.b200sync_sd_shard_phase1_host.argtypes = [vp, vp, C.c_uint64, sz, C.c_uint64, C.c_uint64, C.c_uint64, vp, sz]
+    L.b200sync_sd_shard_phase1_host.restype = C.c_int
     L.b200sync_sd_shard_phase2.argtypes = [vp, C.c_uint32, vp, sz, psz]
     L.b200sync_sd_records_to_tags.argtypes = [vp, vp, sz, vp]
     L.b200sync_sd_copy_metric.argtypes = [vp, vp, sz]

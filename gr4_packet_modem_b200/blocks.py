@@ -237,6 +237,21 @@ class SyncwordDetection:
                                          table.size))
         return table
 
+    def shard_phase1_host(self, x, first_sample_abs: int, first_block: int, n_blocks: int,
+                          total_blocks: int) -> np.ndarray:
+        """Phase 1 with the shard's samples in host memory (b200sync_sd_shard_phase1_host); x is a complex64
+        array or (address, n) of e.g. a pinned torch tensor."""
+        L = _native.lib()
+        if isinstance(x, np.ndarray):
+            x = np.ascontiguousarray(x, dtype=np.complex64)
+            ptr, n = x.ctypes.data, x.size
+        else:
+            ptr, n = x
+        table = np.zeros(self.time_threshold + 1, np.uint16)
+        check(L.b200sync_sd_shard_phase1_host(self._h, C.c_void_p(ptr), first_sample_abs, n, first_block, n_blocks,
+                                              total_blocks, table.ctypes.data, table.size))
+        return table
+
     def shard_phase2(self, entry_offset: int, max_recs: int):
         L = _native.lib()
         recs = self._rec_buffer(max(max_recs, 1))

@@ -125,6 +125,7 @@ struct b200sync_sd {
     float2* h_stage = nullptr;
     cudaEvent_t ev_stage[3] = {nullptr, nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> ev_pieces;  // b200sync_sd_shard_phase1_host: one event per H2D piece
     // shard
     DevBuf<uint16_t> d_table;
     struct {
@@ -391,6 +392,7 @@ void b200sync_sd_destroy(b200sync_sd* sd) {
     if (sd->h_stage) cudaFreeHost(sd->h_stage);
     for (auto& e : sd->ev_stage)
         if (e) cudaEventDestroy(e);
+    for (auto& e : sd->ev_pieces) cudaEventDestroy(e);
     if (sd->copy_stream) cudaStreamDestroy(sd->copy_stream);
     for (auto& ln : sd->lanes)
         if (ln.st) {
@@ -870,14 +872,15 @@ int b200sync_sd_copy_metric(const b200sync_sd* sd, float* zpow, size_t n) {
 }
 
 // ------------------------------------------------------------------------------------------
-int b200sync_sd_shard_phase1(b200sync_sd* sd, const void* d_in, uint64_t first_sample_abs, size_t n_in,
-                             uint64_t first_block, uint64_t n_blocks, uint64_t total_blocks,
-                             void* cuda_stream, uint16_t* table, size_t table_len) {
-    if (!sd || !d_in || !table) return fail(B200SYNC_EINVAL, "null argument");
+// shard phase 1.  h_in != nullptr: the shard's samples are in HOST memory; they are copied into the context's
+// capture buffer in pieces on the copy stream and the correlator runs in chunks behind the copies' events
+// (as b200sync_sd_detect_host does for a whole capture).
+static int shard_phase1_core(b200sync_sd* sd, const float2* d_in, const float2* h_in, uint64_t first_sample_abs,
+                             size_t n_in, uint64_t first_block, uint64_t n_blocks, uint64_t total_blocks,
+                             cudaStream_t st, uint16_t* table, size_t table_len) {
     if (table_len < static_cast<size_t>(sd->T) + 1) return fail(B200SYNC_ENOMEM, "table too small");
     if (first_block + n_blocks > total_blocks || n_blocks == 0) return fail(B200SYNC_EINVAL, "bad shard");
     CU(cudaSetDevice(sd->device));
-    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const long long S = sd->S, F = sd->fft_size, T = sd->T;
     const long long halo = (T + S) / S;  // blocks of metric context needed on each side
     const long long fb = static_cast<long long>(first_block), nbk = static_cast<long long>(n_blocks);
@@ -898,8 +901,34 @@ int b200sync_sd_shard_phase1(b200sync_sd* sd, const void* d_in, uint64_t first_s
     CU(sd->d_table.ensure(static_cast<size_t>(T) + 1));
     sd->ev_valid = false;
     CU(cudaEventRecord(sd->ev[0], st));
-    CU(launch_correlate(static_cast<const float2*>(d_in), in_base, sd->d_zoff.p, z_base, sd->d_hperm.p,
-                        (int)sd->K, (int)sd->S, cb0, cb1 - cb0, sd->d_tw.p, nullptr, 0, 0, sd->num_sms, st));
+    if (h_in == nullptr) {
+        CU(launch_correlate(d_in, in_base, sd->d_zoff.p, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, cb0,
+                            cb1 - cb0, sd->d_tw.p, nullptr, 0, 0, sd->num_sms, st));
+    } else {
+        CU(sd->d_xoff.ensure(n_in));
+        d_in = sd->d_xoff.p;
+        if (!sd->copy_stream) CU(cudaStreamCreateWithFlags(&sd->copy_stream, cudaStreamNonBlocking));
+        const long long piece = 4LL << 20;  // 4 Mi samples = 32 MiB per copy
+        const size_t npieces = (n_in + piece - 1) / piece;
+        while (sd->ev_pieces.size() < npieces) {
+            cudaEvent_t e;
+            CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            sd->ev_pieces.push_back(e);
+        }
+        for (size_t i = 0; i < npieces; ++i) {
+            const size_t off = i * piece, cnt = std::min<size_t>(piece, n_in - off);
+            CU(cudaMemcpyAsync(sd->d_xoff.p + off, h_in + off, cnt * sizeof(float2), cudaMemcpyHostToDevice,
+                               sd->copy_stream));
+            CU(cudaEventRecord(sd->ev_pieces[i], sd->copy_stream));
+        }
+        for (long long b0 = cb0; b0 < cb1; b0 += kOfflineChunkBlocks) {
+            const long long nb = std::min(kOfflineChunkBlocks, cb1 - b0);
+            const long long last_sample = (b0 + nb - 1) * S + F - 1 - in_base;  // relative to the shard's input
+            CU(cudaStreamWaitEvent(st, sd->ev_pieces[static_cast<size_t>(last_sample / piece)], 0));
+            CU(launch_correlate(d_in, in_base, sd->d_zoff.p, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, b0, nb,
+                                sd->d_tw.p, nullptr, 0, 0, sd->num_sms, st));
+        }
+    }
     CU(cudaEventRecord(sd->ev[1], st));
     if (hi > lo) {
         CU(launch_peak_phase1(sd->d_zoff.p, z_base, cb1 * S, lo, hi, sd->T, sd->power_threshold, sd->d_ws.p,
@@ -910,7 +939,7 @@ int b200sync_sd_shard_phase1(b200sync_sd* sd, const void* d_in, uint64_t first_s
         CU(cudaStreamSynchronize(st));
         for (long long j = 0; j <= T; ++j) table[j] = static_cast<uint16_t>(j);  // empty range: identity
     }
-    sd->shard.d_in = static_cast<const float2*>(d_in);
+    sd->shard.d_in = d_in;
     sd->shard.in_base = in_base;
     sd->shard.z_base = z_base;
     sd->shard.lo = lo;
@@ -922,6 +951,22 @@ int b200sync_sd_shard_phase1(b200sync_sd* sd, const void* d_in, uint64_t first_s
     sd->metric_ptr = sd->d_zoff.p;
     sd->metric_base = z_base;
     return 0;
+}
+
+int b200sync_sd_shard_phase1(b200sync_sd* sd, const void* d_in, uint64_t first_sample_abs, size_t n_in,
+                             uint64_t first_block, uint64_t n_blocks, uint64_t total_blocks,
+                             void* cuda_stream, uint16_t* table, size_t table_len) {
+    if (!sd || !d_in || !table) return fail(B200SYNC_EINVAL, "null argument");
+    return shard_phase1_core(sd, static_cast<const float2*>(d_in), nullptr, first_sample_abs, n_in, first_block,
+                             n_blocks, total_blocks, static_cast<cudaStream_t>(cuda_stream), table, table_len);
+}
+
+int b200sync_sd_shard_phase1_host(b200sync_sd* sd, const float* in, uint64_t first_sample_abs, size_t n_in,
+                                  uint64_t first_block, uint64_t n_blocks, uint64_t total_blocks, uint16_t* table,
+                                  size_t table_len) {
+    if (!sd || !in || !table) return fail(B200SYNC_EINVAL, "null argument");
+    return shard_phase1_core(sd, nullptr, reinterpret_cast<const float2*>(in), first_sample_abs, n_in, first_block,
+                             n_blocks, total_blocks, sd->stream, table, table_len);
 }
 
 int b200sync_sd_shard_phase2(b200sync_sd* sd, uint32_t entry_offset, b200sync_detection_record* recs,

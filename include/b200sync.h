@@ -167,6 +167,11 @@ int b200sync_sd_detect_channels_device(b200sync_sd* sd, const void* d_in, size_t
 int b200sync_sd_shard_phase1(b200sync_sd* sd, const void* d_in, uint64_t first_sample_abs, size_t n_in,
                              uint64_t first_block, uint64_t n_blocks, uint64_t total_blocks,
                              void* cuda_stream, uint16_t* table, size_t table_len);
+/* phase 1 with the shard's samples in HOST memory (pageable or pinned): copied in pieces on a copy stream,
+ * the correlator chases the copies (as b200sync_sd_detect_host does for a whole capture). */
+int b200sync_sd_shard_phase1_host(b200sync_sd* sd, const float* in, uint64_t first_sample_abs, size_t n_in,
+                                  uint64_t first_block, uint64_t n_blocks, uint64_t total_blocks, uint16_t* table,
+                                  size_t table_len);
 int b200sync_sd_shard_phase2(b200sync_sd* sd, uint32_t entry_offset, b200sync_detection_record* recs,
                              size_t max_recs, size_t* n_recs);
 

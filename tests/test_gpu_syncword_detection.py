@@ -236,6 +236,13 @@ def test_time_sharded_equals_single_run(rx_params, world):
     got = np.concatenate(got)
     assert len(got) == len(ref_recs) > 20
     assert np.array_equal(got.view(np.uint8), ref_recs.view(np.uint8))
+    # the same with the shards' samples in HOST memory (b200sync_sd_shard_phase1_host: the correlator
+    # chases the H2D copies); contexts are reused, which also covers start-over after a finished shard run
+    tables_h = [sd.shard_phase1_host(x[s.first_sample:s.first_sample + s.n_samples], s.first_sample, s.first_block,
+                                     s.n_blocks, s.total_blocks) for sd, s in zip(ctxs, shards)]
+    assert all(np.array_equal(a, b) for a, b in zip(tables, tables_h))
+    got_h = np.concatenate([sd.shard_phase2(j, n // 769 + 2)[0] for sd, j in zip(ctxs, entry_offsets(tables_h))])
+    assert np.array_equal(got_h.view(np.uint8), ref_recs.view(np.uint8))
 
 
 @pytest.mark.parametrize("n_channels,stride_pad", [(1, 0), (5, 0), (7, 1000)])
