@@ -11,8 +11,12 @@ frequency hypotheses (min/max_freq_bin = -/+4), power_threshold 9.5, time_thresh
   python bench.py [--gpus N] [--steps K] [--warmup W] [--log2n 30] [--bins 4]
   torchrun ... bench.py --gpus N ...      one rank per GPU; time shards + halo, no data-path collective
   python bench.py --impl reference ...    the reference's CPU algorithm (oracle port) on the host cores
+  python bench.py --workload chain        configs[2]: front end -> detection -> CFC + SymbolFilter -> wipe-off + Costas
+  python bench.py --workload channels     configs[4] channel mode (under torchrun: channels partitioned over ranks)
+  python bench.py --bins 16 --esn0 0      configs[3]: low-SNR, K = 33 hypotheses (sweep: scripts/threshold_sweep.py)
 
-A step is one pass of the whole hot path (correlator, peak detector, refine, records to host)
+The capture is written into HBM by the library's own generator (csrc/stimulus.cu, index-pure: every rank
+generates its shard + halo of the same endless stream).  A step is one pass of the whole hot path (correlator, peak detector, refine, records to host)
 over the device-resident capture.  The capture (8 GiB at 2^30) is far larger than L2 (126 MB),
 so no L2 flush is needed between steps.
 """

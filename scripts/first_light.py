@@ -4,13 +4,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gr4_packet_modem_b200 import SyncwordDetection
 from gr4_packet_modem_b200.firdes import unit_energy_rrc, SYNCWORD, BPSK
-from gr4_packet_modem_b200.stimulus import packet_capture_torch
+from gr4_packet_modem_b200.stimulus import DeviceStimulus
 
 logn = int(sys.argv[1]) if len(sys.argv) > 1 else 26
 n = 1 << logn
 dev = torch.device("cuda:0")
 t0 = time.time()
-x = packet_capture_torch(n, dev, seed=1, esn0_db=20.0, cfo=0.005)
+x = DeviceStimulus(seed=1, esn0_db=20.0, cfo=0.005).generate(n, dev)
 torch.cuda.synchronize()
 print(f"generated 2^{logn} samples in {time.time()-t0:.2f}s", flush=True)
 for bins in (4, 0, 16):

@@ -5,10 +5,10 @@ sys.path.insert(0, ".")
 from gr4_packet_modem_b200 import SyncwordDetection, _native
 from gr4_packet_modem_b200.blocks import RECORD_DTYPE
 from gr4_packet_modem_b200.firdes import BPSK, SYNCWORD, unit_energy_rrc
-from gr4_packet_modem_b200.stimulus import packet_capture_torch
+from gr4_packet_modem_b200.stimulus import DeviceStimulus
 n = 1 << 30
 dev = torch.device("cuda", 0)
-x = packet_capture_torch(n, dev, seed=1, esn0_db=20.0, cfo=0.005)
+x = DeviceStimulus(seed=1, esn0_db=20.0, cfo=0.005).generate(n, dev)
 sd = SyncwordDetection(unit_energy_rrc(), SYNCWORD, BPSK, -4, 4, 768, 9.5, device=0)
 L = _native.lib()
 max_recs = n // 769 + 2

@@ -10,9 +10,9 @@ sys.path.insert(0, %r)
 import torch
 from gr4_packet_modem_b200 import SyncwordDetection
 from gr4_packet_modem_b200.firdes import unit_energy_rrc, SYNCWORD, BPSK
-from gr4_packet_modem_b200.stimulus import packet_capture_torch
+from gr4_packet_modem_b200.stimulus import DeviceStimulus
 n = 1 << int(sys.argv[1]); bins = int(sys.argv[2])
-x = packet_capture_torch(n, torch.device("cuda:0"), seed=1, esn0_db=20.0, cfo=0.005)
+x = DeviceStimulus(seed=1, esn0_db=20.0, cfo=0.005).generate(n, torch.device("cuda:0"))
 sd = SyncwordDetection(unit_energy_rrc(), SYNCWORD, BPSK, -bins, bins)
 st = torch.cuda.current_stream().cuda_stream
 tm = []
