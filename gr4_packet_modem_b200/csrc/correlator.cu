@@ -28,7 +28,7 @@ __device__ __forceinline__ void load_twiddles(float2* tw_s, const float2* __rest
 __global__ void __launch_bounds__(kGroupThreads)
 template_spectra_kernel(const float2* __restrict__ td /*[K][2048] zero padded*/,
                         float2* __restrict__ hperm, const float2* __restrict__ tw_g) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];  // 128 B: half-warp LDS.64 rows never straddle a bank row, whatever static shared data precedes
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
     float2* xb = tw_s + kTwTotal;
     load_twiddles(tw_s, tw_g);
@@ -73,12 +73,18 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
                  long long z_base, const float2* __restrict__ hperm, int K, int S, long long b0,
                  long long nb, const float2* __restrict__ tw_g, float2* __restrict__ out_delayed,
                  long long out_base, int delay) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];  // 128 B: half-warp LDS.64 rows never straddle a bank row, whatever static shared data precedes
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
     const int g = threadIdx.x >> 7;
     const int tid = threadIdx.x & 127;
     float2* xb = tw_s + kTwTotal + g * kCorrXchg;
     float2* xb2 = kCorrTwoBuf ? xb + kXchgFloat2 : xb;
+#ifdef B200_TMA_TW
+    // TMA staging of the twiddle table is available but NOT the default here: the copy itself is free (once
+    // per persistent CTA), yet the build with it measured 1.7 % slower over the whole launch (24.94 vs 24.52 ms
+    // at 2^30, same box, A/B twice; not shared-memory alignment — a 128-B aligned base gave the same time —
+    // but a slightly different register allocation / schedule of the steady-state loop).  The front end's tap
+    // table does use it (frontend.cu), where it is neutral to slightly faster.
     {   // the 18 KiB twiddle table: one TMA bulk copy per persistent CTA
         __shared__ __align__(8) unsigned long long tw_bar;
         if (threadIdx.x == 0) mbar_init(&tw_bar, 1);
@@ -86,6 +92,10 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
         if (threadIdx.x == 0) tma_load_1d(tw_s, tw_g, kTwTotal * sizeof(float2), &tw_bar);
         mbar_wait(&tw_bar, 0);
     }
+#else
+    load_twiddles(tw_s, tw_g);
+    __syncthreads();
+#endif
     const int ngroups = blockDim.x >> 7;
     const long long gstride = (long long)gridDim.x * ngroups;
     const int bar_id = 1 + g;
@@ -174,7 +184,7 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
               const float2* __restrict__ tw_g, const unsigned long long* __restrict__ det_idx,
               const unsigned int* __restrict__ det_count, unsigned int det_cap,
               DetectionRecord* __restrict__ recs) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];  // 128 B: half-warp LDS.64 rows never straddle a bank row, whatever static shared data precedes
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
     float2* xb = tw_s + kTwTotal;
     float2* b1out = xb + kXchgFloat2;                      // [kRefineChunk][256]

@@ -104,7 +104,7 @@ __device__ __forceinline__ void rot_factors(const FeParams& P, long long nt, flo
 
 __global__ void __launch_bounds__(kFeThreads, 4)
 frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (tap, diff tap)*/) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];  // 128 B: half-warp LDS.64 rows never straddle a bank row, whatever static shared data precedes
     float2* td_s = reinterpret_cast<float2*>(smem_raw);   // [fs][arm] (tap, diff tap): one broadcast LDS.64 per tap
     float2* xin = td_s + P.fs * P.arm;                    // [kFeXinSlots], skewed
     const int tid = threadIdx.x;
