@@ -358,3 +358,39 @@ def test_full_size_capture_round_trip(rx_params):
         ctxs.append(c)
     got = np.concatenate([c.shard_phase2(j, n // 769 + 2)[0] for c, j in zip(ctxs, entry_offsets(tables))])
     assert np.array_equal(got.view(np.uint8), recs.view(np.uint8))
+
+
+def test_contexts_are_independent_across_threads(rx_params):
+    """SURVEY §8(b) Tier 2: a context is not thread-safe, but distinct contexts (one CUDA stream each) may be
+    driven concurrently from different threads — what GR4 does with one block instance per worker
+    (GR/Scheduler.hpp:387-398).  Four threads stream four different captures through processBulk-sized
+    chunks and bulk calls at the same time; every result equals the single-threaded run."""
+    import threading
+
+    from gr4_packet_modem_b200 import CostasLoop, SyncwordDetection
+    from gr4_packet_modem_b200.stimulus import packet_capture
+
+    caps = [packet_capture(1 << 19, seed=50 + i, esn0_db=6.0, cfo=0.002 * i, payload_bytes=100)[0] for i in range(4)]
+
+    def work(i, out):
+        sd = SyncwordDetection(**rx_params, min_freq_bin=-4, max_freq_bin=4)
+        pos, delayed, tags = sd.run(caps[i], chunk=65536, want_output=True)
+        c, recs, _ = sd.detect_host(caps[i])
+        cl = CostasLoop(0.01, "QPSK")
+        locked = np.concatenate([cl.process_bulk(delayed[a:a + 50000]) for a in range(0, delayed.size, 50000)])
+        out[i] = (pos, delayed.copy(), [t[1] for t in tags], c, recs.copy(), locked)
+
+    seq, par = {}, {}
+    for i in range(4):
+        work(i, seq)
+    ts = [threading.Thread(target=work, args=(i, par)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for i in range(4):
+        a, b = seq[i], par[i]
+        assert a[0] == b[0] and a[2] == b[2] and a[3] == b[3] and len(a[2]) > 20
+        assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+        assert a[4].tobytes() == b[4].tobytes()
+        assert np.array_equal(a[5].view(np.uint32), b[5].view(np.uint32))
