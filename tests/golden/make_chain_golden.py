@@ -1,10 +1,12 @@
-"""Regenerates tests/golden/sync_chain_golden.npz: a seeded 2^17-sample capture and what the ORACLE's
-restated blocks make of it along the receiver chain (PM/packet_receiver.hpp:76-125, 195-218):
+"""Regenerates tests/golden/sync_chain_golden.npz: a seeded 2^17-sample capture and what the REFERENCE's own
+blocks (oracle/_ref/librefblocks.so, see oracle/ref_blocks.cpp) — and, bit for bit the same, the oracle's
+restated blocks — make of it along the receiver chain (PM/packet_receiver.hpp:76-125, 195-218):
 SyncwordDetection (independent radix-2 FFT arithmetic) -> CoarseFrequencyCorrection -> SymbolFilter ->
 SyncwordWipeoff -> CostasLoop (libm trig = the reference's arithmetic).
 
-The reference itself cannot be built here, so these vectors pin the oracle — and through it
-the GPU path — across rounds: tests/test_oracle_golden.py::test_chain_golden_pins_oracle (CPU) and
+The reference's runtime and FFTW cannot be built here; its block sources can, against a stand-in
+runtime with the oracle's radix-2 FFT.  These vectors carry their outputs to the GPU box and pin the oracle —
+and through it the GPU path — across rounds: tests/test_oracle_golden.py::test_chain_golden_pins_oracle (CPU) and
 tests/test_gpu_chain_golden.py (GPU).  Run in the build container:  python tests/golden/make_chain_golden.py"""
 import os
 import sys
@@ -63,6 +65,35 @@ def oracle_chain(po, x, sf_taps, rrc, syncword_bits, bpsk, payload_bytes):
                 symbols=sym, locked=locked)
 
 
+def reference_chain(rb, x, sf_taps, rrc, syncword_bits, bpsk, payload_bytes):
+    """The same chain through the REFERENCE's own blocks (oracle/_ref/librefblocks.so: the reference headers
+    compiled unmodified against a stand-in runtime, FFT = the oracle's radix-2)."""
+    consumed, delayed, tags = rb.SyncwordDetection(rrc, syncword_bits, bpsk, -4, 4, 768, 9.5).run(x, chunk=1 << 16)
+    block = 4 * (128 + 64 - 16 + 4 * (payload_bytes + 4))
+    kept, until = [], -1
+    for t in tags:
+        if t.index >= until:
+            kept.append(t)
+            until = t.index + block
+    cfc_delay = (rrc.size - 1) // 2 + 4
+    corrected = rb.CoarseFrequencyCorrection(cfc_delay).run(delayed, [(t.index, t.freq) for t in kept])
+    sym, otags = rb.SymbolFilter(sf_taps, 32, 4, delay=rrc.size - 1).run(corrected, [(t.index, t) for t in kept], chunk=1 << 30)
+    sw = np.where(np.asarray(syncword_bits) != 0, -1.0, 1.0).astype(np.float32)
+    wiped = rb.SyncwordWipeoff(sw).run(sym, [i for i, _ in otags])
+    locked = rb.CostasLoop(0.01, "BPSK").run(wiped, [(i, q.phase) for i, q in otags])
+    return dict(consumed=np.int64(consumed),
+                tag_index=np.array([t.index for t in tags], np.int64),
+                tag_freq=np.array([t.freq for t in tags], np.float64),
+                tag_phase=np.array([t.phase for t in tags], np.float32),
+                tag_time_est=np.array([t.time_est for t in tags], np.float32),
+                tag_amplitude=np.array([t.amplitude for t in tags], np.float32),
+                tag_freq_bin=np.array([t.freq_bin for t in tags], np.int32),
+                kept_index=np.array([t.index for t in kept], np.int64),
+                symbol_tag_index=np.array([i for i, _ in otags], np.int64),
+                symbol_tag_phase=np.array([q.phase for _, q in otags], np.float32),
+                symbols=sym, locked=locked)
+
+
 def settings():
     from gr4_packet_modem_b200.firdes import BPSK, SYNCWORD, pfb_matched_filter_taps, unit_energy_rrc
 
@@ -78,8 +109,19 @@ def main():
     x, starts = packet_capture(1 << 17, seed=2026, esn0_db=8.0, cfo=0.012, payload_bytes=payload, noise_seed=17)
     rrc, sw, bpsk, sf_taps = settings()
     out = oracle_chain(po, x, sf_taps, rrc, sw, bpsk, payload)
+    from oracle import refblocks as rb
+
+    source = "oracle restatement (reference tree absent)"
+    if rb.available():
+        # the fixture is what the REFERENCE's own block code produces; the oracle must reproduce it bit for bit
+        ref = reference_chain(rb, x, sf_taps, rrc, sw, bpsk, payload)
+        for k, v in ref.items():
+            assert np.atleast_1d(v).tobytes() == np.atleast_1d(out[k]).tobytes(), k
+        out = ref
+        source = "reference blocks (oracle/_ref/librefblocks.so: PM/*.hpp unmodified, stand-in runtime, radix-2 FFT)"
     np.savez_compressed(os.path.join(HERE, "sync_chain_golden.npz"), capture=x, true_starts=starts,
-                        payload_bytes=np.int64(payload), **out)
+                        payload_bytes=np.int64(payload), source=np.array(source), **out)
+    print("source:", source)
     print("tags", out["tag_index"].size, "kept", out["kept_index"].size, "symbols", out["symbols"].size)
 
 
