@@ -22,7 +22,11 @@
 //     two FFT arithmetics (see oracle_fft.hpp) and is validated against the
 //     assertions of test/qa_syncword_detection.cpp on seeded inputs.
 //   * All block state machines are line-by-line restatements; they are checked
-//     against the assertions of the reference's own qa_*.cpp on seeded inputs.
+//     against the assertions of the reference's own qa_*.cpp on seeded inputs,
+//     AND bit for bit against the reference's own block headers compiled
+//     unmodified against a stand-in runtime (oracle/ref_blocks.cpp ->
+//     oracle/_ref/librefblocks.so; tests/test_oracle_vs_reference_blocks.py):
+//     pinned against outputs of the reference itself, FFT rounding excepted.
 // =============================================================================
 #pragma once
 #include <algorithm>

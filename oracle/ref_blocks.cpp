@@ -28,6 +28,7 @@ struct names<gr::packet_modem::Constellation> {
 #include <gnuradio-4.0/packet-modem/rotator.hpp>
 #include <gnuradio-4.0/packet-modem/symbol_filter.hpp>
 #include <gnuradio-4.0/packet-modem/syncword_detection.hpp>
+#include <gnuradio-4.0/packet-modem/syncword_detection_filter.hpp>
 #include <gnuradio-4.0/packet-modem/syncword_wipeoff.hpp>
 
 #include <cstring>
@@ -42,6 +43,8 @@ struct RefTag {  // what crosses the C boundary for a syncword tag
     double freq;
     float amplitude, phase, noise_power, esn0_db, time_est;
     int32_t freq_bin;
+    int32_t no_syncword;  // != 0: the tag carries NO syncword_* keys
+    int32_t other;        // != 0: the tag carries a non-syncword key ("other_key" = other)
 };
 template <typename T>
 T get(const gr::property_map& m, const char* k, T dflt = T{})
@@ -60,14 +63,20 @@ RefTag to_ref_tag(int64_t index, const gr::property_map& m)
     t.esn0_db = get<float>(m, "syncword_esn0_db");
     t.time_est = get<float>(m, "syncword_time_est");
     t.freq_bin = get<int>(m, "syncword_freq_bin");
+    t.no_syncword = m.contains("syncword_amplitude") ? 0 : 1;
+    t.other = get<int>(m, "other_key");
     return t;
 }
 gr::property_map from_ref_tag(const RefTag& t)
 {
-    return gr::property_map{ { "syncword_amplitude", t.amplitude }, { "syncword_phase", t.phase },
-                             { "syncword_freq", t.freq },           { "syncword_freq_bin", t.freq_bin },
-                             { "syncword_noise_power", t.noise_power }, { "syncword_esn0_db", t.esn0_db },
-                             { "syncword_time_est", t.time_est } };
+    gr::property_map m;
+    if (!t.no_syncword)
+        m = gr::property_map{ { "syncword_amplitude", t.amplitude }, { "syncword_phase", t.phase },
+                              { "syncword_freq", t.freq },           { "syncword_freq_bin", t.freq_bin },
+                              { "syncword_noise_power", t.noise_power }, { "syncword_esn0_db", t.esn0_db },
+                              { "syncword_time_est", t.time_est } };
+    if (t.other) m["other_key"] = t.other;
+    return m;
 }
 // one processBulk call: chunk [in, in + n_in) -> out (capacity max_out); tag = merged tag of the first item
 template <typename Blk>
@@ -193,6 +202,45 @@ void refblk_cl_state(void* h, float* phase, float* freq, float* k1, float* k2)
     *freq = b->_freq;
     *k1 = b->_k1;
     *k2 = b->_k2;
+}
+
+// ---- SyncwordDetectionFilter (PM/syncword_detection_filter.hpp): two message inputs, one stream ----
+void* refblk_sdf_create(size_t sps, size_t syncword_size, size_t header_size)
+{
+    auto b = std::make_unique<pm::SyncwordDetectionFilter<>>();
+    b->samples_per_symbol = sps;
+    b->syncword_size = syncword_size;
+    b->header_size = header_size;
+    b->start();
+    return b.release();
+}
+void refblk_sdf_destroy(void* h) { delete static_cast<pm::SyncwordDetectionFilter<>*>(h); }
+// header_kind: 0 none, 1 parsed header with packet_length, 2 invalid_header; returns items consumed or -1
+long long refblk_sdf_process(void* h, int header_kind, uint64_t packet_length, size_t n_ignored, const float* in,
+                             size_t n_in, float* out, size_t n_out, const RefTag* tag_in, size_t* hdr_used,
+                             size_t* ign_used, RefTag* tag_out, int* tag_forwarded, int* in_packet)
+{
+    auto& b = *static_cast<pm::SyncwordDetectionFilter<>*>(h);
+    std::vector<gr::Message> hdr, ign(n_ignored);
+    if (header_kind == 1) hdr.push_back(gr::Message{ gr::property_map{ { "packet_length", packet_length } } });
+    if (header_kind == 2) hdr.push_back(gr::Message{ gr::property_map{ { "invalid_header", true } } });
+    b.clear_input_tag();
+    if (tag_in) b.offer_input_tag(from_ref_tag(*tag_in));
+    gr::InSpan<gr::Message> hs{ std::span<const gr::Message>(hdr) }, gs{ std::span<const gr::Message>(ign) };
+    gr::InSpan<c64> is{ std::span<const c64>(reinterpret_cast<const c64*>(in), n_in) };
+    gr::OutSpan<c64> os{ std::span<c64>(reinterpret_cast<c64*>(out), n_out) };
+    b.out.published_tags.clear();
+    try {
+        if (b.processBulk(hs, gs, is, os) != gr::work::Status::OK) return -1;
+    } catch (const std::exception&) {
+        return -1;
+    }
+    *hdr_used = hs.consumed();
+    *ign_used = gs.consumed();
+    *tag_forwarded = b.out.published_tags.empty() ? 0 : 1;
+    if (*tag_forwarded) *tag_out = to_ref_tag(b.out.published_tags[0].index, b.out.published_tags[0].map);
+    *in_packet = b._in_packet ? 1 : 0;
+    return static_cast<long long>(is.consumed());
 }
 
 // ---- SymbolFilter (PM/symbol_filter.hpp) ----

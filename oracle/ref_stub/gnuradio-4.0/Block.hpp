@@ -14,6 +14,7 @@
 #include <complex>
 #include <cstddef>
 #include <cstdint>
+#include <expected>
 #include <ranges>
 #include <span>
 #include <stdexcept>
@@ -110,21 +111,26 @@ struct PortOut {
     void publishTag(const property_map& map, ssize_t offset) { published_tags.push_back(Tag{ offset, map }); }
 };
 
+struct Error {
+    std::string message;
+};
+struct Message {  // GR/Message.hpp:99-110: only the body is read by the RX-sync blocks
+    std::expected<property_map, Error> data;
+};
+
 template <typename Derived, typename... Args>
 class Block
 {
-    Tag _merged{};
-    bool _has_tag = false;
-
 public:
+    Tag _mergedInputTag{};  // GR/Block.hpp:616-618; blocks may clear it themselves
     std::string name = "ref";
     size_t input_chunk_size = 1;   // gr::Resampling members (GR/Block.hpp)
     size_t output_chunk_size = 1;
-    bool input_tags_present() const { return _has_tag; }
-    const Tag& mergedInputTag() const { return _merged; }
+    bool input_tags_present() const { return !_mergedInputTag.map.empty(); }
+    const Tag& mergedInputTag() const { return _mergedInputTag; }
     // scheduler side
-    void offer_input_tag(const property_map& m) { _merged = Tag{ 0, m }; _has_tag = true; }
-    void clear_input_tag() { _merged = Tag{}; _has_tag = false; }
+    void offer_input_tag(const property_map& m) { _mergedInputTag = Tag{ 0, m }; }
+    void clear_input_tag() { _mergedInputTag = Tag{}; }
     template <typename... A>
     void emitErrorMessage(A&&...) {}
     void requestStop() {}

@@ -23,7 +23,8 @@ _lib = None
 
 class RefTag(C.Structure):
     _fields_ = [("index", C.c_int64), ("freq", C.c_double), ("amplitude", C.c_float), ("phase", C.c_float),
-                ("noise_power", C.c_float), ("esn0_db", C.c_float), ("time_est", C.c_float), ("freq_bin", C.c_int32)]
+                ("noise_power", C.c_float), ("esn0_db", C.c_float), ("time_est", C.c_float), ("freq_bin", C.c_int32),
+                ("no_syncword", C.c_int32), ("other", C.c_int32)]
 
 
 def available() -> bool:
@@ -62,6 +63,12 @@ def lib():
         L.refblk_rs_destroy.argtypes = [vp]
         L.refblk_rs_process.argtypes = [vp, vp, sz, vp, sz, psz, psz]
         L.refblk_interp_fir.argtypes = [vp, sz, sz, vp, sz, vp]
+        L.refblk_sdf_create.restype = vp
+        L.refblk_sdf_create.argtypes = [sz, sz, sz]
+        L.refblk_sdf_destroy.argtypes = [vp]
+        L.refblk_sdf_process.restype = C.c_longlong
+        pi = C.POINTER(C.c_int)
+        L.refblk_sdf_process.argtypes = [vp, C.c_int, C.c_uint64, sz, vp, sz, vp, sz, vp, psz, psz, vp, pi, pi]
         _lib = L
     return _lib
 
@@ -257,3 +264,30 @@ def interpolating_fir(x, taps, interpolation):
     st = lib().refblk_interp_fir(t.ctypes.data, t.size, interpolation, x.ctypes.data, x.size, out.ctypes.data)
     assert st == 0, st
     return out
+
+
+class SyncwordDetectionFilter(_Handle):
+    """gr::packet_modem::SyncwordDetectionFilter itself; one processBulk call per process_bulk()."""
+    _destroy = "refblk_sdf_destroy"
+
+    def __init__(self, samples_per_symbol=4, syncword_size=64, header_size=128):
+        self._h = lib().refblk_sdf_create(samples_per_symbol, syncword_size, header_size)
+
+    def process_bulk(self, x, n_out=None, tag: RefTag | None = None, header=None, n_ignored=0):
+        """header: None | ("parsed", packet_length) | ("invalid",).  Returns
+        (consumed, out, forwarded RefTag or None, header_consumed, ignored_consumed, in_packet)."""
+        x = _c64(x)
+        n_out = x.size if n_out is None else n_out
+        out = np.zeros(n_out, np.complex64)
+        hk, plen = 0, 0
+        if header is not None:
+            hk, plen = (2, 0) if header[0] == "invalid" else (1, int(header[1]))
+        hu, iu = C.c_size_t(0), C.c_size_t(0)
+        to = RefTag()
+        fwd, inpkt = C.c_int(0), C.c_int(0)
+        c = lib().refblk_sdf_process(self._h, hk, plen, n_ignored, x.ctypes.data, x.size, out.ctypes.data, n_out,
+                                     C.byref(tag) if tag is not None else None, C.byref(hu), C.byref(iu), C.byref(to),
+                                     C.byref(fwd), C.byref(inpkt))
+        if c < 0:
+            raise RuntimeError("reference SyncwordDetectionFilter threw")
+        return int(c), out[:c], (to if fwd.value else None), hu.value, iu.value, bool(inpkt.value)

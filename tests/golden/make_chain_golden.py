@@ -127,3 +127,31 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def make_frontend_golden():
+    """tests/golden/frontend_golden.npz: a raw 2^15-sample stream through the REFERENCE's PfbArbResampler
+    (rate 1 + 1.2 ppm, PM/pfb_arb_taps.hpp taps) and Rotator (0.005 rad/sample)."""
+    from gr4_packet_modem_b200.firdes import lowpass_prototype_taps
+    from gr4_packet_modem_b200.stimulus import packet_capture
+    from oracle import pyoracle as po
+    from oracle import refblocks as rb
+
+    po.build(ref=True)
+    assert rb.available(), "needs /root/reference (oracle/_ref/librefblocks.so)"
+    raw, _ = packet_capture(1 << 15, seed=77, esn0_db=12.0, cfo=0.0, payload_bytes=100, noise_seed=5)
+    rate = float(np.float32(1.0) + np.float32(1e-6) * np.float32(1.2))
+    taps = np.asarray(lowpass_prototype_taps(32, 40), np.float32)
+    consumed, resampled = rb.PfbArbResampler(rate, taps, 32).run(raw)
+    rotated = rb.rotator(resampled, 0.005)
+    oc, oy = po.PfbArbResampler(rate, taps, 32, use_double=False).process_bulk(raw, raw.size + 100)
+    assert oc == consumed and oy.tobytes() == resampled.tobytes()
+    assert po.rotator(resampled, 0.005).tobytes() == rotated.tobytes()
+    np.savez_compressed(os.path.join(HERE, "frontend_golden.npz"), raw=raw, rate=np.float32(rate), taps=taps,
+                        phase_incr=np.float32(0.005), resampled=resampled, rotated=rotated,
+                        source=np.array("reference blocks (oracle/_ref/librefblocks.so)"))
+    print("frontend golden:", resampled.size, "outputs")
+
+
+if __name__ == "__main__":
+    make_frontend_golden()

@@ -138,3 +138,47 @@ def test_symbol_filter_is_the_reference(oracle, ref, rx_params):
     assert [i for i, _ in rot] == [i for i, _ in oot]
     assert [np.float32(q.phase).tobytes() for _, q in rot] == [np.float32(p).tobytes() for _, p in oot]
     assert any(t.time_est < 0 for t in tags) and any(t.time_est > 0 for t in tags)
+
+
+def test_detection_filter_state_machine_is_the_reference(oracle, ref):
+    """SyncwordDetectionFilter driven in lock step through 4000 random processBulk calls: chunk sizes, output
+    spans shorter than the input, syncword tags inside and outside packets, tags with other keys, parsed /
+    invalid header messages and ignored_syncword messages arriving early, late or never."""
+    rng = np.random.default_rng(99)
+    r, o = ref.SyncwordDetectionFilter(4, 64, 128), oracle.SyncwordDetectionFilter(4, 64, 128)
+    x = _noise(1 << 16, 1)
+    in_packet_calls = forwarded = dropped = 0
+    for step in range(4000):
+        n = int(rng.integers(1, 3000))
+        a = int(rng.integers(0, x.size - n))
+        n_out = n if rng.random() < 0.7 else int(rng.integers(1, n + 1))
+        kind = rng.random()
+        rt = ot = None
+        if kind < 0.35:
+            rt, ot = ref.RefTag(), oracle.StreamTag()
+            has_sw = rng.random() < 0.8
+            other = int(rng.integers(1, 100)) if rng.random() < 0.3 or not has_sw else 0
+            rt.no_syncword, rt.other = 0 if has_sw else 1, other
+            ot.has_syncword, ot.other = has_sw, other
+            for k, v in (("amplitude", 1.5), ("phase", -0.3), ("freq", 0.0123), ("time_est", 0.25)):
+                setattr(rt, k, v)
+                setattr(ot, k, v)
+        hdr = None
+        h = rng.random()
+        if h < 0.25:
+            hdr = ("parsed", int(rng.integers(1, 400)))
+        elif h < 0.32:
+            hdr = ("invalid",)
+        n_ign = int(rng.random() < 0.1)
+        rr = r.process_bulk(x[a:a + n], n_out, rt, hdr, n_ign)
+        oo = o.process_bulk(x[a:a + n], n_out, ot, hdr, n_ign)
+        assert rr[0] == oo[0] and rr[3:] == oo[3:], step
+        assert np.array_equal(_bits(rr[1]), _bits(oo[1])), step
+        assert (rr[2] is None) == (oo[2] is None), step
+        if rr[2] is not None:
+            assert (rr[2].no_syncword == 0) == bool(oo[2].has_syncword) and rr[2].other == oo[2].other, step
+            forwarded += 1
+        elif rt is not None:
+            dropped += 1
+        in_packet_calls += rr[5]
+    assert in_packet_calls > 500 and forwarded > 300 and dropped > 100   # every branch was exercised
