@@ -182,6 +182,27 @@ def cpu_reference_rate(bins: int, samples_per_thread: int, threads: int, steps: 
     return total / sec / 1e6, sec
 
 
+def reference_block_code_rate(bins: int, esn0: float = 20.0, thr: float = 9.5):
+    """Single-core rate of the REFERENCE's own SyncwordDetection block code (PM/syncword_detection.hpp compiled
+    unmodified against the stand-in runtime, oracle/_ref/librefblocks.so; its FFT is the oracle's radix-2, not
+    FFTW), or None where that library was not built.  Shows that the oracle port is a fair stand-in for the
+    reference's block logic: same FFT, same rate within a few per cent."""
+    try:
+        from gr4_packet_modem_b200.stimulus import packet_capture
+        from oracle import refblocks as rb
+
+        if not rb.available():
+            return None
+        s = rx_settings(bins, thr)
+        x, _ = packet_capture(1 << 21, seed=1, esn0_db=esn0, cfo=0.005)
+        blk = rb.SyncwordDetection(s["rrc_taps"], s["syncword"], s["constellation"], -bins, bins, TAU, thr)
+        t0 = time.perf_counter()
+        c, _, _ = blk.run(x, chunk=65536)
+        return c / (time.perf_counter() - t0) / 1e6
+    except Exception:
+        return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -622,6 +643,7 @@ def main():
         r1, _ = cpu_reference_rate(args.bins, 1 << 22, 1, 1, 1, args.esn0, args.thr)
         rN, _ = cpu_reference_rate(args.bins, 1 << 22, th, 1, 1, args.esn0, args.thr)
         cpu = {"value": rN, "unit": "Msps", "cores": th, "kind": "port", "single_core_msps": r1,
+               "reference_block_code_single_core_msps": reference_block_code_rate(args.bins, args.esn0, args.thr),
                "sample": f"{th} independent streams x 2^22 samples of the same signal model (oracle port, "
                          "radix-2 FFT in place of FFTW)"}
 
