@@ -155,3 +155,34 @@ def make_frontend_golden():
 
 if __name__ == "__main__":
     make_frontend_golden()
+
+
+def make_lowsnr_golden():
+    """tests/golden/lowsnr_golden.npz (BASELINE configs[3] in miniature): Es/N0 1 dB, CFO -0.07 rad/sample,
+    K = 17 hypotheses, power_threshold 8 — what the REFERENCE's SyncwordDetection block tags."""
+    from gr4_packet_modem_b200.stimulus import packet_capture
+    from oracle import pyoracle as po
+    from oracle import refblocks as rb
+
+    po.build(ref=True)
+    assert rb.available(), "needs /root/reference (oracle/_ref/librefblocks.so)"
+    rrc, sw, bpsk, _ = settings()
+    x, starts = packet_capture(1 << 16, seed=404, esn0_db=1.0, cfo=-0.07, payload_bytes=40, noise_seed=9)
+    consumed, delayed, tags = rb.SyncwordDetection(rrc, sw, bpsk, -8, 8, 768, 8.0).run(x, chunk=1 << 16)
+    oc, od, ot = po.SyncwordDetection(rrc, sw, bpsk, -8, 8, 768, 8.0, fft_kind=po.FFT_RADIX2).run(x, chunk=1 << 16,
+                                                                                               want_output=True)
+    assert oc == consumed and od.tobytes() == delayed.tobytes() and [t.index for t in ot] == [t.index for t in tags]
+    np.savez_compressed(os.path.join(HERE, "lowsnr_golden.npz"), capture=x, true_starts=starts,
+                        consumed=np.int64(consumed), bins=np.int64(8), power_threshold=np.float32(8.0),
+                        tag_index=np.array([t.index for t in tags], np.int64),
+                        tag_freq=np.array([t.freq for t in tags], np.float64),
+                        tag_phase=np.array([t.phase for t in tags], np.float32),
+                        tag_time_est=np.array([t.time_est for t in tags], np.float32),
+                        tag_freq_bin=np.array([t.freq_bin for t in tags], np.int32),
+                        tag_esn0_db=np.array([t.esn0_db for t in tags], np.float32),
+                        source=np.array("reference blocks (oracle/_ref/librefblocks.so)"))
+    print("low-SNR golden:", len(tags), "tags of", len(starts), "frames")
+
+
+if __name__ == "__main__":
+    make_lowsnr_golden()

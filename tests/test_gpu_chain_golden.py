@@ -84,3 +84,25 @@ def test_gpu_front_end_matches_reference_golden():
     assert c == raw.size and np.array_equal(y.view(np.uint32), g["resampled"].view(np.uint32))
     c, z = FrontEnd(rate=rate, taps=taps, phase_incr=float(g["phase_incr"])).process_bulk(raw)
     assert z.size == g["rotated"].size and _rel(z, g["rotated"]) < 1e-5
+
+
+def test_gpu_low_snr_matches_reference_golden(rx_params):
+    """tests/golden/lowsnr_golden.npz: the tags of the REFERENCE's SyncwordDetection block at Es/N0 1 dB, CFO
+    -0.07 rad/sample, K = 17, threshold 8.  GPU: same indices and bins exactly (streaming and bulk entry
+    points), estimates within north_star's tolerances."""
+    from gr4_packet_modem_b200 import SyncwordDetection
+
+    g = np.load(os.path.join(GOLDEN, "lowsnr_golden.npz"))
+    b = int(g["bins"])
+    sd = SyncwordDetection(**rx_params, min_freq_bin=-b, max_freq_bin=b, power_threshold=float(g["power_threshold"]))
+    consumed, recs, tags = sd.detect_host(g["capture"])
+    assert consumed == int(g["consumed"]) and len(g["tag_index"]) > 10
+    assert tags["index"].tolist() == g["tag_index"].tolist()
+    assert tags["syncword_freq_bin"].tolist() == g["tag_freq_bin"].tolist()
+    assert np.max(np.abs(tags["syncword_freq"] - g["tag_freq"])) < 1e-5
+    assert np.max(np.abs(np.angle(np.exp(1j * (tags["syncword_phase"].astype(np.float64) - g["tag_phase"]))))) < 1e-3
+    assert np.max(np.abs(tags["syncword_time_est"] - g["tag_time_est"])) < 1e-3
+    assert np.max(np.abs(tags["syncword_esn0_db"] - g["tag_esn0_db"])) < 1e-2
+    sd2 = SyncwordDetection(**rx_params, min_freq_bin=-b, max_freq_bin=b, power_threshold=float(g["power_threshold"]))
+    pos, _, t2 = sd2.run(g["capture"], chunk=5000)
+    assert [t[1] for t in t2] == [i for i in g["tag_index"].tolist() if i < pos]
