@@ -15,6 +15,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <expected>
+#include <numeric>
 #include <ranges>
 #include <span>
 #include <stdexcept>
