@@ -10,7 +10,7 @@ frequency hypotheses (min/max_freq_bin = -/+4), power_threshold 9.5, time_thresh
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--log2n 30] [--bins 4]
   torchrun ... bench.py --gpus N ...      one rank per GPU; time shards + halo, no data-path collective
-  python bench.py --impl reference ...    the reference's CPU algorithm (oracle port) on the host cores
+  python bench.py --impl reference ...    the reference's CPU block code (oracle/_ref, else the oracle port) on the host cores
   python bench.py --workload chain        configs[2]: front end -> detection -> CFC + SymbolFilter -> wipe-off + Costas
   python bench.py --workload channels     configs[4] channel mode (under torchrun: channels partitioned over ranks)
   python bench.py --bins 16 --esn0 0      configs[3]: low-SNR, K = 33 hypotheses (sweep: scripts/threshold_sweep.py)
@@ -146,23 +146,55 @@ def rx_settings(bins: int, thr: float = 9.5):
                 max_freq_bin=bins, time_threshold=TAU, power_threshold=thr)
 
 
+CPU_KIND_NOTE = {
+    "reference": "the reference's own block code (PM/syncword_detection.hpp compiled unmodified from the reference "
+                 "tree against a stand-in GR4 runtime, oracle/_ref/librefblocks.so) with a radix-2 FFT standing in "
+                 "for FFTW 3.3.10, which is not in the tree (DESIGN.md §7)",
+    "port": "oracle port of PM/syncword_detection.hpp (bit-identical to the reference's block code), radix-2 FFT "
+            "in place of FFTW",
+}
+
+
+def cpu_reference_kind(force_port: bool = False) -> str:
+    """"reference": oracle/_ref/librefblocks.so exists — the reference's own SyncwordDetection block code
+    (PM/syncword_detection.hpp compiled unmodified, stand-in GR4 runtime; FFT = radix-2 stand-in for the
+    absent FFTW 3.3.10); "port": the oracle's restatement (bit-identical results, same FFT)."""
+    if force_port:
+        return "port"
+    try:
+        from oracle import refblocks as rb
+
+        return "reference" if rb.available() else "port"
+    except Exception:
+        return "port"
+
+
 def cpu_reference_rate(bins: int, samples_per_thread: int, threads: int, steps: int, warmup: int,
-                       esn0: float = 20.0, thr: float = 9.5):
-    """The reference's CPU algorithm (oracle port, independent radix-2 FFT): `threads` independent
-    streams, one per host thread (one GR4 block instance runs on one worker thread).  Returns
-    (aggregate Msps, seconds per step)."""
+                       esn0: float = 20.0, thr: float = 9.5, kind: str = "port"):
+    """The reference's CPU implementation of the path: `threads` independent streams, one per host thread (one
+    GR4 block instance runs on one worker thread), fed 65536-item chunks like the GR4 ring does.  kind:
+    see cpu_reference_kind().  Returns (aggregate Msps, seconds per step)."""
     from gr4_packet_modem_b200.stimulus import packet_capture
     from oracle import pyoracle as po
 
     po.build(ref=False)
     x, _ = packet_capture(samples_per_thread, seed=1, esn0_db=esn0, cfo=0.005)
     s = rx_settings(bins, thr)
-    sds = [po.SyncwordDetection(s["rrc_taps"], s["syncword"], s["constellation"], -bins, bins, TAU, thr,
-                                fft_kind=po.FFT_RADIX2) for _ in range(threads)]
+    if kind == "reference":
+        from oracle import refblocks as rb
+
+        sds = [rb.SyncwordDetection(s["rrc_taps"], s["syncword"], s["constellation"], -bins, bins, TAU, thr)
+               for _ in range(threads)]
+    else:
+        sds = [po.SyncwordDetection(s["rrc_taps"], s["syncword"], s["constellation"], -bins, bins, TAU, thr,
+                                    fft_kind=po.FFT_RADIX2) for _ in range(threads)]
     consumed = [0] * threads
 
     def work(i):
-        c, _, _ = sds[i].run(x, chunk=65536, want_output=True)
+        if kind == "reference":
+            c, _, _ = sds[i].run(x, chunk=65536)
+        else:
+            c, _, _ = sds[i].run(x, chunk=65536, want_output=True)
         consumed[i] = c
 
     def one_step():
@@ -182,35 +214,15 @@ def cpu_reference_rate(bins: int, samples_per_thread: int, threads: int, steps: 
     return total / sec / 1e6, sec
 
 
-def reference_block_code_rate(bins: int, esn0: float = 20.0, thr: float = 9.5):
-    """Single-core rate of the REFERENCE's own SyncwordDetection block code (PM/syncword_detection.hpp compiled
-    unmodified against the stand-in runtime, oracle/_ref/librefblocks.so; its FFT is the oracle's radix-2, not
-    FFTW), or None where that library was not built.  Shows that the oracle port is a fair stand-in for the
-    reference's block logic: same FFT, same rate within a few per cent."""
-    try:
-        from gr4_packet_modem_b200.stimulus import packet_capture
-        from oracle import refblocks as rb
-
-        if not rb.available():
-            return None
-        s = rx_settings(bins, thr)
-        x, _ = packet_capture(1 << 21, seed=1, esn0_db=esn0, cfo=0.005)
-        blk = rb.SyncwordDetection(s["rrc_taps"], s["syncword"], s["constellation"], -bins, bins, TAU, thr)
-        t0 = time.perf_counter()
-        c, _, _ = blk.run(x, chunk=65536)
-        return c / (time.perf_counter() - t0) / 1e6
-    except Exception:
-        return None
-
-
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     per_thread = 1 << 21
+    kind = cpu_reference_kind()
     rate, sec = cpu_reference_rate(args.bins, per_thread, threads, max(args.steps, 1), max(args.warmup, 1),
-                                   args.esn0, args.thr)
+                                   args.esn0, args.thr, kind)
     K = 2 * args.bins + 1
     line = {
         "impl": "reference", "metric": "complex Msps (cf32) through RX sync (SyncwordDetection)",
@@ -218,11 +230,9 @@ def run_reference(args):
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.log2n, K, args.esn0, args.thr),
-        "cpu_baseline": {"value": rate, "unit": "Msps", "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": rate, "unit": "Msps", "cores": threads, "kind": kind,
                          "sample": f"bounded sample of the workload: {threads} independent streams x 2^21 samples "
-                                   "of the same signal model per step, one per host thread (oracle port of "
-                                   "PM/syncword_detection.hpp, radix-2 FFT in place of FFTW; the reference itself "
-                                   "is unbuildable here, DESIGN.md §7)"},
+                                   "of the same signal model per step, one per host thread; " + CPU_KIND_NOTE[kind]},
         "e2e": {"value": rate, "unit": "Msps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -640,12 +650,13 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu:
         th = os.cpu_count() or 1
-        r1, _ = cpu_reference_rate(args.bins, 1 << 22, 1, 1, 1, args.esn0, args.thr)
-        rN, _ = cpu_reference_rate(args.bins, 1 << 22, th, 1, 1, args.esn0, args.thr)
-        cpu = {"value": rN, "unit": "Msps", "cores": th, "kind": "port", "single_core_msps": r1,
-               "reference_block_code_single_core_msps": reference_block_code_rate(args.bins, args.esn0, args.thr),
-               "sample": f"{th} independent streams x 2^22 samples of the same signal model (oracle port, "
-                         "radix-2 FFT in place of FFTW)"}
+        kind = cpu_reference_kind()
+        r1, _ = cpu_reference_rate(args.bins, 1 << 22, 1, 1, 1, args.esn0, args.thr, kind)
+        rN, _ = cpu_reference_rate(args.bins, 1 << 22, th, 1, 1, args.esn0, args.thr, kind)
+        rP, _ = cpu_reference_rate(args.bins, 1 << 22, 1, 1, 1, args.esn0, args.thr, "port")
+        cpu = {"value": rN, "unit": "Msps", "cores": th, "kind": kind, "single_core_msps": r1,
+               "oracle_port_single_core_msps": rP,
+               "sample": f"{th} independent streams x 2^22 samples of the same signal model; " + CPU_KIND_NOTE[kind]}
 
     line = {
         "metric": "complex Msps (cf32) through RX sync (SyncwordDetection)", "value": value, "unit": "Msps",
