@@ -214,6 +214,29 @@ def cpu_reference_rate(bins: int, samples_per_thread: int, threads: int, steps: 
     return total / sec / 1e6, sec
 
 
+def zero_input_rate(bins: int, kind: str):
+    """benchmarks/benchmark_syncword_detection.cpp in miniature: 2^22 zeros through one block instance."""
+    try:
+        from oracle import pyoracle as po
+
+        s = rx_settings(bins)
+        x = np.zeros(1 << 22, np.complex64)
+        if kind == "reference":
+            from oracle import refblocks as rb
+
+            blk = rb.SyncwordDetection(s["rrc_taps"], s["syncword"], s["constellation"], -bins, bins, TAU, 9.5)
+            t0 = time.perf_counter()
+            c, _, _ = blk.run(x, chunk=65536)
+        else:
+            blk = po.SyncwordDetection(s["rrc_taps"], s["syncword"], s["constellation"], -bins, bins, TAU, 9.5,
+                                       fft_kind=po.FFT_RADIX2)
+            t0 = time.perf_counter()
+            c, _, _ = blk.run(x, chunk=65536, want_output=True)
+        return c / (time.perf_counter() - t0) / 1e6
+    except Exception:
+        return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -234,6 +257,14 @@ def run_reference(args):
                          "sample": f"bounded sample of the workload: {threads} independent streams x 2^21 samples "
                                    "of the same signal model per step, one per host thread; " + CPU_KIND_NOTE[kind]},
         "e2e": {"value": rate, "unit": "Msps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "zero_input_single_core_msps": zero_input_rate(args.bins, kind),
+        "zero_input_note": "BASELINE configs[0]: the reference's own benchmark feeds zeros (NullSource -> Head -> "
+                           "SyncwordDetection -> NullSink, benchmarks/benchmark_syncword_detection.cpp:28-70); one "
+                           "stream, one core, same block code as above.  benchmarks/results.md:35-41 publishes for it, with "
+                           "FFTW on a Ryzen 7 5800X: 49-51 / 29 / 20-21 / 16 / 13 Msps at 0 / 1 / 2 / 3 / 4 frequency "
+                           "bins — i.e. the radix-2 stand-in FFT on this host core understates the real reference by "
+                           "the ratio of that figure to this one",
+        "published_zero_input_msps": {"0": 50.0, "1": 29.0, "2": 20.5, "3": 16.0, "4": 13.0}.get(str(args.bins)),
     }
     print(json.dumps(line))
 
