@@ -646,40 +646,33 @@ int b200sync_sd_detect_host(b200sync_sd* sd, const float* in, size_t n, b200sync
     *n_consumed = 0;
     if (n < sd->fft_size) return 0;
     CU(sd->d_xoff.ensure(n));
-    // H2D on a copy stream in pieces, one event per piece; compute chases the copies
+    // H2D on the context's copy stream in pieces, one (cached) event per piece; compute chases the copies
     const long long piece = 4LL << 20;  // 4 Mi samples = 32 MiB per copy
     const size_t npieces = (n + piece - 1) / piece;
-    cudaStream_t cs;
-    CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-    std::vector<cudaEvent_t> ev(npieces);
+    if (!sd->copy_stream) CU(cudaStreamCreateWithFlags(&sd->copy_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = sd->copy_stream;
+    while (sd->ev_pieces.size() < npieces) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        sd->ev_pieces.push_back(e);
+    }
     int rc = 0;
-    size_t made = 0;
-    for (; made < npieces; ++made) {
-        if (cudaEventCreateWithFlags(&ev[made], cudaEventDisableTiming) != cudaSuccess) {
-            rc = fail(B200SYNC_ECUDA, "cudaEventCreate failed");
+    for (size_t i = 0; i < npieces; ++i) {
+        const size_t off = i * piece;
+        const size_t cnt = std::min<size_t>(piece, n - off);
+        cudaError_t e = cudaMemcpyAsync(sd->d_xoff.p + off, reinterpret_cast<const float2*>(in) + off,
+                                        cnt * sizeof(float2), cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess) e = cudaEventRecord(sd->ev_pieces[i], cs);
+        if (e != cudaSuccess) {
+            rc = fail(B200SYNC_ECUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
             break;
         }
     }
-    if (rc == 0) {
-        for (size_t i = 0; i < npieces; ++i) {
-            const size_t off = i * piece;
-            const size_t cnt = std::min<size_t>(piece, n - off);
-            cudaError_t e = cudaMemcpyAsync(sd->d_xoff.p + off, reinterpret_cast<const float2*>(in) + off,
-                                            cnt * sizeof(float2), cudaMemcpyHostToDevice, cs);
-            if (e == cudaSuccess) e = cudaEventRecord(ev[i], cs);
-            if (e != cudaSuccess) {
-                rc = fail(B200SYNC_ECUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
-                break;
-            }
-        }
-    }
     if (rc == 0)
-        rc = detect_resident(sd, sd->d_xoff.p, n, nullptr, sd->stream, ev.data(), piece, recs, max_recs, n_recs,
-                             n_consumed);
+        rc = detect_resident(sd, sd->d_xoff.p, n, nullptr, sd->stream, sd->ev_pieces.data(), piece, recs, max_recs,
+                             n_recs, n_consumed);
     cudaStreamSynchronize(cs);
     cudaStreamSynchronize(sd->stream);
-    for (size_t i = 0; i < made; ++i) cudaEventDestroy(ev[i]);
-    cudaStreamDestroy(cs);
     return rc;
 }
 
@@ -719,8 +712,8 @@ int b200sync_sd_detect_file(b200sync_sd* sd, const char* filename, uint64_t firs
     if (!sd->h_stage) {
         CU(cudaMallocHost(&sd->h_stage, kSlots * piece * sizeof(float2)));
         for (int i = 0; i < kSlots; ++i) CU(cudaEventCreateWithFlags(&sd->ev_stage[i], cudaEventDisableTiming));
-        CU(cudaStreamCreateWithFlags(&sd->copy_stream, cudaStreamNonBlocking));
     }
+    if (!sd->copy_stream) CU(cudaStreamCreateWithFlags(&sd->copy_stream, cudaStreamNonBlocking));
     cudaStream_t st = sd->stream, cs = sd->copy_stream;
     long long nb_total = 0, P = 0;
     if (int rc = detect_begin(sd, n, nullptr, st, &nb_total, &P)) return rc;
