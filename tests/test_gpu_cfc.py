@@ -208,3 +208,13 @@ def test_cfc_device_span_large(oracle):
     r = (y[a:] * x[a:].conj())
     d = torch.angle(r[1:] * r[:-1].conj()).double().mean().item()
     assert abs(d + float(np.float32(freqs[-1]))) < 1e-6
+
+
+def test_cfc_reference_qa_on_gpu():
+    """test/qa_coarse_frequency_correction.cpp:15-97 through the GPU block."""
+    from gr4_packet_modem_b200 import CoarseFrequencyCorrection
+    from test_oracle_golden import QA_CFC_TAGS, _cfc_reference_qa_check
+
+    x = np.ones(10000, np.complex64)
+    tags = _tags([(i, float(np.float32(f))) for i, f in QA_CFC_TAGS])
+    _cfc_reference_qa_check(CoarseFrequencyCorrection(0).process_bulk(x, tags))

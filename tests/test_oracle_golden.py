@@ -253,8 +253,9 @@ def test_rotator_reference_qa(oracle):
 
 # ---------------------------------------------------------------- CoarseFrequencyCorrection
 def test_coarse_frequency_correction_restatement(oracle):
-    """PM/coarse_frequency_correction.hpp:67-98 (the reference has no QA for this block; the assertions
-    follow its documentation :23-36 and test/qa_rotator.cpp's tolerance): untouched before the first
+    """PM/coarse_frequency_correction.hpp:67-98 with a non-zero `delay`, which the reference's own QA
+    (test/qa_coarse_frequency_correction.cpp, mirrored below in test_coarse_frequency_correction_reference_qa)
+    does not cover; the assertions follow the block's documentation :23-36: untouched before the first
     reset; `delay` samples after a syncword_freq tag the signal is rotated by -freq with phase
     -freq*delay at the reset sample; a newer tag within `delay` samples replaces the pending reset."""
     n = 20000
@@ -407,3 +408,33 @@ def test_chain_golden_pins_oracle(oracle):
     found = gold["tag_index"] - 1537
     assert set(found.tolist()) >= set(int(s) for s in gold["true_starts"] if s + 1537 + 297 < int(gold["consumed"]))
     assert np.all(np.abs(gold["tag_freq"] - 0.012) < 1.5e-3)
+
+
+def _cfc_reference_qa_check(data):
+    """The assertions of test/qa_coarse_frequency_correction.cpp:40-90 on the block's output `data`."""
+    assert np.array_equal(data[:100], np.ones(100, np.complex64))        # the block starts with frequency zero
+    pi = np.float32(np.pi)
+
+    def stretch(a, b, freq):
+        phase = np.float32(0.0)
+        for j in range(a, b):
+            z = np.cos(phase) + 1j * np.sin(phase)
+            assert abs(data[j] - z) < 1e-3, j
+            phase = np.float32(phase - np.float32(freq))
+            if phase < -pi:
+                phase = np.float32(phase + np.float32(2.0) * pi)
+
+    stretch(100, 1000, 0.1)
+    stretch(1000, 1500, 0.1)
+    stretch(1500, 5000, 0.1)
+    assert np.array_equal(data[5000:6500], np.ones(1500, np.complex64))  # syncword_freq = 0: exactly one again
+    stretch(6500, 10000, 0.2)
+
+
+QA_CFC_TAGS = [(100, 0.1), (1000, 0.1), (1500, 0.1), (5000, 0.0), (6500, 0.2)]   # qa_coarse_frequency_correction.cpp:19-25
+
+
+def test_coarse_frequency_correction_reference_qa(oracle):
+    """test/qa_coarse_frequency_correction.cpp:15-97 (delay 0, ones in, five syncword_freq tags)."""
+    tags = [(i, float(np.float32(f))) for i, f in QA_CFC_TAGS]
+    _cfc_reference_qa_check(oracle.CoarseFrequencyCorrection(0).run(np.ones(10000, np.complex64), tags))
