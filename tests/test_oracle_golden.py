@@ -438,3 +438,18 @@ def test_coarse_frequency_correction_reference_qa(oracle):
     """test/qa_coarse_frequency_correction.cpp:15-97 (delay 0, ones in, five syncword_freq tags)."""
     tags = [(i, float(np.float32(f))) for i, f in QA_CFC_TAGS]
     _cfc_reference_qa_check(oracle.CoarseFrequencyCorrection(0).run(np.ones(10000, np.complex64), tags))
+
+
+def test_interpolating_fir_reference_qa(oracle):
+    """test/qa_interpolating_fir_filter.cpp:16-60: interpolation 5, ramp taps 1..23, integers in [-8, 8] in
+    (exact in float32): every output equals the direct convolution of the zero-packed input."""
+    rng = np.random.default_rng(8)
+    n, interp = 20000, 5
+    x = rng.integers(-8, 9, n)
+    taps = np.arange(1, 24, dtype=np.float32)
+    got = oracle.interpolating_fir(x.astype(np.complex64), taps, interp)
+    packed = np.zeros(n * interp, np.int64)
+    packed[::interp] = x
+    want = np.convolve(packed, np.arange(1, 24, dtype=np.int64))[:n * interp]
+    assert got.size == n * interp and np.all(got.imag == 0)
+    assert np.array_equal(got.real.astype(np.int64), want)
