@@ -6,8 +6,10 @@
 // (GR/Block.hpp:777-790).  A tag with a "syncword_amplitude" key that arrives while no syncword is being
 // wiped starts one (:52-61); the multiply itself runs behind b200sync_wo_process.
 //
-// In the receiver this block feeds CostasLoop through PayloadMetadataInsert (PM/packet_receiver.hpp:203-214);
-// CostasLoopB200 can absorb it (`fused_wipeoff_syncword` setting), then this block is left out of the flowgraph.
+// In the receiver this block feeds CostasLoop through PayloadMetadataInsert (PM/packet_receiver.hpp:203-214), which
+// forwards the syncword / header / payload symbols and the syncword tag and drops the inter-packet remainder.
+// CostasLoopB200 can absorb this block (`fused_wipeoff_syncword` setting: the wipe-off then happens behind
+// PayloadMetadataInsert, on the same 64 symbols), and this block is left out of the flowgraph.
 #pragma once
 #include "b200_shell_common.hpp"
 

@@ -350,9 +350,13 @@ int b200sync_cl_process_device(b200sync_cl* c, const void* d_in, size_t n, const
                                size_t n_in_tags, void* d_out, void* cuda_stream);
 /* Fuses a SyncwordWipeoff{syncword} block into the loop's load stage: the span handed to
  * b200sync_cl_process* is then the INPUT of SyncwordWipeoff and the output that of the CostasLoop behind
- * it (PM/packet_receiver.hpp:203-218; PayloadMetadataInsert between them passes items through) — one
+ * it (PM/packet_receiver.hpp:203-218) — one
  * pass over the symbols instead of two, bit-identical to running the two contexts back to back.
- * n_syncword = 0 removes the fusion.  Call after create()/start() and before the first process call. */
+ * n_syncword = 0 removes the fusion.  Call after create()/start() and before the first process call.
+ * In packet_receiver.hpp a PayloadMetadataInsert sits between the two blocks; it forwards the syncword,
+ * header and payload symbols with the syncword tag and drops the inter-packet remainder
+ * (PM/payload_metadata_insert.hpp:18-30).  The wipe-off needs only that tag and the 64 symbols behind it,
+ * which arrive unchanged, so the fused block takes the CostasLoop's place BEHIND PayloadMetadataInsert. */
 int b200sync_cl_fuse_wipeoff(b200sync_cl* c, const float* syncword, uint32_t n_syncword);
 /* the loop state after the last processed item (copied from the device; synchronises) */
 int b200sync_cl_state(b200sync_cl* c, float* phase, float* freq);

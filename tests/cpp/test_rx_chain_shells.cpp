@@ -232,7 +232,8 @@ int main(int argc, char** argv)
     }
 
     // PM/packet_receiver.hpp:117-125, 203-214: SymbolFilter -> SyncwordWipeoff(bipolar syncword) ->
-    // [PayloadMetadataInsert: items pass through] -> CostasLoop (defaults)
+    // [PayloadMetadataInsert: host control logic, not on the hot path; it forwards packet symbols and the syncword
+    //  tag and drops the inter-packet remainder — left out here] -> CostasLoop (defaults)
     std::vector<float> syncword_bipolar;
     for (auto bit : detection.syncword) syncword_bipolar.push_back(bit ? -1.0f : 1.0f);
     std::vector<c64> wiped, locked;
