@@ -156,9 +156,9 @@ int ensure_det(b200sync_sd* sd, size_t cap) {
 // correlate blocks [b0, b0+nb), then decide peaks on [lo, hi)
 int run_chunk(b200sync_sd* sd, const float2* d_in, long long in_base, float* d_z, long long z_base,
               long long b0, long long nb, long long lo, long long hi, float2* d_out_delayed,
-              cudaStream_t st) {
+              long long out_end, cudaStream_t st) {
     CU(launch_correlate(d_in, in_base, d_z, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, b0, nb,
-                        sd->d_tw.p, d_out_delayed, 0, (int)sd->delay, sd->num_sms, st));
+                        sd->d_tw.p, d_out_delayed, 0, out_end, (int)sd->delay, sd->num_sms, st));
     if (hi > lo) {
         const long long z_end = (b0 + nb) * (long long)sd->S;
         CU(launch_peak_phase1(d_z, z_base, z_end, lo, hi, sd->T, sd->power_threshold, sd->d_ws.p,
@@ -509,7 +509,7 @@ int b200sync_sd_process(b200sync_sd* sd, const float* in, size_t n_in, float* ou
         const size_t ws = peak_workspace_bytes_sms(kStreamStepBlocks * S + T + 2, sd->T, sd->num_sms);
         CU(sd->d_ws.ensure(ws));
         if (int rc = ensure_det(sd, static_cast<size_t>((kStreamStepBlocks * S + T + 2) / (T + 1) + 2))) return rc;
-        if (int rc = run_chunk(sd, sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, a0 / S, nb, lo, hi, nullptr, st))
+        if (int rc = run_chunk(sd, sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, a0 / S, nb, lo, hi, nullptr, 0, st))
             return rc;
         sd->z_end = P;
         sd->lo_next = hi;
@@ -620,7 +620,7 @@ static int detect_resident(b200sync_sd* sd, const float2* d_in, size_t n, float2
             const long long last_sample = (b0 + nb - 1) * S + F - 1;
             CU(cudaStreamWaitEvent(st, chunk_ready[last_sample / chunk_samples], 0));
         }
-        if (int rc = run_chunk(sd, d_in, 0, sd->d_zoff.p, 0, b0, nb, 0, 0, d_out_delayed, st)) return rc;
+        if (int rc = run_chunk(sd, d_in, 0, sd->d_zoff.p, 0, b0, nb, 0, 0, d_out_delayed, P, st)) return rc;
         if (!chunk_ready) break;
     }
     return detect_finish(sd, d_in, P, st, recs, max_recs, n_recs, n_consumed);
@@ -740,7 +740,7 @@ int b200sync_sd_detect_file(b200sync_sd* sd, const char* filename, uint64_t firs
             CU(cudaStreamWaitEvent(st, sd->ev_stage[slot], 0));
             for (long long b0 = b_done; b0 < b_ready; b0 += kOfflineChunkBlocks)
                 if (int rc = run_chunk(sd, sd->d_xoff.p, 0, sd->d_zoff.p, 0, b0,
-                                       std::min(kOfflineChunkBlocks, b_ready - b0), 0, 0, nullptr, st))
+                                       std::min(kOfflineChunkBlocks, b_ready - b0), 0, 0, nullptr, 0, st))
                     return rc;
             b_done = b_ready;
         }
@@ -796,7 +796,7 @@ int b200sync_sd_detect_channels_device(b200sync_sd* sd, const void* d_in, size_t
         PeakState* state = sd->d_chan_state.p + c;
         DetectionRecord* drecs = sd->d_chan_recs.p + c * cap;
         CU(launch_correlate(x, 0, ln.z.p, 0, sd->d_hperm.p, (int)sd->K, (int)sd->S, 0, nb_total, sd->d_tw.p,
-                            nullptr, 0, (int)sd->delay, sd->num_sms, ln.st));
+                            nullptr, 0, 0, (int)sd->delay, sd->num_sms, ln.st));
         if (hi_total > 0) {
             CU(launch_peak_phase1(ln.z.p, 0, P, 0, hi_total, sd->T, sd->power_threshold, ln.ws.p, ln.ws.cap,
                                   nullptr, sd->num_sms, ln.st));
@@ -896,7 +896,7 @@ static int shard_phase1_core(b200sync_sd* sd, const float2* d_in, const float2* 
     CU(cudaEventRecord(sd->ev[0], st));
     if (h_in == nullptr) {
         CU(launch_correlate(d_in, in_base, sd->d_zoff.p, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, cb0,
-                            cb1 - cb0, sd->d_tw.p, nullptr, 0, 0, sd->num_sms, st));
+                            cb1 - cb0, sd->d_tw.p, nullptr, 0, 0, 0, sd->num_sms, st));
     } else {
         CU(sd->d_xoff.ensure(n_in));
         d_in = sd->d_xoff.p;
@@ -919,7 +919,7 @@ static int shard_phase1_core(b200sync_sd* sd, const float2* d_in, const float2* 
             const long long last_sample = (b0 + nb - 1) * S + F - 1 - in_base;  // relative to the shard's input
             CU(cudaStreamWaitEvent(st, sd->ev_pieces[static_cast<size_t>(last_sample / piece)], 0));
             CU(launch_correlate(d_in, in_base, sd->d_zoff.p, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, b0, nb,
-                                sd->d_tw.p, nullptr, 0, 0, sd->num_sms, st));
+                                sd->d_tw.p, nullptr, 0, 0, 0, sd->num_sms, st));
         }
     }
     CU(cudaEventRecord(sd->ev[1], st));

@@ -68,11 +68,18 @@ constexpr bool kRegB2 = true;
 constexpr bool kRegB2 = false;
 #endif
 
+#ifdef B200_NO_TMEM
+constexpr bool kCorrTmem = false;  // round-1 form: spectrum in registers, templates through L1, factors in shared memory
+#else
+constexpr bool kCorrTmem = true;
+static_assert(kCorrThreads == 6 * kGroupThreads, "the TMEM column layout (fft2048.cuh) is for 6 FFT groups per CTA");
+#endif
+
 __global__ void __launch_bounds__(kCorrThreads, 1)
 correlate_kernel(const float2* __restrict__ in, long long in_base, float* __restrict__ zpow,
                  long long z_base, const float2* __restrict__ hperm, int K, int S, long long b0,
                  long long nb, const float2* __restrict__ tw_g, float2* __restrict__ out_delayed,
-                 long long out_base, int delay) {
+                 long long out_base, long long out_end, int delay) {
     extern __shared__ __align__(128) unsigned char smem_raw[];  // 128 B: half-warp LDS.64 rows never straddle a bank row, whatever static shared data precedes
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
     const int g = threadIdx.x >> 7;
@@ -94,8 +101,55 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
     }
 #else
     load_twiddles(tw_s, tw_g);
-    __syncthreads();
 #endif
+    // ---- TMEM: allocate the CTA's 512 columns and park the per-thread constants there (fft2048.cuh) ----
+    __shared__ uint32_t tm_slot;
+    uint32_t tm_base = 0, tm_xs = 0;
+    const int Ktm = K < kTmHyp ? K : kTmHyp;  // hypotheses whose template lives in TMEM; the rest come through L1
+    if constexpr (kCorrTmem) {
+        if (threadIdx.x < 32) tmem_alloc(&tm_slot, kTmCols);
+        tmem_fence_before_sync();
+    }
+    __syncthreads();  // twiddles staged, TMEM address published
+    if constexpr (kCorrTmem) {
+        tmem_fence_after_sync();
+        tm_base = tmem_addr(tm_slot, threadIdx.x >> 5, 0);
+        tm_xs = tm_base + kTmXs + 32 * g;
+        const int ngr = blockDim.x >> 7;
+        float2 r[8];
+        // templates: group g parks hypotheses g, g + ngr, ... (every group reads all of them later)
+        for (int k = g; k < Ktm; k += ngr) {
+            const float2* h = hperm + (size_t)k * 16 * kGroupThreads + tid;
+#pragma unroll
+            for (int pi = 0; pi < 2; ++pi) {
+#pragma unroll
+                for (int d = 0; d < 8; ++d) r[d] = __ldg(h + (pi * 8 + d) * kGroupThreads);
+                tmem_st8(tm_base + kTmH + 32 * k + 16 * pi, r);
+            }
+        }
+        if (g == ngr - 1) {  // inter-pass factors of FFT B, the entries fft_b reads from shared memory
+#pragma unroll
+            for (int pi = 0; pi < 2; ++pi) {
+#pragma unroll
+                for (int m3 = 1; m3 < 8; ++m3) r[m3 - 1] = tw_s[kTwL + m3 * 256 + tid + 128 * pi];
+                r[7] = make_float2(0.f, 0.f);
+                tmem_st8(tm_base + kTmT1 + 16 * pi, r);
+            }
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int m2 = 1 + 8 * hf + e;
+                    r[e] = m2 < 16 ? tw_s[kTwS + m2 * 16 + (tid & 15)] : make_float2(0.f, 0.f);
+                }
+                tmem_st8(tm_base + kTmT2 + 16 * hf, r);
+            }
+        }
+        tmem_wait_st();
+        tmem_fence_before_sync();
+        __syncthreads();
+        tmem_fence_after_sync();
+    }
     const int ngroups = blockDim.x >> 7;
     const long long gstride = (long long)gridDim.x * ngroups;
     const int bar_id = 1 + g;
@@ -111,12 +165,14 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) v[n1] = __ldcs(src + 128 * n1 + tid);
         if (out_delayed != nullptr) {
-            // block contract: out[n] = in[n - delay] (PM/syncword_detection.hpp:318-319).
+            // block contract: out[n] = in[n - delay] (PM/syncword_detection.hpp:318-319), published up to
+            // out_end = the number of items the call consumes (:346): nothing is stored at or past it.
             // This block owns samples [s0, s0+S); it has them in registers already.
 #pragma unroll
             for (int n1 = 0; n1 < 16; ++n1) {
                 const int i = 128 * n1 + tid;
-                if (i < S) out_delayed[s0 + i + delay - out_base] = v[n1];
+                const long long o = s0 + i + delay;
+                if (i < S && o < out_end) out_delayed[o - out_base] = v[n1];
             }
         }
         if constexpr (kCorrTwoBuf) group_sync(bar_id);  // previous block's last reads of xb2 are done
@@ -125,20 +181,53 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
         float best[16];
 #pragma unroll
         for (int m1 = 0; m1 < 16; ++m1) best[m1] = -1.0f;  // :303
-        for (int k = 0; k < K; ++k) {
+        if constexpr (kCorrTmem) {
+            // the spectrum moves to the thread's TMEM lane: 32 registers free for the hypothesis loop
+            {
+                float2 r[8];
+#pragma unroll
+                for (int pi = 0; pi < 2; ++pi) {
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) r[d] = xs[pi * 8 + d];
+                    tmem_st8(tm_xs + 16 * pi, r);
+                }
+                tmem_wait_st();
+            }
+            for (int k = 0; k < K; ++k) {
+                float2 c[16];
+                const uint32_t tm_h = tm_base + kTmH + 32 * k;
+                const float2* hg = hperm + (size_t)k * 16 * kGroupThreads + tid;
+                const bool in_tm = k < Ktm;  // uniform over the CTA
+                fft_b_tm(c, xb, tid, bar_id, tm_xs, tm_base, [&](int pi, float2 (&h)[8]) {   // :250-251
+                    if (in_tm) {
+                        tmem_ld8(tm_h + 16 * pi, h);
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < 8; ++d) h[d] = __ldg(hg + (pi * 8 + d) * kGroupThreads);
+                    }
+                });
+#pragma unroll
+                for (int m1 = 0; m1 < 16; ++m1) {
+                    const float p = norm2(c[m1]);  // :307
+                    best[m1] = fmaxf(best[m1], p);  // == the strict '>' update of :308 for the power itself
+                }
+            }
+        } else {
+            for (int k = 0; k < K; ++k) {
 #ifdef B200_WHATIF_H0
-            const float2* h = hperm + tid;
+                const float2* h = hperm + tid;
 #else
-            const float2* h = hperm + (size_t)k * 16 * kGroupThreads + tid;
+                const float2* h = hperm + (size_t)k * 16 * kGroupThreads + tid;
 #endif
-            float2 y[16], c[16];
+                float2 y[16], c[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) y[j] = cmul(xs[j], __ldg(h + j * kGroupThreads));  // :247-249
-            fft_b<kCorrTwoBuf, kRegB1, kRegB2>(y, c, tw_s, xb, tid, bar_id, xb2, t1, t2);   // :250-251
+                for (int j = 0; j < 16; ++j) y[j] = cmul(xs[j], __ldg(h + j * kGroupThreads));  // :247-249
+                fft_b<kCorrTwoBuf, kRegB1, kRegB2>(y, c, tw_s, xb, tid, bar_id, xb2, t1, t2);   // :250-251
 #pragma unroll
-            for (int m1 = 0; m1 < 16; ++m1) {
-                const float p = norm2(c[m1]);  // :307
-                best[m1] = fmaxf(best[m1], p);  // == the strict '>' update of :308 for the power itself
+                for (int m1 = 0; m1 < 16; ++m1) {
+                    const float p = norm2(c[m1]);  // :307
+                    best[m1] = fmaxf(best[m1], p);  // == the strict '>' update of :308 for the power itself
+                }
             }
         }
         // time reversal: lag kk lives at index (F - kk) mod F (:300)
@@ -149,6 +238,11 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
             const int kk = (kFft - m) & (kFft - 1);
             if (kk < S) zdst[kk] = best[m1];
         }
+    }
+    if constexpr (kCorrTmem) {
+        tmem_fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x < 32) tmem_dealloc(tm_slot, kTmCols);
     }
 }
 
@@ -326,8 +420,8 @@ size_t correlate_smem_bytes(int groups) {
 
 cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpow, long long z_base,
                              const float2* d_hperm, int K, int S, long long b0, long long nb,
-                             const float2* d_tw, float2* d_out_delayed, long long out_base, int delay,
-                             int num_sms, cudaStream_t st) {
+                             const float2* d_tw, float2* d_out_delayed, long long out_base, long long out_end,
+                             int delay, int num_sms, cudaStream_t st) {
     if (nb <= 0) return cudaSuccess;
     // function attributes are per device: one flag per ordinal (a process may hold contexts on several GPUs)
     static bool attr_set[64] = {};
@@ -344,7 +438,7 @@ cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpo
     long long want = (nb + groups - 1) / groups;
     int grid = (int)(want < num_sms ? want : num_sms);
     correlate_kernel<<<grid, kCorrThreads, smem, st>>>(d_in, in_base, d_zpow, z_base, d_hperm, K, S, b0,
-                                                        nb, d_tw, d_out_delayed, out_base, delay);
+                                                        nb, d_tw, d_out_delayed, out_base, out_end, delay);
     count_launch();
     return cudaGetLastError();
 }

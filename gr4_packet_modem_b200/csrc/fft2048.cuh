@@ -36,6 +36,7 @@
 #include <stdint.h>
 
 #include "b200sync_internal.h"
+#include "tmem.cuh"
 
 namespace b200sync {
 
@@ -280,6 +281,84 @@ __device__ __forceinline__ void fft_b(float2 (&y)[16], float2 (&c)[16], const fl
 #pragma unroll
     for (int ff = 0; ff < 16; ++ff) y[ff] = xa[ff * kXchgStrideA + tid];
     if constexpr (!TWO_BUF) group_sync(bar_id);  // exchange buffer free again
+    dft16(y);
+#pragma unroll
+    for (int m1 = 0; m1 < 16; ++m1) c[m1] = y[bitrev4(m1)];
+}
+
+// ---- FFT B with its operands in TMEM (correlate_kernel) ------------------------------------------------
+// Same passes, same table entries, same multiplies as fft_b (bit-identical); what changes is where the
+// operands come from.  Everything a thread needs that does not depend on the other threads of the group —
+// its 16 spectrum points, its 16 template points, its 14 + 15 inter-pass factors — is read from the thread's
+// own TMEM lane with tcgen05.ld (tmem.cuh) instead of from registers / L1 / shared memory: the LSU pipe, which
+// bound the kernel (83 % of its wavefront peak in round 1), keeps only the two exchanges, and the spectrum no
+// longer occupies 32 registers for the whole hypothesis loop.
+// TMEM column layout of a CTA (512 columns; the lane is the thread's index inside its FFT group):
+//   [  0,  32)  pass-B1 factors: 16 columns per pi, entry m3-1 = Wt[(tid + 128 pi) m3], m3 = 1..7
+//   [ 32,  64)  pass-B2 factors: entry m2-1 = Wt[8 (tid & 15) m2], m2 = 1..15
+//   [ 64, 320)  conj template spectra of the first kTmHyp = 8 hypotheses, 32 columns each (layout of hperm)
+//   [320, 512)  block spectrum of each of the 6 FFT groups, 32 columns per group
+constexpr int kTmT1 = 0, kTmT2 = 32, kTmH = 64, kTmHyp = 8, kTmXs = 320, kTmCols = 512;
+
+// load_h(pi, h): fills h[0..8) with the conj template points of half pi (a tcgen05.ld or eight global loads)
+template <class LoadH>
+__device__ __forceinline__ void fft_b_tm(float2 (&c)[16], float2* __restrict__ xb, int tid, int bar_id,
+                                         uint32_t tm_xs, uint32_t tm_tw, LoadH&& load_h) {
+    // pass B1
+#pragma unroll
+    for (int pi = 0; pi < 2; ++pi) {
+        float2 xsr[8], h[8], t[8], w[8];
+        const int p = tid + 128 * pi;
+        tmem_ld8(tm_xs + 16 * pi, xsr);
+        load_h(pi, h);
+        tmem_ld8(tm_tw + kTmT1 + 16 * pi, t);
+        tmem_wait_ld();
+        tmem_use(xsr);
+        tmem_use(h);
+        tmem_use(t);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) w[d] = cmul(xsr[d], h[d]);  // PM/syncword_detection.hpp:247-249
+        dft8(w);
+#pragma unroll
+        for (int m3 = 0; m3 < 8; ++m3) {
+            float2 val = w[bitrev3(m3)];
+            if (m3 != 0) val = cmul(val, t[m3 > 0 ? m3 - 1 : 0]);
+            xb[p * kXchgStrideP + m3] = val;
+        }
+    }
+    group_sync(bar_id);
+    // pass B2
+    const int m3 = tid >> 4, f1 = tid & 15;
+    float2 y[16];
+    {
+        float2 t[8];
+#pragma unroll
+        for (int f2 = 0; f2 < 16; ++f2) y[f2] = xb[(f1 + 16 * f2) * kXchgStrideP + m3];
+        tmem_ld8(tm_tw + kTmT2, t);
+        group_sync(bar_id);
+        dft16(y);
+        tmem_wait_ld();
+        tmem_use(t);
+#pragma unroll
+        for (int m2 = 0; m2 < 9; ++m2) {
+            float2 val = y[bitrev4(m2)];
+            if (m2 != 0) val = cmul(val, t[m2 > 0 ? m2 - 1 : 0]);
+            xb[f1 * kXchgStrideA + m2 * 8 + m3] = val;
+        }
+        tmem_ld8(tm_tw + kTmT2 + 16, t);
+        tmem_wait_ld();
+        tmem_use(t);
+#pragma unroll
+        for (int m2 = 9; m2 < 16; ++m2) {
+            const float2 val = cmul(y[bitrev4(m2)], t[m2 - 9]);
+            xb[f1 * kXchgStrideA + m2 * 8 + m3] = val;
+        }
+    }
+    group_sync(bar_id);
+    // pass B3
+#pragma unroll
+    for (int ff = 0; ff < 16; ++ff) y[ff] = xb[ff * kXchgStrideA + tid];
+    group_sync(bar_id);  // exchange buffer free again
     dft16(y);
 #pragma unroll
     for (int m1 = 0; m1 < 16; ++m1) c[m1] = y[bitrev4(m1)];
