@@ -21,14 +21,16 @@
 // un-permuted: the template spectra are stored pre-permuted instead.
 //
 // ARITHMETIC CONTRACT (mirrored bit-for-bit by oracle/oracle_fft.hpp, FftKind::Mirror):
-//   * every add/sub/mul is a separately rounded IEEE binary32 op (__fadd_rn etc. so
-//     nvcc never contracts them), except the complex multiply
+//   * every add/sub/mul/fma is a separately rounded IEEE binary32 op (explicit _rn intrinsics), issued as
+//     packed FP32x2 instructions; the complex multiply is
 //         cmul(a,w) = ( fma(a.x, w.x, -(a.y*w.y)),  fma(a.x, w.y, a.y*w.x) )
 //     and the squared magnitude  norm2(z) = fma(z.y, z.y, z.x*z.x);
 //   * small DFTs are radix-2 decimation-in-frequency stages: (u,v) -> (u+v, (u-v)*w);
-//     w = 1 is skipped, w = -i is a swap/negate, w = W8^1 and W8^3 use
-//         (x,y)*W8^1 = ( c*(x+y),  c*(y-x) ),   (x,y)*W8^3 = ( c*(y-x), -(c*(x+y)) ),  c = float(sqrt(1/2));
-//     W16^{1,3,5,7} use cmul with constants equal to twiddle-table entries;
+//     w = 1 is skipped, w = -i is a swap/negate; W16^{1,3,5,7} use cmul with constants equal to
+//     twiddle-table entries; w = W8^1 / W8^3 leave the UNSCALED terms
+//         e1(d) = (d.x + d.y, d.y - d.x),   e3(d) = (d.y - d.x, (-d.x) + (-d.y))
+//     and the factor c = float(sqrt(1/2)) is applied by the next stage's butterfly, which always pairs the
+//     two such elements:  a = c*ea;  sum = fma(c, eb, a);  dif = fma(-c, eb, a);
 //   * all inter-pass twiddles are entries of one table  Wt[j] = (float(cos(2 pi j/2048)), float(-sin(2 pi j/2048)))
 //     computed in double on the host; a statically-zero exponent skips the multiply.
 #pragma once
@@ -57,36 +59,24 @@ constexpr int kXchgStrideP = 9;     // exchange layout 2: (p*9 + d)
 constexpr int kXchgFloat2 = 256 * kXchgStrideP;  // 2304 float2 = 18432 B (>= 16*129 = 2064)
 constexpr int kXchgFloat2A = 16 * kXchgStrideA;  // 2064 float2 = 16512 B: layout 1 alone
 
-// Blackwell packed FP32x2 (FADD2 / FMUL2 / FFMA2), -DB200_PACKED_FP32: one instruction per complex
-// add instead of two, each half rounded exactly like the scalar op (sm_100_rt.h), so the arithmetic
-// contract is unchanged.  Measured FP32 throughput is the same 128 op/clk/SM (scripts/ubench_f32x2.cu);
-// only issue slots are saved, and in this kernel the register-pair constraints cost more (extra MOVs,
-// 120 B of spills at 80 registers) than they save: 6.32 ms packed vs 6.19 ms scalar at 2^28, K = 9.
-// The scalar form is therefore the default.
-#ifdef B200_PACKED_FP32
+// Complex arithmetic on Blackwell's packed FP32x2 pipe forms (FADD2 / FMUL2 / FFMA2, sm_100_rt.h): a float2
+// is one aligned register pair, one instruction works on both halves, each half rounded exactly like the
+// scalar IEEE op.  The operand modifiers ptxas folds for free (seen in SASS, profiles/r2_sass_excerpt.txt):
+// scalar broadcast `R.F32`, swapped halves `.LO_HI`, whole-pair negation and a per-half sign `.NP`.  With
+// them a complex multiply is TWO instructions and a butterfly's sum and difference one each — half the
+// issue slots of the scalar form; FP32 pipe time is unchanged (a packed instruction occupies the pipe for two
+// passes), so the kernel moves from issue-bound to FP32-pipe-bound.
+// Caution, measured with ptxas 12.9: `mul.rn.f32x2` feeding `add.rn.f32x2` IS contracted into FFMA2 even with
+// -fmad=false.  The contract below therefore never lets a rounded packed product feed a packed add: every
+// multiply-then-add is written as an explicit fma (w8pair), so there is nothing left for ptxas to fuse.
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
-// a * w for a COMPILE-TIME constant w: the swizzled constant (-w.y, w.x) is free, a.x / a.y are
-// broadcast operands:  p = a.y * (-w.y, w.x);  r = a.x * (w.x, w.y) + p   == cmul(a, w) bit for bit
-__device__ __forceinline__ float2 cmul_const(float2 a, float2 w) {
-    const float2 p = __fmul2_rn(make_float2(a.y, a.y), make_float2(-w.y, w.x));
-    return __ffma2_rn(make_float2(a.x, a.x), w, p);
-}
-#else
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
-    return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
-}
-__device__ __forceinline__ float2 csub(float2 a, float2 b) {
-    return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y));
-}
-#endif
+// a * w = ( fma(a.x, w.x, -(a.y*w.y)),  fma(a.x, w.y, a.y*w.x) ):
+//   FMUL2 p = a.y * w.LO_HI ;  FFMA2 r = a.x * w + (-p.x, +p.y)
 __device__ __forceinline__ float2 cmul(float2 a, float2 w) {
-    return make_float2(__fmaf_rn(a.x, w.x, -__fmul_rn(a.y, w.y)),
-                       __fmaf_rn(a.x, w.y, __fmul_rn(a.y, w.x)));
+    const float2 p = __fmul2_rn(make_float2(a.y, a.y), make_float2(w.y, w.x));
+    return __ffma2_rn(make_float2(a.x, a.x), w, make_float2(-p.x, p.y));
 }
-#ifndef B200_PACKED_FP32
-__device__ __forceinline__ float2 cmul_const(float2 a, float2 w) { return cmul(a, w); }
-#endif
 __device__ __forceinline__ float norm2(float2 z) { return __fmaf_rn(z.y, z.y, __fmul_rn(z.x, z.x)); }
 // (x,y) * -i
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
@@ -95,71 +85,70 @@ __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.
 #define B200_COS_PI_8 0.92387953251128675613f
 #define B200_SIN_PI_8 0.38268343236508977173f
 
-// (x,y) * W8^1 = c(1-i)
-__device__ __forceinline__ float2 mul_w8_1(float2 a) {
-    return make_float2(__fmul_rn(B200_SQRT1_2, __fadd_rn(a.x, a.y)),
-                       __fmul_rn(B200_SQRT1_2, __fsub_rn(a.y, a.x)));
+// W8^1 = c(1-i) and W8^3 = -c(1+i), c = sqrt(1/2): d * W8^1 = c * e1(d), d * W8^3 = c * e3(d) with
+//   e1(d) = (d.x + d.y, d.y - d.x),   e3(d) = (d.y - d.x, (-d.x) + (-d.y)).
+// In a radix-2 DIF DFT-8/16 the two elements that carry these factors always meet in the NEXT stage's
+// butterfly, so the scale is applied there (w8pair) instead of being rounded on its own.
+__device__ __forceinline__ float2 w8e1(float2 d) { return __fadd2_rn(d, make_float2(d.y, -d.x)); }
+__device__ __forceinline__ float2 w8e3(float2 d) { return __fadd2_rn(make_float2(d.y, -d.x), make_float2(-d.x, -d.y)); }
+// butterfly of u = c*ea and v = c*eb:  a = rn(c*ea);  sum = fma(c, eb, a);  dif = fma(-c, eb, a)
+__device__ __forceinline__ void w8pair(float2& ea, float2& eb) {
+    const float2 cc = make_float2(B200_SQRT1_2, B200_SQRT1_2);
+    const float2 a = __fmul2_rn(cc, ea);
+    ea = __ffma2_rn(cc, eb, a);
+    eb = __ffma2_rn(make_float2(-B200_SQRT1_2, -B200_SQRT1_2), eb, a);
 }
-// (x,y) * W8^3 = -c(1+i)
-__device__ __forceinline__ float2 mul_w8_3(float2 a) {
-    return make_float2(__fmul_rn(B200_SQRT1_2, __fsub_rn(a.y, a.x)),
-                       -__fmul_rn(B200_SQRT1_2, __fadd_rn(a.x, a.y)));
-}
-
-// multiply by W16^e, e compile-time in [0,8)
-template <int E>
-__device__ __forceinline__ float2 mul_w16(float2 a) {
-    if constexpr (E == 0) return a;
-    else if constexpr (E == 1) return cmul_const(a, make_float2(B200_COS_PI_8, -B200_SIN_PI_8));
-    else if constexpr (E == 2) return mul_w8_1(a);
-    else if constexpr (E == 3) return cmul_const(a, make_float2(B200_SIN_PI_8, -B200_COS_PI_8));
-    else if constexpr (E == 4) return mul_mi(a);
-    else if constexpr (E == 5) return cmul_const(a, make_float2(-B200_SIN_PI_8, -B200_COS_PI_8));
-    else if constexpr (E == 6) return mul_w8_3(a);
-    else return cmul_const(a, make_float2(-B200_COS_PI_8, -B200_SIN_PI_8));
-}
-
-template <int HALF, int STEP, int I>
-__device__ __forceinline__ void bfly(float2& u, float2& v) {
+// plain butterfly: (u, v) -> (u + v, u - v)
+__device__ __forceinline__ void bf(float2& u, float2& v) {
     const float2 s = cadd(u, v);
-    const float2 d = csub(u, v);
+    v = csub(u, v);
     u = s;
-    v = mul_w16<I * STEP>(d);
+}
+// W16^e for odd e: table-entry constants, general complex multiply
+template <int E>
+__device__ __forceinline__ float2 mul_w16_odd(float2 a) {
+    static_assert(E == 1 || E == 3 || E == 5 || E == 7, "odd exponents only");
+    if constexpr (E == 1) return cmul(a, make_float2(B200_COS_PI_8, -B200_SIN_PI_8));
+    else if constexpr (E == 3) return cmul(a, make_float2(B200_SIN_PI_8, -B200_COS_PI_8));
+    else if constexpr (E == 5) return cmul(a, make_float2(-B200_SIN_PI_8, -B200_COS_PI_8));
+    else return cmul(a, make_float2(-B200_COS_PI_8, -B200_SIN_PI_8));
 }
 
 // In-place radix-2 DIF DFT-16.  Input v[n], output v[bitrev4(k)] = X[k].
 __device__ __forceinline__ void dft16(float2 (&v)[16]) {
-    // half = 8, twiddle W16^i
-    bfly<8, 1, 0>(v[0], v[8]);  bfly<8, 1, 1>(v[1], v[9]);
-    bfly<8, 1, 2>(v[2], v[10]); bfly<8, 1, 3>(v[3], v[11]);
-    bfly<8, 1, 4>(v[4], v[12]); bfly<8, 1, 5>(v[5], v[13]);
-    bfly<8, 1, 6>(v[6], v[14]); bfly<8, 1, 7>(v[7], v[15]);
-    // half = 4, twiddle W8^i = W16^{2i}
+    // half = 8, twiddle W16^i on the difference
 #pragma unroll
-    for (int g = 0; g < 16; g += 8) {
-        bfly<4, 2, 0>(v[g + 0], v[g + 4]); bfly<4, 2, 1>(v[g + 1], v[g + 5]);
-        bfly<4, 2, 2>(v[g + 2], v[g + 6]); bfly<4, 2, 3>(v[g + 3], v[g + 7]);
-    }
-    // half = 2, twiddle W4^i = W16^{4i}
-#pragma unroll
-    for (int g = 0; g < 16; g += 4) {
-        bfly<2, 4, 0>(v[g + 0], v[g + 2]); bfly<2, 4, 1>(v[g + 1], v[g + 3]);
-    }
+    for (int i = 0; i < 8; ++i) bf(v[i], v[i + 8]);
+    v[9] = mul_w16_odd<1>(v[9]);
+    v[10] = w8e1(v[10]);                 // x c, applied in the next stage
+    v[11] = mul_w16_odd<3>(v[11]);
+    v[12] = mul_mi(v[12]);
+    v[13] = mul_w16_odd<5>(v[13]);
+    v[14] = w8e3(v[14]);                 // x c, applied in the next stage
+    v[15] = mul_w16_odd<7>(v[15]);
+    // half = 4, twiddle W8^i
+    bf(v[0], v[4]); bf(v[1], v[5]); bf(v[2], v[6]); bf(v[3], v[7]);
+    v[5] = w8e1(v[5]); v[6] = mul_mi(v[6]); v[7] = w8e3(v[7]);
+    bf(v[8], v[12]); bf(v[9], v[13]); w8pair(v[10], v[14]); bf(v[11], v[15]);
+    v[13] = w8e1(v[13]); v[14] = mul_mi(v[14]); v[15] = w8e3(v[15]);
+    // half = 2, twiddle W4^i
+    bf(v[0], v[2]); bf(v[1], v[3]); v[3] = mul_mi(v[3]);
+    bf(v[4], v[6]); w8pair(v[5], v[7]); v[7] = mul_mi(v[7]);
+    bf(v[8], v[10]); bf(v[9], v[11]); v[11] = mul_mi(v[11]);
+    bf(v[12], v[14]); w8pair(v[13], v[15]); v[15] = mul_mi(v[15]);
     // half = 1
 #pragma unroll
-    for (int g = 0; g < 16; g += 2) bfly<1, 8, 0>(v[g], v[g + 1]);
+    for (int g = 0; g < 16; g += 2) bf(v[g], v[g + 1]);
 }
 
 // In-place radix-2 DIF DFT-8.  Input v[n], output v[bitrev3(k)] = X[k].
 __device__ __forceinline__ void dft8(float2 (&v)[8]) {
-    bfly<4, 2, 0>(v[0], v[4]); bfly<4, 2, 1>(v[1], v[5]);
-    bfly<4, 2, 2>(v[2], v[6]); bfly<4, 2, 3>(v[3], v[7]);
+    bf(v[0], v[4]); bf(v[1], v[5]); bf(v[2], v[6]); bf(v[3], v[7]);
+    v[5] = w8e1(v[5]); v[6] = mul_mi(v[6]); v[7] = w8e3(v[7]);
+    bf(v[0], v[2]); bf(v[1], v[3]); v[3] = mul_mi(v[3]);
+    bf(v[4], v[6]); w8pair(v[5], v[7]); v[7] = mul_mi(v[7]);
 #pragma unroll
-    for (int g = 0; g < 8; g += 4) {
-        bfly<2, 4, 0>(v[g + 0], v[g + 2]); bfly<2, 4, 1>(v[g + 1], v[g + 3]);
-    }
-#pragma unroll
-    for (int g = 0; g < 8; g += 2) bfly<1, 8, 0>(v[g], v[g + 1]);
+    for (int g = 0; g < 8; g += 2) bf(v[g], v[g + 1]);
 }
 
 __host__ __device__ constexpr int bitrev4(int k) {

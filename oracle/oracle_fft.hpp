@@ -17,7 +17,8 @@
 //
 //  FftKind::Mirror  — a loop-based restatement of the ARITHMETIC CONTRACT written in
 //      gr4_packet_modem_b200/csrc/fft2048.cuh (16x16x8 decomposition, radix-2 DIF
-//      small DFTs, fma-based complex multiply, one twiddle table).  With it the oracle
+//      small DFTs, fma-based complex multiply, W8 factors folded into the next butterfly,
+//      one twiddle table).  With it the oracle
 //      reproduces the GPU's zpow and detection records bit for bit, which pins every
 //      comparison/threshold/ordering decision of the pipeline, also at low SNR where a
 //      1-ulp difference can flip a threshold test.  It shares no code with the product.
@@ -82,28 +83,45 @@ class Fft
         switch (e) {
         case 0: return a;
         case 1: return cmul_fma(a, c64(kCos, -kSin));
-        case 2: return c64(kC * (x + y), kC * (y - x));
+        case 2: return c64(x + y, y - x);          // e1(d): the factor c is applied by the next stage
         case 3: return cmul_fma(a, c64(kSin, -kCos));
         case 4: return c64(y, -x);
         case 5: return cmul_fma(a, c64(-kSin, -kCos));
-        case 6: return c64(kC * (y - x), -(kC * (x + y)));
+        case 6: return c64(y - x, (-x) + (-y));    // e3(d): the factor c is applied by the next stage
         default: return cmul_fma(a, c64(-kCos, -kSin));
         }
     }
-    // radix-2 DIF, n = 16 or 8; output in bit-reversed order
+    // radix-2 DIF, n = 16 or 8; output in bit-reversed order.  Elements that carry W8^1 / W8^3 keep the
+    // unscaled term and a "pending c" mark; the next stage pairs two such elements and applies c with fmas
+    // (fft2048.cuh: w8pair).
     static void dft_small(c64* v, int n)
     {
+        bool pend[16] = {};
         for (int half = n / 2; half >= 1; half /= 2) {
             const int step = 8 / half;
             for (int g = 0; g < n; g += 2 * half) {
                 for (int i = 0; i < half; ++i) {
                     const c64 u = v[g + i], w = v[g + i + half];
-                    v[g + i] = c64(u.real() + w.real(), u.imag() + w.imag());
-                    const c64 d(u.real() - w.real(), u.imag() - w.imag());
-                    v[g + i + half] = mul_w16(d, i * step);
+                    c64 s, d;
+                    if (pend[g + i] != pend[g + i + half]) throw std::logic_error("mirror: unpaired W8 factor");
+                    if (pend[g + i]) {
+                        const c64 a(kC * u.real(), kC * u.imag());
+                        s = c64(std::fmaf(kC, w.real(), a.real()), std::fmaf(kC, w.imag(), a.imag()));
+                        d = c64(std::fmaf(-kC, w.real(), a.real()), std::fmaf(-kC, w.imag(), a.imag()));
+                        pend[g + i] = pend[g + i + half] = false;
+                    } else {
+                        s = c64(u.real() + w.real(), u.imag() + w.imag());
+                        d = c64(u.real() - w.real(), u.imag() - w.imag());
+                    }
+                    v[g + i] = s;
+                    const int e = i * step;
+                    v[g + i + half] = mul_w16(d, e);
+                    if (e == 2 || e == 6) pend[g + i + half] = true;
                 }
             }
         }
+        for (int i = 0; i < n; ++i)
+            if (pend[i]) throw std::logic_error("mirror: W8 factor left pending");
     }
     static int br4(int k) { return ((k & 1) << 3) | ((k & 2) << 1) | ((k & 4) >> 1) | ((k & 8) >> 3); }
     static int br3(int k) { return ((k & 1) << 2) | (k & 2) | ((k & 4) >> 2); }
