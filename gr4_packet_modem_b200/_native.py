@@ -126,6 +126,10 @@ def lib():
     L.b200sync_sd_info.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_float),
                                    C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
     L.b200sync_sd_process.argtypes = [vp, vp, sz, vp, psz, vp, sz, psz]
+    L.b200sync_sd_tags_ready.argtypes = [vp]
+    L.b200sync_sd_tags_ready.restype = C.c_size_t
+    L.b200sync_sd_drain_tags.argtypes = [vp, vp, sz, psz]
+    L.b200sync_sd_drain_tags.restype = C.c_int
     L.b200sync_sd_detect_device.argtypes = [vp, vp, sz, vp, vp, vp, sz, psz, psz]
     L.b200sync_sd_detect_host.argtypes = [vp, vp, sz, vp, sz, psz, psz]
     L.b200sync_sd_detect_file.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_uint64, vp, sz, psz, psz,

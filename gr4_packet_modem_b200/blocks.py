@@ -125,6 +125,10 @@ class SyncwordDetection:
         base = self._items_consumed
         self._items_consumed += nc.value
         res = [(int(tags[i].index - base), int(tags[i].index), _tag_dict(tags[i])) for i in range(nt.value)]
+        # tags beyond max_tags stay queued in the context and belong to this chunk: fetch them too
+        while L.b200sync_sd_tags_ready(self._h) > 0:
+            check(L.b200sync_sd_drain_tags(self._h, tags, max_tags, C.byref(nt)))
+            res += [(int(tags[i].index - base), int(tags[i].index), _tag_dict(tags[i])) for i in range(nt.value)]
         status = "INSUFFICIENT_INPUT_ITEMS" if rc == 1 else "OK"
         return status, nc.value, (out[:nc.value] if want_output else None), res
 

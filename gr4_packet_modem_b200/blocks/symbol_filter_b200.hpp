@@ -106,7 +106,7 @@ public:
             const int rc = b200sync_sf_process(_ctx, reinterpret_cast<const float*>(inSpan.data()), n, n_tin ? &tin : nullptr,
                                                n_tin, reinterpret_cast<float*>(outSpan.data()), outSpan.size(), &consumed,
                                                &produced, _out_tags.data(), _out_tags.size(), &n_tout);
-            if (rc == B200SYNC_ENOMEM && _out_tags.size() < (1u << 20)) {  // state unchanged: grow and retry
+            if (rc == B200SYNC_ENOMEM && _out_tags.size() < (1u << 20)) {  // tag buffer (not the span: that is ENOSPC); state unchanged: grow and retry
                 _out_tags.resize(_out_tags.size() * 4);
                 continue;
             }

@@ -114,21 +114,23 @@ public:
     {
         if (!_ctx) throw gr::exception("processBulk() before start()");
         size_t consumed = 0, ntags = 0;
-        for (;;) {
-            const int rc = b200sync_sd_process(_ctx, reinterpret_cast<const float*>(inSpan.data()), inSpan.size(),
-                                               reinterpret_cast<float*>(outSpan.data()), &consumed, _tagbuf.data(),
-                                               _tagbuf.size(), &ntags);
-            if (rc == B200SYNC_ENOMEM && consumed == 0) {  // cannot happen after consumption; grow and retry
-                _tagbuf.resize(_tagbuf.size() * 4);
-                continue;
-            }
-            if (rc < 0) throw gr::exception(b200sync_last_error());
-            if (rc == 1) {  // :215-227
-                if (!inSpan.consume(0)) throw gr::exception("consume failed");
-                outSpan.publish(0);
-                return gr::work::Status::INSUFFICIENT_INPUT_ITEMS;
-            }
-            break;
+        const int rc = b200sync_sd_process(_ctx, reinterpret_cast<const float*>(inSpan.data()), inSpan.size(),
+                                           reinterpret_cast<float*>(outSpan.data()), &consumed, _tagbuf.data(),
+                                           _tagbuf.size(), &ntags);
+        if (rc < 0) throw gr::exception(b200sync_last_error());
+        if (rc == 1) {  // :215-227
+            if (!inSpan.consume(0)) throw gr::exception("consume failed");
+            outSpan.publish(0);
+            return gr::work::Status::INSUFFICIENT_INPUT_ITEMS;
+        }
+        // more publishable tags than the buffer held (tiny time_threshold or a very long span): they are
+        // still queued in the context and belong to THIS chunk, so fetch them before publishing
+        for (size_t more = b200sync_sd_tags_ready(_ctx); more > 0; more = b200sync_sd_tags_ready(_ctx)) {
+            if (_tagbuf.size() < ntags + more) _tagbuf.resize(ntags + more);
+            size_t got = 0;
+            if (b200sync_sd_drain_tags(_ctx, _tagbuf.data() + ntags, _tagbuf.size() - ntags, &got) != 0)
+                throw gr::exception(b200sync_last_error());
+            ntags += got;
         }
         for (size_t i = 0; i < ntags; ++i) {
             // tag.index is an absolute output index; publishTag wants the offset in this chunk (:321-324)

@@ -538,9 +538,31 @@ int b200sync_sd_process(b200sync_sd* sd, const float* in, size_t n_in, float* ou
     sd->consumed += j;
     *n_consumed = j;
     // tags whose output index has now been published (:320-325)
+    // The call has committed (state, carry line, consumed count): it can no longer fail.  Tags that do not
+    // fit stay queued; b200sync_sd_tags_ready() reports them and b200sync_sd_drain_tags() hands them out.
     size_t nt = 0;
-    while (!sd->pending.empty() && sd->pending.front().index < sd->consumed) {
-        if (nt >= max_tags) return fail(B200SYNC_ENOMEM, "tag buffer too small");
+    while (nt < max_tags && !sd->pending.empty() && sd->pending.front().index < sd->consumed) {
+        tags[nt++] = sd->pending.front();
+        sd->pending.pop_front();
+    }
+    *n_tags = nt;
+    return 0;
+}
+
+size_t b200sync_sd_tags_ready(const b200sync_sd* sd) {
+    if (!sd) return 0;
+    size_t n = 0;
+    for (const auto& t : sd->pending) {
+        if (t.index >= sd->consumed) break;  // the queue is sorted by index
+        ++n;
+    }
+    return n;
+}
+
+int b200sync_sd_drain_tags(b200sync_sd* sd, b200sync_sd_tag* tags, size_t max_tags, size_t* n_tags) {
+    if (!sd || !n_tags || (!tags && max_tags)) return fail(B200SYNC_EINVAL, "null argument");
+    size_t nt = 0;
+    while (nt < max_tags && !sd->pending.empty() && sd->pending.front().index < sd->consumed) {
         tags[nt++] = sd->pending.front();
         sd->pending.pop_front();
     }

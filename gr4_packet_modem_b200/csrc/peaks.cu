@@ -247,7 +247,13 @@ peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_
     const long long tile_lo = lo + (long long)blockIdx.x * kFastTile;
     const long long q0 = tile_lo - Tpad;                   // absolute index of window element 0
     const int* src = reinterpret_cast<const int*>(zpow) + (q0 - z_base);
-    const int lo_ok = q0 < 0 ? (int)(-q0) : 0;             // first element inside the stream
+    // first element that is both inside the stream and inside the caller's metric buffer: the window origin is
+    // rounded down to a group boundary (Tpad >= T), which can reach below z_base when a caller keeps exactly
+    // the 2T+2 samples of history the decisions need (streaming, short shard halos).  Those pad elements are
+    // never part of a decision window — they only enter the extrema of a group that straddles the window edge,
+    // where a zero can only send the count to the exact per-sample path — so they read as zeros.
+    const long long first_ok = z_base > 0 ? z_base : 0;
+    const int lo_ok = q0 < first_ok ? (int)(first_ok - q0) : 0;
     const long long hi_ll = z_end - q0;                    // first element not yet known
     const int hi_ok = hi_ll < (long long)(nrow * 128) ? (int)hi_ll : nrow * 128;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(src) & 15) == 0;

@@ -588,7 +588,9 @@ int sf_run(b200sync_sf* sf, const float2* d_in, size_t n_in, const b200sync_stre
     }
     if (n_out > max_out || otags.size() > max_out_tags) {
         sf->clock_phase = cp; sf->pfb_arm = arm; sf->scale = sc; sf->pending = pend;
-        return sf_fail(B200SYNC_ENOMEM, "output span or output tag buffer too small");
+        // two causes, two codes: only the tag buffer is something a caller can grow and retry
+        if (n_out > max_out) return sf_fail(B200SYNC_ENOSPC, "output span too small");
+        return sf_fail(B200SYNC_ENOMEM, "output tag buffer too small");
     }
     if (n_out > 0) {
         // drop segments that produce nothing so the binary search is over producing segments only

@@ -30,6 +30,7 @@ extern "C" {
 #define B200SYNC_ECUDA (-2)       /* CUDA runtime failure                                     */
 #define B200SYNC_ENOMEM (-3)      /* caller buffer too small / allocation failed             */
 #define B200SYNC_EUNSUPPORTED (-4)/* valid in the reference, not implemented on the GPU path */
+#define B200SYNC_ENOSPC (-5)      /* output span too small for the items the call would produce */
 
 const char* b200sync_last_error(void);
 /* ABI version of this header (bumped on incompatible change). */
@@ -107,9 +108,14 @@ int b200sync_sd_info(const b200sync_sd* sd, uint32_t* syncword_samples, uint32_t
  *                 return value 1 == INSUFFICIENT_INPUT_ITEMS when n_in < fft_size, :215-227)
  *   tags          tags to publish; tag.index - (items consumed before this call) is the
  *                 offset to pass to out.publishTag(); at most max_tags, count in *n_tags.
- * Host<->device copies happen inside this call. */
+ * Host<->device copies happen inside this call.  Once input has been consumed the call cannot fail:
+ * tags beyond max_tags stay queued inside the context, b200sync_sd_tags_ready() counts those whose output
+ * index has already been published and b200sync_sd_drain_tags() hands them out (same index convention);
+ * a caller publishes them in the same chunk (the shell does, PM/syncword_detection.hpp:320-325). */
 int b200sync_sd_process(b200sync_sd* sd, const float* in, size_t n_in, float* out, size_t* n_consumed,
                         b200sync_sd_tag* tags, size_t max_tags, size_t* n_tags);
+size_t b200sync_sd_tags_ready(const b200sync_sd* sd);
+int b200sync_sd_drain_tags(b200sync_sd* sd, b200sync_sd_tag* tags, size_t max_tags, size_t* n_tags);
 
 /* Offline bulk entry point over a DEVICE-resident capture (no reference counterpart: a
  * 65536-item GR ring chunk is far too small to fill a B200).  Equivalent to start()
@@ -263,7 +269,8 @@ const char* b200sync_sf_last_error(void);
  * (sorted by index; the GR4 shell passes at most one, at index 0, because the runtime cuts chunks at
  * tags).  Consumes all n_in items; produces one item per symbol clock tick; returns the re-indexed
  * tags (delayed by `delay`, placed on the nearest output symbol, syncword_phase adjusted when
- * time_est < 0).  B200SYNC_ENOMEM if max_out / max_out_tags are too small (state unchanged). */
+ * time_est < 0).  B200SYNC_ENOSPC if max_out is too small, B200SYNC_ENOMEM if
+ * max_out_tags is (state unchanged in both cases; only the latter is worth a retry with a larger buffer). */
 int b200sync_sf_process(b200sync_sf* sf, const float* in, size_t n_in, const b200sync_stream_tag* in_tags,
                         size_t n_in_tags, float* out, size_t max_out, size_t* n_consumed, size_t* n_produced,
                         b200sync_stream_tag* out_tags, size_t max_out_tags, size_t* n_out_tags);

@@ -394,3 +394,69 @@ def test_contexts_are_independent_across_threads(rx_params):
         assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
         assert a[4].tobytes() == b[4].tobytes()
         assert np.array_equal(a[5].view(np.uint32), b[5].view(np.uint32))
+
+
+@pytest.mark.parametrize("n", [1 << 20, (1 << 20) + 777, 3 * 1752 + 2048])
+def test_device_delayed_output_stays_inside_n_items(oracle, rx_params, n):
+    """The fused delayed output of detect_device (PM/syncword_detection.hpp:318-319) is published up to the
+    consumed count only: an exactly n-item device buffer followed by a guard area must come back with the
+    guard untouched, and equal to the host-span path's output.  (Round-1 advisor finding: the last block used
+    to store up to `delay` items past the publish limit.)"""
+    import torch
+    from gr4_packet_modem_b200.stimulus import packet_capture
+
+    x, _ = packet_capture(n, seed=5, esn0_db=20.0, cfo=0.005, payload_bytes=200)
+    sd = _gpu(rx_params, min_freq_bin=-4, max_freq_bin=4, power_threshold=9.5)
+    dev = torch.device("cuda:0")
+    d_in = torch.from_numpy(x.view(np.float32)).to(dev)
+    guard = 4096
+    d_out = torch.full((2 * (n + guard),), 777.0, dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    consumed, recs, tags = sd.detect_device(d_in.data_ptr(), n, st, d_out.data_ptr())
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy().view(np.complex64)
+    assert np.all(out[consumed:].view(np.float32) == 777.0), "stored past the publish limit"
+    sd2 = _gpu(rx_params, min_freq_bin=-4, max_freq_bin=4, power_threshold=9.5)
+    c2, out2, tags2 = sd2.run(x, chunk=1 << 18, want_output=True)
+    assert c2 == consumed
+    assert np.array_equal(out[:consumed].view(np.uint32), out2.view(np.uint32))
+
+
+@pytest.mark.parametrize("T", [33, 100, 769, 1000])
+def test_streaming_time_threshold_not_multiple_of_32(oracle, rx_params, T):
+    """Streaming keeps exactly 2T+2 samples of metric history; the fast flags kernel rounds its window origin
+    down to a group boundary, which used to reach below the buffer for T % 32 != 0 (round-1 advisor finding).
+    Decisions must equal the offline run and the oracle's sequential loop for such T."""
+    from gr4_packet_modem_b200.stimulus import packet_capture
+
+    n = 1 << 19
+    x, _ = packet_capture(n, seed=9, esn0_db=6.0, cfo=0.004, payload_bytes=100)
+    kw = dict(min_freq_bin=-2, max_freq_bin=2, power_threshold=8.0, time_threshold=T)
+    sd = _gpu(rx_params, **kw)
+    c_s, _, tags_s = sd.run(x, chunk=40000)
+    sd2 = _gpu(rx_params, **kw)
+    c_o, recs_o, _ = sd2.detect_host(x)
+    o = oracle.SyncwordDetection(**rx_params, **kw, fft_kind=oracle.FFT_MIRROR)
+    oc, _, otags = o.run(x, chunk=1 << 19)
+    want = [t.index for t in otags]
+    assert len(want) > 0
+    assert c_o == oc
+    assert (recs_o["index"] + sd2.delay).tolist() == want
+    assert [idx for _, idx, _ in tags_s] == [i for i in want if i < c_s]
+
+
+def test_process_bulk_more_tags_than_the_buffer_holds(oracle, rx_params):
+    """b200sync_sd_process cannot fail after it has consumed input: tags beyond max_tags stay queued and are
+    drained in the same chunk (round-1 advisor finding: they used to be lost with ENOMEM)."""
+    rng = np.random.default_rng(11)
+    n = 1 << 17
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    kw = dict(min_freq_bin=0, max_freq_bin=0, power_threshold=1.0001, time_threshold=3)
+    sd = _gpu(rx_params, **kw)
+    status, c, _, tags = sd.process_bulk(x, want_output=False, max_tags=7)
+    assert status == "OK" and c > 0
+    sd2 = _gpu(rx_params, **kw)
+    _, c2, _, tags2 = sd2.process_bulk(x, want_output=False, max_tags=1 << 16)
+    assert c2 == c and len(tags2) > 7
+    assert [t[1] for t in tags] == [t[1] for t in tags2]
+    assert all(0 <= off < c for off, _, _ in tags)
