@@ -6,5 +6,5 @@ interface on top of that ABI; there is no CPU fallback — importing the blocks 
 built library raises.
 """
 from .firdes import root_raised_cosine  # noqa: F401
-from .blocks import (SyncwordDetection, DetectionRecord, SyncwordTag, FrontEnd, PfbArbResampler,  # noqa: F401
+from .blocks import (SyncwordDetection, SyncwordDetectionMulti, DetectionRecord, SyncwordTag, FrontEnd, PfbArbResampler,  # noqa: F401
                      Rotator, SymbolFilter, SyncwordDetectionFilter, CoarseFrequencyCorrection, SyncwordWipeoff, CostasLoop)

@@ -65,6 +65,11 @@ class StreamTag(C.Structure):
     ]
 
 
+class Shard(C.Structure):
+    _fields_ = [("device", C.c_int32), ("_pad", C.c_int32), ("first_block", C.c_uint64), ("n_blocks", C.c_uint64),
+                ("total_blocks", C.c_uint64), ("first_sample", C.c_uint64), ("n_samples", C.c_uint64)]
+
+
 class SfConfig(C.Structure):
     _fields_ = [
         ("samples_per_symbol", C.c_uint32),
@@ -196,6 +201,24 @@ def lib():
     L.b200sync_sdf_destroy.argtypes = [vp]
     L.b200sync_sdf_start.argtypes = [vp]
     pi = C.POINTER(C.c_int)
+    u64 = C.c_uint64
+    L.b200sync_sd_shard_phase1_file.argtypes = [vp, C.c_char_p, u64, u64, sz, u64, u64, u64, vp, sz]
+    L.b200sync_sd_multi_create.argtypes = [C.POINTER(SdConfig), vp, sz, C.POINTER(vp)]
+    L.b200sync_sd_multi_destroy.argtypes = [vp]
+    L.b200sync_sd_multi_destroy.restype = None
+    L.b200sync_sd_multi_devices.argtypes = [vp]
+    L.b200sync_sd_multi_devices.restype = sz
+    L.b200sync_sd_multi_context.argtypes = [vp, sz]
+    L.b200sync_sd_multi_context.restype = vp
+    L.b200sync_sd_multi_plan.argtypes = [vp, u64, C.POINTER(Shard)]
+    L.b200sync_sd_multi_detect_device.argtypes = [vp, C.POINTER(vp), u64, vp, sz, psz, psz]
+    L.b200sync_sd_multi_detect_host.argtypes = [vp, vp, u64, vp, sz, psz, psz]
+    L.b200sync_sd_multi_detect_file.argtypes = [vp, C.c_char_p, u64, u64, vp, sz, psz, psz, C.POINTER(u64)]
+    L.b200sync_sd_multi_last_timings.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    for name in ("b200sync_sd_shard_phase1_file", "b200sync_sd_multi_create", "b200sync_sd_multi_plan",
+                 "b200sync_sd_multi_detect_device", "b200sync_sd_multi_detect_host", "b200sync_sd_multi_detect_file",
+                 "b200sync_sd_multi_last_timings"):
+        getattr(L, name).restype = C.c_int
     L.b200sync_sdf_process.argtypes = [vp, vp, sz, vp, sz, vp, vp, sz, psz, psz, psz, vp, pi, pi]
     for name in ("b200sync_sf_create", "b200sync_sf_start", "b200sync_sf_process", "b200sync_sf_process_device",
                  "b200sync_sdf_create", "b200sync_sdf_start", "b200sync_sdf_process"):

@@ -277,6 +277,113 @@ class SyncwordDetection:
         return z
 
 
+class SyncwordDetectionMulti:
+    """ONE SyncwordDetection block over several GPUs of one box (b200sync_sd_multi_*): the capture is cut into
+    contiguous time shards on the reference's own FFT-block grid, one host thread drives each GPU, the shards'
+    chain tables are composed on the host and the detections are gathered on the host — the records equal those
+    of the single-GPU call.  No collective, no NCCL.  devices=None: every visible GPU."""
+
+    def __init__(self, rrc_taps, syncword, constellation, min_freq_bin: int = 0, max_freq_bin: int = 0,
+                 time_threshold: int = 768, power_threshold: float = 9.5, fft_size: int = 2048,
+                 samples_per_symbol: int = 4, devices=None):
+        L = _native.lib()
+        self.rrc_taps = np.ascontiguousarray(rrc_taps, dtype=np.float32)
+        self.syncword = np.ascontiguousarray(syncword, dtype=np.uint8)
+        self.constellation = np.ascontiguousarray(constellation, dtype=np.complex64)
+        self.time_threshold = int(time_threshold)
+        cfg = SdConfig(int(fft_size), int(samples_per_symbol), self.rrc_taps.ctypes.data, self.rrc_taps.size,
+                       self.syncword.ctypes.data, self.syncword.size, self.constellation.ctypes.data,
+                       self.constellation.size, int(min_freq_bin), int(max_freq_bin), self.time_threshold,
+                       float(power_threshold), 0)
+        devs = np.ascontiguousarray(devices if devices is not None else [], dtype=np.int32)
+        h = C.c_void_p()
+        check(L.b200sync_sd_multi_create(C.byref(cfg), devs.ctypes.data if devs.size else None, devs.size, C.byref(h)))
+        self._h = h
+        self.n_devices = int(L.b200sync_sd_multi_devices(self._h))
+        self.delay = 2 * self.time_threshold + 1
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                _native.lib().b200sync_sd_multi_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def plan(self, n: int):
+        """How an n-sample capture is cut: list of dicts (device, first_block, n_blocks, total_blocks,
+        first_sample, n_samples), one per GPU."""
+        sh = (_native.Shard * self.n_devices)()
+        check(_native.lib().b200sync_sd_multi_plan(self._h, int(n), sh))
+        return [{k: int(getattr(s, k)) for k in ("device", "first_block", "n_blocks", "total_blocks", "first_sample",
+                                                  "n_samples")} for s in sh]
+
+    def _tags(self, r):
+        L = _native.lib()
+        tags = np.zeros(len(r), TAG_DTYPE)
+        if len(r):
+            ctx = C.c_void_p(L.b200sync_sd_multi_context(self._h, 0))
+            rr = np.ascontiguousarray(r)
+            check(L.b200sync_sd_records_to_tags(ctx, rr.ctypes.data, len(rr), tags.ctypes.data))
+        return tags
+
+    def _finish(self, recs, nr, nc):
+        r = _copy_records(recs, nr.value)
+        return nc.value, r, self._tags(r)
+
+    def detect_host(self, x, max_recs: int = 0):
+        """Capture in host memory: a complex64 array, or (address, n) of e.g. a pinned torch tensor."""
+        if isinstance(x, np.ndarray):
+            x = np.ascontiguousarray(x, dtype=np.complex64)
+            ptr, n = x.ctypes.data, x.size
+        else:
+            ptr, n = x
+        if max_recs <= 0:
+            max_recs = n // (self.time_threshold + 1) + 2 * self.n_devices + 2
+        recs = np.zeros(max_recs, RECORD_DTYPE)
+        nr, nc = C.c_size_t(0), C.c_size_t(0)
+        check(_native.lib().b200sync_sd_multi_detect_host(self._h, C.c_void_p(ptr), n, recs.ctypes.data, max_recs,
+                                                          C.byref(nr), C.byref(nc)))
+        return self._finish(recs, nr, nc)
+
+    def detect_device(self, shard_ptrs, n: int, max_recs: int = 0):
+        """Capture already resident: shard_ptrs[r] = device address (on plan(n)[r]["device"]) of that shard's
+        samples."""
+        ptrs = (C.c_void_p * self.n_devices)(*[C.c_void_p(int(p)) for p in shard_ptrs])
+        if max_recs <= 0:
+            max_recs = n // (self.time_threshold + 1) + 2 * self.n_devices + 2
+        recs = np.zeros(max_recs, RECORD_DTYPE)
+        nr, nc = C.c_size_t(0), C.c_size_t(0)
+        check(_native.lib().b200sync_sd_multi_detect_device(self._h, ptrs, int(n), recs.ctypes.data, max_recs,
+                                                            C.byref(nr), C.byref(nc)))
+        return self._finish(recs, nr, nc)
+
+    def detect_file(self, filename, first_item: int = 0, max_items: int | None = None, max_recs: int = 0):
+        """Raw cf32 capture file (PM/file_source.hpp format); every GPU's host thread reads its own shard."""
+        import os
+
+        path = os.fsencode(filename)
+        limit = (1 << 64) - 1 if max_items is None else int(max_items)
+        if max_recs <= 0:
+            try:
+                items = max(0, os.path.getsize(filename) // 8 - first_item)
+            except OSError:
+                items = 0
+            max_recs = min(items, limit) // (self.time_threshold + 1) + 2 * self.n_devices + 2
+        recs = np.zeros(max_recs, RECORD_DTYPE)
+        nr, nc, ni = C.c_size_t(0), C.c_size_t(0), C.c_uint64(0)
+        check(_native.lib().b200sync_sd_multi_detect_file(self._h, path, int(first_item), limit, recs.ctypes.data,
+                                                          max_recs, C.byref(nr), C.byref(nc), C.byref(ni)))
+        return self._finish(recs, nr, nc) + (ni.value,)
+
+    def last_timings(self) -> list:
+        a = (C.c_float * self.n_devices)()
+        b = (C.c_float * self.n_devices)()
+        c = (C.c_float * self.n_devices)()
+        check(_native.lib().b200sync_sd_multi_last_timings(self._h, a, b, c))
+        return [{"correlate_ms": a[i], "peaks_ms": b[i], "refine_ms": c[i]} for i in range(self.n_devices)]
+
+
 class FrontEnd:
     """PfbArbResampler<c64,c64,float,float> followed by Rotator<float>, fused in one kernel
     (PM/pfb_arb_resampler.hpp, PM/rotator.hpp; wiring apps/packet_transceiver.cpp:71-75).

@@ -339,6 +339,7 @@ int slide_window(DevBuf<T>& buf, DevBuf<T>& tmp, long long& base, long long end,
 
 namespace b200sync {
 void count_launch(int n) { g_launches += static_cast<uint64_t>(n); }
+int set_last_error(int code, const std::string& msg) { return fail(code, msg); }
 }  // namespace b200sync
 
 extern "C" {
@@ -890,9 +891,11 @@ int b200sync_sd_copy_metric(const b200sync_sd* sd, float* zpow, size_t n) {
 // shard phase 1.  h_in != nullptr: the shard's samples are in HOST memory; they are copied into the context's
 // capture buffer in pieces on the copy stream and the correlator runs in chunks behind the copies' events
 // (as b200sync_sd_detect_host does for a whole capture).
+// f != nullptr: the shard's samples are the next n_in items of the open capture FILE (positioned by the caller); they are
+// read piece by piece into the pinned staging ring and copied from there (as b200sync_sd_detect_file does).
 static int shard_phase1_core(b200sync_sd* sd, const float2* d_in, const float2* h_in, uint64_t first_sample_abs,
                              size_t n_in, uint64_t first_block, uint64_t n_blocks, uint64_t total_blocks,
-                             cudaStream_t st, uint16_t* table, size_t table_len) {
+                             cudaStream_t st, uint16_t* table, size_t table_len, FILE* f = nullptr) {
     if (table_len < static_cast<size_t>(sd->T) + 1) return fail(B200SYNC_ENOMEM, "table too small");
     if (first_block + n_blocks > total_blocks || n_blocks == 0) return fail(B200SYNC_EINVAL, "bad shard");
     CU(cudaSetDevice(sd->device));
@@ -916,7 +919,7 @@ static int shard_phase1_core(b200sync_sd* sd, const float2* d_in, const float2* 
     CU(sd->d_table.ensure(static_cast<size_t>(T) + 1));
     sd->ev_valid = false;
     CU(cudaEventRecord(sd->ev[0], st));
-    if (h_in == nullptr) {
+    if (h_in == nullptr && f == nullptr) {
         CU(launch_correlate(d_in, in_base, sd->d_zoff.p, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, cb0,
                             cb1 - cb0, sd->d_tw.p, nullptr, 0, 0, 0, sd->num_sms, st));
     } else {
@@ -930,18 +933,41 @@ static int shard_phase1_core(b200sync_sd* sd, const float2* d_in, const float2* 
             CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             sd->ev_pieces.push_back(e);
         }
+        constexpr int kSlots = 3;
+        if (f != nullptr && !sd->h_stage) {
+            CU(cudaMallocHost(&sd->h_stage, kSlots * static_cast<size_t>(piece) * sizeof(float2)));
+            for (int i = 0; i < kSlots; ++i) CU(cudaEventCreateWithFlags(&sd->ev_stage[i], cudaEventDisableTiming));
+        }
+        long long b_next = cb0;  // first correlator block not yet enqueued
         for (size_t i = 0; i < npieces; ++i) {
             const size_t off = i * piece, cnt = std::min<size_t>(piece, n_in - off);
-            CU(cudaMemcpyAsync(sd->d_xoff.p + off, h_in + off, cnt * sizeof(float2), cudaMemcpyHostToDevice,
-                               sd->copy_stream));
+            const float2* src = h_in ? h_in + off : nullptr;
+            if (f != nullptr) {
+                const int slot = static_cast<int>(i % kSlots);
+                float2* h = sd->h_stage + static_cast<size_t>(slot) * piece;
+                if (i >= kSlots) CU(cudaEventSynchronize(sd->ev_stage[slot]));  // its previous copy has left the buffer
+                if (std::fread(h, sizeof(float2), cnt, f) != cnt) {               // PM/file_source.hpp:52
+                    cudaStreamSynchronize(sd->copy_stream);
+                    cudaStreamSynchronize(st);
+                    return fail(B200SYNC_EINVAL, std::string("error reading from file: ") +
+                                                     (std::feof(f) ? "file shrank while reading" : std::strerror(errno)));
+                }
+                src = h;
+            }
+            CU(cudaMemcpyAsync(sd->d_xoff.p + off, src, cnt * sizeof(float2), cudaMemcpyHostToDevice, sd->copy_stream));
             CU(cudaEventRecord(sd->ev_pieces[i], sd->copy_stream));
-        }
-        for (long long b0 = cb0; b0 < cb1; b0 += kOfflineChunkBlocks) {
-            const long long nb = std::min(kOfflineChunkBlocks, cb1 - b0);
-            const long long last_sample = (b0 + nb - 1) * S + F - 1 - in_base;  // relative to the shard's input
-            CU(cudaStreamWaitEvent(st, sd->ev_pieces[static_cast<size_t>(last_sample / piece)], 0));
-            CU(launch_correlate(d_in, in_base, sd->d_zoff.p, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, b0, nb,
-                                sd->d_tw.p, nullptr, 0, 0, 0, sd->num_sms, st));
+            if (f != nullptr) CU(cudaEventRecord(sd->ev_stage[i % kSlots], sd->copy_stream));
+            // correlator chunks this piece completes: blocks whose last sample lies before off + cnt
+            const long long have = in_base + static_cast<long long>(off + cnt);
+            const long long b_ready = std::min(cb1, have >= F ? (have - F) / S + 1 : 0LL);
+            if (b_ready > b_next) {
+                CU(cudaStreamWaitEvent(st, sd->ev_pieces[i], 0));
+                for (long long b0 = b_next; b0 < b_ready; b0 += kOfflineChunkBlocks)
+                    CU(launch_correlate(d_in, in_base, sd->d_zoff.p, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, b0,
+                                        std::min(kOfflineChunkBlocks, b_ready - b0), sd->d_tw.p, nullptr, 0, 0, 0,
+                                        sd->num_sms, st));
+                b_next = b_ready;
+            }
         }
     }
     CU(cudaEventRecord(sd->ev[1], st));
@@ -982,6 +1008,22 @@ int b200sync_sd_shard_phase1_host(b200sync_sd* sd, const float* in, uint64_t fir
     if (!sd || !in || !table) return fail(B200SYNC_EINVAL, "null argument");
     return shard_phase1_core(sd, nullptr, reinterpret_cast<const float2*>(in), first_sample_abs, n_in, first_block,
                              n_blocks, total_blocks, sd->stream, table, table_len);
+}
+
+int b200sync_sd_shard_phase1_file(b200sync_sd* sd, const char* filename, uint64_t capture_first_item,
+                                  uint64_t first_sample_abs, size_t n_in, uint64_t first_block, uint64_t n_blocks,
+                                  uint64_t total_blocks, uint16_t* table, size_t table_len) {
+    if (!sd || !filename || !table) return fail(B200SYNC_EINVAL, "null argument");
+    FILE* f = std::fopen(filename, "rb");  // PM/file_source.hpp:31-37
+    if (!f) return fail(B200SYNC_EINVAL, std::string("error opening file: ") + std::strerror(errno));
+    struct Closer {
+        FILE* f;
+        ~Closer() { std::fclose(f); }
+    } closer{f};
+    if (fseeko(f, static_cast<off_t>((capture_first_item + first_sample_abs) * sizeof(float2)), SEEK_SET) != 0)
+        return fail(B200SYNC_EINVAL, std::string("seek failed: ") + std::strerror(errno));
+    return shard_phase1_core(sd, nullptr, nullptr, first_sample_abs, n_in, first_block, n_blocks, total_blocks,
+                             sd->stream, table, table_len, f);
 }
 
 int b200sync_sd_shard_phase2(b200sync_sd* sd, uint32_t entry_offset, b200sync_detection_record* recs,

@@ -4,6 +4,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <string>
+
 #include "../../include/b200sync.h"
 
 namespace b200sync {
@@ -29,6 +31,8 @@ struct PeakState {
 
 // api.cu: every kernel launch site calls this (b200sync_launch_count of the C ABI)
 void count_launch(int n = 1);
+// api.cu: set the calling thread's b200sync_last_error() text and return `code`
+int set_last_error(int code, const std::string& msg);
 
 // correlator.cu
 cudaError_t launch_template_spectra(const float2* d_td, float2* d_hperm, int K, const float2* d_tw,

@@ -178,8 +178,54 @@ int b200sync_sd_shard_phase1(b200sync_sd* sd, const void* d_in, uint64_t first_s
 int b200sync_sd_shard_phase1_host(b200sync_sd* sd, const float* in, uint64_t first_sample_abs, size_t n_in,
                                   uint64_t first_block, uint64_t n_blocks, uint64_t total_blocks, uint16_t* table,
                                   size_t table_len);
+/* phase 1 with the shard's samples in a capture FILE (format of FileSource<c64>, see b200sync_sd_detect_file): items
+ * [capture_first_item + first_sample_abs, + n_in) are read through the pinned staging ring, copies and correlator
+ * overlap the reads. */
+int b200sync_sd_shard_phase1_file(b200sync_sd* sd, const char* filename, uint64_t capture_first_item,
+                                  uint64_t first_sample_abs, size_t n_in, uint64_t first_block, uint64_t n_blocks,
+                                  uint64_t total_blocks, uint16_t* table, size_t table_len);
 int b200sync_sd_shard_phase2(b200sync_sd* sd, uint32_t entry_offset, b200sync_detection_record* recs,
                              size_t max_recs, size_t* n_recs);
+
+/* One capture on several GPUs of one box, detections gathered on the host (BASELINE north_star).
+ * Equivalent to ONE SyncwordDetection block (start() + one processBulk over the whole capture,
+ * PM/syncword_detection.hpp:204-356): the records are those of the single-GPU call, in index order.  The
+ * context owns one b200sync_sd per GPU; every call runs one host thread per GPU (bound to that GPU's local
+ * cores when /sys tells which they are), the shards' (T+1)-entry chain tables are composed in host memory,
+ * and no data moves between GPUs: there is no collective and no NCCL anywhere on this path.
+ *   devices / n_devices   CUDA ordinals to use; n_devices = 0: every visible device.  cfg->device is ignored. */
+typedef struct b200sync_sd_multi b200sync_sd_multi;
+typedef struct b200sync_shard {
+    int32_t device;         /* CUDA ordinal that owns the shard                                         */
+    int32_t _pad;
+    uint64_t first_block;   /* first FFT block the shard decides; blocks are on the stream's own grid   */
+    uint64_t n_blocks;
+    uint64_t total_blocks;  /* blocks of the whole capture, (n - fft_size) / stride + 1 (:238)          */
+    uint64_t first_sample;  /* first input sample the shard needs (one halo block before first_block)   */
+    uint64_t n_samples;     /* input samples the shard needs (halo on both sides included)              */
+} b200sync_shard;
+int b200sync_sd_multi_create(const b200sync_sd_config* cfg, const int* devices, size_t n_devices,
+                             b200sync_sd_multi** out);
+void b200sync_sd_multi_destroy(b200sync_sd_multi* m);
+size_t b200sync_sd_multi_devices(const b200sync_sd_multi* m);
+/* the per-GPU context (e.g. for b200sync_sd_records_to_tags, which needs any one of them) */
+b200sync_sd* b200sync_sd_multi_context(b200sync_sd_multi* m, size_t i);
+/* how an n-sample capture is cut: shards[n_devices] */
+int b200sync_sd_multi_plan(const b200sync_sd_multi* m, uint64_t n, b200sync_shard* shards);
+/* capture already resident: d_shards[r] is a pointer ON shards[r].device to that shard's samples
+ * (absolute samples [first_sample, first_sample + n_samples) of the n-sample capture) */
+int b200sync_sd_multi_detect_device(b200sync_sd_multi* m, const void* const* d_shards, uint64_t n,
+                                    b200sync_detection_record* recs, size_t max_recs, size_t* n_recs,
+                                    size_t* n_consumed);
+/* capture in host memory (pageable or pinned): each GPU pulls its shard, compute chases the copies */
+int b200sync_sd_multi_detect_host(b200sync_sd_multi* m, const float* in, uint64_t n, b200sync_detection_record* recs,
+                                  size_t max_recs, size_t* n_recs, size_t* n_consumed);
+/* capture file (see b200sync_sd_detect_file): each GPU's host thread reads its own shard of the file */
+int b200sync_sd_multi_detect_file(b200sync_sd_multi* m, const char* filename, uint64_t first_item, uint64_t max_items,
+                                  b200sync_detection_record* recs, size_t max_recs, size_t* n_recs, size_t* n_consumed,
+                                  uint64_t* n_items_read);
+/* per-GPU stage times of the last call: arrays of n_devices floats (any may be NULL) */
+int b200sync_sd_multi_last_timings(const b200sync_sd_multi* m, float* correlate_ms, float* peaks_ms, float* refine_ms);
 
 /* output_tag(), PM/syncword_detection.hpp:56-115, evaluated on the host in the reference's
  * own float/double mix from the raw records. */
