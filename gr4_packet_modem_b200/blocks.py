@@ -175,8 +175,10 @@ class SyncwordDetection:
         r = _copy_records(recs, nr.value)
         return nc.value, r, self.records_to_tags(r)
 
-    def detect_host(self, x, max_recs: int = 0):
-        """Whole host capture, H2D pipelined with compute (b200sync_sd_detect_host)."""
+    def detect_host(self, x, max_recs: int = 0, out=None):
+        """Whole host capture, H2D pipelined with compute (b200sync_sd_detect_host).  out: optional host
+        destination of the block's output span (complex64 array or address of >= n items): the input delayed by
+        2*time_threshold+1 (b200sync_sd_detect_host_out)."""
         L = _native.lib()
         if isinstance(x, np.ndarray):
             x = np.ascontiguousarray(x, dtype=np.complex64)
@@ -187,10 +189,20 @@ class SyncwordDetection:
             max_recs = n // (self.time_threshold + 1) + 2
         recs = self._rec_buffer(max_recs)
         nr, nc = C.c_size_t(0), C.c_size_t(0)
-        check(L.b200sync_sd_detect_host(self._h, C.c_void_p(ptr), n, recs.ctypes.data, max_recs, C.byref(nr),
-                                        C.byref(nc)))
+        if out is None:
+            check(L.b200sync_sd_detect_host(self._h, C.c_void_p(ptr), n, recs.ctypes.data, max_recs, C.byref(nr),
+                                            C.byref(nc)))
+        else:
+            optr = out.ctypes.data if isinstance(out, np.ndarray) else int(out)
+            check(L.b200sync_sd_detect_host_out(self._h, C.c_void_p(ptr), n, C.c_void_p(optr), recs.ctypes.data,
+                                                max_recs, C.byref(nr), C.byref(nc)))
         r = _copy_records(recs, nr.value)
         return nc.value, r, self.records_to_tags(r)
+
+    def shard_output(self, d_out_ptr: int, out_first_abs: int, out_len: int) -> None:
+        """The next shard_phase1* call also writes its slice of the delayed output stream (b200sync_sd_shard_output)."""
+        check(_native.lib().b200sync_sd_shard_output(self._h, C.c_void_p(d_out_ptr or None), int(out_first_abs),
+                                                     int(out_len)))
 
     def detect_file(self, filename, first_item: int = 0, max_items: int | None = None, max_recs: int = 0):
         """Whole raw cf32 capture file — the format FileSource<c64> reads (PM/file_source.hpp) — staged

@@ -133,6 +133,8 @@ struct b200sync_sd {
         long long in_base = 0, z_base = 0, lo = 0, hi = 0, P_total = 0;
         cudaStream_t st = nullptr;
         bool valid = false;
+        float2* d_out = nullptr;      // optional delayed output of the NEXT phase 1 (b200sync_sd_shard_output)
+        long long out_first = 0, out_len = 0;
     } shard;
 };
 
@@ -158,7 +160,7 @@ int run_chunk(b200sync_sd* sd, const float2* d_in, long long in_base, float* d_z
               long long b0, long long nb, long long lo, long long hi, float2* d_out_delayed,
               long long out_end, cudaStream_t st) {
     CU(launch_correlate(d_in, in_base, d_z, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, b0, nb,
-                        sd->d_tw.p, d_out_delayed, 0, out_end, (int)sd->delay, sd->num_sms, st));
+                        sd->d_tw.p, d_out_delayed, 0, 0, out_end, (int)sd->delay, sd->num_sms, st));
     if (hi > lo) {
         const long long z_end = (b0 + nb) * (long long)sd->S;
         CU(launch_peak_phase1(d_z, z_base, z_end, lo, hi, sd->T, sd->power_threshold, sd->d_ws.p,
@@ -660,6 +662,35 @@ int b200sync_sd_detect_device(b200sync_sd* sd, const void* d_in, size_t n, void*
                            nullptr, 0, recs, max_recs, n_recs, n_consumed);
 }
 
+// the delay line of the block contract for HOST spans (:318-319): out[i] = in[i - delay], zeros first.  The samples
+// never needed the GPU: a plain copy, spread over a few host threads so that it keeps up with the PCIe link.
+static void host_delay_line(const b200sync_sd* sd, const float* in, float* out, size_t P, std::vector<std::thread>& pool) {
+    const size_t D = static_cast<size_t>(sd->delay);
+    const size_t zeros = std::min(D, P);
+    std::memset(out, 0, zeros * sizeof(c64));
+    if (P <= D) return;
+    const size_t cnt = P - D;
+    const size_t nth = std::max<size_t>(1, std::min<size_t>({8, std::thread::hardware_concurrency() / 2, cnt >> 20}));
+    for (size_t t = 0; t < nth; ++t) {
+        const size_t i0 = cnt * t / nth, i1 = cnt * (t + 1) / nth;
+        pool.emplace_back([=] { std::memcpy(out + 2 * (D + i0), in + 2 * i0, (i1 - i0) * sizeof(c64)); });
+    }
+}
+
+int b200sync_sd_detect_host_out(b200sync_sd* sd, const float* in, size_t n, float* out, b200sync_detection_record* recs,
+                                size_t max_recs, size_t* n_recs, size_t* n_consumed) {
+    if (!sd || !n_recs || !n_consumed || (!in && n) || (!recs && max_recs))
+        return fail(B200SYNC_EINVAL, "null argument");
+    std::vector<std::thread> pool;
+    if (out != nullptr && n >= sd->fft_size) {
+        const size_t P = ((n - sd->fft_size) / sd->S + 1) * sd->S;  // items the call will publish (:346)
+        host_delay_line(sd, in, out, P, pool);
+    }
+    const int rc = b200sync_sd_detect_host(sd, in, n, recs, max_recs, n_recs, n_consumed);
+    for (auto& t : pool) t.join();
+    return rc;
+}
+
 int b200sync_sd_detect_host(b200sync_sd* sd, const float* in, size_t n, b200sync_detection_record* recs,
                             size_t max_recs, size_t* n_recs, size_t* n_consumed) {
     if (!sd || !n_recs || !n_consumed || (!in && n) || (!recs && max_recs))
@@ -819,7 +850,7 @@ int b200sync_sd_detect_channels_device(b200sync_sd* sd, const void* d_in, size_t
         PeakState* state = sd->d_chan_state.p + c;
         DetectionRecord* drecs = sd->d_chan_recs.p + c * cap;
         CU(launch_correlate(x, 0, ln.z.p, 0, sd->d_hperm.p, (int)sd->K, (int)sd->S, 0, nb_total, sd->d_tw.p,
-                            nullptr, 0, 0, (int)sd->delay, sd->num_sms, ln.st));
+                            nullptr, 0, 0, 0, (int)sd->delay, sd->num_sms, ln.st));
         if (hi_total > 0) {
             CU(launch_peak_phase1(ln.z.p, 0, P, 0, hi_total, sd->T, sd->power_threshold, ln.ws.p, ln.ws.cap,
                                   nullptr, sd->num_sms, ln.st));
@@ -919,9 +950,22 @@ static int shard_phase1_core(b200sync_sd* sd, const float2* d_in, const float2* 
     CU(sd->d_table.ensure(static_cast<size_t>(T) + 1));
     sd->ev_valid = false;
     CU(cudaEventRecord(sd->ev[0], st));
+    // optional delayed output (block contract, :318-319): the shard owns output items [fb*S, (fb+nbk)*S) of the
+    // P_total the whole capture publishes; they come from blocks fb-1 .. fb+nbk-1, which the halo covers
+    float2* d_out = sd->shard.d_out;
+    long long out_base = sd->shard.out_first, out_lo = 0, out_hi = 0;
+    sd->shard.d_out = nullptr;  // one call only
+    if (d_out != nullptr) {
+        out_lo = std::max(fb * S, out_base);
+        out_hi = std::min({(fb + nbk) * S, P_total, out_base + sd->shard.out_len});
+        if (out_lo < static_cast<long long>(sd->delay)) {  // the zero-initialised history (:194-199)
+            const long long z1 = std::min<long long>(sd->delay, out_hi);
+            if (z1 > out_lo) CU(cudaMemsetAsync(d_out + (out_lo - out_base), 0, (z1 - out_lo) * sizeof(float2), st));
+        }
+    }
     if (h_in == nullptr && f == nullptr) {
         CU(launch_correlate(d_in, in_base, sd->d_zoff.p, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, cb0,
-                            cb1 - cb0, sd->d_tw.p, nullptr, 0, 0, 0, sd->num_sms, st));
+                            cb1 - cb0, sd->d_tw.p, d_out, out_base, out_lo, out_hi, (int)sd->delay, sd->num_sms, st));
     } else {
         CU(sd->d_xoff.ensure(n_in));
         d_in = sd->d_xoff.p;
@@ -964,8 +1008,8 @@ static int shard_phase1_core(b200sync_sd* sd, const float2* d_in, const float2* 
                 CU(cudaStreamWaitEvent(st, sd->ev_pieces[i], 0));
                 for (long long b0 = b_next; b0 < b_ready; b0 += kOfflineChunkBlocks)
                     CU(launch_correlate(d_in, in_base, sd->d_zoff.p, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, b0,
-                                        std::min(kOfflineChunkBlocks, b_ready - b0), sd->d_tw.p, nullptr, 0, 0, 0,
-                                        sd->num_sms, st));
+                                        std::min(kOfflineChunkBlocks, b_ready - b0), sd->d_tw.p, d_out, out_base, out_lo,
+                                        out_hi, (int)sd->delay, sd->num_sms, st));
                 b_next = b_ready;
             }
         }
@@ -991,6 +1035,14 @@ static int shard_phase1_core(b200sync_sd* sd, const float2* d_in, const float2* 
     sd->metric_n = static_cast<size_t>((cb1 - cb0) * S);
     sd->metric_ptr = sd->d_zoff.p;
     sd->metric_base = z_base;
+    return 0;
+}
+
+int b200sync_sd_shard_output(b200sync_sd* sd, void* d_out_delayed, uint64_t out_first_abs, size_t out_len) {
+    if (!sd) return fail(B200SYNC_EINVAL, "null context");
+    sd->shard.d_out = static_cast<float2*>(d_out_delayed);
+    sd->shard.out_first = static_cast<long long>(out_first_abs);
+    sd->shard.out_len = static_cast<long long>(out_len);
     return 0;
 }
 

@@ -39,8 +39,8 @@ cudaError_t launch_template_spectra(const float2* d_td, float2* d_hperm, int K, 
                                     cudaStream_t st);
 cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpow, long long z_base,
                              const float2* d_hperm, int K, int S, long long b0, long long nb,
-                             const float2* d_tw, float2* d_out_delayed, long long out_base, long long out_end,
-                             int delay, int num_sms, cudaStream_t st);
+                             const float2* d_tw, float2* d_out_delayed, long long out_base, long long out_lo,
+                             long long out_hi, int delay, int num_sms, cudaStream_t st);
 cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_zpow, long long z_base,
                           const float2* d_hperm, int K, int S, int min_freq_bin, const float2* d_tw,
                           const unsigned long long* d_det_idx, const unsigned int* d_det_count,

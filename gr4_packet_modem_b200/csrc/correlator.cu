@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kCorrThreads, 1)
 correlate_kernel(const float2* __restrict__ in, long long in_base, float* __restrict__ zpow,
                  long long z_base, const float2* __restrict__ hperm, int K, int S, long long b0,
                  long long nb, const float2* __restrict__ tw_g, float2* __restrict__ out_delayed,
-                 long long out_base, long long out_end, int delay) {
+                 long long out_base, long long out_lo, long long out_hi, int delay) {
     extern __shared__ __align__(128) unsigned char smem_raw[];  // 128 B: half-warp LDS.64 rows never straddle a bank row, whatever static shared data precedes
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
     const int g = threadIdx.x >> 7;
@@ -165,14 +165,15 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) v[n1] = __ldcs(src + 128 * n1 + tid);
         if (out_delayed != nullptr) {
-            // block contract: out[n] = in[n - delay] (PM/syncword_detection.hpp:318-319), published up to
-            // out_end = the number of items the call consumes (:346): nothing is stored at or past it.
+            // block contract: out[n] = in[n - delay] (PM/syncword_detection.hpp:318-319).  Only output items
+            // [out_lo, out_hi) are stored: out_hi = the number of items the call publishes (:346) — nothing is
+            // stored at or past it — and a time shard stores only the slice it owns.
             // This block owns samples [s0, s0+S); it has them in registers already.
 #pragma unroll
             for (int n1 = 0; n1 < 16; ++n1) {
                 const int i = 128 * n1 + tid;
                 const long long o = s0 + i + delay;
-                if (i < S && o < out_end) out_delayed[o - out_base] = v[n1];
+                if (i < S && o >= out_lo && o < out_hi) out_delayed[o - out_base] = v[n1];
             }
         }
         if constexpr (kCorrTwoBuf) group_sync(bar_id);  // previous block's last reads of xb2 are done
@@ -420,8 +421,8 @@ size_t correlate_smem_bytes(int groups) {
 
 cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpow, long long z_base,
                              const float2* d_hperm, int K, int S, long long b0, long long nb,
-                             const float2* d_tw, float2* d_out_delayed, long long out_base, long long out_end,
-                             int delay, int num_sms, cudaStream_t st) {
+                             const float2* d_tw, float2* d_out_delayed, long long out_base, long long out_lo,
+                             long long out_hi, int delay, int num_sms, cudaStream_t st) {
     if (nb <= 0) return cudaSuccess;
     // function attributes are per device: one flag per ordinal (a process may hold contexts on several GPUs)
     static bool attr_set[64] = {};
@@ -438,7 +439,7 @@ cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpo
     long long want = (nb + groups - 1) / groups;
     int grid = (int)(want < num_sms ? want : num_sms);
     correlate_kernel<<<grid, kCorrThreads, smem, st>>>(d_in, in_base, d_zpow, z_base, d_hperm, K, S, b0,
-                                                        nb, d_tw, d_out_delayed, out_base, out_end, delay);
+                                                        nb, d_tw, d_out_delayed, out_base, out_lo, out_hi, delay);
     count_launch();
     return cudaGetLastError();
 }

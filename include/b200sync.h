@@ -134,6 +134,11 @@ int b200sync_sd_detect_device(b200sync_sd* sd, const void* d_in, size_t n, void*
  * copies overlap compute.  `in` may be pageable or pinned. */
 int b200sync_sd_detect_host(b200sync_sd* sd, const float* in, size_t n, b200sync_detection_record* recs,
                             size_t max_recs, size_t* n_recs, size_t* n_consumed);
+/* The same with the block's output span: out (host, >= items consumed) receives out[i] = in[i - delay], zeros
+ * first (PM/syncword_detection.hpp:318-319).  For host spans the delay line is a host copy (the samples never
+ * needed the GPU); it runs on a few host threads while the GPU works. */
+int b200sync_sd_detect_host_out(b200sync_sd* sd, const float* in, size_t n, float* out,
+                                b200sync_detection_record* recs, size_t max_recs, size_t* n_recs, size_t* n_consumed);
 
 /* Raw capture ingestion: the same over a capture FILE in the format
  * FileSource<std::complex<float>> reads (PM/file_source.hpp:47-53; apps/packet_receiver_file.cpp:29-31;
@@ -170,6 +175,11 @@ int b200sync_sd_detect_channels_device(b200sync_sd* sd, const void* d_in, size_t
  *           shard's first decided sample -> exit offset, written to table[T+1];
  *   phase 2 takes the true entry offset (composition of the previous shards' tables, done by
  *           the caller) and returns the shard's detection records. */
+/* Optional, before a phase-1 call: that call also writes the shard's slice of the delayed output stream
+ * (out[i] = in[i - delay], :318-319).  Shard r owns output items [first_block*S, (first_block+n_blocks)*S) of the
+ * capture; d_out_delayed (device) holds absolute output items [out_first_abs, out_first_abs + out_len), items
+ * outside it are not stored.  The setting is consumed by the next phase-1 call. */
+int b200sync_sd_shard_output(b200sync_sd* sd, void* d_out_delayed, uint64_t out_first_abs, size_t out_len);
 int b200sync_sd_shard_phase1(b200sync_sd* sd, const void* d_in, uint64_t first_sample_abs, size_t n_in,
                              uint64_t first_block, uint64_t n_blocks, uint64_t total_blocks,
                              void* cuda_stream, uint16_t* table, size_t table_len);

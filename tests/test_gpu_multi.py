@@ -68,3 +68,46 @@ def test_multi_device_resident_and_file(rx_params, tmp_path):
     assert items == n and c3 == c1 and np.array_equal(r1.view(np.uint8), r3.view(np.uint8))
     with pytest.raises(Exception, match="error opening file"):
         m.detect_file(os.path.join(tmp_path, "missing.cf32"))
+
+
+def test_shard_delayed_output_and_host_output(rx_params):
+    """The block's output span (input delayed by 2T+1, PM/syncword_detection.hpp:318-319) from the sharded path
+    (every shard writes the slice it owns) and from the host-span bulk call equals the streaming block's."""
+    import torch
+    from gr4_packet_modem_b200 import SyncwordDetection
+    from gr4_packet_modem_b200.sharding import entry_offsets, plan_shards
+    from gr4_packet_modem_b200.stimulus import packet_capture
+
+    n = (1 << 20) + 4321
+    x, _ = packet_capture(n, seed=23, esn0_db=20.0, cfo=0.005, payload_bytes=300)
+    kw = dict(min_freq_bin=-1, max_freq_bin=1, power_threshold=9.5)
+    ref = SyncwordDetection(**rx_params, **kw)
+    c0, out0, tags0 = ref.run(x, chunk=1 << 18, want_output=True)
+    # host-span bulk call with an output span
+    sd = SyncwordDetection(**rx_params, **kw)
+    out_h = np.full(n, 7 + 7j, np.complex64)
+    c1, r1, _ = sd.detect_host(x, out=out_h)
+    assert c1 == c0 and np.array_equal(out_h[:c1].view(np.uint32), out0.view(np.uint32))
+    assert np.all(out_h[c1:] == 7 + 7j)
+    # three shards on one device, each writing its slice into ONE n-item device buffer
+    world = 3
+    shards = plan_shards(n, world, 2048, 1752, 768)
+    dev = torch.device("cuda:0")
+    d_out = torch.full((2 * (c0 + 512),), 5.0, dtype=torch.float32, device=dev)
+    sds = [SyncwordDetection(**rx_params, **kw) for _ in range(world)]
+    bufs, tables = [], []
+    for sh, s in zip(shards, sds):
+        seg = torch.from_numpy(x[sh.first_sample:sh.first_sample + sh.n_samples].view(np.float32).copy()).to(dev)
+        bufs.append(seg)
+        s.shard_output(d_out.data_ptr(), 0, c0)
+        tables.append(s.shard_phase1(seg.data_ptr(), sh.first_sample, sh.n_samples, sh.first_block, sh.n_blocks,
+                                     sh.total_blocks, torch.cuda.current_stream().cuda_stream))
+    idx = []
+    for s, j in zip(sds, entry_offsets(tables)):
+        r, _ = s.shard_phase2(j, n // 769 + 2)
+        idx += (r["index"] + s.delay).tolist()
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().view(np.complex64)
+    assert np.array_equal(got[:c0].view(np.uint32), out0.view(np.uint32))
+    assert np.all(got[c0:].view(np.float32) == 5.0)
+    assert idx == [t[1] for t in tags0]
