@@ -141,6 +141,8 @@ def lib():
     L.b200sync_sd_detect_host_out.restype = C.c_int
     L.b200sync_sd_shard_output.argtypes = [vp, vp, C.c_uint64, sz]
     L.b200sync_sd_shard_output.restype = C.c_int
+    L.b200sync_sd_shard_output_host.argtypes = [vp, vp, C.c_uint64, sz]
+    L.b200sync_sd_shard_output_host.restype = C.c_int
     L.b200sync_sd_detect_file.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_uint64, vp, sz, psz, psz,
                                           C.POINTER(C.c_uint64)]
     L.b200sync_sd_detect_file.restype = C.c_int

@@ -244,6 +244,11 @@ class SyncwordDetection:
         out = [raw[c * max_recs:c * max_recs + int(counts[c])].copy().view(RECORD_DTYPE) for c in range(n_channels)]
         return nc.value, out
 
+    def shard_output_host(self, out_ptr: int, out_first_abs: int, out_len: int) -> None:
+        """... into host memory, for shard_phase1_host (b200sync_sd_shard_output_host)."""
+        check(_native.lib().b200sync_sd_shard_output_host(self._h, C.c_void_p(out_ptr or None), int(out_first_abs),
+                                                          int(out_len)))
+
     def shard_phase1(self, d_in_ptr: int, first_sample_abs: int, n_in: int, first_block: int, n_blocks: int,
                      total_blocks: int, stream_ptr: int = 0) -> np.ndarray:
         L = _native.lib()

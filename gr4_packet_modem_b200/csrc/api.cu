@@ -95,6 +95,11 @@ struct b200sync_sd {
     long long z_base = 0, z_end = 0;
     uint64_t consumed = 0;  // _items_consumed
     long long lo_next = 0;  // first undecided sample
+    unsigned long long r_abs_host = 0;  // host copy of the search position (PeakState::r_abs), streaming path
+    // streaming fast path: pinned staging for pageable input spans, pinned landing buffer for the records
+    unsigned char* h_in_stage = nullptr;
+    DetectionRecord* h_recs_pin = nullptr;
+    size_t h_recs_pin_cap = 0;
     std::vector<c64> carry; // last `delay` input samples (delay line)
     std::deque<b200sync_sd_tag> pending;
     // offline
@@ -106,21 +111,14 @@ struct b200sync_sd {
     // device-side stage timing of the last offline call (CUDA events on the caller's stream)
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     bool ev_valid = false;
-    // batched channel mode: a few lanes (stream + private metric / workspace / detection list) so
-    // that the short serial kernels of one channel overlap the correlator of the next
-    struct Lane {
-        cudaStream_t st = nullptr;
-        DevBuf<float> z;
-        DevBuf<unsigned char> ws;
-        DevBuf<unsigned long long> det_idx;
-    };
-    static constexpr int kLanes = 3;
-    Lane lanes[kLanes];
+    // batched channel mode: metric, workspace and detection lists of all channels of a group side by side
+    DevBuf<float> d_chan_z;
+    DevBuf<unsigned char> d_chan_ws;
+    DevBuf<unsigned long long> d_chan_det;
     DevBuf<PeakState> d_chan_state;
     DevBuf<DetectionRecord> d_chan_recs;
     PeakState* h_chan_state = nullptr;  // pinned
     size_t h_chan_cap = 0;
-    cudaEvent_t ev_chan = nullptr;
     // raw capture ingestion (b200sync_sd_detect_file): pinned staging ring + copy stream
     float2* h_stage = nullptr;
     cudaEvent_t ev_stage[3] = {nullptr, nullptr, nullptr};
@@ -135,12 +133,17 @@ struct b200sync_sd {
         bool valid = false;
         float2* d_out = nullptr;      // optional delayed output of the NEXT phase 1 (b200sync_sd_shard_output)
         long long out_first = 0, out_len = 0;
+        float* h_out = nullptr;       // ... or into HOST memory, for phase1_host (b200sync_sd_shard_output_host)
+        long long h_out_first = 0, h_out_len = 0;
     } shard;
 };
 
 namespace {
 
 constexpr int kTwTotalHost = 256 + 2048;  // == kTwTotal of fft2048.cuh
+constexpr long long kSmallRange = 1LL << 19;      // peak ranges up to this size take the two-launch in-order walk (bitmaps in shared memory)
+constexpr size_t kStageBytes = 4u << 20;          // pinned staging for pageable input spans (streaming)
+constexpr size_t kStagePiece = 128u << 10;        // ... copied and sent piece by piece so memcpy and DMA overlap
 
 int reset_state(b200sync_sd* sd, cudaStream_t st) {
     CU(sd->d_state.ensure(1));
@@ -163,11 +166,73 @@ int run_chunk(b200sync_sd* sd, const float2* d_in, long long in_base, float* d_z
                         sd->d_tw.p, d_out_delayed, 0, 0, out_end, (int)sd->delay, sd->num_sms, st));
     if (hi > lo) {
         const long long z_end = (b0 + nb) * (long long)sd->S;
-        CU(launch_peak_phase1(d_z, z_base, z_end, lo, hi, sd->T, sd->power_threshold, sd->d_ws.p,
-                              sd->d_ws.cap, nullptr, sd->num_sms, st));
-        CU(launch_peak_phase2(lo, hi, sd->T, sd->d_ws.p, sd->d_ws.cap, -1, sd->d_state.p,
-                              sd->d_det_idx.p, (unsigned)sd->d_det_idx.cap, sd->num_sms, st));
+        if (hi - lo <= kSmallRange) {
+            CU(launch_peak_stream(d_z, z_base, z_end, lo, hi, sd->T, sd->power_threshold, sd->d_ws.p, sd->d_ws.cap,
+                                  sd->d_state.p, sd->d_det_idx.p, (unsigned)sd->d_det_idx.cap, sd->num_sms, st));
+        } else {
+            CU(launch_peak_phase1(d_z, z_base, z_end, lo, hi, sd->T, sd->power_threshold, sd->d_ws.p,
+                                  sd->d_ws.cap, nullptr, sd->num_sms, st));
+            CU(launch_peak_phase2(lo, hi, sd->T, sd->d_ws.p, sd->d_ws.cap, -1, sd->d_state.p,
+                                  sd->d_det_idx.p, (unsigned)sd->d_det_idx.cap, sd->num_sms, st));
+        }
     }
+    return 0;
+}
+
+
+// H2D of a host span for the streaming path.  Pinned / registered memory goes straight to the copy engine; a
+// pageable span of ordinary ring-chunk size is staged through the context's own pinned buffer piece by piece (the
+// memcpy of piece i+1 overlaps the DMA of piece i) instead of through the driver's internal staging.
+int stream_h2d(b200sync_sd* sd, float2* d_dst, const float2* h_src, size_t count, cudaStream_t st) {
+    const size_t bytes = count * sizeof(float2);
+    bool pinned = false;
+    if (bytes <= kStageBytes) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, h_src) == cudaSuccess) pinned = (at.type == cudaMemoryTypeHost);
+        else cudaGetLastError();
+    }
+    if (pinned || bytes > kStageBytes) {
+        CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+        return 0;
+    }
+    if (!sd->h_in_stage) CU(cudaMallocHost(&sd->h_in_stage, kStageBytes));
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(h_src);
+    unsigned char* dst = reinterpret_cast<unsigned char*>(d_dst);
+    for (size_t off = 0; off < bytes; off += kStagePiece) {
+        const size_t len = std::min(kStagePiece, bytes - off);
+        std::memcpy(sd->h_in_stage + off, src + off, len);   // every call ends with a stream sync: the buffer is free
+        CU(cudaMemcpyAsync(dst + off, sd->h_in_stage + off, len, cudaMemcpyHostToDevice, st));
+    }
+    return 0;
+}
+
+// refine + result copies, all asynchronous: at most `nmax` records can exist for the decided range, so the state and
+// that many records are copied blind into pinned memory and ONE synchronisation (records_finish) suffices
+int records_enqueue(b200sync_sd* sd, const float2* d_in, long long in_base, const float* d_z, long long z_base,
+                    size_t nmax, cudaStream_t st) {
+    nmax = std::min(nmax, sd->d_det_idx.cap);
+    if (sd->h_recs_pin_cap < nmax) {
+        if (sd->h_recs_pin) cudaFreeHost(sd->h_recs_pin);
+        sd->h_recs_pin = nullptr;
+        sd->h_recs_pin_cap = 0;
+        CU(cudaMallocHost(&sd->h_recs_pin, sizeof(DetectionRecord) * (nmax + 64)));
+        sd->h_recs_pin_cap = nmax + 64;
+    }
+    CU(launch_refine(d_in, in_base, d_z, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->min_bin, sd->d_tw.p,
+                     sd->d_det_idx.p, &sd->d_state.p->det_count, (unsigned)std::max<size_t>(nmax, 1), sd->d_recs.p,
+                     sd->num_sms, st));
+    CU(cudaMemcpyAsync(sd->h_state, sd->d_state.p, sizeof(PeakState), cudaMemcpyDeviceToHost, st));
+    if (nmax > 0)
+        CU(cudaMemcpyAsync(sd->h_recs_pin, sd->d_recs.p, sizeof(DetectionRecord) * nmax, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemsetAsync(&sd->d_state.p->det_count, 0, sizeof(unsigned int), st));  // the list has been drained
+    return 0;
+}
+int records_finish(b200sync_sd* sd, size_t nmax, cudaStream_t st, const DetectionRecord** recs, size_t* n) {
+    CU(cudaStreamSynchronize(st));
+    const size_t cnt = sd->h_state->det_count;
+    if (cnt > std::min(nmax, sd->d_det_idx.cap)) return fail(B200SYNC_ENOMEM, "internal detection list overflow");
+    *recs = sd->h_recs_pin;
+    *n = cnt;
     return 0;
 }
 
@@ -310,6 +375,7 @@ int do_start(b200sync_sd* sd) {
     CU(cudaStreamSynchronize(sd->stream));
     sd->consumed = 0;
     sd->lo_next = 0;
+    sd->r_abs_host = 0;
     sd->x_base = sd->x_end = 0;
     sd->z_base = sd->z_end = 0;
     sd->carry.assign(sd->delay, c64(0.0f, 0.0f));
@@ -390,18 +456,14 @@ void b200sync_sd_destroy(b200sync_sd* sd) {
     for (auto& e : sd->ev)
         if (e) cudaEventDestroy(e);
     if (sd->h_state) cudaFreeHost(sd->h_state);
+    if (sd->h_in_stage) cudaFreeHost(sd->h_in_stage);
+    if (sd->h_recs_pin) cudaFreeHost(sd->h_recs_pin);
     if (sd->h_chan_state) cudaFreeHost(sd->h_chan_state);
-    if (sd->ev_chan) cudaEventDestroy(sd->ev_chan);
     if (sd->h_stage) cudaFreeHost(sd->h_stage);
     for (auto& e : sd->ev_stage)
         if (e) cudaEventDestroy(e);
     for (auto& e : sd->ev_pieces) cudaEventDestroy(e);
     if (sd->copy_stream) cudaStreamDestroy(sd->copy_stream);
-    for (auto& ln : sd->lanes)
-        if (ln.st) {
-            cudaStreamSynchronize(ln.st);
-            cudaStreamDestroy(ln.st);
-        }
     delete sd;
 }
 
@@ -441,6 +503,24 @@ int b200sync_sd_records_to_tags(const b200sync_sd* sd, const b200sync_detection_
     }
     for (auto& th : pool) th.join();
     return 0;
+}
+
+// delay line of the streaming block (:318-319): out[i] = stream[C + i - delay]; then remember the last `delay` items
+static void host_delay_line_stream(b200sync_sd* sd, const float* in, float* out, size_t j) {
+    const size_t D = static_cast<size_t>(sd->delay);
+    const c64* cin = reinterpret_cast<const c64*>(in);
+    if (out) {
+        c64* cout = reinterpret_cast<c64*>(out);
+        const size_t from_carry = std::min(D, j);
+        std::memcpy(cout, sd->carry.data(), from_carry * sizeof(c64));
+        if (j > D) std::memcpy(cout + D, cin, (j - D) * sizeof(c64));
+    }
+    if (j >= D) {
+        std::memcpy(sd->carry.data(), cin + (j - D), D * sizeof(c64));
+    } else {
+        std::memmove(sd->carry.data(), sd->carry.data() + j, (D - j) * sizeof(c64));
+        std::memcpy(sd->carry.data() + (D - j), cin, j * sizeof(c64));
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -484,8 +564,8 @@ int b200sync_sd_process(b200sync_sd* sd, const float* in, size_t n_in, float* ou
             if (int rc = slide_window(sd->d_x, sd->d_xtmp, sd->x_base, sd->x_end, keep_x, st)) return rc;
             if (sd->x_end < keep_x) sd->x_end = keep_x;
         }
-        CU(cudaMemcpyAsync(sd->d_x.p + (a0 - sd->x_base), hin + (a0 - C),
-                           sizeof(float2) * static_cast<size_t>(need_end - a0), cudaMemcpyHostToDevice, st));
+        if (int rc = stream_h2d(sd, sd->d_x.p + (a0 - sd->x_base), hin + (a0 - C), static_cast<size_t>(need_end - a0), st))
+            return rc;
         sd->x_end = need_end;
         // --- metric window: [P_prev - 2T - 2, P)
         long long keep_z = P_prev - 2 * T - 2;
@@ -512,32 +592,56 @@ int b200sync_sd_process(b200sync_sd* sd, const float* in, size_t n_in, float* ou
         const size_t ws = peak_workspace_bytes_sms(kStreamStepBlocks * S + T + 2, sd->T, sd->num_sms);
         CU(sd->d_ws.ensure(ws));
         if (int rc = ensure_det(sd, static_cast<size_t>((kStreamStepBlocks * S + T + 2) / (T + 1) + 2))) return rc;
-        if (int rc = run_chunk(sd, sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, a0 / S, nb, lo, hi, nullptr, 0, st))
-            return rc;
+        const size_t nmax = static_cast<size_t>((hi - lo) / (T + 1) + 2);
+        // (the fused walk keeps the detection list in shared memory: at most 1024 entries, i.e. not for tiny T)
+        const bool small = hi > lo && hi - lo <= kSmallRange && nmax <= 1024 && nmax + 1 <= sd->d_recs.cap;
+        if (small) {
+            // streaming-sized step: correlator, flags, [walk + refine] — three launches, one D2H, one synchronisation
+            CU(launch_correlate(sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S,
+                                a0 / S, nb, sd->d_tw.p, nullptr, 0, 0, 0, (int)sd->delay, sd->num_sms, st));
+            StreamWalk walk;
+            CU(launch_peak_flags_stream(sd->d_z.p, sd->z_base, P, lo, hi, sd->T, sd->power_threshold, sd->d_ws.p,
+                                        sd->d_ws.cap, sd->num_sms, st, &walk));
+            walk.r_abs_in = sd->r_abs_host;
+            walk.state_out = sd->d_state.p;
+            walk.header = reinterpret_cast<PeakState*>(sd->d_recs.p);   // slot 0 of the record buffer
+            CU(launch_refine(sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S,
+                             sd->min_bin, sd->d_tw.p, sd->d_det_idx.p, &sd->d_state.p->det_count, (unsigned)nmax,
+                             sd->d_recs.p + 1, sd->num_sms, st, 1, 0, 0, 0, &walk));
+            if (sd->h_recs_pin_cap < nmax + 1) {
+                if (sd->h_recs_pin) cudaFreeHost(sd->h_recs_pin);
+                sd->h_recs_pin = nullptr;
+                sd->h_recs_pin_cap = 0;
+                CU(cudaMallocHost(&sd->h_recs_pin, sizeof(DetectionRecord) * (nmax + 65)));
+                sd->h_recs_pin_cap = nmax + 65;
+            }
+            CU(cudaMemcpyAsync(sd->h_recs_pin, sd->d_recs.p, sizeof(DetectionRecord) * (nmax + 1), cudaMemcpyDeviceToHost, st));
+        } else {
+            if (int rc = run_chunk(sd, sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, a0 / S, nb, lo, hi, nullptr, 0, st))
+                return rc;
+            if (int rc = records_enqueue(sd, sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, nmax, st)) return rc;
+        }
         sd->z_end = P;
         sd->lo_next = hi;
-        std::vector<DetectionRecord> recs;
-        if (int rc = collect_records(sd, sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, st, recs)) return rc;
-        for (const auto& r : recs) sd->pending.push_back(make_tag(sd, r));
         done_blocks += nb;
+        // the delay line of host spans (:318-319) is host work: do it while the GPU runs the last step
+        if (done_blocks >= nb_total) host_delay_line_stream(sd, in, out, static_cast<size_t>(j_total));
+        const DetectionRecord* recs = nullptr;
+        size_t nrec = 0;
+        if (small) {
+            CU(cudaStreamSynchronize(st));
+            const PeakState* hs = reinterpret_cast<const PeakState*>(sd->h_recs_pin);
+            if (hs->det_count > nmax) return fail(B200SYNC_ENOMEM, "internal detection list overflow");
+            sd->r_abs_host = hs->r_abs;
+            recs = sd->h_recs_pin + 1;
+            nrec = hs->det_count;
+        } else {
+            if (int rc = records_finish(sd, nmax, st, &recs, &nrec)) return rc;
+            if (hi > lo) sd->r_abs_host = sd->h_state->r_abs;
+        }
+        for (size_t i = 0; i < nrec; ++i) sd->pending.push_back(make_tag(sd, recs[i]));
     }
-
-    // delay line (:318-319): out[i] = stream[C + i - delay]
-    const size_t D = static_cast<size_t>(sd->delay);
     const size_t j = static_cast<size_t>(j_total);
-    const c64* cin = reinterpret_cast<const c64*>(in);
-    if (out) {
-        c64* cout = reinterpret_cast<c64*>(out);
-        const size_t from_carry = std::min(D, j);
-        std::memcpy(cout, sd->carry.data(), from_carry * sizeof(c64));
-        if (j > D) std::memcpy(cout + D, cin, (j - D) * sizeof(c64));
-    }
-    if (j >= D) {
-        std::memcpy(sd->carry.data(), cin + (j - D), D * sizeof(c64));
-    } else {
-        std::memmove(sd->carry.data(), sd->carry.data() + j, (D - j) * sizeof(c64));
-        std::memcpy(sd->carry.data() + (D - j), cin, j * sizeof(c64));
-    }
     sd->consumed += j;
     *n_consumed = j;
     // tags whose output index has now been published (:320-325)
@@ -811,7 +915,7 @@ int b200sync_sd_detect_channels_device(b200sync_sd* sd, const void* d_in, size_t
         return fail(B200SYNC_EINVAL, "null argument");
     if (n_channels > 1 && channel_stride < n) return fail(B200SYNC_EINVAL, "channel_stride smaller than n");
     CU(cudaSetDevice(sd->device));
-    cudaStream_t caller = static_cast<cudaStream_t>(cuda_stream);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const long long S = sd->S, F = sd->fft_size, T = sd->T;
     *n_consumed = 0;
     for (size_t c = 0; c < n_channels; ++c) n_recs[c] = 0;
@@ -820,9 +924,18 @@ int b200sync_sd_detect_channels_device(b200sync_sd* sd, const void* d_in, size_t
     const long long P = nb_total * S;
     const long long hi_total = std::max(0LL, P - T - 1);
     const size_t cap = std::max<size_t>(64, static_cast<size_t>(P / (T + 1) + 2));
-    const size_t ws_bytes = peak_workspace_bytes_sms(hi_total + 1, sd->T, sd->num_sms);
+    // Channels in groups of at most 65535 (gridDim.y) and of at most ~2^31 samples of metric: ONE launch of every
+    // kernel per group — correlator over channel x block, peak stage and refine with the channel on blockIdx.y —
+    // where round 1 issued the whole kernel sequence once per channel.
+    const size_t z_stride = (static_cast<size_t>(P) + 64 + 31) & ~size_t(31);
+    const size_t ws_stride = (peak_plan_bytes(std::max(1LL, hi_total), sd->T, sd->num_sms) + 255) & ~size_t(255);
+    size_t per_group = std::max<size_t>(1, (size_t(1) << 31) / z_stride);
+    per_group = std::min<size_t>({per_group, n_channels, 65535});
     CU(sd->d_chan_state.ensure(n_channels));
     CU(sd->d_chan_recs.ensure(n_channels * cap));
+    CU(sd->d_chan_det.ensure(n_channels * cap));
+    CU(sd->d_chan_z.ensure(per_group * z_stride));
+    CU(sd->d_chan_ws.ensure(per_group * ws_stride));
     if (sd->h_chan_cap < n_channels) {
         if (sd->h_chan_state) cudaFreeHost(sd->h_chan_state);
         sd->h_chan_state = nullptr;
@@ -830,38 +943,28 @@ int b200sync_sd_detect_channels_device(b200sync_sd* sd, const void* d_in, size_t
         CU(cudaMallocHost(&sd->h_chan_state, sizeof(PeakState) * n_channels));
         sd->h_chan_cap = n_channels;
     }
-    if (!sd->ev_chan) CU(cudaEventCreateWithFlags(&sd->ev_chan, cudaEventDisableTiming));
-    const int nl = static_cast<int>(std::min<size_t>(b200sync_sd::kLanes, n_channels));
-    for (int l = 0; l < nl; ++l) {
-        auto& ln = sd->lanes[l];
-        if (!ln.st) CU(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
-        CU(ln.z.ensure(static_cast<size_t>(P) + 64));
-        CU(ln.ws.ensure(ws_bytes));
-        CU(ln.det_idx.ensure(cap));
-    }
-    // the lanes start after everything already enqueued on the caller's stream (the capture itself)
-    CU(cudaMemsetAsync(sd->d_chan_state.p, 0, sizeof(PeakState) * n_channels, caller));
-    CU(cudaEventRecord(sd->ev_chan, caller));
-    for (int l = 0; l < nl; ++l) CU(cudaStreamWaitEvent(sd->lanes[l].st, sd->ev_chan, 0));
+    CU(cudaMemsetAsync(sd->d_chan_state.p, 0, sizeof(PeakState) * n_channels, st));
     const float2* base = static_cast<const float2*>(d_in);
-    for (size_t c = 0; c < n_channels; ++c) {
-        auto& ln = sd->lanes[c % nl];
-        const float2* x = base + c * channel_stride;
-        PeakState* state = sd->d_chan_state.p + c;
-        DetectionRecord* drecs = sd->d_chan_recs.p + c * cap;
-        CU(launch_correlate(x, 0, ln.z.p, 0, sd->d_hperm.p, (int)sd->K, (int)sd->S, 0, nb_total, sd->d_tw.p,
-                            nullptr, 0, 0, 0, (int)sd->delay, sd->num_sms, ln.st));
+    for (size_t c0 = 0; c0 < n_channels; c0 += per_group) {
+        const int nch = static_cast<int>(std::min(per_group, n_channels - c0));
+        const float2* x = base + c0 * channel_stride;
+        PeakState* state = sd->d_chan_state.p + c0;
+        CU(launch_correlate(x, 0, sd->d_chan_z.p, 0, sd->d_hperm.p, (int)sd->K, (int)sd->S, 0, nb_total * nch,
+                            sd->d_tw.p, nullptr, 0, 0, 0, (int)sd->delay, sd->num_sms, st, nb_total,
+                            static_cast<long long>(channel_stride), static_cast<long long>(z_stride)));
         if (hi_total > 0) {
-            CU(launch_peak_phase1(ln.z.p, 0, P, 0, hi_total, sd->T, sd->power_threshold, ln.ws.p, ln.ws.cap,
-                                  nullptr, sd->num_sms, ln.st));
-            CU(launch_peak_phase2(0, hi_total, sd->T, ln.ws.p, ln.ws.cap, -1, state, ln.det_idx.p,
-                                  (unsigned)cap, sd->num_sms, ln.st));
+            CU(launch_peak_phase1(sd->d_chan_z.p, 0, P, 0, hi_total, sd->T, sd->power_threshold, sd->d_chan_ws.p,
+                                  ws_stride, nullptr, sd->num_sms, st, nch, static_cast<long long>(z_stride), ws_stride));
+            CU(launch_peak_phase2(0, hi_total, sd->T, sd->d_chan_ws.p, ws_stride, -1, state,
+                                  sd->d_chan_det.p + c0 * cap, (unsigned)cap, sd->num_sms, st, nch, ws_stride, cap));
         }
-        CU(launch_refine(x, 0, ln.z.p, 0, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->min_bin, sd->d_tw.p,
-                         ln.det_idx.p, &state->det_count, (unsigned)cap, drecs, sd->num_sms, ln.st));
-        CU(cudaMemcpyAsync(sd->h_chan_state + c, state, sizeof(PeakState), cudaMemcpyDeviceToHost, ln.st));
+        CU(launch_refine(x, 0, sd->d_chan_z.p, 0, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->min_bin, sd->d_tw.p,
+                         sd->d_chan_det.p + c0 * cap, &state->det_count, (unsigned)cap, sd->d_chan_recs.p + c0 * cap,
+                         sd->num_sms, st, nch, static_cast<long long>(channel_stride), static_cast<long long>(z_stride),
+                         static_cast<long long>(cap)));
     }
-    for (int l = 0; l < nl; ++l) CU(cudaStreamSynchronize(sd->lanes[l].st));
+    CU(cudaMemcpyAsync(sd->h_chan_state, sd->d_chan_state.p, sizeof(PeakState) * n_channels, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     // exact-size record copies, then the reference's "tag already published" filter per channel
     std::vector<DetectionRecord>& h = sd->h_recs;
     size_t total = 0;
@@ -875,10 +978,10 @@ int b200sync_sd_detect_channels_device(b200sync_sd* sd, const void* d_in, size_t
         const size_t cnt = sd->h_chan_state[c].det_count;
         if (cnt)
             CU(cudaMemcpyAsync(h.data() + off, sd->d_chan_recs.p + c * cap, sizeof(DetectionRecord) * cnt,
-                               cudaMemcpyDeviceToHost, sd->lanes[0].st));
+                               cudaMemcpyDeviceToHost, st));
         off += cnt;
     }
-    CU(cudaStreamSynchronize(sd->lanes[0].st));
+    CU(cudaStreamSynchronize(st));
     off = 0;
     for (size_t c = 0; c < n_channels; ++c) {
         const size_t cnt = sd->h_chan_state[c].det_count;
@@ -963,6 +1066,33 @@ static int shard_phase1_core(b200sync_sd* sd, const float2* d_in, const float2* 
             if (z1 > out_lo) CU(cudaMemsetAsync(d_out + (out_lo - out_base), 0, (z1 - out_lo) * sizeof(float2), st));
         }
     }
+    // host spans: the shard's slice of the delay line is a host copy of samples it already holds (halo included)
+    std::vector<std::thread> host_copy;
+    struct Joiner {
+        std::vector<std::thread>& p;
+        ~Joiner() { for (auto& t : p) t.join(); }
+    } joiner{host_copy};
+    float* h_out = sd->shard.h_out;
+    sd->shard.h_out = nullptr;
+    if (h_out != nullptr && h_in != nullptr) {
+        const long long D = static_cast<long long>(sd->delay), ob = sd->shard.h_out_first;
+        const long long lo_o = std::max(fb * S, ob), hi_o = std::min({(fb + nbk) * S, P_total, ob + sd->shard.h_out_len});
+        if (hi_o > lo_o) {
+            const long long z1 = std::min(D, hi_o);
+            if (z1 > lo_o) std::memset(h_out + 2 * (lo_o - ob), 0, static_cast<size_t>(z1 - lo_o) * sizeof(c64));
+            const long long c0 = std::max(lo_o, D), cnt = hi_o - c0;
+            if (cnt > 0) {
+                const size_t nth = std::max<size_t>(1, std::min<size_t>({8, std::thread::hardware_concurrency() / 2,
+                                                                         static_cast<size_t>(cnt >> 20)}));
+                const float* src = reinterpret_cast<const float*>(h_in) + 2 * (c0 - D - in_base);
+                float* dst = h_out + 2 * (c0 - ob);
+                for (size_t t = 0; t < nth; ++t) {
+                    const size_t i0 = cnt * t / nth, i1 = cnt * (t + 1) / nth;
+                    host_copy.emplace_back([=] { std::memcpy(dst + 2 * i0, src + 2 * i0, (i1 - i0) * sizeof(c64)); });
+                }
+            }
+        }
+    }
     if (h_in == nullptr && f == nullptr) {
         CU(launch_correlate(d_in, in_base, sd->d_zoff.p, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, cb0,
                             cb1 - cb0, sd->d_tw.p, d_out, out_base, out_lo, out_hi, (int)sd->delay, sd->num_sms, st));
@@ -1043,6 +1173,14 @@ int b200sync_sd_shard_output(b200sync_sd* sd, void* d_out_delayed, uint64_t out_
     sd->shard.d_out = static_cast<float2*>(d_out_delayed);
     sd->shard.out_first = static_cast<long long>(out_first_abs);
     sd->shard.out_len = static_cast<long long>(out_len);
+    return 0;
+}
+
+int b200sync_sd_shard_output_host(b200sync_sd* sd, float* out_delayed, uint64_t out_first_abs, size_t out_len) {
+    if (!sd) return fail(B200SYNC_EINVAL, "null context");
+    sd->shard.h_out = out_delayed;
+    sd->shard.h_out_first = static_cast<long long>(out_first_abs);
+    sd->shard.h_out_len = static_cast<long long>(out_len);
     return 0;
 }
 

@@ -29,6 +29,20 @@ struct PeakState {
     unsigned int _pad;
 };
 
+// Streaming: the in-order peak walk fused in front of the refine stage (correlator.cu refine_kernel).  cand / pass:
+// the bitmaps of [lo, hi) written by the flags kernel; r_abs_in: where the search resumes (the host knows it from
+// the previous call); CTA 0 writes the new PeakState to state_out and to header (the slot in front of the records,
+// so that one D2H copy brings state and records).
+struct StreamWalk {
+    const uint32_t* cand = nullptr;
+    const uint32_t* pass = nullptr;
+    long long range = 0, lo = 0, hi = 0;
+    int T = 0;
+    unsigned long long r_abs_in = 0;
+    PeakState* state_out = nullptr;
+    PeakState* header = nullptr;
+};
+
 // api.cu: every kernel launch site calls this (b200sync_launch_count of the C ABI)
 void count_launch(int n = 1);
 // api.cu: set the calling thread's b200sync_last_error() text and return `code`
@@ -40,11 +54,18 @@ cudaError_t launch_template_spectra(const float2* d_td, float2* d_hperm, int K, 
 cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpow, long long z_base,
                              const float2* d_hperm, int K, int S, long long b0, long long nb,
                              const float2* d_tw, float2* d_out_delayed, long long out_base, long long out_lo,
-                             long long out_hi, int delay, int num_sms, cudaStream_t st);
+                             long long out_hi, int delay, int num_sms, cudaStream_t st, long long nb_chan = 0,
+                             long long in_chan_stride = 0, long long z_chan_stride = 0);
 cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_zpow, long long z_base,
                           const float2* d_hperm, int K, int S, int min_freq_bin, const float2* d_tw,
                           const unsigned long long* d_det_idx, const unsigned int* d_det_count,
-                          unsigned int det_cap, DetectionRecord* d_recs, int num_sms, cudaStream_t st);
+                          unsigned int det_cap, DetectionRecord* d_recs, int num_sms, cudaStream_t st, int nch = 1,
+                          long long in_chan_stride = 0, long long z_chan_stride = 0, long long det_chan_stride = 0,
+                          const StreamWalk* walk = nullptr);
+// flags only (streaming): fills *walk's cand / pass / range / lo / hi / T for the fused walk of launch_refine
+cudaError_t launch_peak_flags_stream(const float* d_zpow, long long z_base, long long z_end, long long lo, long long hi,
+                                     int T, float power_threshold, void* d_ws, size_t ws_bytes, int num_sms,
+                                     cudaStream_t st, StreamWalk* walk);
 
 // peaks.cu
 struct PeakWorkspace;  // opaque: bitmaps, tables, per-segment entry states
@@ -56,10 +77,14 @@ cudaError_t launch_peak_phase1(const float* d_zpow, long long z_base, long long 
                                long long hi, int T,
                                float power_threshold, void* d_ws, size_t ws_bytes,
                                uint16_t* d_range_table /*[T+1] or nullptr*/, int num_sms,
-                               cudaStream_t st);
+                               cudaStream_t st, int nch = 1, long long z_stride = 0, size_t ws_stride = 0);
+size_t peak_plan_bytes(long long range, int T, int num_sms);  // workspace of one channel for exactly this range
+cudaError_t launch_peak_stream(const float* d_zpow, long long z_base, long long z_end, long long lo, long long hi,
+                               int T, float power_threshold, void* d_ws, size_t ws_bytes, PeakState* d_state,
+                               unsigned long long* d_det_idx, unsigned int det_cap, int num_sms, cudaStream_t st);
 cudaError_t launch_peak_phase2(long long lo, long long hi, int T, void* d_ws, size_t ws_bytes,
                                int j_in /*-1: derive from state->r_abs*/, PeakState* d_state,
                                unsigned long long* d_det_idx, unsigned int det_cap, int num_sms,
-                               cudaStream_t st);
+                               cudaStream_t st, int nch = 1, size_t ws_stride = 0, size_t det_stride = 0);
 
 }  // namespace b200sync

@@ -14,6 +14,9 @@
 #include "b200sync_internal.h"
 #include "fft2048.cuh"
 #include "tma.cuh"
+#include "peak_walk.cuh"
+
+#include <cstdlib>
 
 namespace b200sync {
 
@@ -75,11 +78,16 @@ constexpr bool kCorrTmem = true;
 static_assert(kCorrThreads == 6 * kGroupThreads, "the TMEM column layout (fft2048.cuh) is for 6 FFT groups per CTA");
 #endif
 
+// SPLIT: all groups of a CTA share one block and split the hypotheses (low latency, few blocks);
+// BATCH: channel x block grid of the batched channel mode.  Separate instantiations keep the persistent
+// single-stream shape free of their registers.
+template <bool SPLIT, bool BATCH>
 __global__ void __launch_bounds__(kCorrThreads, 1)
 correlate_kernel(const float2* __restrict__ in, long long in_base, float* __restrict__ zpow,
                  long long z_base, const float2* __restrict__ hperm, int K, int S, long long b0,
                  long long nb, const float2* __restrict__ tw_g, float2* __restrict__ out_delayed,
-                 long long out_base, long long out_lo, long long out_hi, int delay) {
+                 long long out_base, long long out_lo, long long out_hi, int delay, long long nb_chan,
+                 long long in_chan_stride, long long z_chan_stride) {
     extern __shared__ __align__(128) unsigned char smem_raw[];  // 128 B: half-warp LDS.64 rows never straddle a bank row, whatever static shared data precedes
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
     const int g = threadIdx.x >> 7;
@@ -158,13 +166,28 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
     if constexpr (kRegB1) load_b1_twiddles(t1, tw_s, tid);
     if constexpr (kRegB2) load_b2_twiddles(t2, tw_s, tid);
 
-    for (long long blk = (long long)blockIdx.x * ngroups + g; blk < nb; blk += gstride) {
-        const long long s0 = (b0 + blk) * (long long)S;  // absolute first sample of the block
-        const float2* src = in + (s0 - in_base);
+    // ksplit > 1 (few blocks, e.g. one processBulk span of the streaming path): ALL groups of the CTA work on the
+    // same block — each transforms it (FFT A, redundantly) and takes every ngroups-th hypothesis — and the
+    // per-sample maxima are merged through shared memory.  A block's latency drops from 1 + K transforms to
+    // 1 + ceil(K / ngroups); max() commutes, so the metric is bit-identical.
+    constexpr bool split = SPLIT;
+    const long long blk_first = split ? (long long)blockIdx.x : (long long)blockIdx.x * ngroups + g;
+    const long long blk_step = split ? (long long)gridDim.x : gstride;
+    const int k_first = split ? g : 0, k_step = split ? ngroups : 1;
+    for (long long blk = blk_first; blk < nb; blk += blk_step) {
+        // batched channel mode (nb_chan > 0): nb = channels x nb_chan blocks, channel c's stream and metric lie
+        // c * stride after the first channel's; every channel has its own block grid starting at b0
+        long long bb = blk, ch = 0;
+        if constexpr (BATCH) {
+            ch = blk / nb_chan;
+            bb = blk - ch * nb_chan;
+        }
+        const long long s0 = (b0 + bb) * (long long)S;  // absolute first sample of the block
+        const float2* src = in + ch * in_chan_stride + (s0 - in_base);
         float2 v[16], xs[16];
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) v[n1] = __ldcs(src + 128 * n1 + tid);
-        if (out_delayed != nullptr) {
+        if (out_delayed != nullptr && (!split || g == 0)) {
             // block contract: out[n] = in[n - delay] (PM/syncword_detection.hpp:318-319).  Only output items
             // [out_lo, out_hi) are stored: out_hi = the number of items the call publishes (:346) — nothing is
             // stored at or past it — and a time shard stores only the slice it owns.
@@ -194,7 +217,7 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
                 }
                 tmem_wait_st();
             }
-            for (int k = 0; k < K; ++k) {
+            for (int k = k_first; k < K; k += k_step) {
                 float2 c[16];
                 const uint32_t tm_h = tm_base + kTmH + 32 * k;
                 const float2* hg = hperm + (size_t)k * 16 * kGroupThreads + tid;
@@ -214,7 +237,7 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
                 }
             }
         } else {
-            for (int k = 0; k < K; ++k) {
+            for (int k = k_first; k < K; k += k_step) {
 #ifdef B200_WHATIF_H0
                 const float2* h = hperm + tid;
 #else
@@ -231,14 +254,30 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
                 }
             }
         }
-        // time reversal: lag kk lives at index (F - kk) mod F (:300)
-        float* zdst = zpow + (s0 - z_base);
+        if (split) {   // merge the groups' maxima: every group parks its 16 values in its own exchange buffer
+            float* mine = reinterpret_cast<float*>(xb);
 #pragma unroll
-        for (int m1 = 0; m1 < 16; ++m1) {
-            const int m = 128 * m1 + tid;
-            const int kk = (kFft - m) & (kFft - 1);
-            if (kk < S) zdst[kk] = best[m1];
+            for (int m1 = 0; m1 < 16; ++m1) mine[m1 * kGroupThreads + tid] = best[m1];
+            __syncthreads();
+            if (g == 0) {
+                for (int gg = 1; gg < ngroups; ++gg) {
+                    const float* other = reinterpret_cast<const float*>(tw_s + kTwTotal + gg * kCorrXchg);
+#pragma unroll
+                    for (int m1 = 0; m1 < 16; ++m1) best[m1] = fmaxf(best[m1], other[m1 * kGroupThreads + tid]);
+                }
+            }
         }
+        // time reversal: lag kk lives at index (F - kk) mod F (:300)
+        if (!split || g == 0) {
+            float* zdst = zpow + ch * z_chan_stride + (s0 - z_base);
+#pragma unroll
+            for (int m1 = 0; m1 < 16; ++m1) {
+                const int m = 128 * m1 + tid;
+                const int kk = (kFft - m) & (kFft - 1);
+                if (kk < S) zdst[kk] = best[m1];
+            }
+        }
+        if (split) __syncthreads();   // the exchange buffers are free again
     }
     if constexpr (kCorrTmem) {
         tmem_fence_before_sync();
@@ -278,8 +317,17 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
               long long z_base, const float2* __restrict__ hperm, int K, int S, int min_freq_bin,
               const float2* __restrict__ tw_g, const unsigned long long* __restrict__ det_idx,
               const unsigned int* __restrict__ det_count, unsigned int det_cap,
-              DetectionRecord* __restrict__ recs) {
+              DetectionRecord* __restrict__ recs, long long in_chan_stride, long long z_chan_stride,
+              long long det_chan_stride, StreamWalk walk) {
     extern __shared__ __align__(128) unsigned char smem_raw[];  // 128 B: half-warp LDS.64 rows never straddle a bank row, whatever static shared data precedes
+    {   // batched channel mode: blockIdx.y is the channel; det_count points into an array of PeakState
+        const long long ch = blockIdx.y;
+        in += ch * in_chan_stride;
+        zpow += ch * z_chan_stride;
+        det_idx += ch * det_chan_stride;
+        recs += ch * det_chan_stride;
+        det_count += ch * (long long)(sizeof(PeakState) / sizeof(unsigned int));
+    }
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
     float2* xb = tw_s + kTwTotal;
     float2* b1out = xb + kXchgFloat2;                      // [kRefineChunk][256]
@@ -287,7 +335,49 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
     float2* corr_s = b2out + kRefineChunk * 16;            // [kMaxHyp + 1]
     float* xpow = reinterpret_cast<float*>(corr_s + kMaxHyp + 1);  // [2048]
     __shared__ float noise_s;
-    unsigned int n = *det_count;
+    __shared__ unsigned int n_walk;
+    unsigned int n;
+    const unsigned long long* dets = det_idx;
+    if (walk.cand != nullptr) {
+        // Streaming: the in-order walk of the peak detector fused in front of the refine stage.  EVERY CTA walks
+        // the (small) bitmaps itself, from shared memory, and so knows the whole detection list without a
+        // kernel boundary; CTA d then refines detection d.  CTA 0 publishes the new search position and the count.
+        unsigned long long* det_s = reinterpret_cast<unsigned long long*>(xpow + kFft);   // [det_cap]
+        uint32_t* cand_s = reinterpret_cast<uint32_t*>(det_s + det_cap);
+        const int nwords = (int)((walk.range + 31) >> 5);
+        uint32_t* pass_s = cand_s + nwords;
+        for (int i = threadIdx.x; i < nwords; i += kRefineThreads) {
+            cand_s[i] = walk.cand[i];
+            pass_s[i] = walk.pass[i];
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const long long j0 = (walk.r_abs_in > (unsigned long long)walk.lo) ? (long long)(walk.r_abs_in - (unsigned long long)walk.lo) : 0;
+            unsigned int cnt = 0;
+            const long long j = peak_walk_warp(cand_s, pass_s, nwords, walk.range, walk.T, j0, [&](long long found) {
+                if (threadIdx.x == 0 && cnt < det_cap) det_s[cnt] = (unsigned long long)(walk.lo + found);
+                ++cnt;
+            });
+            if (threadIdx.x == 0) {
+                n_walk = cnt;
+                if (blockIdx.x == 0) {
+                    const long long r_end = walk.lo + j;
+                    PeakState st;
+                    st.r_abs = (unsigned long long)(r_end > walk.hi ? r_end : walk.hi);
+                    st.det_count = cnt;
+                    st._pad = 0;
+                    *walk.header = st;          // the host reads the count (and the records behind it) from here
+                    st.det_count = 0;           // the device-side list counts as drained
+                    *walk.state_out = st;
+                }
+            }
+        }
+        __syncthreads();
+        n = n_walk;
+        dets = det_s;
+    } else {
+        n = *det_count;
+    }
     if (n > det_cap) n = det_cap;
     if (blockIdx.x >= n) return;  // the grid is sized for the worst case; idle CTAs leave at once
     load_twiddles(tw_s, tw_g);
@@ -295,7 +385,7 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
     const int tid = threadIdx.x;
     const bool fft_warp = tid < kGroupThreads;
     for (unsigned int d = blockIdx.x; d < n; d += gridDim.x) {
-        const long long p = (long long)det_idx[d];
+        const long long p = (long long)dets[d];
         const long long b = p / S;
         const int kk = (int)(p - b * S);
         const int m = (kFft - kk) & (kFft - 1);            // output index of FFT B, m = 128 m1 + 8 m2 + m3
@@ -422,24 +512,51 @@ size_t correlate_smem_bytes(int groups) {
 cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpow, long long z_base,
                              const float2* d_hperm, int K, int S, long long b0, long long nb,
                              const float2* d_tw, float2* d_out_delayed, long long out_base, long long out_lo,
-                             long long out_hi, int delay, int num_sms, cudaStream_t st) {
+                             long long out_hi, int delay, int num_sms, cudaStream_t st, long long nb_chan,
+                             long long in_chan_stride, long long z_chan_stride) {
     if (nb <= 0) return cudaSuccess;
     // function attributes are per device: one flag per ordinal (a process may hold contexts on several GPUs)
     static bool attr_set[64] = {};
-    const int groups = kCorrThreads / kGroupThreads;
-    const size_t smem = correlate_smem_bytes(groups);
+    const int max_groups = kCorrThreads / kGroupThreads;
+    const size_t smem_max = correlate_smem_bytes(max_groups);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        e = cudaFuncSetAttribute(correlate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(correlate_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(correlate_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(correlate_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    long long want = (nb + groups - 1) / groups;
+    // Few blocks (one processBulk span of the streaming path is 37 blocks): what the caller waits for is the
+    // LATENCY of a block.  Up to one block per SM: a CTA per block, its groups splitting the hypotheses (ksplit);
+    // more: fewer groups per CTA so the blocks spread over all SMs; many blocks: the persistent 6-group shape.
+    int groups = max_groups, ksplit = 1;
+    static int forced = -1;  // development override: B200SYNC_SMALL_GROUPS=1..6
+    if (forced < 0) {
+        const char* v = getenv("B200SYNC_SMALL_GROUPS");
+        forced = v ? atoi(v) : 0;
+    }
+    if (nb_chan == 0 && nb <= num_sms && K >= 2 && d_out_delayed == nullptr) {
+        groups = K < max_groups ? K : max_groups;
+        if (K > max_groups && K <= 2 * max_groups) groups = (K + 1) / 2;   // e.g. K = 9: 5 groups, two rounds at most
+        if (forced > 0) groups = forced;
+        if (groups > max_groups) groups = max_groups;
+        ksplit = groups;
+    } else if (nb < (long long)max_groups * num_sms) {
+        groups = (int)((nb + num_sms - 1) / num_sms);
+        if (forced > 0) groups = forced;
+        if (groups < 1) groups = 1;
+        if (groups > max_groups) groups = max_groups;
+    }
+    const size_t smem = correlate_smem_bytes(groups);
+    long long want = ksplit > 1 ? nb : (nb + groups - 1) / groups;
     int grid = (int)(want < num_sms ? want : num_sms);
-    correlate_kernel<<<grid, kCorrThreads, smem, st>>>(d_in, in_base, d_zpow, z_base, d_hperm, K, S, b0,
-                                                        nb, d_tw, d_out_delayed, out_base, out_lo, out_hi, delay);
+    auto kern = ksplit > 1 ? correlate_kernel<true, false> : (nb_chan > 0 ? correlate_kernel<false, true> : correlate_kernel<false, false>);
+    kern<<<grid, groups * kGroupThreads, smem, st>>>(d_in, in_base, d_zpow, z_base, d_hperm, K, S, b0, nb, d_tw,
+                                                     d_out_delayed, out_base, out_lo, out_hi, delay, nb_chan,
+                                                     in_chan_stride, z_chan_stride);
     count_launch();
     return cudaGetLastError();
 }
@@ -447,11 +564,29 @@ cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpo
 cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_zpow, long long z_base,
                           const float2* d_hperm, int K, int S, int min_freq_bin, const float2* d_tw,
                           const unsigned long long* d_det_idx, const unsigned int* d_det_count,
-                          unsigned int det_cap, DetectionRecord* d_recs, int num_sms, cudaStream_t st) {
-    const size_t smem = sizeof(float2) * (size_t)(kTwTotal + kXchgFloat2 + kRefineChunk * (256 + 16) + kMaxHyp + 1) +
-                        sizeof(float) * kFft;
-    cudaError_t e = cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                          unsigned int det_cap, DetectionRecord* d_recs, int num_sms, cudaStream_t st, int nch,
+                          long long in_chan_stride, long long z_chan_stride, long long det_chan_stride,
+                          const StreamWalk* walk) {
+    const size_t smem_base = sizeof(float2) * (size_t)(kTwTotal + kXchgFloat2 + kRefineChunk * (256 + 16) + kMaxHyp + 1) +
+                             sizeof(float) * kFft;
+    // the attribute (and the occupancy figure) is for the largest streaming walk: 2^19-sample bitmaps + the list
+    const size_t smem = smem_base + 2 * sizeof(uint32_t) * ((1u << 19) / 32 + 1) + sizeof(unsigned long long) * 1024;
+    size_t smem_launch = smem_base;
+    StreamWalk w{};
+    if (walk != nullptr) {
+        w = *walk;
+        smem_launch = smem_base + 2 * sizeof(uint32_t) * (size_t)((w.range + 31) / 32 + 1) + sizeof(unsigned long long) * det_cap;
+        if (smem_launch > smem || nch != 1) return cudaErrorInvalidValue;
+    }
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        e = cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
     // exactly one resident wave (shared memory allows 3 CTAs per SM): a grid of 4 per SM ran a second,
     // one-third-full wave that took as long as the first
     static int per_sm = 0;
@@ -461,11 +596,12 @@ cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_
         if (per_sm < 1) per_sm = 1;
     }
     int grid = num_sms * per_sm;
+    if (nch > 1) grid = (grid + nch - 1) / nch;  // the channels share the one resident wave
     if ((unsigned)grid > det_cap) grid = (int)det_cap;
     if (grid < 1) grid = 1;
-    refine_kernel<<<grid, kRefineThreads, smem, st>>>(d_in, in_base, d_zpow, z_base, d_hperm, K, S,
-                                                  min_freq_bin, d_tw, d_det_idx, d_det_count, det_cap,
-                                                  d_recs);
+    refine_kernel<<<dim3((unsigned)grid, (unsigned)nch), kRefineThreads, smem_launch, st>>>(
+        d_in, in_base, d_zpow, z_base, d_hperm, K, S, min_freq_bin, d_tw, d_det_idx, d_det_count, det_cap, d_recs,
+        in_chan_stride, z_chan_stride, det_chan_stride, w);
     count_launch();
     return cudaGetLastError();
 }

@@ -23,8 +23,10 @@
 //   chain_emit_kernel   each warp re-walks its segment from its now-known entry
 //                       state and appends examined&&passing peaks to the list
 #include <climits>
+#include <type_traits>
 
 #include "b200sync_internal.h"
+#include "peak_walk.cuh"
 
 namespace b200sync {
 
@@ -32,6 +34,19 @@ constexpr int kFlagsTile = 4096;    // peaks decided per CTA
 constexpr int kFlagsThreads = 512;
 constexpr int kScanThreads = 1024;  // >= T+1
 constexpr int kPlanTile = 8192;     // == kFastTile (a multiple of kFlagsTile)
+
+// Batched channel mode: blockIdx.y is the channel; every per-channel array of a kernel lies `stride` bytes (or
+// elements, as named) after the previous channel's.  Single-stream launches pass zeros and gridDim.y = 1.
+struct PeakBatch {
+    long long z_stride;      // floats between the metric arrays of consecutive channels
+    size_t ws_stride;        // bytes between the workspaces of consecutive channels
+    size_t det_stride;       // entries between the detection lists of consecutive channels
+};
+template <typename T>
+__device__ __forceinline__ T* ws_at(T* p, size_t stride_bytes) {
+    return reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(const_cast<typename std::remove_const<T>::type*>(p)) +
+                                (size_t)blockIdx.y * stride_bytes);
+}
 
 struct PeakPlan {
     long long range;   // hi - lo
@@ -99,8 +114,11 @@ __device__ __forceinline__ float warp_scan_max(float v, int lane) {
 __global__ void __launch_bounds__(kFlagsThreads)
 peak_flags_generic_kernel(const float* __restrict__ zpow, long long z_base, long long z_end, long long lo,
                   long long hi, int T, float thr, uint32_t* __restrict__ cand_bits,
-                  uint32_t* __restrict__ pass_bits) {
+                  uint32_t* __restrict__ pass_bits, PeakBatch pb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    zpow += (long long)blockIdx.y * pb.z_stride;
+    cand_bits = ws_at(cand_bits, pb.ws_stride);
+    pass_bits = ws_at(pass_bits, pb.ws_stride);
     const int n = kFlagsTile + 2 * T;
     float* z = reinterpret_cast<float*>(smem_raw);
     float* Sx = z + n;   // prefix max within W-blocks
@@ -203,7 +221,8 @@ peak_flags_generic_kernel(const float* __restrict__ zpow, long long z_base, long
 // Ordering is done on the int32 bit patterns of zpow, which is the float ordering because zpow is
 // a squared magnitude (>= +0; not NaN for finite input).
 // ---------------------------------------------------------------------------------
-constexpr int kFastTile = 8192;   // peaks decided per CTA
+constexpr int kFastTile = 8192;   // peaks decided per CTA (captures)
+constexpr int kFastTileSmall = 2048;  // ... for streaming-sized ranges: more CTAs, a quarter of the latency each
 constexpr int kFastThreads = 512;
 
 __device__ __forceinline__ int warp_incl_scan_max(int v, int lane) {
@@ -218,33 +237,37 @@ __device__ __forceinline__ int warp_incl_scan_max(int v, int lane) {
 struct FastGeom {
     int Tpad, ng, nrow;
 };
-__host__ __device__ inline FastGeom fast_geom(int T) {
+__host__ __device__ inline FastGeom fast_geom(int T, int tile) {
     FastGeom g;
     g.Tpad = (T + 31) & ~31;                          // window origin is group aligned with the tile
-    const int n = g.Tpad + kFastTile + T + 1;         // window elements that can be referenced
+    const int n = g.Tpad + tile + T + 1;              // window elements that can be referenced
     g.ng = (n + 31) >> 5;
     g.nrow = (g.ng + 4 + 3) >> 2;                     // rows of 128 samples, >= 4 groups of slack
     return g;
 }
 
+template <int TILE>
 __global__ void __launch_bounds__(kFastThreads)
 peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_end, long long lo,
                   long long hi, int T, float thr, uint32_t* __restrict__ cand_bits,
-                  uint32_t* __restrict__ pass_bits) {
+                  uint32_t* __restrict__ pass_bits, PeakBatch pb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const FastGeom geo = fast_geom(T);
+    zpow += (long long)blockIdx.y * pb.z_stride;
+    cand_bits = ws_at(cand_bits, pb.ws_stride);
+    pass_bits = ws_at(pass_bits, pb.ws_stride);
+    const FastGeom geo = fast_geom(T, TILE);
     const int Tpad = geo.Tpad, nrow = geo.nrow;
     int* z = reinterpret_cast<int*>(smem_raw);             // [nrow * 128] bit patterns of zpow
     int* gmax = z + nrow * 128;                            // [nrow * 4]
     int* gmin = gmax + nrow * 4;                           // [nrow * 4]
-    int* gM = gmin + nrow * 4;                             // [kFastTile / 32] max of the q whole groups
-    uint32_t* passw = reinterpret_cast<uint32_t*>(gM + kFastTile / 32);          // [kFastTile / 32]
-    int* ncand_s = reinterpret_cast<int*>(passw + kFastTile / 32);
-    unsigned short* cand_list = reinterpret_cast<unsigned short*>(ncand_s + 1);  // [kFastTile] worst case
+    int* gM = gmin + nrow * 4;                             // [TILE / 32] max of the q whole groups
+    uint32_t* passw = reinterpret_cast<uint32_t*>(gM + TILE / 32);          // [TILE / 32]
+    int* ncand_s = reinterpret_cast<int*>(passw + TILE / 32);
+    unsigned short* cand_list = reinterpret_cast<unsigned short*>(ncand_s + 1);  // [TILE] worst case
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kFastThreads / 32;
-    const long long tile_lo = lo + (long long)blockIdx.x * kFastTile;
+    const long long tile_lo = lo + (long long)blockIdx.x * TILE;
     const long long q0 = tile_lo - Tpad;                   // absolute index of window element 0
     const int* src = reinterpret_cast<const int*>(zpow) + (q0 - z_base);
     // first element that is both inside the stream and inside the caller's metric buffer: the window origin is
@@ -300,7 +323,7 @@ peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_
     const int q = (T - 31) >> 5;         // whole groups inside every forward window of a group
     const int d = T - 32 * q - 32;       // remainder reaches element (lane + d) of group G+q+1, d in [-1, 30]
     const int G0 = Tpad >> 5;
-    if (tid < kFastTile / 32) {
+    if (tid < TILE / 32) {
         int m = INT_MIN;
         for (int k = 1; k <= q; ++k) m = max(m, gmax[G0 + tid + k]);
         gM[tid] = m;
@@ -309,22 +332,22 @@ peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_
     __syncthreads();
 
     const long long rem_ll = hi - tile_lo;
-    const int nvalid = rem_ll < (long long)kFastTile ? (int)rem_ll : kFastTile;  // p < hi
+    const int nvalid = rem_ll < (long long)TILE ? (int)rem_ll : TILE;  // p < hi
     const int tv_need = 2 * T + 1;
     uint32_t* cw = cand_bits + (tile_lo - lo) / 32;
     uint32_t* pw = pass_bits + (tile_lo - lo) / 32;
     const int4* z4 = reinterpret_cast<const int4*>(z + Tpad);
     // ---- candidates: written to the bitmap and queued for the threshold test
-    for (int it = warp; it < kFastTile / 128; it += kWarps) {
+    for (int it = warp; it < TILE / 128; it += kWarps) {
         // 128 samples per step: lane holds 4 consecutive samples of tile group 4*it + (lane >> 3)
         const int4 v = z4[it * 32 + lane];
         const int Mq = gM[4 * it + (lane >> 3)];
         const bool poss = !(Mq > v.x) || !(Mq > v.y) || !(Mq > v.z) || !(Mq > v.w);
-        const uint32_t pb = __ballot_sync(0xffffffffu, poss);
+        const uint32_t possb = __ballot_sync(0xffffffffu, poss);
         uint32_t cand_out = 0u;                  // lane j (< 4) keeps the word of group 4*it + j
-        if (pb != 0u) {                          // rare: about one group in q+1 holds a possible candidate
+        if (possb != 0u) {                       // rare: about one group in q+1 holds a possible candidate
             for (int j = 0; j < 4; ++j) {
-                if (((pb >> (8 * j)) & 0xffu) == 0u) continue;   // warp-uniform
+                if (((possb >> (8 * j)) & 0xffu) == 0u) continue;   // warp-uniform
                 const int w = 4 * it + j;
                 const int G = G0 + w;
                 const int zi = z[32 * G + lane];
@@ -414,7 +437,7 @@ peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_
         if (lane == 0 && 2 * cnt >= tv_need) atomicOr(&passw[tp >> 5], 1u << (tp & 31));
     }
     __syncthreads();
-    if (tid < kFastTile / 32) pw[tid] = passw[tid];
+    if (tid < TILE / 32) pw[tid] = passw[tid];
 }
 
 // bits [fstart + 32*lane, +32) of a piece of length L starting at bit fstart
@@ -448,7 +471,10 @@ __device__ __forceinline__ int piece_next(uint32_t w, uint32_t nz, int x) {
 // (its table is not written); 0 -> general table in tables[seg].
 __global__ void __launch_bounds__(128)
 chain_tables_kernel(const uint32_t* __restrict__ cand_bits, long long range, int T, int M, long long nfr,
-                    long long nseg, uint16_t* __restrict__ tables, uint32_t* __restrict__ segflag) {
+                    long long nseg, uint16_t* __restrict__ tables, uint32_t* __restrict__ segflag, PeakBatch pb) {
+    cand_bits = ws_at(cand_bits, pb.ws_stride);
+    tables = ws_at(tables, pb.ws_stride);
+    segflag = ws_at(segflag, pb.ws_stride);
     const int lane = threadIdx.x & 31;
     const long long seg = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (seg >= nseg) return;
@@ -508,8 +534,12 @@ chain_tables_kernel(const uint32_t* __restrict__ cand_bits, long long range, int
 __global__ void __launch_bounds__(kScanThreads)
 chain_scan_kernel(const uint16_t* __restrict__ tables, const uint32_t* __restrict__ segflag, long long nseg_ll,
                   int T, int mode, int j_in_param, PeakState* __restrict__ state, long long lo, long long hi,
-                  uint16_t* __restrict__ seg_jin, uint16_t* __restrict__ range_table) {
+                  uint16_t* __restrict__ seg_jin, uint16_t* __restrict__ range_table, PeakBatch pb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    tables = ws_at(tables, pb.ws_stride);
+    segflag = ws_at(segflag, pb.ws_stride);
+    if (seg_jin != nullptr) seg_jin = ws_at(seg_jin, pb.ws_stride);
+    if (state != nullptr) state += blockIdx.y;
     const int nseg = (int)nseg_ll;
     uint32_t* flags = reinterpret_cast<uint32_t*>(smem_raw);         // [nseg]
     uint16_t* jin_s = reinterpret_cast<uint16_t*>(flags + nseg);     // [nseg + 1] entry state per segment
@@ -592,7 +622,12 @@ __global__ void __launch_bounds__(128)
 chain_emit_kernel(const uint32_t* __restrict__ cand_bits, const uint32_t* __restrict__ pass_bits,
                   long long range, int T, int M, long long nfr, long long nseg,
                   const uint16_t* __restrict__ seg_jin, long long lo, unsigned long long* __restrict__ slots,
-                  uint32_t* __restrict__ seg_count) {
+                  uint32_t* __restrict__ seg_count, PeakBatch pb) {
+    cand_bits = ws_at(cand_bits, pb.ws_stride);
+    pass_bits = ws_at(pass_bits, pb.ws_stride);
+    seg_jin = ws_at(seg_jin, pb.ws_stride);
+    slots = ws_at(slots, pb.ws_stride);
+    seg_count = ws_at(seg_count, pb.ws_stride);
     const int lane = threadIdx.x & 31;
     const long long seg = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (seg >= nseg) return;
@@ -635,7 +670,10 @@ chain_emit_kernel(const uint32_t* __restrict__ cand_bits, const uint32_t* __rest
 // exclusive scan of the per-segment detection counts (one CTA; nseg <= 32 * num_sms + 1)
 __global__ void __launch_bounds__(1024)
 det_offsets_kernel(const uint32_t* __restrict__ seg_count, int nseg, uint32_t* __restrict__ seg_off,
-                   PeakState* __restrict__ state) {
+                   PeakState* __restrict__ state, PeakBatch pb) {
+    seg_count = ws_at(seg_count, pb.ws_stride);
+    seg_off = ws_at(seg_off, pb.ws_stride);
+    state += blockIdx.y;
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t carry_s;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -677,7 +715,10 @@ det_offsets_kernel(const uint32_t* __restrict__ seg_count, int nseg, uint32_t* _
 
 __global__ void __launch_bounds__(128)
 det_gather_kernel(const unsigned long long* __restrict__ slots, const uint32_t* __restrict__ seg_off, int M,
-                  long long nseg, unsigned long long* __restrict__ det_idx, unsigned int det_cap) {
+                  long long nseg, unsigned long long* __restrict__ det_idx, unsigned int det_cap, PeakBatch pb) {
+    slots = ws_at(slots, pb.ws_stride);
+    seg_off = ws_at(seg_off, pb.ws_stride);
+    det_idx += (size_t)blockIdx.y * pb.det_stride;
     const int lane = threadIdx.x & 31;
     const long long seg = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (seg >= nseg) return;
@@ -687,42 +728,99 @@ det_gather_kernel(const unsigned long long* __restrict__ slots, const uint32_t* 
 }
 
 // ---------------------------------------------------------------------------------
-static cudaError_t set_smem_attr(const void* fn, size_t bytes) {
-    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+// Streaming-sized ranges (one processBulk span: tens of thousands of samples, at most a few dozen examined peaks):
+// the walk of PM/syncword_detection.hpp:267-298 over the candidate / threshold bitmaps by ONE warp, in order — 32
+// bitmap words per probe, a jump of T+1 after every examined peak.  Replaces chain_tables + chain_scan + chain_emit +
+// det_offsets + det_gather (five launches whose parallelism only pays on captures of many millions of samples).
+constexpr int kSmallThreads = 256;
+__global__ void __launch_bounds__(kSmallThreads)
+chain_small_kernel(const uint32_t* __restrict__ cand_bits, const uint32_t* __restrict__ pass_bits, long long range,
+                   int T, long long lo, long long hi, PeakState* __restrict__ state,
+                   unsigned long long* __restrict__ det_idx, unsigned int det_cap, PeakBatch pb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cand_bits = ws_at(cand_bits, pb.ws_stride);
+    pass_bits = ws_at(pass_bits, pb.ws_stride);
+    state += blockIdx.y;
+    det_idx += (size_t)blockIdx.y * pb.det_stride;
+    // both bitmaps into shared memory first (coalesced, all threads): the walk below is a chain of DEPENDENT
+    // probes, and from global memory every probe would cost an L2 round trip
+    const int nwords = (int)((range + 31) >> 5);
+    uint32_t* cand_s = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* pass_s = cand_s + nwords;
+    for (int i = threadIdx.x; i < nwords; i += kSmallThreads) {
+        cand_s[i] = cand_bits[i];
+        pass_s[i] = pass_bits[i];
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const unsigned long long r = state->r_abs;
+    const long long j0 = (r > (unsigned long long)lo) ? (long long)(r - (unsigned long long)lo) : 0;  // search offset in the range
+    unsigned int cnt = 0;
+    const long long j = peak_walk_warp(cand_s, pass_s, nwords, range, T, j0, [&](long long found) {
+        if (lane == 0 && cnt < det_cap) det_idx[cnt] = (unsigned long long)(lo + found);
+        ++cnt;
+    });
+    if (lane == 0) {
+        const long long r_end = lo + j;
+        state->r_abs = (unsigned long long)(r_end > hi ? r_end : hi);
+        state->det_count = cnt;
+    }
 }
 
-cudaError_t launch_peak_phase1(const float* d_zpow, long long z_base, long long z_end, long long lo,
-                               long long hi, int T, float power_threshold, void* d_ws, size_t ws_bytes,
-                               uint16_t* d_range_table, int num_sms, cudaStream_t st) {
+// ---------------------------------------------------------------------------------
+// cudaFuncSetAttribute costs microseconds per call and the streaming path launches these kernels per span: remember
+// the largest size already granted per (function, device)
+static cudaError_t set_smem_attr(const void* fn, size_t bytes) {
+    struct Slot { const void* fn; int dev; size_t bytes; };
+    static Slot slots[64] = {};
+    static int nslots = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    for (int i = 0; i < nslots; ++i)
+        if (slots[i].fn == fn && slots[i].dev == dev) {
+            if (bytes <= slots[i].bytes) return cudaSuccess;
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (e == cudaSuccess) slots[i].bytes = bytes;
+            return e;
+        }
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess && nslots < 64) slots[nslots++] = Slot{fn, dev, bytes};  // benign race: worst case a repeated call
+    return e;
+}
+
+// candidate + threshold bitmaps of [lo, hi) (the per-sample part of a6); nch channels side by side (blockIdx.y)
+static cudaError_t launch_flags(const float* d_zpow, long long z_base, long long z_end, long long lo, long long hi,
+                                int T, float power_threshold, const PeakPlan& pl, unsigned char* ws, int nch,
+                                const PeakBatch& pb, cudaStream_t st, bool zero_padding = true) {
     const long long range = hi - lo;
-    if (range <= 0) return cudaSuccess;
-    const PeakPlan pl = make_plan(range, T, num_sms);
-    if (pl.total > ws_bytes) return cudaErrorInvalidValue;
-    unsigned char* ws = static_cast<unsigned char*>(d_ws);
-    uint32_t* cand = reinterpret_cast<uint32_t*>(ws + pl.off_cand);
-    uint32_t* pass = reinterpret_cast<uint32_t*>(ws + pl.off_pass);
-    uint16_t* tables = reinterpret_cast<uint16_t*>(ws + pl.off_tables);
     cudaError_t e;
     const bool fast = T >= 32;
-    const int tile = fast ? kFastTile : kFlagsTile;
+    const bool small = fast && range <= (1LL << 18);
+    const int tile = fast ? (small ? kFastTileSmall : kFastTile) : kFlagsTile;
     const long long ntiles = (range + tile - 1) / tile;
     // zero the padding words past the last tile (tiles write every word they own)
     const long long written = ntiles * (tile / 32);
-    if (written < pl.nwords) {
+    for (int c = 0; zero_padding && c < nch && written < pl.nwords; ++c) {
+        uint32_t* cand = reinterpret_cast<uint32_t*>(ws + (size_t)c * pb.ws_stride + pl.off_cand);
+        uint32_t* pass = reinterpret_cast<uint32_t*>(ws + (size_t)c * pb.ws_stride + pl.off_pass);
         e = cudaMemsetAsync(cand + written, 0, sizeof(uint32_t) * (pl.nwords - written), st);
         if (e != cudaSuccess) return e;
         e = cudaMemsetAsync(pass + written, 0, sizeof(uint32_t) * (pl.nwords - written), st);
         if (e != cudaSuccess) return e;
     }
-    uint32_t* segflag = reinterpret_cast<uint32_t*>(ws + pl.off_flag);
+    uint32_t* cand = reinterpret_cast<uint32_t*>(ws + pl.off_cand);
+    uint32_t* pass = reinterpret_cast<uint32_t*>(ws + pl.off_pass);
+    const dim3 grid((unsigned)ntiles, (unsigned)nch);
     if (fast) {
-        const FastGeom geo = fast_geom(T);
-        const size_t smem = sizeof(int) * ((size_t)geo.nrow * 128 + 2 * (size_t)geo.nrow * 4 + 2 * (kFastTile / 32) + 1) +
-                            sizeof(unsigned short) * kFastTile;
-        e = set_smem_attr((const void*)peak_flags_kernel, smem);
+        const FastGeom geo = fast_geom(T, tile);
+        const size_t smem = sizeof(int) * ((size_t)geo.nrow * 128 + 2 * (size_t)geo.nrow * 4 + 2 * (tile / 32) + 1) +
+                            sizeof(unsigned short) * tile;
+        auto kern = small ? peak_flags_kernel<kFastTileSmall> : peak_flags_kernel<kFastTile>;
+        e = set_smem_attr((const void*)kern, smem);
         if (e != cudaSuccess) return e;
-        peak_flags_kernel<<<(unsigned)ntiles, kFastThreads, smem, st>>>(d_zpow, z_base, z_end, lo, hi, T,
-                                                                       power_threshold, cand, pass);
+        kern<<<grid, kFastThreads, smem, st>>>(d_zpow, z_base, z_end, lo, hi, T, power_threshold, cand, pass, pb);
         count_launch();
     } else {
         const int n = kFlagsTile + 2 * T;
@@ -730,14 +828,35 @@ cudaError_t launch_peak_phase1(const float* d_zpow, long long z_base, long long 
                             sizeof(unsigned short) * kFlagsTile;
         e = set_smem_attr((const void*)peak_flags_generic_kernel, smem);
         if (e != cudaSuccess) return e;
-        peak_flags_generic_kernel<<<(unsigned)ntiles, kFlagsThreads, smem, st>>>(d_zpow, z_base, z_end, lo, hi,
-                                                                                T, power_threshold, cand, pass);
+        peak_flags_generic_kernel<<<grid, kFlagsThreads, smem, st>>>(d_zpow, z_base, z_end, lo, hi, T,
+                                                                     power_threshold, cand, pass, pb);
         count_launch();
     }
-    e = cudaGetLastError();
+    return cudaGetLastError();
+}
+
+size_t peak_plan_bytes(long long range, int T, int num_sms) { return make_plan(range, T, num_sms).total; }
+
+// nch > 1: batched channel mode — d_zpow, d_ws, d_state, d_det_idx are the first channel's; the others follow at
+// z_stride floats / ws_stride bytes / one PeakState / det_stride entries
+cudaError_t launch_peak_phase1(const float* d_zpow, long long z_base, long long z_end, long long lo,
+                               long long hi, int T, float power_threshold, void* d_ws, size_t ws_bytes,
+                               uint16_t* d_range_table, int num_sms, cudaStream_t st, int nch, long long z_stride,
+                               size_t ws_stride) {
+    const long long range = hi - lo;
+    if (range <= 0) return cudaSuccess;
+    const PeakPlan pl = make_plan(range, T, num_sms);
+    if (pl.total > ws_bytes) return cudaErrorInvalidValue;
+    if (nch > 1 && (d_range_table != nullptr || ws_stride < pl.total)) return cudaErrorInvalidValue;
+    const PeakBatch pb{z_stride, ws_stride, 0};
+    unsigned char* ws = static_cast<unsigned char*>(d_ws);
+    uint32_t* cand = reinterpret_cast<uint32_t*>(ws + pl.off_cand);
+    uint16_t* tables = reinterpret_cast<uint16_t*>(ws + pl.off_tables);
+    uint32_t* segflag = reinterpret_cast<uint32_t*>(ws + pl.off_flag);
+    cudaError_t e = launch_flags(d_zpow, z_base, z_end, lo, hi, T, power_threshold, pl, ws, nch, pb, st);
     if (e != cudaSuccess) return e;
-    chain_tables_kernel<<<(unsigned)((pl.nseg + 3) / 4), 128, 0, st>>>(cand, range, T, pl.M, pl.nfr,
-                                                                       pl.nseg, tables, segflag);
+    chain_tables_kernel<<<dim3((unsigned)((pl.nseg + 3) / 4), (unsigned)nch), 128, 0, st>>>(cand, range, T, pl.M, pl.nfr,
+                                                                                           pl.nseg, tables, segflag, pb);
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -746,20 +865,63 @@ cudaError_t launch_peak_phase1(const float* d_zpow, long long z_base, long long 
         e = set_smem_attr((const void*)chain_scan_kernel, ssm);
         if (e != cudaSuccess) return e;
         chain_scan_kernel<<<1, kScanThreads, ssm, st>>>(tables, segflag, pl.nseg, T, 0, -1, nullptr, lo, hi,
-                                                        nullptr, d_range_table);
+                                                        nullptr, d_range_table, pb);
         count_launch();
         e = cudaGetLastError();
     }
     return e;
 }
 
-cudaError_t launch_peak_phase2(long long lo, long long hi, int T, void* d_ws, size_t ws_bytes, int j_in,
-                               PeakState* d_state, unsigned long long* d_det_idx, unsigned int det_cap,
-                               int num_sms, cudaStream_t st) {
+// both phases for a streaming-sized range: two launches (flags, in-order walk) instead of seven
+cudaError_t launch_peak_stream(const float* d_zpow, long long z_base, long long z_end, long long lo, long long hi,
+                               int T, float power_threshold, void* d_ws, size_t ws_bytes, PeakState* d_state,
+                               unsigned long long* d_det_idx, unsigned int det_cap, int num_sms, cudaStream_t st) {
     const long long range = hi - lo;
     if (range <= 0) return cudaSuccess;
     const PeakPlan pl = make_plan(range, T, num_sms);
     if (pl.total > ws_bytes) return cudaErrorInvalidValue;
+    const PeakBatch pb{0, 0, 0};
+    unsigned char* ws = static_cast<unsigned char*>(d_ws);
+    uint32_t* cand = reinterpret_cast<uint32_t*>(ws + pl.off_cand);
+    uint32_t* pass = reinterpret_cast<uint32_t*>(ws + pl.off_pass);
+    cudaError_t e = launch_flags(d_zpow, z_base, z_end, lo, hi, T, power_threshold, pl, ws, 1, pb, st);
+    if (e != cudaSuccess) return e;
+    const size_t ssm = 2 * sizeof(uint32_t) * (size_t)((range + 31) >> 5);
+    e = set_smem_attr((const void*)chain_small_kernel, ssm);
+    if (e != cudaSuccess) return e;
+    chain_small_kernel<<<1, kSmallThreads, ssm, st>>>(cand, pass, range, T, lo, hi, d_state, d_det_idx, det_cap, pb);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// flags only; the walk runs fused in front of the refine stage (it reads words < (range+31)/32 only: no padding needed)
+cudaError_t launch_peak_flags_stream(const float* d_zpow, long long z_base, long long z_end, long long lo, long long hi,
+                                     int T, float power_threshold, void* d_ws, size_t ws_bytes, int num_sms,
+                                     cudaStream_t st, StreamWalk* walk) {
+    const long long range = hi - lo;
+    if (range <= 0) return cudaErrorInvalidValue;
+    const PeakPlan pl = make_plan(range, T, num_sms);
+    if (pl.total > ws_bytes) return cudaErrorInvalidValue;
+    const PeakBatch pb{0, 0, 0};
+    unsigned char* ws = static_cast<unsigned char*>(d_ws);
+    walk->cand = reinterpret_cast<uint32_t*>(ws + pl.off_cand);
+    walk->pass = reinterpret_cast<uint32_t*>(ws + pl.off_pass);
+    walk->range = range;
+    walk->lo = lo;
+    walk->hi = hi;
+    walk->T = T;
+    return launch_flags(d_zpow, z_base, z_end, lo, hi, T, power_threshold, pl, ws, 1, pb, st, false);
+}
+
+cudaError_t launch_peak_phase2(long long lo, long long hi, int T, void* d_ws, size_t ws_bytes, int j_in,
+                               PeakState* d_state, unsigned long long* d_det_idx, unsigned int det_cap,
+                               int num_sms, cudaStream_t st, int nch, size_t ws_stride, size_t det_stride) {
+    const long long range = hi - lo;
+    if (range <= 0) return cudaSuccess;
+    const PeakPlan pl = make_plan(range, T, num_sms);
+    if (pl.total > ws_bytes) return cudaErrorInvalidValue;
+    if (nch > 1 && ws_stride < pl.total) return cudaErrorInvalidValue;
+    const PeakBatch pb{0, ws_stride, det_stride};
     unsigned char* ws = static_cast<unsigned char*>(d_ws);
     uint32_t* cand = reinterpret_cast<uint32_t*>(ws + pl.off_cand);
     uint32_t* pass = reinterpret_cast<uint32_t*>(ws + pl.off_pass);
@@ -769,25 +931,24 @@ cudaError_t launch_peak_phase2(long long lo, long long hi, int T, void* d_ws, si
     const size_t ssm = sizeof(uint32_t) * (size_t)pl.nseg + sizeof(uint16_t) * (size_t)(pl.nseg + 2 + T + 2);
     cudaError_t e = set_smem_attr((const void*)chain_scan_kernel, ssm);
     if (e != cudaSuccess) return e;
-    chain_scan_kernel<<<1, kScanThreads, ssm, st>>>(tables, segflag, pl.nseg, T, 1, j_in, d_state, lo, hi, jin,
-                                                    nullptr);
+    chain_scan_kernel<<<dim3(1, (unsigned)nch), kScanThreads, ssm, st>>>(tables, segflag, pl.nseg, T, 1, j_in, d_state,
+                                                                        lo, hi, jin, nullptr, pb);
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     unsigned long long* slots = reinterpret_cast<unsigned long long*>(ws + pl.off_slots);
     uint32_t* segcnt = reinterpret_cast<uint32_t*>(ws + pl.off_segcnt);
     uint32_t* segoff = reinterpret_cast<uint32_t*>(ws + pl.off_segoff);
-    chain_emit_kernel<<<(unsigned)((pl.nseg + 3) / 4), 128, 0, st>>>(cand, pass, range, T, pl.M, pl.nfr,
-                                                                     pl.nseg, jin, lo, slots, segcnt);
+    const dim3 gseg((unsigned)((pl.nseg + 3) / 4), (unsigned)nch);
+    chain_emit_kernel<<<gseg, 128, 0, st>>>(cand, pass, range, T, pl.M, pl.nfr, pl.nseg, jin, lo, slots, segcnt, pb);
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    det_offsets_kernel<<<1, 1024, 0, st>>>(segcnt, (int)pl.nseg, segoff, d_state);
+    det_offsets_kernel<<<dim3(1, (unsigned)nch), 1024, 0, st>>>(segcnt, (int)pl.nseg, segoff, d_state, pb);
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    det_gather_kernel<<<(unsigned)((pl.nseg + 3) / 4), 128, 0, st>>>(slots, segoff, pl.M, pl.nseg, d_det_idx,
-                                                                    det_cap);
+    det_gather_kernel<<<gseg, 128, 0, st>>>(slots, segoff, pl.M, pl.nseg, d_det_idx, det_cap, pb);
     count_launch();
     return cudaGetLastError();
 }

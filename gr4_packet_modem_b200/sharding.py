@@ -52,7 +52,9 @@ def entry_offsets(tables: list[np.ndarray]) -> list[int]:
 
 def gather_entry_offset(table: np.ndarray, rank: int, world: int, group=None, device=None) -> int:
     """all_gather the ranks' chain tables (T+1 small integers each — the path's only exchange) with
-    torch.distributed and return this rank's entry offset."""
+    torch.distributed and return this rank's entry offset.  The tables are host arrays and stay host bytes: with
+    `device=None` (the default, and what bench.py does) the tensors are CPU tensors and travel over the gloo
+    backend of the process group — nothing goes through a GPU or NCCL."""
     import torch
     import torch.distributed as dist
 

@@ -180,6 +180,8 @@ int b200sync_sd_detect_channels_device(b200sync_sd* sd, const void* d_in, size_t
  * capture; d_out_delayed (device) holds absolute output items [out_first_abs, out_first_abs + out_len), items
  * outside it are not stored.  The setting is consumed by the next phase-1 call. */
 int b200sync_sd_shard_output(b200sync_sd* sd, void* d_out_delayed, uint64_t out_first_abs, size_t out_len);
+/* the same into HOST memory, for b200sync_sd_shard_phase1_host (a host copy on a few threads while the GPU works) */
+int b200sync_sd_shard_output_host(b200sync_sd* sd, float* out_delayed, uint64_t out_first_abs, size_t out_len);
 int b200sync_sd_shard_phase1(b200sync_sd* sd, const void* d_in, uint64_t first_sample_abs, size_t n_in,
                              uint64_t first_block, uint64_t n_blocks, uint64_t total_blocks,
                              void* cuda_stream, uint16_t* table, size_t table_len);
