@@ -120,7 +120,8 @@ def workload_config(log2n: int, K: int, esn0: float = 20.0, thr: float = 9.5) ->
             "samples_per_gpu": 1 << log2n, "fft_size": FFT, "time_threshold": TAU, "power_threshold": thr,
             "l2": "inputs (8 B/sample resident capture) larger than L2; no flush needed",
             "contract": "block contract: delayed output span written (16 B/sample); the reference arm does the same",
-            "sharding": "contiguous time shards + 1-block halo; (T+1)-entry chain tables exchanged as host bytes (gloo)"}
+            "sharding": "contiguous time shards + 1-block halo; (T+1)-entry chain tables exchanged as host bytes "
+                        "(shared memory between the ranks of the box, gloo as fallback); no NCCL on the data path"}
 
 
 def measured_traffic(log2n: int, K: int, contract: str = "block", kernel: str = "correlate_kernel"):
@@ -782,7 +783,23 @@ def main():
     lib = _native.lib()
 
     # ---- this rank's time shard of a world*n_per-sample capture (shard + halo blocks) ----
-    from gr4_packet_modem_b200.sharding import gather_entry_offset, plan_shards
+    from gr4_packet_modem_b200.sharding import SharedTableExchange, gather_entry_offset, plan_shards
+
+    # the shards' chain tables travel as host bytes: through a shared-memory segment when all ranks share the box
+    # (they do: one node), else over the gloo backend.  Either way nothing touches a GPU or NCCL.
+    xchg = None
+    if world > 1:
+        try:
+            xchg = SharedTableExchange(f"b200sync_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}", rank, world, TAU + 1)
+        except Exception as e:
+            sys.stderr.write(f"rank {rank}: shared-memory exchange unavailable ({e!r}); using gloo\n")
+        ok = torch.tensor([1 if xchg is not None else 0], dtype=torch.int64)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            xchg = None
+
+    def entry_offset(table):
+        return xchg.entry_offset(table) if xchg is not None else gather_entry_offset(table, rank, world)
 
     total_n = n_per * world
     shard = plan_shards(total_n, world, FFT, S, TAU)[rank]
@@ -806,7 +823,7 @@ def main():
             sd.shard_output(d_out.data_ptr(), out_first, out_len)
         table = sd.shard_phase1(x.data_ptr(), seg0, seg_n, fb, nbk, total_blocks, stream)
         # T+1 small integers per rank, exchanged as host bytes: the only exchange of the path
-        j = gather_entry_offset(table, rank, world)
+        j = entry_offset(table)
         recs, _ = sd.shard_phase2(j, max_recs)
         return nbk * S, len(recs)
 
@@ -871,7 +888,7 @@ def main():
             if with_out:
                 sd.shard_output_host(hout.data_ptr(), out_first, out_len)
             table = sd.shard_phase1_host((hx.data_ptr(), n_host), seg0, fb, nbk, total_blocks)
-            j = gather_entry_offset(table, rank, world)
+            j = entry_offset(table)
             recs, _ = sd.shard_phase2(j, max_recs)
             return nbk * S, len(recs)
 
@@ -892,6 +909,9 @@ def main():
                        "threads during the call; records come back over PCIe"}
         del hx, hout
 
+    if xchg is not None:
+        barrier()
+        xchg.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

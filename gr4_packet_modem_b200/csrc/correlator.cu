@@ -591,7 +591,7 @@ cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_
     // one-third-full wave that took as long as the first
     static int per_sm = 0;
     if (per_sm == 0) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, refine_kernel, kRefineThreads, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, refine_kernel, kRefineThreads, smem_base);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
     }

@@ -64,3 +64,85 @@ def gather_entry_offset(table: np.ndarray, rank: int, world: int, group=None, de
     allt = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(allt, t, group=group)
     return entry_offsets([a.cpu().numpy() for a in allt])[rank]
+
+
+class SharedTableExchange:
+    """The same exchange for ranks on ONE box without any network stack: every rank writes its (T+1)-entry table into
+    its slot of a POSIX shared-memory segment and bumps its sequence counter; a rank spins until the ranks in front of
+    it have published the step and composes their tables.  ~10 us instead of the ~300 us of a loopback all_gather; the
+    tables never leave host memory (north_star: detections and tables are gathered on the host, no NCCL).
+    Tables are double-buffered by step parity and a rank does not overwrite a slot before every later rank has
+    finished reading the step that used it, so ranks may run ahead of each other freely.
+    Rank 0 creates the segment, the others retry until it exists."""
+
+    def __init__(self, name: str, rank: int, world: int, table_len: int):
+        import time
+        from multiprocessing import shared_memory
+
+        self.rank, self.world, self.n = rank, world, table_len
+        tab_bytes = (4 * table_len + 63) // 64 * 64
+        self._stride = 64 + 2 * tab_bytes                   # [seq int64 | done int64 | pad] + two tables
+        size = self._stride * world
+        if rank == 0:
+            try:
+                old = shared_memory.SharedMemory(name=name)
+                old.close()
+                old.unlink()
+            except FileNotFoundError:
+                pass
+            self._shm = shared_memory.SharedMemory(name=name, create=True, size=size)
+            self._shm.buf[:size] = bytes(size)
+        else:
+            deadline = time.time() + 60
+            while True:
+                try:
+                    self._shm = shared_memory.SharedMemory(name=name)
+                    try:  # Python < 3.13 registers attached segments with the resource tracker too: only rank 0 owns it
+                        from multiprocessing import resource_tracker
+
+                        resource_tracker.unregister(self._shm._name, "shared_memory")
+                    except Exception:
+                        pass
+                    if self._shm.size >= size:
+                        break
+                    self._shm.close()
+                except FileNotFoundError:
+                    pass
+                if time.time() > deadline:
+                    raise TimeoutError(f"shared table segment {name} did not appear")
+                time.sleep(0.01)
+        buf = self._shm.buf
+        self._seq = [np.ndarray((1,), np.int64, buf, r * self._stride) for r in range(world)]
+        self._done = [np.ndarray((1,), np.int64, buf, r * self._stride + 8) for r in range(world)]
+        self._tab = [[np.ndarray((table_len,), np.int32, buf, r * self._stride + 64 + par * tab_bytes) for par in (0, 1)]
+                     for r in range(world)]
+        self._step = 0
+
+    def entry_offset(self, table: np.ndarray) -> int:
+        """Publish this rank's table for the next step, wait for the tables of the ranks in front, return this
+        rank's entry offset (0 at the stream start, then through every earlier shard's table)."""
+        self._step += 1
+        s, par = self._step, self._step & 1
+        for r in range(self.rank + 1, self.world):     # the slot was last used by step s-2: its readers must be done
+            d = self._done[r]
+            while d[0] < s - 2:
+                pass
+        self._tab[self.rank][par][:] = table
+        self._seq[self.rank][0] = s                    # x86 keeps the two stores in order
+        j = 0
+        for r in range(self.rank):
+            q = self._seq[r]
+            while q[0] < s:
+                pass
+            j = int(self._tab[r][par][j])
+        self._done[self.rank][0] = s
+        return j
+
+    def close(self):
+        self._seq = self._done = self._tab = None
+        try:
+            self._shm.close()
+            if self.rank == 0:
+                self._shm.unlink()
+        except Exception:
+            pass

@@ -125,3 +125,40 @@ def test_gloo_world2_exchange():
     cand = rng.random(4000) < 0.05
     assert res[0][1] == 0
     assert res[0][2] + res[1][2] == sequential_examined(cand, 4000, 31)
+
+
+def _xchg_worker(rank, world, name, q):
+    import time
+
+    from gr4_packet_modem_b200.sharding import SharedTableExchange, entry_offsets
+
+    ex = SharedTableExchange(name, rank, world, 769)
+    rng = np.random.default_rng(5)
+    for step in range(200):
+        tabs = [rng.integers(0, 769, 769).astype(np.uint16) for _ in range(world)]
+        if rank == world - 1 and step % 7 == 0:
+            time.sleep(0.001)  # a slow reader: earlier ranks run ahead
+        j = ex.entry_offset(tabs[rank])
+        if j != entry_offsets(tabs)[rank]:
+            q.put((rank, step, "mismatch"))
+            return
+    time.sleep(0.1)
+    ex.close()
+    q.put((rank, 200, "ok"))
+
+
+def test_shared_memory_table_exchange_three_ranks():
+    """The same-box exchange bench.py uses instead of a collective: tables as host bytes in a shared segment,
+    double-buffered, ranks free to run ahead — every rank must get the composition of the shards before it."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    name = f"b200sync_test_{os.getpid()}"
+    ps = [ctx.Process(target=_xchg_worker, args=(r, 3, name, q)) for r in range(3)]
+    for p in ps:
+        p.start()
+    for p in ps:
+        p.join(timeout=120)
+    res = sorted(q.get(timeout=5) for _ in range(3))
+    assert [r[2] for r in res] == ["ok"] * 3, res
