@@ -15,6 +15,7 @@
 #include <cmath>
 #include <complex>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <new>
@@ -102,7 +103,10 @@ struct b200sync_sd {
     size_t h_recs_pin_cap = 0;
     std::vector<c64> carry; // last `delay` input samples (delay line)
     std::deque<b200sync_sd_tag> pending;
-    // offline
+    // offline: metric, and the correlator's group extrema of it for the peak stage (gm_* in b200sync_internal.h)
+    DevBuf<float2> d_gm;
+    long long gm_b0 = 0, gm_blocks = 0;   // rows of d_gm valid for the current offline / shard call (0: none)
+    DevBuf<float2> d_chan_gm;
     DevBuf<float> d_zoff;
     DevBuf<float2> d_xoff;
     size_t metric_n = 0;
@@ -124,6 +128,12 @@ struct b200sync_sd {
     cudaEvent_t ev_stage[3] = {nullptr, nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> ev_pieces;  // b200sync_sd_shard_phase1_host: one event per H2D piece
+    // host output span of the bulk host-span calls when it is pinned: the correlator writes the delayed stream into
+    // d_outoff and a second copy stream sends finished pieces back while later pieces are still coming up (PCIe is
+    // full duplex; a host-side memcpy would cost the host memory system twice the bytes)
+    DevBuf<float2> d_outoff;
+    cudaStream_t d2h_stream = nullptr;
+    std::vector<cudaEvent_t> ev_out;
     // shard
     DevBuf<uint16_t> d_table;
     struct {
@@ -162,8 +172,10 @@ int ensure_det(b200sync_sd* sd, size_t cap) {
 int run_chunk(b200sync_sd* sd, const float2* d_in, long long in_base, float* d_z, long long z_base,
               long long b0, long long nb, long long lo, long long hi, float2* d_out_delayed,
               long long out_end, cudaStream_t st) {
+    float2* gm = (d_z == sd->d_zoff.p && sd->gm_blocks > 0) ? sd->d_gm.p : nullptr;   // offline metric only
     CU(launch_correlate(d_in, in_base, d_z, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, b0, nb,
-                        sd->d_tw.p, d_out_delayed, 0, 0, out_end, (int)sd->delay, sd->num_sms, st));
+                        sd->d_tw.p, d_out_delayed, 0, 0, out_end, (int)sd->delay, sd->num_sms, st, 0, 0, 0, gm,
+                        sd->gm_b0, 0));
     if (hi > lo) {
         const long long z_end = (b0 + nb) * (long long)sd->S;
         if (hi - lo <= kSmallRange) {
@@ -463,6 +475,8 @@ void b200sync_sd_destroy(b200sync_sd* sd) {
     for (auto& e : sd->ev_stage)
         if (e) cudaEventDestroy(e);
     for (auto& e : sd->ev_pieces) cudaEventDestroy(e);
+    for (auto& e : sd->ev_out) cudaEventDestroy(e);
+    if (sd->d2h_stream) cudaStreamDestroy(sd->d2h_stream);
     if (sd->copy_stream) cudaStreamDestroy(sd->copy_stream);
     delete sd;
 }
@@ -685,6 +699,12 @@ static int detect_begin(b200sync_sd* sd, size_t n, float2* d_out_delayed, cudaSt
     *nb_total = (static_cast<long long>(n) - F) / S + 1;
     *P = *nb_total * S;
     CU(sd->d_zoff.ensure(static_cast<size_t>(*P) + 64));
+    sd->gm_b0 = 0;
+    sd->gm_blocks = 0;
+    if (gm_supported((int)sd->S, sd->T)) {
+        CU(sd->d_gm.ensure(static_cast<size_t>(*nb_total) * gm_groups_per_block((int)sd->S) * kGmF2PerGroup));
+        sd->gm_blocks = *nb_total;
+    }
     const long long hi_total = std::max(0LL, *P - T - 1);
     CU(sd->d_ws.ensure(peak_workspace_bytes_sms(hi_total + 1, sd->T, sd->num_sms)));
     if (int rc = ensure_det(sd, static_cast<size_t>(*P / (T + 1) + 2))) return rc;
@@ -707,7 +727,8 @@ static int detect_finish(b200sync_sd* sd, const float2* d_in, long long P, cudaS
     CU(cudaEventRecord(sd->ev[1], st));
     if (hi_total > 0) {
         CU(launch_peak_phase1(sd->d_zoff.p, 0, P, 0, hi_total, sd->T, sd->power_threshold, sd->d_ws.p,
-                              sd->d_ws.cap, nullptr, sd->num_sms, st));
+                              sd->d_ws.cap, nullptr, sd->num_sms, st, 1, 0, 0, sd->gm_blocks > 0 ? sd->d_gm.p : nullptr,
+                              sd->gm_b0, sd->gm_blocks, (int)sd->S, 0));
         CU(launch_peak_phase2(0, hi_total, sd->T, sd->d_ws.p, sd->d_ws.cap, -1, sd->d_state.p,
                               sd->d_det_idx.p, (unsigned)sd->d_det_idx.cap, sd->num_sms, st));
     }
@@ -731,16 +752,44 @@ static int detect_finish(b200sync_sd* sd, const float2* d_in, long long P, cudaS
     return 0;
 }
 
+// How the delayed output span of a HOST-span bulk call is produced when the span is pinned.  Measured on this pool
+// (profiles/r2_e2e_output_path.md): one GPU alone is fastest with a host-side copy on a few threads (5.8 vs 5.0 Gsps:
+// a concurrent D2H stream slows the H2D stream from 53 to 40 GB/s), while several GPUs of one box saturate the
+// host's memory system, where the copy costs 16 B/sample of host traffic and a D2H write only 8.  Default: host
+// copy for the single-GPU bulk call, D2H for time shards.  B200SYNC_HOST_OUTPUT=d2h|memcpy overrides both.
+static bool host_output_by_d2h(bool sharded) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* v = std::getenv("B200SYNC_HOST_OUTPUT");
+        forced = !v ? 0 : (std::strcmp(v, "d2h") == 0 ? 1 : (std::strcmp(v, "memcpy") == 0 ? 2 : 0));
+    }
+    return forced == 1 || (forced == 0 && sharded);
+}
+
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// h_out_pinned != nullptr: the delayed output goes to d_out_delayed (device) AND is sent back to that pinned host
+// span piece by piece on the context's D2H stream, behind the correlator chunk that completes each piece
 static int detect_resident(b200sync_sd* sd, const float2* d_in, size_t n, float2* d_out_delayed,
                            cudaStream_t st, cudaEvent_t* chunk_ready, long long chunk_samples,
                            b200sync_detection_record* recs, size_t max_recs, size_t* n_recs,
-                           size_t* n_consumed) {
+                           size_t* n_consumed, float2* h_out_pinned = nullptr) {
     const long long S = sd->S, F = sd->fft_size;
     *n_recs = 0;
     *n_consumed = 0;
     if (n < static_cast<size_t>(F)) return 0;
     long long nb_total = 0, P = 0;
     if (int rc = detect_begin(sd, n, d_out_delayed, st, &nb_total, &P)) return rc;
+    if (h_out_pinned && !sd->d2h_stream) CU(cudaStreamCreateWithFlags(&sd->d2h_stream, cudaStreamNonBlocking));
+    long long out_done = 0;  // output items already on their way to the host
+    size_t piece_i = 0;
     // correlator in chunks (so it can chase H2D copies)
     for (long long b0 = 0; b0 < nb_total; b0 += kOfflineChunkBlocks) {
         const long long nb = chunk_ready ? std::min(kOfflineChunkBlocks, nb_total - b0) : nb_total;
@@ -750,9 +799,29 @@ static int detect_resident(b200sync_sd* sd, const float2* d_in, size_t n, float2
             CU(cudaStreamWaitEvent(st, chunk_ready[last_sample / chunk_samples], 0));
         }
         if (int rc = run_chunk(sd, d_in, 0, sd->d_zoff.p, 0, b0, nb, 0, 0, d_out_delayed, P, st)) return rc;
+        if (h_out_pinned) {
+            // blocks [0, b0+nb) have written output items [0, (b0+nb)*S + delay) (zeros first, detect_begin)
+            const long long upto = std::min(P, (b0 + nb) * S + static_cast<long long>(sd->delay));
+            if (upto > out_done) {
+                if (sd->ev_out.size() <= piece_i) {
+                    cudaEvent_t e;
+                    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                    sd->ev_out.push_back(e);
+                }
+                CU(cudaEventRecord(sd->ev_out[piece_i], st));
+                CU(cudaStreamWaitEvent(sd->d2h_stream, sd->ev_out[piece_i], 0));
+                CU(cudaMemcpyAsync(h_out_pinned + out_done, d_out_delayed + out_done,
+                                   static_cast<size_t>(upto - out_done) * sizeof(float2), cudaMemcpyDeviceToHost,
+                                   sd->d2h_stream));
+                out_done = upto;
+                ++piece_i;
+            }
+        }
         if (!chunk_ready) break;
     }
-    return detect_finish(sd, d_in, P, st, recs, max_recs, n_recs, n_consumed);
+    const int rc = detect_finish(sd, d_in, P, st, recs, max_recs, n_recs, n_consumed);
+    if (h_out_pinned) cudaStreamSynchronize(sd->d2h_stream);
+    return rc;
 }
 
 int b200sync_sd_detect_device(b200sync_sd* sd, const void* d_in, size_t n, void* d_out_delayed,
@@ -781,14 +850,22 @@ static void host_delay_line(const b200sync_sd* sd, const float* in, float* out, 
     }
 }
 
+static int detect_host_core(b200sync_sd* sd, const float* in, size_t n, float2* h_out_pinned,
+                            b200sync_detection_record* recs, size_t max_recs, size_t* n_recs, size_t* n_consumed);
+
 int b200sync_sd_detect_host_out(b200sync_sd* sd, const float* in, size_t n, float* out, b200sync_detection_record* recs,
                                 size_t max_recs, size_t* n_recs, size_t* n_consumed) {
     if (!sd || !n_recs || !n_consumed || (!in && n) || (!recs && max_recs))
         return fail(B200SYNC_EINVAL, "null argument");
+    if (out != nullptr && n >= sd->fft_size && host_output_by_d2h(false) && is_pinned_host(out)) {
+        // pinned output span: the GPU writes the delayed stream and sends it back over the other PCIe direction
+        CU(cudaSetDevice(sd->device));
+        return detect_host_core(sd, in, n, reinterpret_cast<float2*>(out), recs, max_recs, n_recs, n_consumed);
+    }
     std::vector<std::thread> pool;
     if (out != nullptr && n >= sd->fft_size) {
         const size_t P = ((n - sd->fft_size) / sd->S + 1) * sd->S;  // items the call will publish (:346)
-        host_delay_line(sd, in, out, P, pool);
+        host_delay_line(sd, in, out, P, pool);                      // pageable span: host threads copy it
     }
     const int rc = b200sync_sd_detect_host(sd, in, n, recs, max_recs, n_recs, n_consumed);
     for (auto& t : pool) t.join();
@@ -800,10 +877,16 @@ int b200sync_sd_detect_host(b200sync_sd* sd, const float* in, size_t n, b200sync
     if (!sd || !n_recs || !n_consumed || (!in && n) || (!recs && max_recs))
         return fail(B200SYNC_EINVAL, "null argument");
     CU(cudaSetDevice(sd->device));
+    return detect_host_core(sd, in, n, nullptr, recs, max_recs, n_recs, n_consumed);
+}
+
+static int detect_host_core(b200sync_sd* sd, const float* in, size_t n, float2* h_out_pinned,
+                            b200sync_detection_record* recs, size_t max_recs, size_t* n_recs, size_t* n_consumed) {
     *n_recs = 0;
     *n_consumed = 0;
     if (n < sd->fft_size) return 0;
     CU(sd->d_xoff.ensure(n));
+    if (h_out_pinned) CU(sd->d_outoff.ensure(n));
     // H2D on the context's copy stream in pieces, one (cached) event per piece; compute chases the copies
     const long long piece = 4LL << 20;  // 4 Mi samples = 32 MiB per copy
     const size_t npieces = (n + piece - 1) / piece;
@@ -827,8 +910,8 @@ int b200sync_sd_detect_host(b200sync_sd* sd, const float* in, size_t n, b200sync
         }
     }
     if (rc == 0)
-        rc = detect_resident(sd, sd->d_xoff.p, n, nullptr, sd->stream, sd->ev_pieces.data(), piece, recs, max_recs,
-                             n_recs, n_consumed);
+        rc = detect_resident(sd, sd->d_xoff.p, n, h_out_pinned ? sd->d_outoff.p : nullptr, sd->stream,
+                             sd->ev_pieces.data(), piece, recs, max_recs, n_recs, n_consumed, h_out_pinned);
     cudaStreamSynchronize(cs);
     cudaStreamSynchronize(sd->stream);
     return rc;
@@ -936,6 +1019,9 @@ int b200sync_sd_detect_channels_device(b200sync_sd* sd, const void* d_in, size_t
     CU(sd->d_chan_det.ensure(n_channels * cap));
     CU(sd->d_chan_z.ensure(per_group * z_stride));
     CU(sd->d_chan_ws.ensure(per_group * ws_stride));
+    const bool use_gm = gm_supported((int)sd->S, sd->T);
+    const size_t gm_stride = static_cast<size_t>(nb_total) * gm_groups_per_block((int)sd->S) * kGmF2PerGroup;
+    if (use_gm) CU(sd->d_chan_gm.ensure(per_group * gm_stride));
     if (sd->h_chan_cap < n_channels) {
         if (sd->h_chan_state) cudaFreeHost(sd->h_chan_state);
         sd->h_chan_state = nullptr;
@@ -951,10 +1037,13 @@ int b200sync_sd_detect_channels_device(b200sync_sd* sd, const void* d_in, size_t
         PeakState* state = sd->d_chan_state.p + c0;
         CU(launch_correlate(x, 0, sd->d_chan_z.p, 0, sd->d_hperm.p, (int)sd->K, (int)sd->S, 0, nb_total * nch,
                             sd->d_tw.p, nullptr, 0, 0, 0, (int)sd->delay, sd->num_sms, st, nb_total,
-                            static_cast<long long>(channel_stride), static_cast<long long>(z_stride)));
+                            static_cast<long long>(channel_stride), static_cast<long long>(z_stride),
+                            use_gm ? sd->d_chan_gm.p : nullptr, 0, static_cast<long long>(gm_stride)));
         if (hi_total > 0) {
             CU(launch_peak_phase1(sd->d_chan_z.p, 0, P, 0, hi_total, sd->T, sd->power_threshold, sd->d_chan_ws.p,
-                                  ws_stride, nullptr, sd->num_sms, st, nch, static_cast<long long>(z_stride), ws_stride));
+                                  ws_stride, nullptr, sd->num_sms, st, nch, static_cast<long long>(z_stride), ws_stride,
+                                  use_gm ? sd->d_chan_gm.p : nullptr, 0, nb_total, (int)sd->S,
+                                  static_cast<long long>(gm_stride)));
             CU(launch_peak_phase2(0, hi_total, sd->T, sd->d_chan_ws.p, ws_stride, -1, state,
                                   sd->d_chan_det.p + c0 * cap, (unsigned)cap, sd->num_sms, st, nch, ws_stride, cap));
         }
@@ -1047,6 +1136,13 @@ static int shard_phase1_core(b200sync_sd* sd, const float2* d_in, const float2* 
     const long long hi = (fb + nbk == tb) ? dec_end : std::min((fb + nbk) * S, dec_end);
     const long long z_base = cb0 * S;
     CU(sd->d_zoff.ensure(static_cast<size_t>((cb1 - cb0) * S) + 64));
+    sd->gm_b0 = cb0;
+    sd->gm_blocks = 0;
+    if (gm_supported((int)sd->S, sd->T)) {
+        CU(sd->d_gm.ensure(static_cast<size_t>(cb1 - cb0) * gm_groups_per_block((int)sd->S) * kGmF2PerGroup));
+        sd->gm_blocks = cb1 - cb0;
+    }
+    float2* const gm = sd->gm_blocks > 0 ? sd->d_gm.p : nullptr;
     CU(sd->d_ws.ensure(peak_workspace_bytes_sms(hi - lo + 1, sd->T, sd->num_sms)));
     if (int rc = ensure_det(sd, static_cast<size_t>((hi - lo) / (T + 1) + 2))) return rc;
     if (int rc = reset_state(sd, st)) return rc;
@@ -1074,6 +1170,47 @@ static int shard_phase1_core(b200sync_sd* sd, const float2* d_in, const float2* 
     } joiner{host_copy};
     float* h_out = sd->shard.h_out;
     sd->shard.h_out = nullptr;
+    // pinned host output span: the correlator writes the slice into d_outoff and finished pieces travel back on the
+    // D2H stream (the other PCIe direction) instead of costing the host memory system a read and a write
+    float2* h_out_d2h = nullptr;
+    long long d2h_done = 0;   // output items (absolute) already on their way back
+    size_t d2h_piece = 0;
+    if (h_out != nullptr && h_in != nullptr && d_out == nullptr && host_output_by_d2h(true) && is_pinned_host(h_out)) {
+        const long long ob = sd->shard.h_out_first;
+        out_lo = std::max(fb * S, ob);
+        out_hi = std::min({(fb + nbk) * S, P_total, ob + sd->shard.h_out_len});
+        if (out_hi > out_lo) {
+            CU(sd->d_outoff.ensure(static_cast<size_t>(out_hi - out_lo)));
+            d_out = sd->d_outoff.p;
+            out_base = out_lo;
+            h_out_d2h = reinterpret_cast<float2*>(h_out) + (out_lo - ob);
+            d2h_done = out_lo;
+            if (!sd->d2h_stream) CU(cudaStreamCreateWithFlags(&sd->d2h_stream, cudaStreamNonBlocking));
+            if (out_lo < static_cast<long long>(sd->delay)) {
+                const long long z1 = std::min<long long>(sd->delay, out_hi);
+                if (z1 > out_lo) CU(cudaMemsetAsync(d_out, 0, (z1 - out_lo) * sizeof(float2), st));
+            }
+        }
+        h_out = nullptr;
+    }
+    // outputs complete once blocks [.., b_end) have run: items below b_end*S + delay
+    auto send_back = [&](long long b_end) -> int {
+        if (!h_out_d2h) return 0;
+        const long long upto = std::min(out_hi, b_end * S + static_cast<long long>(sd->delay));
+        if (upto <= d2h_done) return 0;
+        if (sd->ev_out.size() <= d2h_piece) {
+            cudaEvent_t e;
+            CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            sd->ev_out.push_back(e);
+        }
+        CU(cudaEventRecord(sd->ev_out[d2h_piece], st));
+        CU(cudaStreamWaitEvent(sd->d2h_stream, sd->ev_out[d2h_piece], 0));
+        CU(cudaMemcpyAsync(h_out_d2h + (d2h_done - out_lo), d_out + (d2h_done - out_base),
+                           static_cast<size_t>(upto - d2h_done) * sizeof(float2), cudaMemcpyDeviceToHost, sd->d2h_stream));
+        d2h_done = upto;
+        ++d2h_piece;
+        return 0;
+    };
     if (h_out != nullptr && h_in != nullptr) {
         const long long D = static_cast<long long>(sd->delay), ob = sd->shard.h_out_first;
         const long long lo_o = std::max(fb * S, ob), hi_o = std::min({(fb + nbk) * S, P_total, ob + sd->shard.h_out_len});
@@ -1095,7 +1232,8 @@ static int shard_phase1_core(b200sync_sd* sd, const float2* d_in, const float2* 
     }
     if (h_in == nullptr && f == nullptr) {
         CU(launch_correlate(d_in, in_base, sd->d_zoff.p, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, cb0,
-                            cb1 - cb0, sd->d_tw.p, d_out, out_base, out_lo, out_hi, (int)sd->delay, sd->num_sms, st));
+                            cb1 - cb0, sd->d_tw.p, d_out, out_base, out_lo, out_hi, (int)sd->delay, sd->num_sms, st, 0, 0,
+                            0, gm, cb0, 0));
     } else {
         CU(sd->d_xoff.ensure(n_in));
         d_in = sd->d_xoff.p;
@@ -1139,21 +1277,23 @@ static int shard_phase1_core(b200sync_sd* sd, const float2* d_in, const float2* 
                 for (long long b0 = b_next; b0 < b_ready; b0 += kOfflineChunkBlocks)
                     CU(launch_correlate(d_in, in_base, sd->d_zoff.p, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, b0,
                                         std::min(kOfflineChunkBlocks, b_ready - b0), sd->d_tw.p, d_out, out_base, out_lo,
-                                        out_hi, (int)sd->delay, sd->num_sms, st));
+                                        out_hi, (int)sd->delay, sd->num_sms, st, 0, 0, 0, gm, cb0, 0));
                 b_next = b_ready;
+                if (int rc = send_back(b_ready)) return rc;
             }
         }
     }
     CU(cudaEventRecord(sd->ev[1], st));
     if (hi > lo) {
         CU(launch_peak_phase1(sd->d_zoff.p, z_base, cb1 * S, lo, hi, sd->T, sd->power_threshold, sd->d_ws.p,
-                              sd->d_ws.cap, sd->d_table.p, sd->num_sms, st));
+                              sd->d_ws.cap, sd->d_table.p, sd->num_sms, st, 1, 0, 0, gm, cb0, cb1 - cb0, (int)sd->S, 0));
         CU(cudaMemcpyAsync(table, sd->d_table.p, sizeof(uint16_t) * (T + 1), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     } else {
         CU(cudaStreamSynchronize(st));
         for (long long j = 0; j <= T; ++j) table[j] = static_cast<uint16_t>(j);  // empty range: identity
     }
+    if (h_out_d2h) CU(cudaStreamSynchronize(sd->d2h_stream));
     sd->shard.d_in = d_in;
     sd->shard.in_base = in_base;
     sd->shard.z_base = z_base;

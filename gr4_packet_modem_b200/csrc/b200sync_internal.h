@@ -55,7 +55,25 @@ cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpo
                              const float2* d_hperm, int K, int S, long long b0, long long nb,
                              const float2* d_tw, float2* d_out_delayed, long long out_base, long long out_lo,
                              long long out_hi, int delay, int num_sms, cudaStream_t st, long long nb_chan = 0,
-                             long long in_chan_stride = 0, long long z_chan_stride = 0);
+                             long long in_chan_stride = 0, long long z_chan_stride = 0, float2* d_gm = nullptr,
+                             long long gm_b0 = 0, long long gm_chan_stride = 0);
+// Group extrema of the metric (d_gm): per FFT block, group 0 = lag 0 alone, group q >= 1 = lags 32q-31 .. 32q (clipped to
+// the stride S) — the 32 consecutive samples a warp of the correlator holds.  (max, min) per group, written by the
+// correlator, read by the peak stage instead of the samples themselves.
+// Row of a group: 8 floats = [max, -, -, -, min of samples 0..7, 8..15, 16..23, 24..31 of the group].
+constexpr int kGmF2PerGroup = 4;   // float2 per group
+inline int gm_groups_per_block(int S) { return 1 + (S - 1 + 31) / 32; }
+// MEASURED DEAD END, off unless built with -DB200_GM_FLAGS (round 2, 2^30 samples, one B200): the peak stage drops
+// from 3.56 to 2.57 ms at K = 9 (flags kernel 2.9 -> 1.9 ms), but the correlator's epilogue that produces the extrema
+// (REDUX + 3 shuffles per 32 samples, 5 scattered stores per group) costs 1.07 ms of its own at K = 9 and 1.5 ms at
+// K = 1, where it matters most: no net gain, so the tile-based flags kernel stays the default.  A first version with
+// one minimum per group decided only half of the threshold tests from the extrema (noise maxima sit where ~50 % of
+// the groups hold a sample below the threshold) and was 2x slower than the tile kernel.
+#ifdef B200_GM_FLAGS
+inline bool gm_supported(int S, int T) { return S >= 64 && S <= 2016 && T >= 32 && T <= 1023; }
+#else
+inline bool gm_supported(int, int) { return false; }
+#endif
 cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_zpow, long long z_base,
                           const float2* d_hperm, int K, int S, int min_freq_bin, const float2* d_tw,
                           const unsigned long long* d_det_idx, const unsigned int* d_det_count,
@@ -77,7 +95,9 @@ cudaError_t launch_peak_phase1(const float* d_zpow, long long z_base, long long 
                                long long hi, int T,
                                float power_threshold, void* d_ws, size_t ws_bytes,
                                uint16_t* d_range_table /*[T+1] or nullptr*/, int num_sms,
-                               cudaStream_t st, int nch = 1, long long z_stride = 0, size_t ws_stride = 0);
+                               cudaStream_t st, int nch = 1, long long z_stride = 0, size_t ws_stride = 0,
+                               const float2* d_gm = nullptr, long long gm_b0 = 0, long long gm_blocks = 0, int S = 0,
+                               long long gm_chan_stride = 0);
 size_t peak_plan_bytes(long long range, int T, int num_sms);  // workspace of one channel for exactly this range
 cudaError_t launch_peak_stream(const float* d_zpow, long long z_base, long long z_end, long long lo, long long hi,
                                int T, float power_threshold, void* d_ws, size_t ws_bytes, PeakState* d_state,

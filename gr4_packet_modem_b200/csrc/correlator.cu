@@ -87,7 +87,8 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
                  long long z_base, const float2* __restrict__ hperm, int K, int S, long long b0,
                  long long nb, const float2* __restrict__ tw_g, float2* __restrict__ out_delayed,
                  long long out_base, long long out_lo, long long out_hi, int delay, long long nb_chan,
-                 long long in_chan_stride, long long z_chan_stride) {
+                 long long in_chan_stride, long long z_chan_stride, float2* __restrict__ gm, long long gm_b0,
+                 int gm_ng, long long gm_chan_stride) {
     extern __shared__ __align__(128) unsigned char smem_raw[];  // 128 B: half-warp LDS.64 rows never straddle a bank row, whatever static shared data precedes
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
     const int g = threadIdx.x >> 7;
@@ -275,6 +276,33 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
                 const int m = 128 * m1 + tid;
                 const int kk = (kFft - m) & (kFft - 1);
                 if (kk < S) zdst[kk] = best[m1];
+            }
+            if (gm != nullptr) {
+                // Group extrema for the peak stage (peaks.cu: peak_flags_gm_kernel): a warp holds 32 CONSECUTIVE
+                // samples per m1 — lags 32q-31 .. 32q with q = 64 - 4 m1 - warp — so REDUX gives the maximum of that
+                // group of the metric and three butterfly shuffles the minimum of each of its four 8-sample
+                // quarters; lag 0 (thread 0, m1 = 0) is group 0 on its own.  The peak stage then reads 20 B per 32
+                // samples instead of every sample.  (zpow >= +0: unsigned bit order.)
+                // Row layout: [max, -, -, -, min of lags 32q-31.., min of 32q-23.., min of 32q-15.., min of 32q-7..]
+                float* grow = reinterpret_cast<float*>(gm + ch * gm_chan_stride + ((b0 + bb) - gm_b0) * gm_ng * kGmF2PerGroup);
+                const int wq = tid >> 5, lane = tid & 31;
+#pragma unroll
+                for (int m1 = 0; m1 < 16; ++m1) {
+                    const int m = 128 * m1 + tid;
+                    const int kk = (kFft - m) & (kFft - 1);
+                    const bool valid = kk < S;
+                    const unsigned bits = __float_as_uint(best[m1]);
+                    const unsigned mx = __reduce_max_sync(0xffffffffu, valid ? bits : 0u);
+                    unsigned mn = valid ? bits : 0x7f800000u;   // (a REDUX with quarter-warp masks measured 3x slower)
+                    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 1));
+                    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 2));
+                    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 4));
+                    const int q = (m1 == 0 && wq == 0) ? 0 : 64 - 4 * m1 - wq;
+                    if (q < gm_ng) {
+                        if (lane == 0) grow[8 * q] = __uint_as_float(mx);
+                        if ((lane & 7) == 0) grow[8 * q + 4 + (3 - (lane >> 3))] = __uint_as_float(mn);   // ascending lag order
+                    }
+                }
             }
         }
         if (split) __syncthreads();   // the exchange buffers are free again
@@ -513,7 +541,8 @@ cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpo
                              const float2* d_hperm, int K, int S, long long b0, long long nb,
                              const float2* d_tw, float2* d_out_delayed, long long out_base, long long out_lo,
                              long long out_hi, int delay, int num_sms, cudaStream_t st, long long nb_chan,
-                             long long in_chan_stride, long long z_chan_stride) {
+                             long long in_chan_stride, long long z_chan_stride, float2* d_gm, long long gm_b0,
+                             long long gm_chan_stride) {
     if (nb <= 0) return cudaSuccess;
     // function attributes are per device: one flag per ordinal (a process may hold contexts on several GPUs)
     static bool attr_set[64] = {};
@@ -556,7 +585,8 @@ cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpo
     auto kern = ksplit > 1 ? correlate_kernel<true, false> : (nb_chan > 0 ? correlate_kernel<false, true> : correlate_kernel<false, false>);
     kern<<<grid, groups * kGroupThreads, smem, st>>>(d_in, in_base, d_zpow, z_base, d_hperm, K, S, b0, nb, d_tw,
                                                      d_out_delayed, out_base, out_lo, out_hi, delay, nb_chan,
-                                                     in_chan_stride, z_chan_stride);
+                                                     in_chan_stride, z_chan_stride, d_gm, gm_b0, gm_groups_per_block(S),
+                                                     gm_chan_stride);
     count_launch();
     return cudaGetLastError();
 }

@@ -440,6 +440,214 @@ peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_
     if (tid < TILE / 32) pw[tid] = passw[tid];
 }
 
+// ---------------------------------------------------------------------------------
+// Flags from the correlator's group extrema (T in [32, 1023], stride S in [64, 2016]).
+//
+// The correlator leaves, per FFT block, (max, min) of every GROUP of the metric: group 0 = the block's first
+// sample, group q >= 1 = samples 32q-31 .. 32q of the block (clipped to S) — b200sync_internal.h.  Groups tile the
+// stream without gaps, in order, with lengths 1, 32, ..., 32, (S-1) % 32.  This kernel decides the candidate and
+// threshold bitmaps of [lo, hi) reading those 8 bytes per group, and the samples themselves only where the
+// extrema cannot decide:
+//   * a group can hold a candidate only if its maximum is >= the maximum M of the groups that lie entirely
+//     inside the forward window (p, p+T] of EVERY sample of the group (about T/32 - 1 groups): one compare per group
+//     rejects ~ (1 - 32/T) of them.  The others load their <= 32 samples and the <= 62 samples between the last whole
+//     group and p+T, and decide every sample exactly (suffix maximum | M | prefix maximum of the remainder);
+//   * the threshold test of a candidate (count of window samples below zpow[p]/thr, :273-279) gets a lower bound
+//     from the groups entirely below the threshold and an upper bound from the groups entirely not below; almost
+//     every candidate is decided by the bounds (a real peak: nearly everything is below; a noise maximum: nearly
+//     nothing is), only the rest counts the undecided groups sample by sample.
+// DRAM traffic: 0.25 B/sample of extrema + the samples of ~1 group in T/32, instead of 4 B/sample.
+// The bitmaps are pre-zeroed; bits are set with atomicOr (groups are not aligned to bitmap words).
+// ---------------------------------------------------------------------------------
+constexpr int kGmThreads = 256;
+constexpr int kGmGroups = 512;    // groups decided per CTA
+constexpr int kGmAhead = 40;      // whole groups a forward window can hold: <= 1023/32 + 2
+
+struct GmGeom {
+    const float2* gm;        // rows of the first channel: kGmF2PerGroup float2 per group, block b at (b - b0) * ng groups
+    long long b0;            // block of row 0
+    long long n_blocks;      // blocks available
+    long long chan_stride;   // float2 between channels
+    int S, ng;
+    unsigned inv_s, inv_ng;  // ceil(2^32 / S), ceil(2^32 / ng): exact quotients for arguments below 2^16
+};
+// positions and groups RELATIVE to the CTA's base block (all below 2^16): 32-bit arithmetic, no divisions
+__device__ __forceinline__ int gm_group_of(int x, int S, int ng, unsigned inv_s) {
+    const int b = (int)__umulhi((unsigned)x, inv_s);
+    const int kk = x - b * S;
+    return b * ng + ((kk + 31) >> 5);
+}
+__device__ __forceinline__ void gm_span(int g, int S, int ng, unsigned inv_ng, int& start, int& len, int& q) {
+    const int b = (int)__umulhi((unsigned)g, inv_ng);
+    q = g - b * ng;
+    const int k0 = q ? 32 * q - 31 : 0;
+    start = b * S + k0;
+    len = q ? min(32, S - k0) : 1;
+}
+
+__global__ void __launch_bounds__(kGmThreads)
+peak_flags_gm_kernel(const float* __restrict__ zpow, long long z_base, long long z_end, GmGeom gg, long long lo,
+                     long long hi, int T, float thr, uint32_t* __restrict__ cand_bits,
+                     uint32_t* __restrict__ pass_bits, PeakBatch pb) {
+    __shared__ int gmax_s[kGmGroups + kGmAhead];
+    zpow += (long long)blockIdx.y * pb.z_stride;
+    cand_bits = ws_at(cand_bits, pb.ws_stride);
+    pass_bits = ws_at(pass_bits, pb.ws_stride);
+    const float4* gm4 = reinterpret_cast<const float4*>(gg.gm + (long long)blockIdx.y * gg.chan_stride);   // 2 float4 per group
+    const int S = gg.S, ng = gg.ng;
+    const unsigned inv_s = gg.inv_s, inv_ng = gg.inv_ng;
+    // ---- the CTA's frame: base block B0 such that every sample it can reference lies at or after B0 * S
+    const long long b_lo = lo / S;
+    const long long G_lo = b_lo * ng + (((int)(lo - b_lo * S) + 31) >> 5);
+    const long long Gc0 = G_lo + (long long)blockIdx.x * kGmGroups;      // first group of the CTA (absolute)
+    const long long bc = Gc0 / ng;                                        // its block
+    const long long B0 = bc - (T + S - 1) / S > 0 ? bc - (T + S - 1) / S : 0;
+    const long long P0 = B0 * S, G0 = B0 * ng;
+    const int g_c0 = (int)(Gc0 - G0);                                     // relative group of the CTA's first group
+    const int x_lo = (int)max(lo - P0, -1000000LL), x_hi = (int)min(hi - P0, 1000000LL);   // [lo, hi) in the frame
+    const int x_zend = (int)min(z_end - P0, 1000000LL);
+    const long long bit0 = P0 - lo;                                       // bitmap bit of frame position x: x + bit0
+    const int* zb = reinterpret_cast<const int*>(zpow) + (P0 - z_base);   // zb[x] = bits of zpow at frame position x
+    const long long g_first = gg.b0 * ng - G0, g_last = (gg.b0 + gg.n_blocks) * ng - 1 - G0;   // relative groups with a row
+    const float4* row0 = gm4 + (G0 - gg.b0 * ng) * 2;                     // row of relative group 0
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < kGmGroups + kGmAhead; i += kGmThreads) {
+        const long long g = (long long)g_c0 + i;
+        gmax_s[i] = (g >= g_first && g <= g_last) ? __float_as_int(__ldg(&row0[2 * g].x)) : INT_MIN;
+    }
+    __syncthreads();
+    const int total = 2 * T + 1;
+    const int g_hi = gm_group_of(x_hi - 1, S, ng, inv_s);                 // last group that touches [lo, hi)
+    for (int r = 0; r < kGmGroups / (kGmThreads / 32) / 32; ++r) {
+        const int i = (warp * (kGmGroups / (kGmThreads / 32))) + r * 32 + lane;   // this lane's group inside the CTA
+        const int g = g_c0 + i;
+        int st = 0, ln = 0, q = 0, M = INT_MIN, r0 = 0;
+        bool poss = false;
+        if (g <= g_hi) {
+            gm_span(g, S, ng, inv_ng, st, ln, q);
+            // last group that ends at or before st + T (inside the window of the group's FIRST sample, hence of all)
+            const int pe = st + T;
+            int ge = gm_group_of(pe, S, ng, inv_s), se, le, qe;
+            gm_span(ge, S, ng, inv_ng, se, le, qe);
+            if (se + le - 1 != pe) {
+                --ge;
+                gm_span(ge, S, ng, inv_ng, se, le, qe);
+            }
+            r0 = se + le;                          // first sample after the last whole group
+            for (int k = g + 1; k <= ge; ++k) M = max(M, gmax_s[k - g_c0]);
+            poss = st < x_hi && st + ln > x_lo && !(M > gmax_s[i]);
+        }
+        uint32_t possb = __ballot_sync(0xffffffffu, poss);
+        while (possb != 0u) {                      // warp-uniform: one possible group at a time, a lane per sample
+            const int src = __ffs(possb) - 1;
+            possb &= possb - 1;
+            const int gst = __shfl_sync(0xffffffffu, st, src);
+            const int gln = __shfl_sync(0xffffffffu, ln, src);
+            const int gM = __shfl_sync(0xffffffffu, M, src);
+            const int gr0 = __shfl_sync(0xffffffffu, r0, src);
+            const int x = gst + lane;
+            const bool in_group = lane < gln;
+            const int zi = in_group ? __ldg(zb + x) : INT_MIN;
+            // remainder: samples gr0 .. x+T (at most 62 of them)
+            const int ia = gr0 + lane, ib = gr0 + 32 + lane;
+            const int za = ia < x_zend ? __ldg(zb + ia) : INT_MIN;
+            const int zc = ib < x_zend ? __ldg(zb + ib) : INT_MIN;
+            // exclusive suffix maximum inside the group
+            int sfx = zi;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const int t = __shfl_down_sync(0xffffffffu, sfx, dd);
+                if (lane + dd < 32) sfx = max(sfx, t);
+            }
+            sfx = __shfl_down_sync(0xffffffffu, sfx, 1);
+            if (lane == 31) sfx = INT_MIN;
+            const int pa = warp_incl_scan_max(za, lane);
+            const int pb2 = warp_incl_scan_max(zc, lane);
+            const int e = x + T - gr0;
+            const int ra = __shfl_sync(0xffffffffu, pa, e & 31);
+            const int rb = __shfl_sync(0xffffffffu, pb2, e & 31);
+            const int ga = __shfl_sync(0xffffffffu, pa, 31);
+            const int rem = e < 0 ? INT_MIN : (e < 32 ? ra : max(ga, rb));
+            const bool cand = in_group && x >= x_lo && x < x_hi && !(max(max(sfx, gM), rem) > zi);
+            if (cand) atomicOr(cand_bits + ((x + bit0) >> 5), 1u << ((x + bit0) & 31));
+            uint32_t candw = __ballot_sync(0xffffffffu, cand);
+            // ---- threshold test of every candidate of the group (:273-279)
+            while (candw != 0u) {
+                const int cl = __ffs(candw) - 1;
+                candw &= candw - 1;
+                const int xc = gst + cl;
+                const float tvf = __fdiv_rn(__int_as_float(__shfl_sync(0xffffffffu, zi, cl)), thr);
+                if (!(tvf > 0.0f)) continue;       // zpow >= 0: nothing is below a non-positive threshold
+                const int tv = __float_as_int(tvf);
+                const int w_hi = xc + T;
+                int w_lo = xc - T;
+                int below = 0, notbelow = 0;
+                if (w_lo < 0) {                    // only with P0 = 0: the zero-initialised history before the stream, 0 < tv
+                    if (lane == 0) below = -w_lo;
+                    w_lo = 0;
+                }
+                const int gwa = gm_group_of(w_lo, S, ng, inv_s), gwb = gm_group_of(w_hi, S, ng, inv_s);
+                uint32_t need[3];
+#pragma unroll
+                for (int rr = 0; rr < 3; ++rr) {
+                    const int gi = gwa + lane + 32 * rr;
+                    bool nd = false;
+                    if (gi <= gwb) {
+                        int si, li, qi;
+                        gm_span(gi, S, ng, inv_ng, si, li, qi);
+                        if (si >= w_lo && si + li - 1 <= w_hi && gi >= g_first && gi <= g_last) {
+                            const float4 mx = __ldg(row0 + 2 * gi);
+                            if (__float_as_int(mx.x) < tv) {
+                                below += li;
+                            } else {
+                                // quarter minima, ascending: quarter j covers samples 8j .. 8j+7 of the group (group
+                                // 0, one sample, sits in quarter 3)
+                                const float4 mn = __ldg(row0 + 2 * gi + 1);
+                                const int m4[4] = {__float_as_int(mn.x), __float_as_int(mn.y), __float_as_int(mn.z),
+                                                   __float_as_int(mn.w)};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int sl = qi ? max(0, min(8, li - 8 * j)) : (j == 3 ? 1 : 0);
+                                    if (sl > 0) {
+                                        if (!(m4[j] < tv)) notbelow += sl;
+                                        else nd = true;
+                                    }
+                                }
+                            }
+                        } else {
+                            nd = true;
+                        }
+                    }
+                    need[rr] = __ballot_sync(0xffffffffu, nd);
+                }
+                below = __reduce_add_sync(0xffffffffu, below);
+                notbelow = __reduce_add_sync(0xffffffffu, notbelow);
+                bool pass;
+                if (2 * below >= total) pass = true;
+                else if (2 * (total - notbelow) < total) pass = false;
+                else {                             // the bounds do not decide: count the undecided groups exactly
+                    int cnt = 0;
+#pragma unroll
+                    for (int rr = 0; rr < 3; ++rr) {
+                        uint32_t nb = need[rr];
+                        while (nb != 0u) {
+                            const int gl = __ffs(nb) - 1;
+                            nb &= nb - 1;
+                            int si, li, qi;
+                            gm_span(gwa + gl + 32 * rr, S, ng, inv_ng, si, li, qi);
+                            const int xq = si + lane;
+                            if (lane < li && xq >= w_lo && xq <= w_hi && xq < x_zend && __ldg(zb + xq) < tv) ++cnt;
+                        }
+                    }
+                    cnt = __reduce_add_sync(0xffffffffu, cnt);
+                    pass = 2 * (below + cnt) >= total;
+                }
+                if (pass && lane == 0) atomicOr(pass_bits + ((xc + bit0) >> 5), 1u << ((xc + bit0) & 31));
+            }
+        }
+    }
+}
+
 // bits [fstart + 32*lane, +32) of a piece of length L starting at bit fstart
 __device__ __forceinline__ uint32_t piece_word(const uint32_t* __restrict__ bits, long long fstart, int L,
                                                int lane) {
@@ -793,9 +1001,27 @@ static cudaError_t set_smem_attr(const void* fn, size_t bytes) {
 // candidate + threshold bitmaps of [lo, hi) (the per-sample part of a6); nch channels side by side (blockIdx.y)
 static cudaError_t launch_flags(const float* d_zpow, long long z_base, long long z_end, long long lo, long long hi,
                                 int T, float power_threshold, const PeakPlan& pl, unsigned char* ws, int nch,
-                                const PeakBatch& pb, cudaStream_t st, bool zero_padding = true) {
+                                const PeakBatch& pb, cudaStream_t st, bool zero_padding = true,
+                                const GmGeom* gg = nullptr) {
     const long long range = hi - lo;
     cudaError_t e;
+    if (gg != nullptr && gg->gm != nullptr) {
+        // from the correlator's group extrema: bitmaps zeroed, bits set atomically
+        for (int c = 0; c < nch; ++c) {
+            e = cudaMemsetAsync(ws + (size_t)c * pb.ws_stride + pl.off_cand, 0, sizeof(uint32_t) * pl.nwords, st);
+            if (e != cudaSuccess) return e;
+            e = cudaMemsetAsync(ws + (size_t)c * pb.ws_stride + pl.off_pass, 0, sizeof(uint32_t) * pl.nwords, st);
+            if (e != cudaSuccess) return e;
+        }
+        const long long b_lo = lo / gg->S, b_hi = (hi - 1) / gg->S;
+        const long long ngroups = (b_hi - b_lo + 1) * gg->ng;   // upper bound of the groups touching [lo, hi)
+        const dim3 grid((unsigned)((ngroups + kGmGroups - 1) / kGmGroups), (unsigned)nch);
+        peak_flags_gm_kernel<<<grid, kGmThreads, 0, st>>>(d_zpow, z_base, z_end, *gg, lo, hi, T, power_threshold,
+                                                         reinterpret_cast<uint32_t*>(ws + pl.off_cand),
+                                                         reinterpret_cast<uint32_t*>(ws + pl.off_pass), pb);
+        count_launch();
+        return cudaGetLastError();
+    }
     const bool fast = T >= 32;
     const bool small = fast && range <= (1LL << 18);
     const int tile = fast ? (small ? kFastTileSmall : kFastTile) : kFlagsTile;
@@ -842,7 +1068,8 @@ size_t peak_plan_bytes(long long range, int T, int num_sms) { return make_plan(r
 cudaError_t launch_peak_phase1(const float* d_zpow, long long z_base, long long z_end, long long lo,
                                long long hi, int T, float power_threshold, void* d_ws, size_t ws_bytes,
                                uint16_t* d_range_table, int num_sms, cudaStream_t st, int nch, long long z_stride,
-                               size_t ws_stride) {
+                               size_t ws_stride, const float2* d_gm, long long gm_b0, long long gm_blocks, int S,
+                               long long gm_chan_stride) {
     const long long range = hi - lo;
     if (range <= 0) return cudaSuccess;
     const PeakPlan pl = make_plan(range, T, num_sms);
@@ -853,7 +1080,12 @@ cudaError_t launch_peak_phase1(const float* d_zpow, long long z_base, long long 
     uint32_t* cand = reinterpret_cast<uint32_t*>(ws + pl.off_cand);
     uint16_t* tables = reinterpret_cast<uint16_t*>(ws + pl.off_tables);
     uint32_t* segflag = reinterpret_cast<uint32_t*>(ws + pl.off_flag);
-    cudaError_t e = launch_flags(d_zpow, z_base, z_end, lo, hi, T, power_threshold, pl, ws, nch, pb, st);
+    const int ngr = S > 0 ? gm_groups_per_block(S) : 1;
+    GmGeom gg{d_gm, gm_b0, gm_blocks, gm_chan_stride, S, ngr,
+              S > 0 ? (unsigned)((0x100000000ULL + S - 1) / S) : 0u, (unsigned)((0x100000000ULL + ngr - 1) / ngr)};
+    const bool use_gm = d_gm != nullptr && gm_supported(S, T);
+    cudaError_t e = launch_flags(d_zpow, z_base, z_end, lo, hi, T, power_threshold, pl, ws, nch, pb, st, true,
+                                 use_gm ? &gg : nullptr);
     if (e != cudaSuccess) return e;
     chain_tables_kernel<<<dim3((unsigned)((pl.nseg + 3) / 4), (unsigned)nch), 128, 0, st>>>(cand, range, T, pl.M, pl.nfr,
                                                                                            pl.nseg, tables, segflag, pb);

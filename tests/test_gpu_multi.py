@@ -111,3 +111,56 @@ def test_shard_delayed_output_and_host_output(rx_params):
     assert np.array_equal(got[:c0].view(np.uint32), out0.view(np.uint32))
     assert np.all(got[c0:].view(np.float32) == 5.0)
     assert idx == [t[1] for t in tags0]
+
+
+@pytest.mark.parametrize("mode", ["d2h", "memcpy"])
+def test_pinned_host_output_comes_back_over_pcie(rx_params, mode):
+    """A PINNED host output span takes the other path: the correlator writes the delayed stream on the device and
+    finished pieces are copied back on a D2H stream (bulk host call and sharded host call).  Same bits as the
+    streaming block's output span."""
+    import subprocess
+    import sys
+
+    if os.environ.get("B200SYNC_HOST_OUTPUT") != mode:
+        # the library reads the override once per process: run this very test in a child with it set
+        env = dict(os.environ, B200SYNC_HOST_OUTPUT=mode)
+        r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", f"{__file__}::test_pinned_host_output_comes_back_over_pcie[{mode}]"],
+                           env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        return
+    import torch
+    from gr4_packet_modem_b200 import SyncwordDetection
+    from gr4_packet_modem_b200.sharding import entry_offsets, plan_shards
+    from gr4_packet_modem_b200.stimulus import packet_capture
+
+    n = (1 << 21) + 77
+    x, _ = packet_capture(n, seed=31, esn0_db=20.0, cfo=0.005, payload_bytes=300)
+    kw = dict(min_freq_bin=-1, max_freq_bin=1, power_threshold=9.5)
+    c0, out0, tags0 = SyncwordDetection(**rx_params, **kw).run(x, chunk=1 << 18, want_output=True)
+    hx = torch.empty(n, dtype=torch.complex64, pin_memory=True)
+    hx.copy_(torch.from_numpy(x))
+    hout = torch.full((n,), 9.0, dtype=torch.complex64, pin_memory=True)
+    sd = SyncwordDetection(**rx_params, **kw)
+    c1, r1, _ = sd.detect_host((hx.data_ptr(), n), out=hout.data_ptr())
+    got = hout.numpy()
+    assert c1 == c0 and np.array_equal(got[:c1].view(np.uint32), out0.view(np.uint32))
+    assert np.all(got[c1:] == 9.0)
+    assert (r1["index"] + sd.delay).tolist() == [t[1] for t in tags0]
+    # sharded, every shard's slice into ONE pinned host buffer
+    world = 3
+    shards = plan_shards(n, world, 2048, 1752, 768)
+    hout.fill_(4.0)
+    sds = [SyncwordDetection(**rx_params, **kw) for _ in range(world)]
+    tables = []
+    for sh, s in zip(shards, sds):
+        s.shard_output_host(hout.data_ptr(), 0, c0)
+        tables.append(s.shard_phase1_host((hx.data_ptr() + 8 * sh.first_sample, sh.n_samples), sh.first_sample,
+                                          sh.first_block, sh.n_blocks, sh.total_blocks))
+    idx = []
+    for s, j in zip(sds, entry_offsets(tables)):
+        r, _ = s.shard_phase2(j, n // 769 + 2)
+        idx += (r["index"] + s.delay).tolist()
+    got = hout.numpy()
+    assert np.array_equal(got[:c0].view(np.uint32), out0.view(np.uint32))
+    assert np.all(got[c0:] == 4.0)
+    assert idx == [t[1] for t in tags0]
