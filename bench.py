@@ -375,7 +375,9 @@ def measure_chain(args, log2n: int, steps: int, warmup: int, e2e: bool, cpu: boo
     n_y = fe.max_output(n)
     y = torch.empty(n_y, dtype=torch.complex64, device=dev)        # conditioned stream
     dl = torch.empty(n_y, dtype=torch.complex64, device=dev)       # SyncwordDetection's delayed output
-    sym = torch.empty(n_y // 4 + 1024, dtype=torch.complex64, device=dev)
+    # one symbol per 4 samples, plus at most one extra per syncword tag (PM/symbol_filter.hpp:160-189); with that much room
+    # the bulk call may pipeline its host replay against the kernel (it cannot fail half way)
+    sym = torch.empty(n_y // 4 + n_y // (TAU + 1) + 1024, dtype=torch.complex64, device=dev)
     # PM/packet_receiver.hpp:117-125, 203-214: SyncwordWipeoff(bipolar syncword) fused into CostasLoop (defaults)
     cl = CostasLoop(0.01, "BPSK")
     cl.fuse_wipeoff(np.where(np.asarray(SYNCWORD) != 0, -1.0, 1.0).astype(np.float32))

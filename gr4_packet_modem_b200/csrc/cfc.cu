@@ -90,6 +90,14 @@ __global__ void cfc_expand_kernel(const CfcSeed* __restrict__ seeds, CfcSegment*
 
 cudaError_t cfc_upload_segments(const std::vector<CfcSeed>& seeds, CfcSeed** d_seeds, CfcSegment** d_segs, size_t* cap,
                                 cudaStream_t st) {
+    return cfc_upload_segments(seeds.data(), seeds.size(), d_seeds, d_segs, cap, st);
+}
+
+// `seeds` may point into pinned memory: then the copy is truly asynchronous (a pageable source makes
+// cudaMemcpyAsync wait for the stream first, which would serialise a pipelined caller)
+cudaError_t cfc_upload_segments(const CfcSeed* seeds_p, size_t n_seeds, CfcSeed** d_seeds, CfcSegment** d_segs, size_t* cap,
+                                cudaStream_t st) {
+    struct View { const CfcSeed* p; size_t n; size_t size() const { return n; } const CfcSeed* data() const { return p; } } seeds{seeds_p, n_seeds};
     if (*cap < seeds.size()) {
         if (*d_seeds) cudaFree(*d_seeds);
         if (*d_segs) cudaFree(*d_segs);

@@ -70,6 +70,8 @@ private:
 // keeps `seeds` alive until the stream has been synchronised.
 cudaError_t cfc_upload_segments(const std::vector<CfcSeed>& seeds, CfcSeed** d_seeds, CfcSegment** d_segs, size_t* cap,
                                 cudaStream_t st);
+cudaError_t cfc_upload_segments(const CfcSeed* seeds, size_t n_seeds, CfcSeed** d_seeds, CfcSegment** d_segs, size_t* cap,
+                                cudaStream_t st);
 
 #ifdef __CUDACC__
 // Walks forward from segment index `sg` to the segment of absolute sample n (segments sorted by start).

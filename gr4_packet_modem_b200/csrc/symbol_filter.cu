@@ -410,6 +410,9 @@ struct b200sync_sf {
     float2* d_out = nullptr;
     size_t in_cap = 0, out_cap = 0;
     cudaStream_t stream = nullptr;
+    // pinned staging for the segment lists of a pipelined bulk call (sf_process_pipelined)
+    unsigned char* h_pin = nullptr;
+    size_t h_pin_cap = 0, h_pin_used = 0;
     // fused CoarseFrequencyCorrection in front of the filter (b200sync_sf_fuse_cfc)
     bool cfc_on = false;
     uint32_t cfc_delay = 0;
@@ -567,9 +570,11 @@ int sf_plan(b200sync_sf* sf, size_t n_in, const b200sync_stream_tag* in_tags, si
     return 0;
 }
 
+// pinned: the segment lists are staged in the context's pinned buffer (room reserved by the caller) and the call
+// returns WITHOUT synchronising — the caller runs several spans back to back and synchronises once.
 int sf_run(b200sync_sf* sf, const float2* d_in, size_t n_in, const b200sync_stream_tag* in_tags, size_t n_in_tags,
            float2* d_out, size_t max_out, cudaStream_t st, size_t* n_consumed, size_t* n_produced,
-           b200sync_stream_tag* out_tags, size_t max_out_tags, size_t* n_out_tags) {
+           b200sync_stream_tag* out_tags, size_t max_out_tags, size_t* n_out_tags, bool pinned = false) {
     *n_consumed = *n_produced = 0;
     if (n_out_tags) *n_out_tags = 0;
     if (n_in == 0) return 0;
@@ -606,7 +611,15 @@ int sf_run(b200sync_sf* sf, const float2* d_in, size_t n_in, const b200sync_stre
             SCU(cudaMalloc(&sf->d_segs, (prod.size() + 64) * sizeof(SfSegment)));
             sf->segs_cap = prod.size() + 64;
         }
-        SCU(cudaMemcpyAsync(sf->d_segs, prod.data(), prod.size() * sizeof(SfSegment), cudaMemcpyHostToDevice, st));
+        const SfSegment* seg_src = prod.data();
+        if (pinned) {
+            const size_t bytes = prod.size() * sizeof(SfSegment);
+            if (sf->h_pin_used + bytes > sf->h_pin_cap) return sf_fail(B200SYNC_ENOMEM, "internal: pinned staging too small");
+            std::memcpy(sf->h_pin + sf->h_pin_used, prod.data(), bytes);
+            seg_src = reinterpret_cast<const SfSegment*>(sf->h_pin + sf->h_pin_used);
+            sf->h_pin_used += (bytes + 63) & ~size_t(63);
+        }
+        SCU(cudaMemcpyAsync(sf->d_segs, seg_src, prod.size() * sizeof(SfSegment), cudaMemcpyHostToDevice, st));
         SfParams P{};
         P.in = d_in;
         P.in_base = static_cast<long long>(sf->abs_in);
@@ -626,7 +639,16 @@ int sf_run(b200sync_sf* sf, const float2* d_in, size_t n_in, const b200sync_stre
             const long long back = static_cast<long long>(sf->abs_in) - sf->hist_len;
             sf->cfc.advance(n_in, in_tags, n_in_tags);
             sf->cfc.live_segments(back, sf->cfc_live);
-            SCU(cfc_upload_segments(sf->cfc_live, &sf->d_cfc_seeds, &sf->d_cfc, &sf->cfc_cap, st));
+            if (pinned) {
+                const size_t bytes = sf->cfc_live.size() * sizeof(CfcSeed);
+                if (sf->h_pin_used + bytes > sf->h_pin_cap) return sf_fail(B200SYNC_ENOMEM, "internal: pinned staging too small");
+                std::memcpy(sf->h_pin + sf->h_pin_used, sf->cfc_live.data(), bytes);
+                const CfcSeed* src = reinterpret_cast<const CfcSeed*>(sf->h_pin + sf->h_pin_used);
+                sf->h_pin_used += (bytes + 63) & ~size_t(63);
+                SCU(cfc_upload_segments(src, sf->cfc_live.size(), &sf->d_cfc_seeds, &sf->d_cfc, &sf->cfc_cap, st));
+            } else {
+                SCU(cfc_upload_segments(sf->cfc_live, &sf->d_cfc_seeds, &sf->d_cfc, &sf->cfc_cap, st));
+            }
             P.cfc = sf->d_cfc;
             P.n_cfc = static_cast<int>(sf->cfc_live.size());
         }
@@ -663,7 +685,7 @@ int sf_run(b200sync_sf* sf, const float2* d_in, size_t n_in, const b200sync_stre
             SCU(cudaGetLastError());
         }
         // the pageable `prod` vector must outlive the async copy
-        SCU(cudaStreamSynchronize(st));
+        if (!pinned) SCU(cudaStreamSynchronize(st));
     }
     {
         const int nxt = sf->hist_cur ^ 1;
@@ -687,6 +709,56 @@ int sf_run(b200sync_sf* sf, const float2* d_in, size_t n_in, const b200sync_stre
     return 0;
 }
 
+}  // namespace
+
+namespace {
+// A bulk span with thousands of tags (a whole capture): the host replay of the tag state machine costs as much as the
+// filter kernel (3-4 ms each at 2^30 samples, 43 000 tags).  Cut the span at tag positions into a few sub-spans and
+// run them back to back — exactly what consecutive processBulk calls do, the block's state carries across — with the
+// segment lists staged in pinned memory and no synchronisation in between: the replay of sub-span i+1 then runs
+// while the GPU filters sub-span i.  Only taken when no sub-call can fail for lack of room (so the call still either
+// succeeds or leaves the block untouched).
+int sf_process_pipelined(b200sync_sf* sf, const float2* d_in, size_t n_in, const b200sync_stream_tag* in_tags,
+                         size_t n_in_tags, float2* d_out, size_t max_out, cudaStream_t st, size_t* n_consumed,
+                         size_t* n_produced, b200sync_stream_tag* out_tags, size_t max_out_tags, size_t* n_out_tags) {
+    const size_t G = std::min<size_t>(16, std::max<size_t>(2, n_in_tags / 2048));
+    const size_t need_pin = (2 * n_in_tags + 4 * G + 64) * sizeof(SfSegment) +
+                            (sf->cfc_on ? (n_in_tags + 8 * G + 64) * sizeof(CfcSeed) + 64 * G : 0) + 64 * G;
+    if (sf->h_pin_cap < need_pin) {
+        if (sf->h_pin) cudaFreeHost(sf->h_pin);
+        sf->h_pin = nullptr;
+        sf->h_pin_cap = 0;
+        SCU(cudaMallocHost(&sf->h_pin, need_pin + need_pin / 4));
+        sf->h_pin_cap = need_pin + need_pin / 4;
+    }
+    sf->h_pin_used = 0;
+    size_t produced = 0, ntags_out = 0, ti = 0, pos = 0;
+    std::vector<b200sync_stream_tag> sub;
+    for (size_t g = 0; g < G; ++g) {
+        // sub-span g ends where tag number (g+1) * n_tags / G sits (a tag then opens the next sub-span)
+        const size_t t_end = (g + 1 == G) ? n_in_tags : (g + 1) * n_in_tags / G;
+        const size_t end = (g + 1 == G) ? n_in : static_cast<size_t>(in_tags[t_end].index);
+        if (end <= pos) continue;
+        sub.assign(in_tags + ti, in_tags + t_end);
+        for (auto& t : sub) t.index -= pos;
+        size_t c = 0, p = 0, nt = 0;
+        if (int rc = sf_run(sf, d_in + pos, end - pos, sub.data(), sub.size(), d_out + produced, max_out - produced, st, &c,
+                            &p, out_tags + ntags_out, max_out_tags - ntags_out, &nt, true)) {
+            cudaStreamSynchronize(st);
+            return rc;
+        }
+        for (size_t i = 0; i < nt; ++i) out_tags[ntags_out + i].index += produced;   // offsets in the whole call's output
+        ntags_out += nt;
+        produced += p;
+        pos = end;
+        ti = t_end;
+    }
+    SCU(cudaStreamSynchronize(st));
+    *n_consumed = n_in;
+    *n_produced = produced;
+    if (n_out_tags) *n_out_tags = ntags_out;
+    return 0;
+}
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -739,6 +811,7 @@ void b200sync_sf_destroy(b200sync_sf* sf) {
     if (sf->d_cfc_seeds) cudaFree(sf->d_cfc_seeds);
     if (sf->d_in) cudaFree(sf->d_in);
     if (sf->d_out) cudaFree(sf->d_out);
+    if (sf->h_pin) cudaFreeHost(sf->h_pin);
     delete sf;
 }
 
@@ -764,6 +837,11 @@ int b200sync_sf_process_device(b200sync_sf* sf, const void* d_in, size_t n_in, c
         (!out_tags && max_out_tags))
         return sf_fail(B200SYNC_EINVAL, "null argument");
     SCU(cudaSetDevice(sf->device));
+    // many tags and room to spare: pipeline the host replay against the kernel (see sf_process_pipelined)
+    if (n_in_tags >= 4096 && max_out >= n_in / sf->sps + n_in_tags + 2 && max_out_tags >= n_in_tags + sf->pending.size())
+        return sf_process_pipelined(sf, static_cast<const float2*>(d_in), n_in, in_tags, n_in_tags,
+                                    static_cast<float2*>(d_out), max_out, static_cast<cudaStream_t>(cuda_stream), n_consumed,
+                                    n_produced, out_tags, max_out_tags, n_out_tags);
     return sf_run(sf, static_cast<const float2*>(d_in), n_in, in_tags, n_in_tags, static_cast<float2*>(d_out), max_out,
                   static_cast<cudaStream_t>(cuda_stream), n_consumed, n_produced, out_tags, max_out_tags, n_out_tags);
 }

@@ -328,7 +328,10 @@ const char* b200sync_sf_last_error(void);
  * tags).  Consumes all n_in items; produces one item per symbol clock tick; returns the re-indexed
  * tags (delayed by `delay`, placed on the nearest output symbol, syncword_phase adjusted when
  * time_est < 0).  B200SYNC_ENOSPC if max_out is too small, B200SYNC_ENOMEM if
- * max_out_tags is (state unchanged in both cases; only the latter is worth a retry with a larger buffer). */
+ * max_out_tags is (state unchanged in both cases; only the latter is worth a retry with a larger buffer).
+ * A device-span call with >= 4096 tags whose output span holds n_in / sps + n_in_tags + 2 items (no tag pattern can
+ * produce more) and whose tag buffer holds n_in_tags + pending tags overlaps the host replay of the tag state machine
+ * with the kernel: the span is run as a few consecutive sub-spans without synchronising in between. */
 int b200sync_sf_process(b200sync_sf* sf, const float* in, size_t n_in, const b200sync_stream_tag* in_tags,
                         size_t n_in_tags, float* out, size_t max_out, size_t* n_consumed, size_t* n_produced,
                         b200sync_stream_tag* out_tags, size_t max_out_tags, size_t* n_out_tags);

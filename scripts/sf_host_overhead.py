@@ -12,7 +12,7 @@ ntags = int(sys.argv[2]) if len(sys.argv) > 2 else 43000
 n = 1 << log2n
 dev = torch.device("cuda", 0)
 x = torch.randn(n, 2, device=dev).view(torch.complex64) if False else torch.view_as_complex(torch.randn(n, 2, device=dev))
-sym = torch.empty(n // 4 + 1024, dtype=torch.complex64, device=dev)
+sym = torch.empty(n // 4 + ntags + 1024, dtype=torch.complex64, device=dev)
 rng = np.random.default_rng(1)
 it = np.zeros(ntags, STREAM_TAG_DTYPE)
 it["index"] = np.sort(rng.choice(n - 10, ntags, replace=False))

@@ -192,3 +192,54 @@ def test_detection_filter_matches_oracle(oracle):
         pos += gc
     assert pos == n
     assert out_tags_g == out_tags_o == [(12345, 1.0), (30000, 3.0), (31000, 5.0), (70000, 6.0)]
+
+
+@pytest.mark.parametrize("fused", [None, 26])
+def test_bulk_span_with_thousands_of_tags_equals_chunked_calls(fused):
+    """A whole-capture span (>= 4096 tags) takes the pipelined path (host replay of sub-span i+1 while the GPU
+    filters sub-span i).  It must give exactly what the same stream gives through many small processBulk calls:
+    symbols bit for bit, the same re-indexed tags — with and without the fused CoarseFrequencyCorrection."""
+    import torch
+    from gr4_packet_modem_b200 import SymbolFilter
+    from gr4_packet_modem_b200.blocks import STREAM_TAG_DTYPE
+    from gr4_packet_modem_b200.firdes import pfb_matched_filter_taps
+
+    n, ntags = 1 << 22, 9000
+    rng = np.random.default_rng(77)
+    dev = torch.device("cuda:0")
+    x = torch.view_as_complex(torch.from_numpy(rng.standard_normal((n, 2)).astype(np.float32))).to(dev)
+    it = np.zeros(ntags, STREAM_TAG_DTYPE)
+    it["index"] = np.sort(rng.choice(np.arange(16, n - 16), ntags, replace=False))
+    it["has_syncword"] = 1
+    it["sw"]["syncword_amplitude"] = rng.uniform(0.5, 2.0, ntags)
+    it["sw"]["syncword_freq"] = rng.uniform(-0.05, 0.05, ntags)
+    it["sw"]["syncword_phase"] = rng.uniform(-3, 3, ntags)
+    it["sw"]["syncword_time_est"] = rng.uniform(-0.5, 0.5, ntags)
+    st = torch.cuda.current_stream().cuda_stream
+    taps = pfb_matched_filter_taps()
+    # one bulk call
+    sf = SymbolFilter(taps, 32, 4, delay=44, fused_cfc_delay=fused)
+    out_a = torch.zeros(n // 4 + ntags + 64, dtype=torch.complex64, device=dev)
+    c_a, p_a, t_a = sf.process_device(x.data_ptr(), n, out_a.data_ptr(), out_a.numel(), it, st)
+    # the same stream in 64 calls
+    sf2 = SymbolFilter(taps, 32, 4, delay=44, fused_cfc_delay=fused)
+    out_b = torch.zeros_like(out_a)
+    pos = prod = 0
+    tags_b = []
+    step = n // 64
+    while pos < n:
+        m = min(step, n - pos)
+        sel = it[(it["index"] >= pos) & (it["index"] < pos + m)].copy()
+        sel["index"] -= pos
+        c, p, t = sf2.process_device(x.data_ptr() + 8 * pos, m, out_b.data_ptr() + 8 * prod, out_b.numel() - prod, sel, st)
+        assert c == m
+        t = t.copy()
+        t["index"] += prod
+        tags_b.append(t)
+        pos += c
+        prod += p
+    torch.cuda.synchronize()
+    tags_b = np.concatenate(tags_b)
+    assert c_a == n and p_a == prod
+    assert np.array_equal(out_a[:p_a].cpu().numpy().view(np.uint32), out_b[:prod].cpu().numpy().view(np.uint32))
+    assert len(t_a) == len(tags_b) and np.array_equal(t_a.view(np.uint8), tags_b.view(np.uint8))
