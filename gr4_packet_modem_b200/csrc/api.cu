@@ -178,7 +178,7 @@ int run_chunk(b200sync_sd* sd, const float2* d_in, long long in_base, float* d_z
                         sd->gm_b0, 0));
     if (hi > lo) {
         const long long z_end = (b0 + nb) * (long long)sd->S;
-        if (hi - lo <= kSmallRange) {
+        if (hi - lo <= kSmallRange || sd->T > kMaxTimeThreshold) {
             CU(launch_peak_stream(d_z, z_base, z_end, lo, hi, sd->T, sd->power_threshold, sd->d_ws.p, sd->d_ws.cap,
                                   sd->d_state.p, sd->d_det_idx.p, (unsigned)sd->d_det_idx.cap, sd->num_sms, st));
         } else {
@@ -321,8 +321,8 @@ int do_start(b200sync_sd* sd) {
         return fail(B200SYNC_EUNSUPPORTED, "only fft_size = 2048 is implemented on the GPU path");
     sd->K = static_cast<uint32_t>(sd->max_bin - sd->min_bin + 1);
     if (sd->K > (uint32_t)kMaxHyp) return fail(B200SYNC_EUNSUPPORTED, "too many frequency hypotheses (max 129)");
-    if (sd->time_threshold > (uint64_t)kMaxTimeThreshold)
-        return fail(B200SYNC_EUNSUPPORTED, "time_threshold > 1023 is not implemented on the GPU path");
+    if (sd->time_threshold > (uint64_t)kMaxTimeThresholdSeq)
+        return fail(B200SYNC_EUNSUPPORTED, "time_threshold > 4095 is not implemented on the GPU path");
     if (!(sd->power_threshold > 0.0f)) return fail(B200SYNC_EINVAL, "power_threshold must be positive");
     sd->S = sd->fft_size - sd->L + 1;
     sd->T = static_cast<int>(sd->time_threshold);
@@ -725,7 +725,11 @@ static int detect_finish(b200sync_sd* sd, const float2* d_in, long long P, cudaS
     const long long T = sd->T;
     const long long hi_total = std::max(0LL, P - T - 1);
     CU(cudaEventRecord(sd->ev[1], st));
-    if (hi_total > 0) {
+    if (hi_total > 0 && sd->T > kMaxTimeThreshold) {
+        // beyond the parallel chain kernels' range: generic flags + the in-order walk over the whole capture
+        CU(launch_peak_stream(sd->d_zoff.p, 0, P, 0, hi_total, sd->T, sd->power_threshold, sd->d_ws.p, sd->d_ws.cap,
+                              sd->d_state.p, sd->d_det_idx.p, (unsigned)sd->d_det_idx.cap, sd->num_sms, st));
+    } else if (hi_total > 0) {
         CU(launch_peak_phase1(sd->d_zoff.p, 0, P, 0, hi_total, sd->T, sd->power_threshold, sd->d_ws.p,
                               sd->d_ws.cap, nullptr, sd->num_sms, st, 1, 0, 0, sd->gm_blocks > 0 ? sd->d_gm.p : nullptr,
                               sd->gm_b0, sd->gm_blocks, (int)sd->S, 0));
@@ -997,6 +1001,8 @@ int b200sync_sd_detect_channels_device(b200sync_sd* sd, const void* d_in, size_t
     if (!sd || !n_recs || !n_consumed || (!d_in && n && n_channels) || (!recs && max_recs_per_channel))
         return fail(B200SYNC_EINVAL, "null argument");
     if (n_channels > 1 && channel_stride < n) return fail(B200SYNC_EINVAL, "channel_stride smaller than n");
+    if (sd->T > kMaxTimeThreshold)
+        return fail(B200SYNC_EUNSUPPORTED, "batched channel mode needs time_threshold <= 1023 (one detect_device call per channel works)");
     CU(cudaSetDevice(sd->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const long long S = sd->S, F = sd->fft_size, T = sd->T;
@@ -1119,6 +1125,8 @@ int b200sync_sd_copy_metric(const b200sync_sd* sd, float* zpow, size_t n) {
 static int shard_phase1_core(b200sync_sd* sd, const float2* d_in, const float2* h_in, uint64_t first_sample_abs,
                              size_t n_in, uint64_t first_block, uint64_t n_blocks, uint64_t total_blocks,
                              cudaStream_t st, uint16_t* table, size_t table_len, FILE* f = nullptr) {
+    if (sd->T > kMaxTimeThreshold)
+        return fail(B200SYNC_EUNSUPPORTED, "time-sharded operation needs time_threshold <= 1023 (the chain tables have T+1 <= 1024 entries)");
     if (table_len < static_cast<size_t>(sd->T) + 1) return fail(B200SYNC_ENOMEM, "table too small");
     if (first_block + n_blocks > total_blocks || n_blocks == 0) return fail(B200SYNC_EINVAL, "bad shard");
     CU(cudaSetDevice(sd->device));

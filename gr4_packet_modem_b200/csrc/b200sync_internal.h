@@ -17,7 +17,9 @@ constexpr int kGroupThreads = 128; // threads cooperating on one FFT block
 #endif
 constexpr int kCorrThreads = B200_CORR_THREADS;  // 6 FFT groups per CTA, 1 persistent CTA per SM
 constexpr int kMaxHyp = 129;       // max frequency hypotheses (min/max_freq_bin = -/+64)
-constexpr int kMaxTimeThreshold = 1023;  // chain kernels keep one bitmap word per lane
+constexpr int kMaxTimeThreshold = 1023;  // parallel chain kernels keep one bitmap word per lane; the time-sharded and
+                                         // batched-channel entry points need them
+constexpr int kMaxTimeThresholdSeq = 4095;  // beyond 1023 the peak walk runs in order (one warp): any capture, slower
 
 using DetectionRecord = b200sync_detection_record;
 

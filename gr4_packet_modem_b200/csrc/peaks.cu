@@ -941,6 +941,7 @@ det_gather_kernel(const unsigned long long* __restrict__ slots, const uint32_t* 
 // bitmap words per probe, a jump of T+1 after every examined peak.  Replaces chain_tables + chain_scan + chain_emit +
 // det_offsets + det_gather (five launches whose parallelism only pays on captures of many millions of samples).
 constexpr int kSmallThreads = 256;
+constexpr long long kWalkPiece = 1LL << 19;   // bitmap bits staged in shared memory at a time (2 x 64 KiB)
 __global__ void __launch_bounds__(kSmallThreads)
 chain_small_kernel(const uint32_t* __restrict__ cand_bits, const uint32_t* __restrict__ pass_bits, long long range,
                    int T, long long lo, long long hi, PeakState* __restrict__ state,
@@ -950,26 +951,38 @@ chain_small_kernel(const uint32_t* __restrict__ cand_bits, const uint32_t* __res
     pass_bits = ws_at(pass_bits, pb.ws_stride);
     state += blockIdx.y;
     det_idx += (size_t)blockIdx.y * pb.det_stride;
-    // both bitmaps into shared memory first (coalesced, all threads): the walk below is a chain of DEPENDENT
-    // probes, and from global memory every probe would cost an L2 round trip
-    const int nwords = (int)((range + 31) >> 5);
-    uint32_t* cand_s = reinterpret_cast<uint32_t*>(smem_raw);
-    uint32_t* pass_s = cand_s + nwords;
-    for (int i = threadIdx.x; i < nwords; i += kSmallThreads) {
-        cand_s[i] = cand_bits[i];
-        pass_s[i] = pass_bits[i];
-    }
-    __syncthreads();
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
+    // The walk is a chain of DEPENDENT probes: from global memory every probe would cost an L2 round trip, so the
+    // bitmaps go through shared memory, a piece of 2^19 bits at a time (coalesced, all threads), and one warp walks
+    // each piece.  Longer ranges than one piece only occur where the parallel chain kernels do not apply
+    // (time_threshold > 1023).
+    const int lane = threadIdx.x & 31;
     const unsigned long long r = state->r_abs;
-    const long long j0 = (r > (unsigned long long)lo) ? (long long)(r - (unsigned long long)lo) : 0;  // search offset in the range
+    long long j = (r > (unsigned long long)lo) ? (long long)(r - (unsigned long long)lo) : 0;  // search offset in the range
     unsigned int cnt = 0;
-    const long long j = peak_walk_warp(cand_s, pass_s, nwords, range, T, j0, [&](long long found) {
-        if (lane == 0 && cnt < det_cap) det_idx[cnt] = (unsigned long long)(lo + found);
-        ++cnt;
-    });
-    if (lane == 0) {
+    const int piece_words = (int)(min(range, kWalkPiece) + 31) >> 5;
+    uint32_t* cand_s = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* pass_s = cand_s + piece_words;
+    for (long long p0 = 0; p0 < range; p0 += kWalkPiece) {
+        const long long plen = min(kWalkPiece, range - p0);
+        const int nwords = (int)((plen + 31) >> 5);
+        const long long w0 = p0 >> 5;   // kWalkPiece is a multiple of 32
+        __syncthreads();
+        for (int i = threadIdx.x; i < nwords; i += kSmallThreads) {
+            cand_s[i] = cand_bits[w0 + i];
+            pass_s[i] = pass_bits[w0 + i];
+        }
+        __syncthreads();
+        if (threadIdx.x < 32 && j < p0 + plen) {
+            const long long jr = j > p0 ? j - p0 : 0;
+            const long long je = peak_walk_warp(cand_s, pass_s, nwords, plen, T, jr, [&](long long found) {
+                if (lane == 0 && cnt < det_cap) det_idx[cnt] = (unsigned long long)(lo + p0 + found);
+                ++cnt;
+            });
+            j = p0 + je;
+        }
+        // (j and cnt live in warp 0 only; the other warps just stage)
+    }
+    if (threadIdx.x == 0) {
         const long long r_end = lo + j;
         state->r_abs = (unsigned long long)(r_end > hi ? r_end : hi);
         state->det_count = cnt;
@@ -1022,7 +1035,7 @@ static cudaError_t launch_flags(const float* d_zpow, long long z_base, long long
         count_launch();
         return cudaGetLastError();
     }
-    const bool fast = T >= 32;
+    const bool fast = T >= 32 && T <= kMaxTimeThreshold;   // beyond: the generic (van Herk) kernel, any T
     const bool small = fast && range <= (1LL << 18);
     const int tile = fast ? (small ? kFastTileSmall : kFastTile) : kFlagsTile;
     const long long ntiles = (range + tile - 1) / tile;
@@ -1118,7 +1131,7 @@ cudaError_t launch_peak_stream(const float* d_zpow, long long z_base, long long 
     uint32_t* pass = reinterpret_cast<uint32_t*>(ws + pl.off_pass);
     cudaError_t e = launch_flags(d_zpow, z_base, z_end, lo, hi, T, power_threshold, pl, ws, 1, pb, st);
     if (e != cudaSuccess) return e;
-    const size_t ssm = 2 * sizeof(uint32_t) * (size_t)((range + 31) >> 5);
+    const size_t ssm = 2 * sizeof(uint32_t) * (size_t)(((range < kWalkPiece ? range : kWalkPiece) + 31) >> 5);
     e = set_smem_attr((const void*)chain_small_kernel, ssm);
     if (e != cudaSuccess) return e;
     chain_small_kernel<<<1, kSmallThreads, ssm, st>>>(cand, pass, range, T, lo, hi, d_state, d_det_idx, det_cap, pb);

@@ -181,7 +181,30 @@ def test_settings_errors(rx_params):
         _gpu(dict(rx_params, syncword=np.zeros(600, np.uint8)))
 
 
-@pytest.mark.parametrize("T", [0, 1, 5, 31, 32, 33, 100, 500, 1023])
+def test_settings_the_gpu_path_refuses(rx_params):
+    """Settings the reference accepts and this build does not implement fail LOUDLY at start() with
+    B200SYNC_EUNSUPPORTED — never a silent fallback (the reference: any power-of-two fft_size,
+    PM/syncword_detection.hpp:133 / ALG/fourier/fftw.hpp:182-184; any time_threshold, :140; any bin range)."""
+    import torch
+    from gr4_packet_modem_b200.blocks import B200SyncError
+
+    for fft_size in (1024, 4096):
+        with pytest.raises(B200SyncError, match="only fft_size = 2048"):
+            _gpu(rx_params, fft_size=fft_size)
+    with pytest.raises(B200SyncError, match="too many frequency hypotheses"):
+        _gpu(rx_params, min_freq_bin=-65, max_freq_bin=65)
+    with pytest.raises(B200SyncError, match="time_threshold > 4095"):
+        _gpu(rx_params, time_threshold=4096)
+    # time_threshold in (1023, 4095] works for one stream, but not for the entry points built on the chain tables
+    sd = _gpu(rx_params, time_threshold=2000)
+    x = torch.zeros(1 << 16, dtype=torch.complex64, device="cuda:0")
+    with pytest.raises(B200SyncError, match="time-sharded operation needs time_threshold <= 1023"):
+        sd.shard_phase1(x.data_ptr(), 0, 1 << 16, 0, 10, 36)
+    with pytest.raises(B200SyncError, match="batched channel mode needs time_threshold <= 1023"):
+        sd.detect_channels_device(x.data_ptr(), 2, 1 << 15, 1 << 15)
+
+
+@pytest.mark.parametrize("T", [0, 1, 5, 31, 32, 33, 100, 500, 1023, 1024, 2047, 4095])
 def test_time_threshold_sweep_bit_exact(oracle, rx_params, T):
     """Both flags kernels (generic T < 32, group-scan T >= 32) and the chain kernels for every
     piece length, against the oracle's sequential state machine, on a noisy capture with many
@@ -197,7 +220,11 @@ def test_time_threshold_sweep_bit_exact(oracle, rx_params, T):
     assert consumed == oc
     assert tags["index"].tolist() == [t.index for t in otags]
     if T >= 31:  # tiny windows of a 4x-oversampled correlation never pass the threshold test
-        assert len(tags) > 10
+        assert len(tags) > (10 if T <= 1023 else 3)
+    if T > 1023:  # beyond the parallel chain kernels: also the streaming path, in odd chunks
+        sd2 = _gpu(rx_params, min_freq_bin=-1, max_freq_bin=1, power_threshold=4.0, time_threshold=T)
+        c2, _, t2 = sd2.run(x, chunk=50000)
+        assert [i for _, i, _ in t2] == [t.index for t in otags if t.index < c2]
     # and streaming in odd chunks
     sd.start()
     c2, _, t2 = sd.run(x, chunk=7001)
