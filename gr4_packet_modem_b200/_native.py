@@ -106,6 +106,8 @@ class FeConfig(C.Structure):
         ("enable_resampler", C.c_uint32),
         ("enable_rotator", C.c_uint32),
         ("device", C.c_int32),
+        ("rate_is_f64", C.c_uint32),
+        ("rate_f64", C.c_double),
     ]
 
 

@@ -407,8 +407,12 @@ class FrontEnd:
     Settings carry the reference names: rate, taps, filter_size, phase_incr."""
 
     def __init__(self, rate: float = 1.0, taps=None, filter_size: int = 32, phase_incr: float = 0.0,
-                 enable_resampler: bool = True, enable_rotator: bool = True, device: int = 0):
-        self.rate = float(np.float32(rate))
+                 enable_resampler: bool = True, enable_rotator: bool = True, device: int = 0,
+                 rate_dtype=np.float32):
+        """rate_dtype: np.float32 = PfbArbResampler<.., TRate = float> (the default template argument),
+        np.float64 = TRate = double (what test/qa_pfb_arb_resampler.cpp instantiates)."""
+        self.rate_is_f64 = np.dtype(rate_dtype) == np.float64
+        self.rate = float(rate) if self.rate_is_f64 else float(np.float32(rate))
         self.taps = np.ascontiguousarray(taps if taps is not None else np.zeros(0), dtype=np.float32)
         self.filter_size = int(filter_size)
         self.phase_incr = float(np.float32(phase_incr))
@@ -426,7 +430,7 @@ class FrontEnd:
         self._destroy()
         cfg = FeConfig(self.rate, self.taps.ctypes.data if self.taps.size else None, self.taps.size,
                        self.filter_size, self.phase_incr, int(self.enable_resampler), int(self.enable_rotator),
-                       self.device)
+                       self.device, int(self.rate_is_f64), float(self.rate))
         h = C.c_void_p()
         check_fe(L.b200sync_fe_create(C.byref(cfg), C.byref(h)))
         self._h = h
@@ -790,10 +794,12 @@ class SyncwordDetectionFilter:
 
 
 class PfbArbResampler(FrontEnd):
-    """gr::packet_modem::PfbArbResampler<c64, c64, float, float> alone (PM/pfb_arb_resampler.hpp)."""
+    """gr::packet_modem::PfbArbResampler<c64, c64, float, TRate> alone (PM/pfb_arb_resampler.hpp); TRate = float
+    unless rate_dtype=np.float64."""
 
-    def __init__(self, rate: float, taps, filter_size: int = 32, device: int = 0):
-        super().__init__(rate=rate, taps=taps, filter_size=filter_size, enable_rotator=False, device=device)
+    def __init__(self, rate: float, taps, filter_size: int = 32, device: int = 0, rate_dtype=np.float32):
+        super().__init__(rate=rate, taps=taps, filter_size=filter_size, enable_rotator=False, device=device,
+                         rate_dtype=rate_dtype)
 
 
 class Rotator(FrontEnd):

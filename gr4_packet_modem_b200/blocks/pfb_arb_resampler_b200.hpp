@@ -7,6 +7,8 @@
 // `filter_size`; PM/rotator.hpp:42 `phase_incr`); reflection lists as :187-188 and rotator.hpp:70.
 // All DSP is behind the C ABI (b200sync_fe_*); the shell only moves spans and counts.
 #pragma once
+#include <type_traits>
+
 #include "b200_shell_common.hpp"
 
 namespace gr::packet_modem {
@@ -20,13 +22,17 @@ struct FrontEndCtx {
     FrontEndCtx& operator=(const FrontEndCtx&) = delete;
     ~FrontEndCtx() { b200sync_fe_destroy(ctx); }
 
-    void configure(float rate, const std::vector<float>& taps, size_t filter_size, float phase_incr, bool resampler,
+    // TRate = float or double, as the reference's fourth template argument (PM/pfb_arb_resampler.hpp:14-22)
+    template <typename TRate>
+    void configure(TRate rate, const std::vector<float>& taps, size_t filter_size, float phase_incr, bool resampler,
                    bool rotator, int device)
     {
         b200sync_fe_destroy(ctx);
         ctx = nullptr;
         b200sync_fe_config cfg{};
-        cfg.rate = rate;
+        cfg.rate = static_cast<float>(rate);
+        cfg.rate_is_f64 = std::is_same_v<TRate, double> ? 1u : 0u;
+        cfg.rate_f64 = static_cast<double>(rate);
         cfg.taps = taps.empty() ? nullptr : taps.data();
         cfg.n_taps = static_cast<uint32_t>(taps.size());
         cfg.filter_size = static_cast<uint32_t>(filter_size);
@@ -54,11 +60,13 @@ struct FrontEndCtx {
 };
 }  // namespace b200_detail
 
-class PfbArbResamplerB200
+// TRate: the reference's PfbArbResampler<TIn, TOut, TTaps, TRate> with TIn = TOut = c64, TTaps = float
+template <typename TRate = float>
+class PfbArbResamplerB200T
 #if B200SYNC_HAVE_GR4
-    : public gr::Block<PfbArbResamplerB200>
+    : public gr::Block<PfbArbResamplerB200T<TRate>>
 #else
-    : public gr::BlockShim<PfbArbResamplerB200>
+    : public gr::BlockShim<PfbArbResamplerB200T<TRate>>
 #endif
 {
     b200_detail::FrontEndCtx _fe;
@@ -72,14 +80,14 @@ public:
     gr::PortInShim<std::complex<float>> in;
     gr::PortOutShim<std::complex<float>> out;
 #endif
-    float rate{ 1.0 };
+    TRate rate{ 1.0 };
     std::vector<float> taps;
     size_t filter_size = 32;
     int device = 0;  // extra: CUDA device ordinal
 
     void settingsChanged(const gr::property_map& /* old_settings */, const gr::property_map& /* new_settings */)
     {
-        _fe.configure(rate, taps, filter_size, 0.0f, true, false, device);
+        _fe.template configure<TRate>(rate, taps, filter_size, 0.0f, true, false, device);
     }
 
     template <typename TIn, typename TOut>
@@ -88,6 +96,8 @@ public:
         return _fe.process(inSpan, outSpan);
     }
 };
+using PfbArbResamplerB200 = PfbArbResamplerB200T<float>;
+using PfbArbResamplerB200Double = PfbArbResamplerB200T<double>;   // test/qa_pfb_arb_resampler.cpp:45-69
 
 // The reference Rotator is a processOne block; a GPU block works on spans, so the shell exposes
 // processBulk (same items out as items in, same tags: default forwarding policy).  The NCO phase is
@@ -172,7 +182,7 @@ public:
 }  // namespace gr::packet_modem
 
 #if B200SYNC_HAVE_GR4
-ENABLE_REFLECTION(gr::packet_modem::PfbArbResamplerB200, in, out, rate, taps, filter_size, device);
+ENABLE_REFLECTION_FOR_TEMPLATE(gr::packet_modem::PfbArbResamplerB200T, in, out, rate, taps, filter_size, device);
 ENABLE_REFLECTION(gr::packet_modem::RotatorB200, in, out, phase_incr, device);
 ENABLE_REFLECTION(gr::packet_modem::RxFrontEndB200, in, out, rate, taps, filter_size, phase_incr, device);
 #endif

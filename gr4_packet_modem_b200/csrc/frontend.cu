@@ -11,7 +11,11 @@
 //     tot = n*Kf,  acc = tot ? ((tot-1) mod 2^24) + 1 : 0,  wraps = (tot-acc) / 2^24      [units 2^-24]
 //     Lf  = L0 + n*decim + wraps,  inputs consumed c = Lf / filter_size,  arm = Lf % filter_size
 //     y[n] = sum_k taps[arm][k] x[c-1-k]  +  float(acc) * sum_k diff[arm][k] x[c-1-k]
-// (verified against the sequential loop by tests/test_oracle_golden.py).  Each output is then
+// (verified against the sequential loop by tests/test_oracle_golden.py).  TRate = double (the reference's own QA
+// uses it, test/qa_pfb_arb_resampler.cpp:45-69) is the same statement with units of 2^-52 and 128-bit products
+// (filter_size/rate >= 1 keeps every partial sum below 2 and a multiple of 2^-52, so the double accumulator is
+// exact as well); the interpolation factor is then float(double(acc)), as in the reference (:156-159).
+// Each output is then
 // independent: one thread computes R consecutive outputs; when they share one arm and advance one
 // input per output (always, except at the rare wrap events, for the |rate-1| << 1 of an SFO model)
 // a register window slides over the inputs and each tap pair is read once per R outputs.
@@ -26,6 +30,7 @@
 #include <new>
 #include <numbers>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "b200sync_internal.h"
@@ -52,7 +57,7 @@ struct FeParams {
     float2* out;             // out[i] is absolute output sample out_base + i
     long long out_base;
     long long n_out;
-    unsigned long long Kf;   // filt_rate in units of 2^-24
+    unsigned long long Kf;   // filt_rate in units of 2^-24 (TRate = float) or 2^-52 (TRate = double)
     int decim, L0, fs, arm;  // decim_rate, initial _last_filter, filter_size, taps per arm
     int do_resample, do_rotate;
     double theta;            // effective rotation per sample
@@ -60,14 +65,32 @@ struct FeParams {
     float2 wr[kFeR];         // (cos, sin)(r * theta), r = 0..R-1: rotation of output r relative to output 0
 };
 
+// WIDE = false: TRate = float, units 2^-24, 64-bit products.  WIDE = true: TRate = double, units 2^-52, 128-bit.
+template <bool WIDE>
+struct FeTime {
+    using U = typename std::conditional<WIDE, unsigned __int128, unsigned long long>::type;
+    static constexpr int Q = WIDE ? 52 : 24;
+    static __device__ __forceinline__ U tot(long long n, unsigned long long Kf) { return (U)(unsigned long long)n * (U)Kf; }
+    static __device__ __forceinline__ unsigned long long frac(U t) {   // the accumulator after the step, in units
+        return t ? (unsigned long long)((t - 1) & (((U)1 << Q) - 1)) + 1 : 0ull;
+    }
+    static __device__ __forceinline__ unsigned long long wraps(U t, unsigned long long a) { return (unsigned long long)((t - a) >> Q); }
+    static __device__ __forceinline__ float acc(unsigned long long a) {
+        // exact in the accumulator's type, then static_cast<float>(_phase_acc) (:156-159)
+        return WIDE ? (float)((double)a * (1.0 / 4503599627370496.0)) : (float)a * (1.0f / 16777216.0f);
+    }
+};
+
+template <bool WIDE>
 __device__ __forceinline__ void timing(const FeParams& P, long long n, long long& c, int& arm, float& acc) {
-    const unsigned long long tot = (unsigned long long)n * P.Kf;
-    const unsigned long long a = tot ? ((tot - 1) & 0xFFFFFFull) + 1 : 0ull;
-    const unsigned long long wraps = (tot - a) >> 24;
+    using FT = FeTime<WIDE>;
+    const typename FT::U tot = FT::tot(n, P.Kf);
+    const unsigned long long a = FT::frac(tot);
+    const unsigned long long wraps = FT::wraps(tot, a);
     const unsigned long long Lf = (unsigned long long)P.L0 + (unsigned long long)n * (unsigned long long)P.decim + wraps;
     c = (long long)(Lf / (unsigned)P.fs);
     arm = (int)(Lf % (unsigned)P.fs);
-    acc = (float)a * (1.0f / 16777216.0f);  // exact: a <= 2^24
+    acc = FT::acc(a);
 }
 
 // (cos, sin) of n * theta, reduced in double (PM/rotator.hpp:56-65 with the recurrence in closed form)
@@ -102,8 +125,10 @@ __device__ __forceinline__ void rot_factors(const FeParams& P, long long nt, flo
     }
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(kFeThreads, 4)
 frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (tap, diff tap)*/) {
+    using FT = FeTime<WIDE>;
     extern __shared__ __align__(128) unsigned char smem_raw[];  // 128 B: half-warp LDS.64 rows never straddle a bank row, whatever static shared data precedes
     float2* td_s = reinterpret_cast<float2*>(smem_raw);   // [fs][arm] (tap, diff tap): one broadcast LDS.64 per tap
     float2* xin = td_s + P.fs * P.arm;                    // [kFeXinSlots], skewed
@@ -145,8 +170,8 @@ frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (t
     long long c_first, c_last;
     int arm_dummy;
     float acc_dummy;
-    timing(P, n0, c_first, arm_dummy, acc_dummy);
-    timing(P, n_end - 1, c_last, arm_dummy, acc_dummy);
+    timing<WIDE>(P, n0, c_first, arm_dummy, acc_dummy);
+    timing<WIDE>(P, n_end - 1, c_last, arm_dummy, acc_dummy);
     const long long lo = c_first - P.arm - 1;  // one spare element: the window prefetch reads x[c-1-arm]
     const int span = (int)min((long long)kFeTileIn + 1, c_last - lo);
     const bool staged = span <= kFeTileIn;
@@ -173,21 +198,20 @@ frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (t
     long long c0;
     int arm0;
     float acc[kFeR];
-    timing(P, nt, c0, arm0, acc[0]);
-    const unsigned long long tot0 = (unsigned long long)nt * P.Kf;
-    const unsigned long long a0 = tot0 ? ((tot0 - 1) & 0xFFFFFFull) + 1 : 0ull;
-    const unsigned long long wraps0 = (tot0 - a0) >> 24;
+    timing<WIDE>(P, nt, c0, arm0, acc[0]);
+    const typename FT::U tot0 = FT::tot(nt, P.Kf);
+    const unsigned long long a0 = FT::frac(tot0);
+    const unsigned long long wraps0 = FT::wraps(tot0, a0);
     int dL[kFeR];  // Lf(nt + r) - Lf(nt)
     dL[0] = 0;
     bool fast = staged && (nt + kFeR <= n_end);
 #pragma unroll
     for (int r = 1; r < kFeR; ++r) {
-        const unsigned long long tot = tot0 + (unsigned long long)r * P.Kf;
-        const unsigned long long a = ((tot - 1) & 0xFFFFFFull) + 1;  // tot > 0 for r >= 1 unless Kf == 0
-        const unsigned long long aa = tot ? a : 0ull;
-        const unsigned long long wraps = (tot - aa) >> 24;
+        const typename FT::U tot = tot0 + (typename FT::U)((unsigned long long)r * P.Kf);
+        const unsigned long long aa = FT::frac(tot);
+        const unsigned long long wraps = FT::wraps(tot, aa);
         dL[r] = r * P.decim + (int)(wraps - wraps0);
-        acc[r] = (float)aa * (1.0f / 16777216.0f);
+        acc[r] = FT::acc(aa);
         fast = fast && (dL[r] == r * P.fs);
     }
     float2 y[kFeR];
@@ -300,6 +324,8 @@ int fe_fail(int code, const std::string& m) {
 struct b200sync_fe {
     // settings
     float rate = 1.0f, phase_incr = 0.0f;
+    double rate_f64 = 1.0;      // TRate = double (rate_is_f64)
+    bool wide = false;
     std::vector<float> taps;
     uint32_t fs = 32;
     bool do_resample = true, do_rotate = true;
@@ -327,9 +353,10 @@ namespace {
 // number of outputs the reference loop produces when n_in more inputs arrive (PM/pfb_arb_resampler.hpp:129-167):
 // output n is produced iff c(n-1) < total_in (the outer `while (in_item < end)`) and c(n) <= total_in
 void host_timing(const b200sync_fe* fe, unsigned long long n, unsigned long long& c) {
+    const int Q = fe->wide ? 52 : 24;
     const unsigned __int128 tot = (unsigned __int128)n * fe->Kf;
-    const unsigned long long a = tot ? (unsigned long long)((tot - 1) & 0xFFFFFF) + 1 : 0ull;
-    const unsigned long long wraps = (unsigned long long)((tot - a) >> 24);
+    const unsigned long long a = tot ? (unsigned long long)((tot - 1) & (((unsigned __int128)1 << Q) - 1)) + 1 : 0ull;
+    const unsigned long long wraps = (unsigned long long)((tot - a) >> Q);
     const unsigned long long Lf = (unsigned long long)fe->L0 + n * (unsigned long long)fe->decim + wraps;
     c = Lf / fe->fs;
 }
@@ -357,16 +384,29 @@ int fe_setup(b200sync_fe* fe) {
     if (fe->do_resample) {
         if (fe->fs == 0) return fe_fail(B200SYNC_EINVAL, "filter_size cannot be 0");
         if (fe->taps.size() < 2) return fe_fail(B200SYNC_EINVAL, "taps must have at least 2 entries");
-        if (!(fe->rate > 0.0f)) return fe_fail(B200SYNC_EINVAL, "rate must be positive");
+        if (!fe->wide && !(fe->rate > 0.0f)) return fe_fail(B200SYNC_EINVAL, "rate must be positive");
         fe->arm = static_cast<int>((fe->taps.size() + fe->fs - 1) / fe->fs);
-        const float float_rate = static_cast<float>(fe->fs) / fe->rate;  // :115
-        if (!(float_rate >= 1.0f))
-            return fe_fail(B200SYNC_EUNSUPPORTED, "rate > filter_size is not implemented on the GPU path");
-        fe->decim = static_cast<int>(std::floor(float_rate));
-        const float filt = float_rate - static_cast<float>(fe->decim);
-        const double kf = static_cast<double>(filt) * 16777216.0;
-        if (kf != std::floor(kf)) return fe_fail(B200SYNC_EUNSUPPORTED, "filt_rate is not a multiple of 2^-24");
-        fe->Kf = static_cast<unsigned long long>(kf);
+        if (fe->wide) {
+            // TRate = double (PM/pfb_arb_resampler.hpp:115-118 in double)
+            if (!(fe->rate_f64 > 0.0)) return fe_fail(B200SYNC_EINVAL, "rate must be positive");
+            const double float_rate = static_cast<double>(fe->fs) / fe->rate_f64;
+            if (!(float_rate >= 1.0))
+                return fe_fail(B200SYNC_EUNSUPPORTED, "rate > filter_size is not implemented on the GPU path");
+            fe->decim = static_cast<int>(std::floor(float_rate));
+            const double filt = float_rate - static_cast<double>(fe->decim);
+            const double kf = filt * 4503599627370496.0;  // units of 2^-52: exact scaling
+            if (kf != std::floor(kf)) return fe_fail(B200SYNC_EUNSUPPORTED, "filt_rate is not a multiple of 2^-52");
+            fe->Kf = static_cast<unsigned long long>(kf);
+        } else {
+            const float float_rate = static_cast<float>(fe->fs) / fe->rate;  // :115
+            if (!(float_rate >= 1.0f))
+                return fe_fail(B200SYNC_EUNSUPPORTED, "rate > filter_size is not implemented on the GPU path");
+            fe->decim = static_cast<int>(std::floor(float_rate));
+            const float filt = float_rate - static_cast<float>(fe->decim);
+            const double kf = static_cast<double>(filt) * 16777216.0;
+            if (kf != std::floor(kf)) return fe_fail(B200SYNC_EUNSUPPORTED, "filt_rate is not a multiple of 2^-24");
+            fe->Kf = static_cast<unsigned long long>(kf);
+        }
         fe->L0 = static_cast<int>((fe->taps.size() / 2) % fe->fs);
         if (static_cast<size_t>(fe->fs) * (fe->arm + 1) * 8 > 96 * 1024)
             return fe_fail(B200SYNC_EUNSUPPORTED, "tap set too large for shared memory");
@@ -459,9 +499,10 @@ int fe_run(b200sync_fe* fe, const float2* d_in, size_t n_in, float2* d_out, size
         const size_t smem = fe->do_resample
                                 ? sizeof(float2) * (static_cast<size_t>(P.fs) * P.arm + static_cast<size_t>(kFeXinSlots))
                                 : 0;
-        FCU(cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        auto kern = fe->wide ? frontend_kernel<true> : frontend_kernel<false>;
+        FCU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = static_cast<unsigned>((n_out + kFeTileOut - 1) / kFeTileOut);
-        frontend_kernel<<<grid, kFeThreads, smem, st>>>(P, reinterpret_cast<const float2*>(fe->d_taps));
+        kern<<<grid, kFeThreads, smem, st>>>(P, reinterpret_cast<const float2*>(fe->d_taps));
         count_launch();
         FCU(cudaGetLastError());
     }
@@ -492,6 +533,8 @@ int b200sync_fe_create(const b200sync_fe_config* cfg, b200sync_fe** out) {
     b200sync_fe* fe = new (std::nothrow) b200sync_fe();
     if (!fe) return fe_fail(B200SYNC_ENOMEM, "out of memory");
     fe->rate = cfg->rate;
+    fe->wide = cfg->rate_is_f64 != 0;
+    fe->rate_f64 = fe->wide ? cfg->rate_f64 : static_cast<double>(cfg->rate);
     fe->phase_incr = cfg->phase_incr;
     if (cfg->taps && cfg->n_taps) fe->taps.assign(cfg->taps, cfg->taps + cfg->n_taps);
     fe->do_resample = cfg->enable_resampler != 0;
@@ -533,7 +576,7 @@ int b200sync_fe_start(b200sync_fe* fe) {
 size_t b200sync_fe_max_output(const b200sync_fe* fe, size_t n_in) {
     if (!fe) return 0;
     if (!fe->do_resample) return n_in;
-    return static_cast<size_t>(static_cast<double>(n_in) * static_cast<double>(fe->rate) * 1.0001) + 64;
+    return static_cast<size_t>(static_cast<double>(n_in) * (fe->wide ? fe->rate_f64 : static_cast<double>(fe->rate)) * 1.0001) + 64;
 }
 
 int b200sync_fe_process_device(b200sync_fe* fe, const void* d_in, size_t n_in, void* d_out, size_t max_out,

@@ -268,6 +268,8 @@ typedef struct b200sync_fe_config {
     uint32_t enable_resampler; /* 0: bypass the resampler (Rotator block alone)                       */
     uint32_t enable_rotator;   /* 0: bypass the rotator (PfbArbResampler block alone)                 */
     int32_t device;
+    uint32_t rate_is_f64;      /* 1: TRate = double — the rate is rate_f64, `rate` is ignored; the timing recurrence */
+    double rate_f64;           /*    then runs in double like PfbArbResampler<.., double> (test/qa_pfb_arb_resampler.cpp) */
 } b200sync_fe_config;
 
 typedef struct b200sync_fe b200sync_fe;

@@ -151,3 +151,48 @@ def test_frontend_errors():
 
     with pytest.raises(B200SyncError, match="filter_size cannot be 0|taps"):
         FrontEnd(rate=1.0, taps=np.zeros(0, np.float32))
+
+
+@pytest.mark.parametrize("rate", [1.1234, 1.0 + 1.2e-6, 1.0 - 40e-6, 0.75, 2.5, 1.0 / 3.0])
+def test_resampler_double_rate_bit_exact(oracle, rate):
+    """TRate = double — what the reference's own QA instantiates (test/qa_pfb_arb_resampler.cpp:45-69): the
+    timing recurrence runs in double (exact: 128-bit closed form in units of 2^-52), the interpolation factor is
+    float(double(acc)).  Output count and every sample bit for bit against the oracle's sequential loop, in one
+    span and in odd chunks."""
+    from gr4_packet_modem_b200 import PfbArbResampler
+
+    n = 250000
+    x = _signal(n, 5)
+    o = oracle.PfbArbResampler(rate, taps(), 32, use_double=True)
+    oc, oy = o.process_bulk(x, int(n * rate) + 1000)
+    r = PfbArbResampler(rate, taps(), rate_dtype=np.float64)
+    c, y = r.process_bulk(x)
+    assert c == oc == n and y.size == oy.size
+    assert np.array_equal(y.view(np.uint32), oy.view(np.uint32))
+    o2 = oracle.PfbArbResampler(rate, taps(), 32, use_double=True)
+    r2 = PfbArbResampler(rate, taps(), rate_dtype=np.float64)
+    ys = []
+    for p in range(0, n, 33333):
+        seg = x[p:p + 33333]
+        oc2, oy2 = o2.process_bulk(seg, int(seg.size * rate) + 64)
+        c2, y2 = r2.process_bulk(seg)
+        assert (c2, y2.size) == (oc2, oy2.size)
+        ys.append(y2)
+    assert np.array_equal(np.concatenate(ys).view(np.uint32), oy.view(np.uint32))
+    if rate == 1.1234:   # the float instantiation really is a different block (the two agree for some rates)
+        yf = PfbArbResampler(rate, taps()).process_bulk(x)[1]
+        assert yf.size != y.size or not np.array_equal(yf, y)
+
+
+def test_reference_qa_pfb_arb_resampler_double():
+    """test/qa_pfb_arb_resampler.cpp:45-69 against the GPU block: complex exponential f = 0.01, rate 1.1234 as a
+    double — output count within +-5, samples within 3e-3 of the ideal exponential after the transient."""
+    from gr4_packet_modem_b200 import PfbArbResampler
+
+    n, freq, rate = 100000, 0.01, 1.1234
+    v = np.exp(1j * freq * np.arange(n)).astype(np.complex64)
+    c, y = PfbArbResampler(rate, taps(), rate_dtype=np.float64).process_bulk(v)
+    assert c == n and abs(y.size - int(n * rate)) <= 5
+    k = np.arange(1000, y.size)
+    expected = np.exp(1j * (np.angle(y[1000]) + freq / rate * (k - 1000)))
+    assert np.max(np.abs(y[1000:] - expected)) < 3e-3
