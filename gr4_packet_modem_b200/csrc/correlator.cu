@@ -277,6 +277,7 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
                 const int kk = (kFft - m) & (kFft - 1);
                 if (kk < S) zdst[kk] = best[m1];
             }
+#ifdef B200_GM_FLAGS   // measured dead end, see gm_supported() in b200sync_internal.h
             if (gm != nullptr) {
                 // Group extrema for the peak stage (peaks.cu: peak_flags_gm_kernel): a warp holds 32 CONSECUTIVE
                 // samples per m1 — lags 32q-31 .. 32q with q = 64 - 4 m1 - warp — so REDUX gives the maximum of that
@@ -304,6 +305,7 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
                     }
                 }
             }
+#endif
         }
         if (split) __syncthreads();   // the exchange buffers are free again
     }
