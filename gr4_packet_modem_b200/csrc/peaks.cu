@@ -204,22 +204,23 @@ peak_flags_generic_kernel(const float* __restrict__ zpow, long long z_base, long
 
 
 // ---------------------------------------------------------------------------------
-// Fast flags kernel for T >= 32: no per-sample scans, 4 samples per lane.
+// Fast flags kernel for T >= 32: no per-sample scans, and no per-sample work at all for most groups.
 //
 // The tile's zpow window is staged once in shared memory (128-bit loads/stores) together with
-// the maximum and minimum of every aligned 32-sample group.  For a sample p of group G the
-// forward window (p, p+T] is
+// the maximum of every aligned 32-sample group.  For a sample p of group G the forward window (p, p+T] is
 //     rest of group G after p  |  q whole groups G+1..G+q  |  a remainder of <= 62 samples,
-// q = (T-31)/32.  Almost every sample is smaller than the maximum M_G of the q whole groups and
-// is rejected by ONE compare; only a group that holds a sample >= M_G (about one in q+1)
-// computes the two partial maxima, with warp-shuffle scans.  The threshold test of a candidate
-// (count of window samples below zpow[p]/thr, :273-279) consults the group extrema first: a group
-// entirely below or entirely not below the threshold is settled by one lane, only groups that
-// straddle it are counted sample by sample (128 samples per warp step).  That bounds the cost on
-// degenerate inputs (constant capture: every sample is a candidate) as well.
+// q = (T-31)/32.  A group whose maximum is below the maximum M_G of its q whole groups holds no candidate: ONE
+// compare per GROUP rejects about q in q+1 of them; only the others compute the two partial maxima, with
+// warp-shuffle scans, and decide their 32 samples exactly.  The threshold test of a candidate (count of window
+// samples below zpow[p]/thr, :273-279) consults the group maxima first: groups entirely below the threshold are
+// settled by one lane each (a real peak: nearly all of them, the few left are counted with masks); a noise
+// maximum, whose threshold lies near the median of its window, counts the 2T+1 samples directly (3 instructions
+// per 32 samples).  The minimum of the whole staged window settles the degenerate capture (constant input: every
+// sample is a candidate, nothing is below the threshold) and bounds the cost there.
 //
 // Ordering is done on the int32 bit patterns of zpow, which is the float ordering because zpow is
-// a squared magnitude (>= +0; not NaN for finite input).
+// a squared magnitude (>= +0; not NaN for finite input); the direct count takes the sign bit of the difference
+// of two such patterns (both in [0, 2^31): no overflow).
 // ---------------------------------------------------------------------------------
 constexpr int kFastTile = 8192;   // peaks decided per CTA (captures)
 constexpr int kFastTileSmall = 2048;  // ... for streaming-sized ranges: more CTAs, a quarter of the latency each
@@ -257,23 +258,24 @@ peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_
     pass_bits = ws_at(pass_bits, pb.ws_stride);
     const FastGeom geo = fast_geom(T, TILE);
     const int Tpad = geo.Tpad, nrow = geo.nrow;
+    constexpr int kWarps = kFastThreads / 32;
     int* z = reinterpret_cast<int*>(smem_raw);             // [nrow * 128] bit patterns of zpow
     int* gmax = z + nrow * 128;                            // [nrow * 4]
-    int* gmin = gmax + nrow * 4;                           // [nrow * 4]
-    int* gM = gmin + nrow * 4;                             // [TILE / 32] max of the q whole groups
+    int* gM = gmax + nrow * 4;                             // [TILE / 32] max of the q whole groups
     uint32_t* passw = reinterpret_cast<uint32_t*>(gM + TILE / 32);          // [TILE / 32]
-    int* ncand_s = reinterpret_cast<int*>(passw + TILE / 32);
-    unsigned short* cand_list = reinterpret_cast<unsigned short*>(ncand_s + 1);  // [TILE] worst case
+    int* wmin = reinterpret_cast<int*>(passw + TILE / 32);                  // [kWarps] minimum of a warp's rows
+    int* ncand_s = wmin + kWarps;                                           // [2]: candidates, possible groups
+    unsigned short* poss_list = reinterpret_cast<unsigned short*>(ncand_s + 2);  // [TILE / 32]
+    unsigned short* cand_list = poss_list + TILE / 32;                      // [TILE] worst case
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int kWarps = kFastThreads / 32;
     const long long tile_lo = lo + (long long)blockIdx.x * TILE;
     const long long q0 = tile_lo - Tpad;                   // absolute index of window element 0
     const int* src = reinterpret_cast<const int*>(zpow) + (q0 - z_base);
     // first element that is both inside the stream and inside the caller's metric buffer: the window origin is
     // rounded down to a group boundary (Tpad >= T), which can reach below z_base when a caller keeps exactly
     // the 2T+2 samples of history the decisions need (streaming, short shard halos).  Those pad elements are
-    // never part of a decision window — they only enter the extrema of a group that straddles the window edge,
+    // never part of a decision window — they only enter the maximum of a group that straddles the window edge,
     // where a zero can only send the count to the exact per-sample path — so they read as zeros.
     const long long first_ok = z_base > 0 ? z_base : 0;
     const int lo_ok = q0 < first_ok ? (int)(first_ok - q0) : 0;
@@ -282,121 +284,140 @@ peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_
     const bool vec_ok = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
     // ---- stage rows of 128 samples; out-of-stream / not-yet-known samples read as 0 (the
     //      zero-initialised HistoryBuffer before the stream start)
-    for (int r0 = warp; r0 < nrow; r0 += 2 * kWarps) {
-        int4 v[2];
+    int rmin = INT_MAX;                                    // minimum of everything this thread staged
+    auto put_row = [&](int r, const int4& v) {             // the row into shared memory + its four groups' maxima
+        *reinterpret_cast<int4*>(z + r * 128 + 4 * lane) = v;
+        int mx = max(max(v.x, v.y), max(v.z, v.w));
+        rmin = min(rmin, min(min(v.x, v.y), min(v.z, v.w)));
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int r = r0 + u * kWarps;
-            const int e0 = r * 128 + 4 * lane;
-            v[u] = make_int4(0, 0, 0, 0);
-            if (r < nrow) {
-                if (vec_ok && e0 >= lo_ok && e0 + 3 < hi_ok) {
-                    v[u] = __ldg(reinterpret_cast<const int4*>(src + e0));
-                } else {
-                    if (e0 + 0 >= lo_ok && e0 + 0 < hi_ok) v[u].x = __ldg(src + e0 + 0);
-                    if (e0 + 1 >= lo_ok && e0 + 1 < hi_ok) v[u].y = __ldg(src + e0 + 1);
-                    if (e0 + 2 >= lo_ok && e0 + 2 < hi_ok) v[u].z = __ldg(src + e0 + 2);
-                    if (e0 + 3 >= lo_ok && e0 + 3 < hi_ok) v[u].w = __ldg(src + e0 + 3);
-                }
+        for (int dd = 1; dd < 8; dd <<= 1)                 // 8 lanes hold one 32-sample group
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, dd));
+        if ((lane & 7) == 0) gmax[r * 4 + (lane >> 3)] = mx;
+    };
+    if (vec_ok && lo_ok == 0 && hi_ok == nrow * 128) {
+        // interior tile (all but the first and last few of a capture): no per-element bounds, four rows in flight
+        const int4* src4 = reinterpret_cast<const int4*>(src) + lane;
+        for (int r0 = warp; r0 < nrow; r0 += 4 * kWarps) {
+            int4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + u * kWarps;
+                if (r < nrow) v[u] = __ldg(src4 + r * 32);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + u * kWarps;
+                if (r < nrow) put_row(r, v[u]);
             }
         }
+    } else {
+        for (int r0 = warp; r0 < nrow; r0 += 2 * kWarps) {
+            int4 v[2];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int r = r0 + u * kWarps;
-            if (r < nrow) {
-                *reinterpret_cast<int4*>(z + r * 128 + 4 * lane) = v[u];
-                int mx = max(max(v[u].x, v[u].y), max(v[u].z, v[u].w));
-                int mn = min(min(v[u].x, v[u].y), min(v[u].z, v[u].w));
+            for (int u = 0; u < 2; ++u) {
+                const int r = r0 + u * kWarps;
+                const int e0 = r * 128 + 4 * lane;
+                v[u] = make_int4(0, 0, 0, 0);
+                if (r < nrow) {
+                    if (vec_ok && e0 >= lo_ok && e0 + 3 < hi_ok) {
+                        v[u] = __ldg(reinterpret_cast<const int4*>(src + e0));
+                    } else {
+                        if (e0 + 0 >= lo_ok && e0 + 0 < hi_ok) v[u].x = __ldg(src + e0 + 0);
+                        if (e0 + 1 >= lo_ok && e0 + 1 < hi_ok) v[u].y = __ldg(src + e0 + 1);
+                        if (e0 + 2 >= lo_ok && e0 + 2 < hi_ok) v[u].z = __ldg(src + e0 + 2);
+                        if (e0 + 3 >= lo_ok && e0 + 3 < hi_ok) v[u].w = __ldg(src + e0 + 3);
+                    }
+                }
+            }
 #pragma unroll
-                for (int dd = 1; dd < 8; dd <<= 1) {   // 8 lanes hold one 32-sample group
-                    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, dd));
-                    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, dd));
-                }
-                if ((lane & 7) == 0) {
-                    gmax[r * 4 + (lane >> 3)] = mx;
-                    gmin[r * 4 + (lane >> 3)] = mn;
-                }
+            for (int u = 0; u < 2; ++u) {
+                const int r = r0 + u * kWarps;
+                if (r < nrow) put_row(r, v[u]);
             }
         }
     }
+    rmin = __reduce_min_sync(0xffffffffu, rmin);
+    if (lane == 0) wmin[warp] = rmin;
+    if (tid < 2) ncand_s[tid] = 0;
     __syncthreads();
     const int q = (T - 31) >> 5;         // whole groups inside every forward window of a group
     const int d = T - 32 * q - 32;       // remainder reaches element (lane + d) of group G+q+1, d in [-1, 30]
     const int G0 = Tpad >> 5;
-    if (tid < TILE / 32) {
-        int m = INT_MIN;
-        for (int k = 1; k <= q; ++k) m = max(m, gmax[G0 + tid + k]);
-        gM[tid] = m;
-    }
-    if (tid == 0) *ncand_s = 0;
-    __syncthreads();
-
     const long long rem_ll = hi - tile_lo;
     const int nvalid = rem_ll < (long long)TILE ? (int)rem_ll : TILE;  // p < hi
     const int tv_need = 2 * T + 1;
     uint32_t* cw = cand_bits + (tile_lo - lo) / 32;
     uint32_t* pw = pass_bits + (tile_lo - lo) / 32;
-    const int4* z4 = reinterpret_cast<const int4*>(z + Tpad);
-    // ---- candidates: written to the bitmap and queued for the threshold test
-    for (int it = warp; it < TILE / 128; it += kWarps) {
-        // 128 samples per step: lane holds 4 consecutive samples of tile group 4*it + (lane >> 3)
-        const int4 v = z4[it * 32 + lane];
-        const int Mq = gM[4 * it + (lane >> 3)];
-        const bool poss = !(Mq > v.x) || !(Mq > v.y) || !(Mq > v.z) || !(Mq > v.w);
-        const uint32_t possb = __ballot_sync(0xffffffffu, poss);
-        uint32_t cand_out = 0u;                  // lane j (< 4) keeps the word of group 4*it + j
-        if (possb != 0u) {                       // rare: about one group in q+1 holds a possible candidate
-            for (int j = 0; j < 4; ++j) {
-                if (((possb >> (8 * j)) & 0xffu) == 0u) continue;   // warp-uniform
-                const int w = 4 * it + j;
-                const int G = G0 + w;
-                const int zi = z[32 * G + lane];
-                const int M = gM[w];
-                const bool valid = (32 * w + lane) < nvalid;
-                // exclusive suffix maximum inside the group
-                int s = zi;
-#pragma unroll
-                for (int dd = 1; dd < 32; dd <<= 1) {
-                    const int t = __shfl_down_sync(0xffffffffu, s, dd);
-                    if (lane + dd < 32) s = max(s, t);
-                }
-                s = __shfl_down_sync(0xffffffffu, s, 1);
-                if (lane == 31) s = INT_MIN;
-                // remainder: elements 0..e of group G+q+1 (continuing into G+q+2), e = lane + d
-                const int A = G + q + 1;
-                const int pa = warp_incl_scan_max(z[32 * A + lane], lane);
-                const int pbm = warp_incl_scan_max(z[32 * A + 32 + lane], lane);
-                const int e = lane + d;
-                const int ra = __shfl_sync(0xffffffffu, pa, e & 31);
-                const int rb = __shfl_sync(0xffffffffu, pbm, e & 31);
-                const int ga = __shfl_sync(0xffffffffu, pa, 31);
-                const int rem = e < 0 ? INT_MIN : (e < 32 ? ra : max(ga, rb));
-                const int fwd = max(max(s, M), rem);
-                const bool cand = valid && !(fwd > zi);
-                const uint32_t candw = __ballot_sync(0xffffffffu, cand);
-                if (candw != 0u) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(ncand_s, __popc(candw));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (cand) cand_list[base + __popc(candw & ((1u << lane) - 1u))] = (unsigned short)(32 * w + lane);
-                }
-                if (lane == j) cand_out = candw;
-            }
-        }
-        if (lane < 4) {
-            cw[4 * it + lane] = cand_out;
-            passw[4 * it + lane] = 0u;
-        }
+    // ---- one thread per tile group: the maximum M of the q whole groups inside the forward window of every
+    //      sample of the group.  A group whose own maximum is below M holds no candidate (about q in q+1 of them):
+    //      settled here by ONE compare per group; the others are queued.
+    static_assert((TILE / 32) % 32 == 0 && TILE / 32 <= kFastThreads, "whole warps of tile groups");
+    if (tid < TILE / 32) {
+        int m = INT_MIN;
+#pragma unroll 4
+        for (int k = 1; k <= q; ++k) m = max(m, gmax[G0 + tid + k]);
+        gM[tid] = m;
+        const bool poss = 32 * tid < nvalid && !(m > gmax[G0 + tid]);
+        const uint32_t possw = __ballot_sync(0xffffffffu, poss);
+        int base = 0;
+        if (lane == 0 && possw != 0u) base = atomicAdd(ncand_s + 1, __popc(possw));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (poss) poss_list[base + __popc(possw & ((1u << lane) - 1u))] = (unsigned short)tid;
+        else cw[tid] = 0u;
+        passw[tid] = 0u;
     }
     __syncthreads();
-    // ---- threshold test of every candidate (:273-279), spread over all warps of the CTA
-    const int ncand = *ncand_s;
+    // ---- candidates of the queued groups, decided exactly: written to the bitmap and queued for the threshold test
+    const int nposs = ncand_s[1];
+    for (int pi = warp; pi < nposs; pi += kWarps) {
+        const int w = poss_list[pi];
+        const int G = G0 + w;
+        const int zi = z[32 * G + lane];
+        const int M = gM[w];
+        const bool valid = (32 * w + lane) < nvalid;
+        // exclusive suffix maximum inside the group
+        int s = zi;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const int t = __shfl_down_sync(0xffffffffu, s, dd);
+            if (lane + dd < 32) s = max(s, t);
+        }
+        s = __shfl_down_sync(0xffffffffu, s, 1);
+        if (lane == 31) s = INT_MIN;
+        // remainder: elements 0..e of group G+q+1 (continuing into G+q+2), e = lane + d
+        const int A = G + q + 1;
+        const int pa = warp_incl_scan_max(z[32 * A + lane], lane);
+        const int pbm = warp_incl_scan_max(z[32 * A + 32 + lane], lane);
+        const int e = lane + d;
+        const int ra = __shfl_sync(0xffffffffu, pa, e & 31);
+        const int rb = __shfl_sync(0xffffffffu, pbm, e & 31);
+        const int ga = __shfl_sync(0xffffffffu, pa, 31);
+        const int rem = e < 0 ? INT_MIN : (e < 32 ? ra : max(ga, rb));
+        const int fwd = max(max(s, M), rem);
+        const bool cand = valid && !(fwd > zi);
+        const uint32_t candw = __ballot_sync(0xffffffffu, cand);
+        if (candw != 0u) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(ncand_s, __popc(candw));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (cand) cand_list[base + __popc(candw & ((1u << lane) - 1u))] = (unsigned short)(32 * w + lane);
+        }
+        if (lane == 0) cw[w] = candw;
+    }
+    __syncthreads();
+    // ---- threshold test of every candidate (:273-279), spread over all warps of the CTA.  The group maxima settle
+    //      the groups entirely below the threshold (a real peak: nearly all of them) with one lane each; the minimum
+    //      of the whole staged window settles the degenerate capture (constant input: every sample is a candidate and
+    //      nothing is below the threshold), which bounds the cost there.
+    const int ncand = ncand_s[0];
+    const int tmin = __reduce_min_sync(0xffffffffu, lane < kWarps ? wmin[lane] : INT_MAX);
     for (int ci = warp; ci < ncand; ci += kWarps) {
         const int tp = cand_list[ci];
         const int ic = Tpad + tp;
         const float tvf = __fdiv_rn(__int_as_float(z[ic]), thr);
         if (!(tvf > 0.0f)) continue;        // zpow >= 0: nothing is below a non-positive threshold
         const int tv = __float_as_int(tvf);
+        if (tv <= tmin) continue;           // nothing in the window is below the threshold
         const int w_lo = ic - T, w_hi = ic + T;
         const int g_first = w_lo >> 5, g_last = w_hi >> 5;   // at most 65 groups
         int cnt = 0;
@@ -407,9 +428,29 @@ peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_
             bool nd = false;
             if (gi <= g_last) {
                 if (gmax[gi] < tv) cnt += min(32 * gi + 31, w_hi) - max(32 * gi, w_lo) + 1;
-                else if (gmin[gi] < tv) nd = true;
+                else nd = true;
             }
             need[r] = __ballot_sync(0xffffffffu, nd);
+        }
+        if (__popc(need[0]) + __popc(need[1]) + __popc(need[2]) > 6) {
+            // many groups reach the threshold — the usual noise maximum, whose threshold sits near the median of
+            // the window: count the 2T+1 samples directly, lane-strided (conflict-free, no alignment, no masks).
+            // Sign bit of the difference of two bit patterns = the compare (no overflow: see the header).
+            const int* zw = z + w_lo + lane;
+            const int nfull = tv_need >> 5;
+            unsigned c0 = 0u, c1 = 0u;
+            const unsigned utv = (unsigned)tv;   // unsigned wrap-around arithmetic keeps the compiler from turning it back into compares
+            int k = 0;
+#pragma unroll 4
+            for (; k + 1 < nfull; k += 2) {
+                c0 += ((unsigned)zw[32 * k] - utv) >> 31;
+                c1 += ((unsigned)zw[32 * k + 32] - utv) >> 31;
+            }
+            if (k < nfull) c0 += ((unsigned)zw[32 * k] - utv) >> 31;
+            if (lane < (tv_need & 31)) c1 += ((unsigned)zw[32 * nfull] - utv) >> 31;
+            cnt = (int)__reduce_add_sync(0xffffffffu, c0 + c1);
+            if (lane == 0 && 2 * cnt >= tv_need) atomicOr(&passw[tp >> 5], 1u << (tp & 31));
+            continue;
         }
         const int nchunk = ((g_last - g_first) >> 2) + 1;   // 4 groups = 128 samples per step
         const unsigned span = 2u * (unsigned)T;
@@ -420,12 +461,8 @@ peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_
             const uint32_t word = (ch >> 3) == 0 ? need[0] : ((ch >> 3) == 1 ? need[1] : need[2]);
             const uint32_t nib = (word >> (4 * (ch & 7))) & 0xfu;
             if (nib == 0u) continue;                        // warp-uniform
-            const int4 x = *reinterpret_cast<const int4*>(zc0 + 128 * ch);
-            const int cbase = 32 * g_first + 128 * ch - w_lo;   // window offset of the chunk's first sample
-            if (nib == 0xfu && cbase >= 0 && (unsigned)(cbase + 127) <= span) {
-                // interior chunk, all four groups straddle the threshold: no masks needed
-                cnt += (x.x < tv) + (x.y < tv) + (x.z < tv) + (x.w < tv);
-            } else if (nib & mybit) {
+            if (nib & mybit) {
+                const int4 x = *reinterpret_cast<const int4*>(zc0 + 128 * ch);
                 const int o = o0 + 128 * ch;
                 cnt += ((unsigned)(o + 0) <= span && x.x < tv) ? 1 : 0;
                 cnt += ((unsigned)(o + 1) <= span && x.y < tv) ? 1 : 0;
@@ -1054,8 +1091,8 @@ static cudaError_t launch_flags(const float* d_zpow, long long z_base, long long
     const dim3 grid((unsigned)ntiles, (unsigned)nch);
     if (fast) {
         const FastGeom geo = fast_geom(T, tile);
-        const size_t smem = sizeof(int) * ((size_t)geo.nrow * 128 + 2 * (size_t)geo.nrow * 4 + 2 * (tile / 32) + 1) +
-                            sizeof(unsigned short) * tile;
+        const size_t smem = sizeof(int) * ((size_t)geo.nrow * 128 + (size_t)geo.nrow * 4 + 2 * (tile / 32) + kFastThreads / 32 + 2) +
+                            sizeof(unsigned short) * (tile + tile / 32);
         auto kern = small ? peak_flags_kernel<kFastTileSmall> : peak_flags_kernel<kFastTile>;
         e = set_smem_attr((const void*)kern, smem);
         if (e != cudaSuccess) return e;
