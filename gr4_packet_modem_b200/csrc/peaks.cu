@@ -248,7 +248,7 @@ __host__ __device__ inline FastGeom fast_geom(int T, int tile) {
 }
 
 template <int TILE>
-__global__ void __launch_bounds__(kFastThreads)
+__global__ void __launch_bounds__(kFastThreads, 4)   // 4 CTAs of 512 threads = every warp slot of the SM: <= 32 registers
 peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_end, long long lo,
                   long long hi, int T, float thr, uint32_t* __restrict__ cand_bits,
                   uint32_t* __restrict__ pass_bits, PeakBatch pb) {
@@ -262,11 +262,9 @@ peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_
     int* z = reinterpret_cast<int*>(smem_raw);             // [nrow * 128] bit patterns of zpow
     int* gmax = z + nrow * 128;                            // [nrow * 4]
     int* gM = gmax + nrow * 4;                             // [TILE / 32] max of the q whole groups
-    uint32_t* passw = reinterpret_cast<uint32_t*>(gM + TILE / 32);          // [TILE / 32]
-    int* wmin = reinterpret_cast<int*>(passw + TILE / 32);                  // [kWarps] minimum of a warp's rows
-    int* ncand_s = wmin + kWarps;                                           // [2]: candidates, possible groups
-    unsigned short* poss_list = reinterpret_cast<unsigned short*>(ncand_s + 2);  // [TILE / 32]
-    unsigned short* cand_list = poss_list + TILE / 32;                      // [TILE] worst case
+    int* wmin = gM + TILE / 32;                            // [kWarps] minimum of a warp's share (degenerate captures)
+    int* nposs_s = wmin + kWarps;                          // [1] possible groups
+    unsigned short* poss_list = reinterpret_cast<unsigned short*>(nposs_s + 1);  // [TILE / 32]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long tile_lo = lo + (long long)blockIdx.x * TILE;
@@ -284,15 +282,14 @@ peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_
     const bool vec_ok = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
     // ---- stage rows of 128 samples; out-of-stream / not-yet-known samples read as 0 (the
     //      zero-initialised HistoryBuffer before the stream start)
-    int rmin = INT_MAX;                                    // minimum of everything this thread staged
+    int* const gmax_lane = gmax + (lane >> 3);
     auto put_row = [&](int r, const int4& v) {             // the row into shared memory + its four groups' maxima
         *reinterpret_cast<int4*>(z + r * 128 + 4 * lane) = v;
         int mx = max(max(v.x, v.y), max(v.z, v.w));
-        rmin = min(rmin, min(min(v.x, v.y), min(v.z, v.w)));
 #pragma unroll
         for (int dd = 1; dd < 8; dd <<= 1)                 // 8 lanes hold one 32-sample group
             mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, dd));
-        if ((lane & 7) == 0) gmax[r * 4 + (lane >> 3)] = mx;
+        if ((lane & 7) == 0) gmax_lane[r * 4] = mx;
     };
     if (vec_ok && lo_ok == 0 && hi_ok == nrow * 128) {
         // interior tile (all but the first and last few of a capture): no per-element bounds, four rows in flight
@@ -336,9 +333,7 @@ peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_
             }
         }
     }
-    rmin = __reduce_min_sync(0xffffffffu, rmin);
-    if (lane == 0) wmin[warp] = rmin;
-    if (tid < 2) ncand_s[tid] = 0;
+    if (tid == 0) *nposs_s = 0;
     __syncthreads();
     const int q = (T - 31) >> 5;         // whole groups inside every forward window of a group
     const int d = T - 32 * q - 32;       // remainder reaches element (lane + d) of group G+q+1, d in [-1, 30]
@@ -350,25 +345,62 @@ peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_
     uint32_t* pw = pass_bits + (tile_lo - lo) / 32;
     // ---- one thread per tile group: the maximum M of the q whole groups inside the forward window of every
     //      sample of the group.  A group whose own maximum is below M holds no candidate (about q in q+1 of them):
-    //      settled here by ONE compare per group; the others are queued.
+    //      settled here by ONE compare per group — both its bitmap words are zero; the others are queued.
     static_assert((TILE / 32) % 32 == 0 && TILE / 32 <= kFastThreads, "whole warps of tile groups");
     if (tid < TILE / 32) {
+        // sliding maximum over q <= 31 consecutive group maxima by doubling: the warp's 32 outputs need the 32 + q - 1
+        // entries after G0 + tid, held as (a, b) = elements lane and lane + 32; after the levels 1, 2, .. p/2 an
+        // element is the maximum of p = 2^floor(log2 q) consecutive entries and two of those cover q
+        const int* gsrc = gmax + G0 + tid + 1;
+        int a = gsrc[0];
+        int b = G0 + tid + 33 < nrow * 4 ? gsrc[32] : INT_MIN;   // beyond the staged groups: never part of a used window
         int m = INT_MIN;
-#pragma unroll 4
-        for (int k = 1; k <= q; ++k) m = max(m, gmax[G0 + tid + k]);
+        if (q > 0) {
+            int p = 1;
+            for (; 2 * p <= q; p *= 2) {
+                const int ta = __shfl_down_sync(0xffffffffu, a, p);
+                const int tb = __shfl_up_sync(0xffffffffu, b, 32 - p);
+                const int tc = __shfl_down_sync(0xffffffffu, b, p);
+                a = max(a, lane + p < 32 ? ta : tb);
+                b = max(b, lane + p < 32 ? tc : b);
+            }
+            const int sft = q - p;                          // in [0, p)
+            const int ta = __shfl_down_sync(0xffffffffu, a, sft);
+            const int tb = __shfl_up_sync(0xffffffffu, b, (32 - sft) & 31);
+            m = max(a, (sft == 0 || lane + sft < 32) ? ta : tb);
+        }
         gM[tid] = m;
         const bool poss = 32 * tid < nvalid && !(m > gmax[G0 + tid]);
         const uint32_t possw = __ballot_sync(0xffffffffu, poss);
         int base = 0;
-        if (lane == 0 && possw != 0u) base = atomicAdd(ncand_s + 1, __popc(possw));
+        if (lane == 0 && possw != 0u) base = atomicAdd(nposs_s, __popc(possw));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (poss) poss_list[base + __popc(possw & ((1u << lane) - 1u))] = (unsigned short)tid;
-        else cw[tid] = 0u;
-        passw[tid] = 0u;
+        if (poss) {
+            poss_list[base + __popc(possw & ((1u << lane) - 1u))] = (unsigned short)tid;
+        } else {
+            cw[tid] = 0u;
+            pw[tid] = 0u;
+        }
     }
     __syncthreads();
-    // ---- candidates of the queued groups, decided exactly: written to the bitmap and queued for the threshold test
-    const int nposs = ncand_s[1];
+    const int nposs = *nposs_s;
+    // The minimum of the whole staged window settles the degenerate capture (constant input: every sample is a
+    // candidate and nothing is below its threshold) and bounds the cost there; a plausible capture queues about
+    // TILE / (T+1) groups and never takes this branch (CTA-uniform).
+    int tmin = INT_MIN;
+    if (nposs > TILE / 128) {
+        int rmin = INT_MAX;
+        for (int i = tid; i < nrow * 32; i += kFastThreads) {
+            const int4 v = reinterpret_cast<const int4*>(z)[i];
+            rmin = min(rmin, min(min(v.x, v.y), min(v.z, v.w)));
+        }
+        rmin = __reduce_min_sync(0xffffffffu, rmin);
+        if (lane == 0) wmin[warp] = rmin;
+        __syncthreads();
+        tmin = __reduce_min_sync(0xffffffffu, lane < kWarps ? wmin[lane] : INT_MAX);
+    }
+    // ---- a warp per queued group: its candidates decided exactly, then the threshold test of each (:273-279).
+    //      The warp owns both bitmap words of the group: no atomics, no second queue.
     for (int pi = warp; pi < nposs; pi += kWarps) {
         const int w = poss_list[pi];
         const int G = G0 + w;
@@ -396,85 +428,73 @@ peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_
         const int fwd = max(max(s, M), rem);
         const bool cand = valid && !(fwd > zi);
         const uint32_t candw = __ballot_sync(0xffffffffu, cand);
-        if (candw != 0u) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(ncand_s, __popc(candw));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (cand) cand_list[base + __popc(candw & ((1u << lane) - 1u))] = (unsigned short)(32 * w + lane);
-        }
-        if (lane == 0) cw[w] = candw;
-    }
-    __syncthreads();
-    // ---- threshold test of every candidate (:273-279), spread over all warps of the CTA.  The group maxima settle
-    //      the groups entirely below the threshold (a real peak: nearly all of them) with one lane each; the minimum
-    //      of the whole staged window settles the degenerate capture (constant input: every sample is a candidate and
-    //      nothing is below the threshold), which bounds the cost there.
-    const int ncand = ncand_s[0];
-    const int tmin = __reduce_min_sync(0xffffffffu, lane < kWarps ? wmin[lane] : INT_MAX);
-    for (int ci = warp; ci < ncand; ci += kWarps) {
-        const int tp = cand_list[ci];
-        const int ic = Tpad + tp;
-        const float tvf = __fdiv_rn(__int_as_float(z[ic]), thr);
-        if (!(tvf > 0.0f)) continue;        // zpow >= 0: nothing is below a non-positive threshold
-        const int tv = __float_as_int(tvf);
-        if (tv <= tmin) continue;           // nothing in the window is below the threshold
-        const int w_lo = ic - T, w_hi = ic + T;
-        const int g_first = w_lo >> 5, g_last = w_hi >> 5;   // at most 65 groups
-        int cnt = 0;
-        uint32_t need[3];
+        uint32_t passw = 0u;
+        for (uint32_t left = candw; left != 0u; left &= left - 1u) {
+            const int lp = __ffs(left) - 1;
+            const int ic = 32 * G + lp;
+            const float tvf = __fdiv_rn(__int_as_float(__shfl_sync(0xffffffffu, zi, lp)), thr);
+            if (!(tvf > 0.0f)) continue;        // zpow >= 0: nothing is below a non-positive threshold
+            const int tv = __float_as_int(tvf);
+            if (tv <= tmin) continue;           // nothing in the window is below the threshold
+            const int w_lo = ic - T, w_hi = ic + T;
+            const int g_first = w_lo >> 5, g_last = w_hi >> 5;   // at most 65 groups
+            int cnt = 0;
+            uint32_t need[3];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const int gi = g_first + 32 * r + lane;
-            bool nd = false;
-            if (gi <= g_last) {
-                if (gmax[gi] < tv) cnt += min(32 * gi + 31, w_hi) - max(32 * gi, w_lo) + 1;
-                else nd = true;
+            for (int r = 0; r < 3; ++r) {
+                const int gi = g_first + 32 * r + lane;
+                bool nd = false;
+                if (gi <= g_last) {
+                    if (gmax[gi] < tv) cnt += min(32 * gi + 31, w_hi) - max(32 * gi, w_lo) + 1;
+                    else nd = true;
+                }
+                need[r] = __ballot_sync(0xffffffffu, nd);
             }
-            need[r] = __ballot_sync(0xffffffffu, nd);
-        }
-        if (__popc(need[0]) + __popc(need[1]) + __popc(need[2]) > 6) {
-            // many groups reach the threshold — the usual noise maximum, whose threshold sits near the median of
-            // the window: count the 2T+1 samples directly, lane-strided (conflict-free, no alignment, no masks).
-            // Sign bit of the difference of two bit patterns = the compare (no overflow: see the header).
-            const int* zw = z + w_lo + lane;
-            const int nfull = tv_need >> 5;
-            unsigned c0 = 0u, c1 = 0u;
-            const unsigned utv = (unsigned)tv;   // unsigned wrap-around arithmetic keeps the compiler from turning it back into compares
-            int k = 0;
+            if (__popc(need[0]) + __popc(need[1]) + __popc(need[2]) > 6) {
+                // many groups reach the threshold — the usual noise maximum, whose threshold sits near the median of
+                // the window: count the 2T+1 samples directly, lane-strided (conflict-free, no alignment, no masks; a
+                // 128-bit variant with masked end chunks measured slower).
+                // Sign bit of the difference of two bit patterns = the compare (no overflow: see the header).
+                const int* zw = z + w_lo + lane;
+                const int nfull = tv_need >> 5;
+                unsigned c0 = 0u, c1 = 0u;
+                const unsigned utv = (unsigned)tv;   // unsigned wrap-around arithmetic keeps the compiler from turning it back into compares
+                int k = 0;
 #pragma unroll 4
-            for (; k + 1 < nfull; k += 2) {
-                c0 += ((unsigned)zw[32 * k] - utv) >> 31;
-                c1 += ((unsigned)zw[32 * k + 32] - utv) >> 31;
+                for (; k + 1 < nfull; k += 2) {
+                    c0 += ((unsigned)zw[32 * k] - utv) >> 31;
+                    c1 += ((unsigned)zw[32 * k + 32] - utv) >> 31;
+                }
+                if (k < nfull) c0 += ((unsigned)zw[32 * k] - utv) >> 31;
+                if (lane < (tv_need & 31)) c1 += ((unsigned)zw[32 * nfull] - utv) >> 31;
+                cnt = (int)(c0 + c1);
+            } else {
+                const int nchunk = ((g_last - g_first) >> 2) + 1;   // 4 groups = 128 samples per step
+                const unsigned span = 2u * (unsigned)T;
+                const int* zc0 = z + 32 * g_first + 4 * lane;
+                const int o0 = 32 * g_first + 4 * lane - w_lo;      // window offset of this lane's first sample
+                const uint32_t mybit = 1u << (lane >> 3);
+                for (int ch = 0; ch < nchunk; ++ch) {
+                    const uint32_t word = (ch >> 3) == 0 ? need[0] : ((ch >> 3) == 1 ? need[1] : need[2]);
+                    const uint32_t nib = (word >> (4 * (ch & 7))) & 0xfu;
+                    if (nib & mybit) {
+                        const int4 x = *reinterpret_cast<const int4*>(zc0 + 128 * ch);
+                        const int o = o0 + 128 * ch;
+                        cnt += ((unsigned)(o + 0) <= span && x.x < tv) ? 1 : 0;
+                        cnt += ((unsigned)(o + 1) <= span && x.y < tv) ? 1 : 0;
+                        cnt += ((unsigned)(o + 2) <= span && x.z < tv) ? 1 : 0;
+                        cnt += ((unsigned)(o + 3) <= span && x.w < tv) ? 1 : 0;
+                    }
+                }
             }
-            if (k < nfull) c0 += ((unsigned)zw[32 * k] - utv) >> 31;
-            if (lane < (tv_need & 31)) c1 += ((unsigned)zw[32 * nfull] - utv) >> 31;
-            cnt = (int)__reduce_add_sync(0xffffffffu, c0 + c1);
-            if (lane == 0 && 2 * cnt >= tv_need) atomicOr(&passw[tp >> 5], 1u << (tp & 31));
-            continue;
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (2 * cnt >= tv_need) passw |= 1u << lp;
         }
-        const int nchunk = ((g_last - g_first) >> 2) + 1;   // 4 groups = 128 samples per step
-        const unsigned span = 2u * (unsigned)T;
-        const int* zc0 = z + 32 * g_first + 4 * lane;
-        const int o0 = 32 * g_first + 4 * lane - w_lo;      // window offset of this lane's first sample
-        const uint32_t mybit = 1u << (lane >> 3);
-        for (int ch = 0; ch < nchunk; ++ch) {
-            const uint32_t word = (ch >> 3) == 0 ? need[0] : ((ch >> 3) == 1 ? need[1] : need[2]);
-            const uint32_t nib = (word >> (4 * (ch & 7))) & 0xfu;
-            if (nib == 0u) continue;                        // warp-uniform
-            if (nib & mybit) {
-                const int4 x = *reinterpret_cast<const int4*>(zc0 + 128 * ch);
-                const int o = o0 + 128 * ch;
-                cnt += ((unsigned)(o + 0) <= span && x.x < tv) ? 1 : 0;
-                cnt += ((unsigned)(o + 1) <= span && x.y < tv) ? 1 : 0;
-                cnt += ((unsigned)(o + 2) <= span && x.z < tv) ? 1 : 0;
-                cnt += ((unsigned)(o + 3) <= span && x.w < tv) ? 1 : 0;
-            }
+        if (lane == 0) {
+            cw[w] = candw;
+            pw[w] = passw;
         }
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if (lane == 0 && 2 * cnt >= tv_need) atomicOr(&passw[tp >> 5], 1u << (tp & 31));
     }
-    __syncthreads();
-    if (tid < TILE / 32) pw[tid] = passw[tid];
 }
 
 // ---------------------------------------------------------------------------------
@@ -1091,8 +1111,8 @@ static cudaError_t launch_flags(const float* d_zpow, long long z_base, long long
     const dim3 grid((unsigned)ntiles, (unsigned)nch);
     if (fast) {
         const FastGeom geo = fast_geom(T, tile);
-        const size_t smem = sizeof(int) * ((size_t)geo.nrow * 128 + (size_t)geo.nrow * 4 + 2 * (tile / 32) + kFastThreads / 32 + 2) +
-                            sizeof(unsigned short) * (tile + tile / 32);
+        const size_t smem = sizeof(int) * ((size_t)geo.nrow * 128 + (size_t)geo.nrow * 4 + tile / 32 + kFastThreads / 32 + 1) +
+                            sizeof(unsigned short) * (tile / 32);
         auto kern = small ? peak_flags_kernel<kFastTileSmall> : peak_flags_kernel<kFastTile>;
         e = set_smem_attr((const void*)kern, smem);
         if (e != cudaSuccess) return e;
