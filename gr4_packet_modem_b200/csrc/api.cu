@@ -76,6 +76,8 @@ struct b200sync_sd {
     int device = 0, num_sms = 148;
     // derived (:148, :161-164, :236)
     uint32_t L = 0, S = 0, K = 0;
+    bool generic = false;   // correlator_generic.cu: every fft_size but 2048 (and 2048 under B200SYNC_FORCE_GENERIC)
+    int fft_arg = kFft;     // what the launchers get: fft_size, | kGenericFlag for a forced 2048
     float self_corr = 0.0f;
     int T = 0;
     uint64_t delay = 0;
@@ -173,7 +175,7 @@ int run_chunk(b200sync_sd* sd, const float2* d_in, long long in_base, float* d_z
               long long b0, long long nb, long long lo, long long hi, float2* d_out_delayed,
               long long out_end, cudaStream_t st) {
     float2* gm = (d_z == sd->d_zoff.p && sd->gm_blocks > 0) ? sd->d_gm.p : nullptr;   // offline metric only
-    CU(launch_correlate(d_in, in_base, d_z, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, b0, nb,
+    CU(launch_correlate(d_in, in_base, d_z, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->fft_arg, b0, nb,
                         sd->d_tw.p, d_out_delayed, 0, 0, out_end, (int)sd->delay, sd->num_sms, st, 0, 0, 0, gm,
                         sd->gm_b0, 0));
     if (hi > lo) {
@@ -230,7 +232,7 @@ int records_enqueue(b200sync_sd* sd, const float2* d_in, long long in_base, cons
         CU(cudaMallocHost(&sd->h_recs_pin, sizeof(DetectionRecord) * (nmax + 64)));
         sd->h_recs_pin_cap = nmax + 64;
     }
-    CU(launch_refine(d_in, in_base, d_z, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->min_bin, sd->d_tw.p,
+    CU(launch_refine(d_in, in_base, d_z, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->fft_arg, sd->min_bin, sd->d_tw.p,
                      sd->d_det_idx.p, &sd->d_state.p->det_count, (unsigned)std::max<size_t>(nmax, 1), sd->d_recs.p,
                      sd->num_sms, st));
     CU(cudaMemcpyAsync(sd->h_state, sd->d_state.p, sizeof(PeakState), cudaMemcpyDeviceToHost, st));
@@ -253,7 +255,7 @@ int records_finish(b200sync_sd* sd, size_t nmax, cudaStream_t st, const Detectio
 // synchronises once to learn the count and once for the records.
 int collect_records(b200sync_sd* sd, const float2* d_in, long long in_base, const float* d_z,
                     long long z_base, cudaStream_t st, std::vector<DetectionRecord>& out) {
-    CU(launch_refine(d_in, in_base, d_z, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->min_bin,
+    CU(launch_refine(d_in, in_base, d_z, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->fft_arg, sd->min_bin,
                      sd->d_tw.p, sd->d_det_idx.p, &sd->d_state.p->det_count, (unsigned)sd->d_det_idx.cap,
                      sd->d_recs.p, sd->num_sms, st));
     CU(cudaMemcpyAsync(sd->h_state, sd->d_state.p, sizeof(PeakState), cudaMemcpyDeviceToHost, st));
@@ -317,8 +319,15 @@ int do_start(b200sync_sd* sd) {
         if (s >= sd->constellation.size()) return fail(B200SYNC_EINVAL, "syncword symbol outside constellation");
     sd->L = static_cast<uint32_t>((sd->syncword.size() - 1) * sd->sps + sd->rrc_taps.size());
     if (sd->L > sd->fft_size) return fail(B200SYNC_EINVAL, "fft_size too small");
-    if (sd->fft_size != (uint32_t)kFft)
-        return fail(B200SYNC_EUNSUPPORTED, "only fft_size = 2048 is implemented on the GPU path");
+    if ((sd->fft_size & (sd->fft_size - 1)) != 0)
+        return fail(B200SYNC_EINVAL, "FFT size must be 2^N");   // ALG/fourier/fftw.hpp:182-184
+    {
+        const char* fg = getenv("B200SYNC_FORCE_GENERIC");     // tests / A-B runs: fft_size 2048 on the generic path too
+        sd->generic = sd->fft_size != (uint32_t)kFft || (fg && fg[0] == '1');
+        sd->fft_arg = (int)sd->fft_size | (sd->generic && sd->fft_size == (uint32_t)kFft ? kGenericFlag : 0);
+    }
+    if (sd->generic && !generic_fft_supported(sd->fft_size))
+        return fail(B200SYNC_EUNSUPPORTED, "fft_size outside [64, 8192] is not implemented on the GPU path");
     sd->K = static_cast<uint32_t>(sd->max_bin - sd->min_bin + 1);
     if (sd->K > (uint32_t)kMaxHyp) return fail(B200SYNC_EUNSUPPORTED, "too many frequency hypotheses (max 129)");
     if (sd->time_threshold > (uint64_t)kMaxTimeThresholdSeq)
@@ -339,11 +348,12 @@ int do_start(b200sync_sd* sd) {
     sd->self_corr = 0.0f;
     for (auto x : sw) sd->self_corr += x.real() * x.real() + x.imag() * x.imag();
 
-    std::vector<c64> td(static_cast<size_t>(sd->K) * kFft, c64(0.0f, 0.0f));
+    const size_t F = sd->fft_size;
+    std::vector<c64> td(static_cast<size_t>(sd->K) * F, c64(0.0f, 0.0f));
     for (int bin = sd->min_bin; bin <= sd->max_bin; ++bin) {
         double phase = 0.0;
         const double incr = static_cast<double>(bin) * std::numbers::pi / static_cast<double>(sd->L);
-        c64* dst = td.data() + static_cast<size_t>(bin - sd->min_bin) * kFft;
+        c64* dst = td.data() + static_cast<size_t>(bin - sd->min_bin) * F;
         for (uint32_t n = 0; n < sd->L; ++n) {
             const float er = static_cast<float>(std::cos(phase)), ei = static_cast<float>(std::sin(phase));
             const c64 x = sw[n];
@@ -365,6 +375,17 @@ int do_start(b200sync_sd* sd) {
         for (int f1 = 0; f1 < 16; ++f1) tw[m2 * 16 + f1] = wt[8 * f1 * m2];
     for (int m3 = 0; m3 < 8; ++m3)
         for (int p = 0; p < 256; ++p) tw[256 + m3 * 256 + p] = wt[p * m3];
+    if (sd->generic) {
+        // correlator_generic.cu: per-stage radix-2 factors, stage of length s at offset s/2 - 1:
+        // (float cos a, float sin a), a = -2 pi j / s in double (the oracle's independent arithmetic)
+        tw.assign(F, make_float2(0.0f, 0.0f));
+        size_t o = 0;
+        for (size_t s = 2; s <= F; s *= 2)
+            for (size_t j = 0; j < s / 2; ++j) {
+                const double a = -2.0 * std::numbers::pi * static_cast<double>(j) / static_cast<double>(s);
+                tw[o++] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(std::sin(a)));
+            }
+    }
     CU(cudaSetDevice(sd->device));
     cudaDeviceProp prop{};
     CU(cudaGetDeviceProperties(&prop, sd->device));
@@ -375,13 +396,13 @@ int do_start(b200sync_sd* sd) {
     for (auto& e : sd->ev)
         if (!e) CU(cudaEventCreate(&e));
     if (!sd->h_state) CU(cudaMallocHost(&sd->h_state, sizeof(PeakState)));
-    CU(sd->d_tw.ensure(kTwTotalHost));
-    CU(sd->d_hperm.ensure(static_cast<size_t>(sd->K) * kFft));
+    CU(sd->d_tw.ensure(tw.size()));
+    CU(sd->d_hperm.ensure(static_cast<size_t>(sd->K) * F));
     DevBuf<float2> d_td;
     CU(d_td.ensure(td.size()));
     CU(cudaMemcpyAsync(d_td.p, td.data(), td.size() * sizeof(float2), cudaMemcpyHostToDevice, sd->stream));
     CU(cudaMemcpyAsync(sd->d_tw.p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, sd->stream));
-    CU(launch_template_spectra(d_td.p, sd->d_hperm.p, (int)sd->K, sd->d_tw.p, sd->stream));
+    CU(launch_template_spectra(d_td.p, sd->d_hperm.p, (int)sd->K, sd->d_tw.p, sd->stream, sd->fft_arg));
     // streaming state (:191-201)
     if (int rc = reset_state(sd, sd->stream)) return rc;
     CU(cudaStreamSynchronize(sd->stream));
@@ -608,10 +629,10 @@ int b200sync_sd_process(b200sync_sd* sd, const float* in, size_t n_in, float* ou
         if (int rc = ensure_det(sd, static_cast<size_t>((kStreamStepBlocks * S + T + 2) / (T + 1) + 2))) return rc;
         const size_t nmax = static_cast<size_t>((hi - lo) / (T + 1) + 2);
         // (the fused walk keeps the detection list in shared memory: at most 1024 entries, i.e. not for tiny T)
-        const bool small = hi > lo && hi - lo <= kSmallRange && nmax <= 1024 && nmax + 1 <= sd->d_recs.cap;
+        const bool small = !sd->generic && hi > lo && hi - lo <= kSmallRange && nmax <= 1024 && nmax + 1 <= sd->d_recs.cap;
         if (small) {
             // streaming-sized step: correlator, flags, [walk + refine] — three launches, one D2H, one synchronisation
-            CU(launch_correlate(sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S,
+            CU(launch_correlate(sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->fft_arg,
                                 a0 / S, nb, sd->d_tw.p, nullptr, 0, 0, 0, (int)sd->delay, sd->num_sms, st));
             StreamWalk walk;
             CU(launch_peak_flags_stream(sd->d_z.p, sd->z_base, P, lo, hi, sd->T, sd->power_threshold, sd->d_ws.p,
@@ -619,7 +640,7 @@ int b200sync_sd_process(b200sync_sd* sd, const float* in, size_t n_in, float* ou
             walk.r_abs_in = sd->r_abs_host;
             walk.state_out = sd->d_state.p;
             walk.header = reinterpret_cast<PeakState*>(sd->d_recs.p);   // slot 0 of the record buffer
-            CU(launch_refine(sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S,
+            CU(launch_refine(sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->fft_arg,
                              sd->min_bin, sd->d_tw.p, sd->d_det_idx.p, &sd->d_state.p->det_count, (unsigned)nmax,
                              sd->d_recs.p + 1, sd->num_sms, st, 1, 0, 0, 0, &walk));
             if (sd->h_recs_pin_cap < nmax + 1) {
@@ -1041,7 +1062,7 @@ int b200sync_sd_detect_channels_device(b200sync_sd* sd, const void* d_in, size_t
         const int nch = static_cast<int>(std::min(per_group, n_channels - c0));
         const float2* x = base + c0 * channel_stride;
         PeakState* state = sd->d_chan_state.p + c0;
-        CU(launch_correlate(x, 0, sd->d_chan_z.p, 0, sd->d_hperm.p, (int)sd->K, (int)sd->S, 0, nb_total * nch,
+        CU(launch_correlate(x, 0, sd->d_chan_z.p, 0, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->fft_arg, 0, nb_total * nch,
                             sd->d_tw.p, nullptr, 0, 0, 0, (int)sd->delay, sd->num_sms, st, nb_total,
                             static_cast<long long>(channel_stride), static_cast<long long>(z_stride),
                             use_gm ? sd->d_chan_gm.p : nullptr, 0, static_cast<long long>(gm_stride)));
@@ -1053,7 +1074,7 @@ int b200sync_sd_detect_channels_device(b200sync_sd* sd, const void* d_in, size_t
             CU(launch_peak_phase2(0, hi_total, sd->T, sd->d_chan_ws.p, ws_stride, -1, state,
                                   sd->d_chan_det.p + c0 * cap, (unsigned)cap, sd->num_sms, st, nch, ws_stride, cap));
         }
-        CU(launch_refine(x, 0, sd->d_chan_z.p, 0, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->min_bin, sd->d_tw.p,
+        CU(launch_refine(x, 0, sd->d_chan_z.p, 0, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->fft_arg, sd->min_bin, sd->d_tw.p,
                          sd->d_chan_det.p + c0 * cap, &state->det_count, (unsigned)cap, sd->d_chan_recs.p + c0 * cap,
                          sd->num_sms, st, nch, static_cast<long long>(channel_stride), static_cast<long long>(z_stride),
                          static_cast<long long>(cap)));
@@ -1239,7 +1260,7 @@ static int shard_phase1_core(b200sync_sd* sd, const float2* d_in, const float2* 
         }
     }
     if (h_in == nullptr && f == nullptr) {
-        CU(launch_correlate(d_in, in_base, sd->d_zoff.p, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, cb0,
+        CU(launch_correlate(d_in, in_base, sd->d_zoff.p, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->fft_arg, cb0,
                             cb1 - cb0, sd->d_tw.p, d_out, out_base, out_lo, out_hi, (int)sd->delay, sd->num_sms, st, 0, 0,
                             0, gm, cb0, 0));
     } else {
@@ -1283,7 +1304,7 @@ static int shard_phase1_core(b200sync_sd* sd, const float2* d_in, const float2* 
             if (b_ready > b_next) {
                 CU(cudaStreamWaitEvent(st, sd->ev_pieces[i], 0));
                 for (long long b0 = b_next; b0 < b_ready; b0 += kOfflineChunkBlocks)
-                    CU(launch_correlate(d_in, in_base, sd->d_zoff.p, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, b0,
+                    CU(launch_correlate(d_in, in_base, sd->d_zoff.p, z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->fft_arg, b0,
                                         std::min(kOfflineChunkBlocks, b_ready - b0), sd->d_tw.p, d_out, out_base, out_lo,
                                         out_hi, (int)sd->delay, sd->num_sms, st, 0, 0, 0, gm, cb0, 0));
                 b_next = b_ready;

@@ -10,12 +10,14 @@
 
 namespace b200sync {
 
-constexpr int kFft = 2048;         // the only fft_size the kernels implement (reference default)
+constexpr int kFft = 2048;         // the fft_size correlator.cu is hand-scheduled for (reference default); every other
+                                   // power of two in [64, 8192] takes correlator_generic.cu
 constexpr int kGroupThreads = 128; // threads cooperating on one FFT block
 #ifndef B200_CORR_THREADS
 #define B200_CORR_THREADS 768
 #endif
 constexpr int kCorrThreads = B200_CORR_THREADS;  // 6 FFT groups per CTA, 1 persistent CTA per SM
+constexpr int kGenericFlag = 1 << 30;  // or-ed into the `fft` argument of the launchers: fft_size 2048 on the generic path
 constexpr int kMaxHyp = 129;       // max frequency hypotheses (min/max_freq_bin = -/+64)
 constexpr int kMaxTimeThreshold = 1023;  // parallel chain kernels keep one bitmap word per lane; the time-sharded and
                                          // batched-channel entry points need them
@@ -51,10 +53,12 @@ void count_launch(int n = 1);
 int set_last_error(int code, const std::string& msg);
 
 // correlator.cu
+// `fft`: fft_size of the context (| kGenericFlag, below); anything but plain 2048 dispatches to correlator_generic.cu,
+// where d_hperm holds natural-order conj spectra and d_tw the per-stage radix-2 factors (fft - 1 entries)
 cudaError_t launch_template_spectra(const float2* d_td, float2* d_hperm, int K, const float2* d_tw,
-                                    cudaStream_t st);
+                                    cudaStream_t st, int fft);
 cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpow, long long z_base,
-                             const float2* d_hperm, int K, int S, long long b0, long long nb,
+                             const float2* d_hperm, int K, int S, int fft, long long b0, long long nb,
                              const float2* d_tw, float2* d_out_delayed, long long out_base, long long out_lo,
                              long long out_hi, int delay, int num_sms, cudaStream_t st, long long nb_chan = 0,
                              long long in_chan_stride = 0, long long z_chan_stride = 0, float2* d_gm = nullptr,
@@ -77,7 +81,7 @@ inline bool gm_supported(int S, int T) { return S >= 64 && S <= 2016 && T >= 32 
 inline bool gm_supported(int, int) { return false; }
 #endif
 cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_zpow, long long z_base,
-                          const float2* d_hperm, int K, int S, int min_freq_bin, const float2* d_tw,
+                          const float2* d_hperm, int K, int S, int fft, int min_freq_bin, const float2* d_tw,
                           const unsigned long long* d_det_idx, const unsigned int* d_det_count,
                           unsigned int det_cap, DetectionRecord* d_recs, int num_sms, cudaStream_t st, int nch = 1,
                           long long in_chan_stride = 0, long long z_chan_stride = 0, long long det_chan_stride = 0,
@@ -86,6 +90,22 @@ cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_
 cudaError_t launch_peak_flags_stream(const float* d_zpow, long long z_base, long long z_end, long long lo, long long hi,
                                      int T, float power_threshold, void* d_ws, size_t ws_bytes, int num_sms,
                                      cudaStream_t st, StreamWalk* walk);
+
+// correlator_generic.cu: any power-of-two fft_size in [64, 8192], radix-2 arithmetic (= the oracle's independent FFT).
+// `fft` carries kGenericFlag when the context runs fft_size 2048 on the generic path (B200SYNC_FORCE_GENERIC, tests).
+bool generic_fft_supported(unsigned fft);
+cudaError_t launch_template_spectra_generic(int fft, const float2* d_td, float2* d_hc, int K, const float2* d_tw,
+                                            cudaStream_t st);
+cudaError_t launch_correlate_generic(int fft, const float2* d_in, long long in_base, float* d_zpow, long long z_base,
+                                     const float2* d_hc, int K, int S, long long b0, long long nb, const float2* d_tw,
+                                     float2* d_out_delayed, long long out_base, long long out_lo, long long out_hi,
+                                     int delay, int num_sms, cudaStream_t st, long long nb_chan,
+                                     long long in_chan_stride, long long z_chan_stride);
+cudaError_t launch_refine_generic(int fft, const float2* d_in, long long in_base, const float* d_zpow, long long z_base,
+                                  const float2* d_hc, int K, int S, int min_freq_bin, const float2* d_tw,
+                                  const unsigned long long* d_det_idx, const unsigned int* d_det_count,
+                                  unsigned int det_cap, DetectionRecord* d_recs, int num_sms, cudaStream_t st, int nch,
+                                  long long in_chan_stride, long long z_chan_stride, long long det_chan_stride);
 
 // peaks.cu
 struct PeakWorkspace;  // opaque: bitmaps, tables, per-segment entry states

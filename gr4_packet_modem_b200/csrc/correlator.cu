@@ -525,7 +525,8 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
 // host launchers
 // ---------------------------------------------------------------------------------
 cudaError_t launch_template_spectra(const float2* d_td, float2* d_hperm, int K, const float2* d_tw,
-                                    cudaStream_t st) {
+                                    cudaStream_t st, int fft) {
+    if (fft != kFft) return launch_template_spectra_generic(fft & ~kGenericFlag, d_td, d_hperm, K, d_tw, st);
     const size_t smem = sizeof(float2) * (size_t)(kTwTotal + kXchgFloat2);
     cudaError_t e = cudaFuncSetAttribute(template_spectra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
@@ -540,12 +541,16 @@ size_t correlate_smem_bytes(int groups) {
 }
 
 cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpow, long long z_base,
-                             const float2* d_hperm, int K, int S, long long b0, long long nb,
+                             const float2* d_hperm, int K, int S, int fft, long long b0, long long nb,
                              const float2* d_tw, float2* d_out_delayed, long long out_base, long long out_lo,
                              long long out_hi, int delay, int num_sms, cudaStream_t st, long long nb_chan,
                              long long in_chan_stride, long long z_chan_stride, float2* d_gm, long long gm_b0,
                              long long gm_chan_stride) {
     if (nb <= 0) return cudaSuccess;
+    if (fft != kFft)   // another fft_size, or 2048 forced onto the generic path (kGenericFlag)
+        return launch_correlate_generic(fft & ~kGenericFlag, d_in, in_base, d_zpow, z_base, d_hperm, K, S, b0, nb, d_tw,
+                                        d_out_delayed, out_base, out_lo, out_hi, delay, num_sms, st, nb_chan,
+                                        in_chan_stride, z_chan_stride);
     // function attributes are per device: one flag per ordinal (a process may hold contexts on several GPUs)
     static bool attr_set[64] = {};
     const int max_groups = kCorrThreads / kGroupThreads;
@@ -594,11 +599,17 @@ cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpo
 }
 
 cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_zpow, long long z_base,
-                          const float2* d_hperm, int K, int S, int min_freq_bin, const float2* d_tw,
+                          const float2* d_hperm, int K, int S, int fft, int min_freq_bin, const float2* d_tw,
                           const unsigned long long* d_det_idx, const unsigned int* d_det_count,
                           unsigned int det_cap, DetectionRecord* d_recs, int num_sms, cudaStream_t st, int nch,
                           long long in_chan_stride, long long z_chan_stride, long long det_chan_stride,
                           const StreamWalk* walk) {
+    if (fft != kFft) {
+        if (walk != nullptr) return cudaErrorInvalidValue;   // the fused walk exists on the 2048 path only
+        return launch_refine_generic(fft & ~kGenericFlag, d_in, in_base, d_zpow, z_base, d_hperm, K, S, min_freq_bin, d_tw,
+                                     d_det_idx, d_det_count, det_cap, d_recs, num_sms, st, nch, in_chan_stride,
+                                     z_chan_stride, det_chan_stride);
+    }
     const size_t smem_base = sizeof(float2) * (size_t)(kTwTotal + kXchgFloat2 + kRefineChunk * (256 + 16) + kMaxHyp + 1) +
                              sizeof(float) * kFft;
     // the attribute (and the occupancy figure) is for the largest streaming walk: 2^19-sample bitmaps + the list

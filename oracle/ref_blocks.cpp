@@ -109,9 +109,11 @@ size_t refblk_sizeof_tag() { return sizeof(RefTag); }
 
 // ---- SyncwordDetection (PM/syncword_detection.hpp) ----
 void* refblk_sd_create(const float* rrc, size_t n_rrc, const uint8_t* sw, size_t n_sw, const float* constellation,
-                       size_t n_const, int min_bin, int max_bin, size_t time_threshold, float power_threshold)
+                       size_t n_const, int min_bin, int max_bin, size_t time_threshold, float power_threshold,
+                       size_t fft_size)
 {
     auto b = std::make_unique<pm::SyncwordDetection>();
+    if (fft_size != 0) b->fft_size = fft_size;   // PM/syncword_detection.hpp:133 (default 2048)
     b->rrc_taps.assign(rrc, rrc + n_rrc);
     b->syncword.assign(sw, sw + n_sw);
     b->constellation.clear();

@@ -39,7 +39,7 @@ def lib():
         L.refblk_sizeof_tag.restype = sz
         assert L.refblk_sizeof_tag() == C.sizeof(RefTag)
         L.refblk_sd_create.restype = vp
-        L.refblk_sd_create.argtypes = [vp, sz, vp, sz, vp, sz, C.c_int, C.c_int, sz, C.c_float]
+        L.refblk_sd_create.argtypes = [vp, sz, vp, sz, vp, sz, C.c_int, C.c_int, sz, C.c_float, sz]
         L.refblk_sd_destroy.argtypes = [vp]
         L.refblk_sd_process.argtypes = [vp, vp, sz, vp, psz, vp, sz, psz]
         L.refblk_rotator.argtypes = [C.c_float, vp, sz, vp]
@@ -101,12 +101,13 @@ class SyncwordDetection(_Handle):
     _destroy = "refblk_sd_destroy"
 
     def __init__(self, rrc_taps, syncword, constellation, min_freq_bin=0, max_freq_bin=0, time_threshold=768,
-                 power_threshold=9.5):
+                 power_threshold=9.5, fft_size=2048):
         rrc = np.ascontiguousarray(rrc_taps, np.float32)
         sw = np.ascontiguousarray(syncword, np.uint8)
         cst = _c64(constellation)
         self._h = lib().refblk_sd_create(rrc.ctypes.data, rrc.size, sw.ctypes.data, sw.size, cst.ctypes.data, cst.size,
-                                         min_freq_bin, max_freq_bin, time_threshold, power_threshold)
+                                         min_freq_bin, max_freq_bin, time_threshold, power_threshold, int(fft_size))
+        self.fft_size = int(fft_size)
         if not self._h:
             raise ValueError("reference SyncwordDetection::start() threw")
         self.published = 0
@@ -116,7 +117,7 @@ class SyncwordDetection(_Handle):
         x = _c64(x)
         outs, tags, pos = [], [], 0
         tb = (RefTag * 4096)()
-        while x.size - pos >= 2048:
+        while x.size - pos >= self.fft_size:
             seg = x[pos:pos + chunk]
             out = np.empty(seg.size, np.complex64)
             c, nt = C.c_size_t(0), C.c_size_t(0)

@@ -184,13 +184,14 @@ def test_settings_errors(rx_params):
 def test_settings_the_gpu_path_refuses(rx_params):
     """Settings the reference accepts and this build does not implement fail LOUDLY at start() with
     B200SYNC_EUNSUPPORTED — never a silent fallback (the reference: any power-of-two fft_size,
-    PM/syncword_detection.hpp:133 / ALG/fourier/fftw.hpp:182-184; any time_threshold, :140; any bin range)."""
+    PM/syncword_detection.hpp:133 / ALG/fourier/fftw.hpp:182-184 — here 64 ... 8192; any time_threshold, :140; any bin range)."""
     import torch
     from gr4_packet_modem_b200.blocks import B200SyncError
 
-    for fft_size in (1024, 4096):
-        with pytest.raises(B200SyncError, match="only fft_size = 2048"):
-            _gpu(rx_params, fft_size=fft_size)
+    with pytest.raises(B200SyncError, match="FFT size must be 2\\^N"):      # the reference throws too (fftw.hpp:182-184)
+        _gpu(rx_params, fft_size=3000)
+    with pytest.raises(B200SyncError, match="fft_size outside \\[64, 8192\\]"):
+        _gpu(rx_params, fft_size=16384)
     with pytest.raises(B200SyncError, match="too many frequency hypotheses"):
         _gpu(rx_params, min_freq_bin=-65, max_freq_bin=65)
     with pytest.raises(B200SyncError, match="time_threshold > 4095"):
@@ -487,3 +488,121 @@ def test_process_bulk_more_tags_than_the_buffer_holds(oracle, rx_params):
     assert c2 == c and len(tags2) > 7
     assert [t[1] for t in tags] == [t[1] for t in tags2]
     assert all(0 <= off < c for off, _, _ in tags)
+
+
+def _assert_bit_exact_vs_oracle(sd, recs, tags, o, oc, otags, bins):
+    zp, _ = o.metric(oc)
+    assert np.array_equal(sd.metric(oc).view(np.uint32), zp.view(np.uint32)), "metric not bit-exact"
+    assert (recs["index"] + sd.delay).tolist() == [t.index for t in otags]
+    for r, t, ot in zip(recs, tags, otags):
+        for a, b in [(r["corr_re"], ot.corr_re), (r["corr_im"], ot.corr_im), (r["pow"], ot.pow),
+                     (r["pow_prev"], ot.pow_prev), (r["pow_next"], ot.pow_next), (r["noise_power"], ot.noise_power)]:
+            assert np.float32(a).view(np.uint32) == np.float32(b).view(np.uint32)
+        assert r["freq_bin"] == ot.freq_bin
+        if -bins < r["freq_bin"] < bins:
+            assert np.float32(r["pow_left"]) == np.float32(ot.pow_left)
+            assert np.float32(r["pow_right"]) == np.float32(ot.pow_right)
+        assert t["syncword_freq"] == ot.freq
+        assert np.float32(t["syncword_amplitude"]) == np.float32(ot.amplitude)
+        assert np.float32(t["syncword_phase"]) == np.float32(ot.phase)
+        assert np.float32(t["syncword_time_est"]) == np.float32(ot.time_est)
+        assert np.float32(t["syncword_esn0_db"]) == np.float32(ot.esn0_db)
+
+
+@pytest.mark.parametrize("fft_size,esn0_db,bins,T", [(512, 20.0, 4, 768), (1024, 3.0, 2, 768), (4096, 20.0, 4, 768),
+                                                     (4096, 0.0, 8, 300), (8192, 6.0, 1, 768), (1024, 20.0, 0, 40)])
+def test_other_fft_sizes_bit_exact_vs_independent_oracle(oracle, rx_params, fft_size, esn0_db, bins, T):
+    """fft_size != 2048 (PM/syncword_detection.hpp:133; the reference takes any 2^N): correlator_generic.cu runs the
+    oracle's INDEPENDENT radix-2 arithmetic op for op, so metric, detections, records and estimates are bit for bit
+    those of the CPU restatement (and of the reference's block code over the same FFT) — offline and streaming."""
+    from gr4_packet_modem_b200.stimulus import packet_capture
+
+    n = (1 << 19) + 777
+    x, _ = packet_capture(n, seed=5, esn0_db=esn0_db, cfo=0.004, payload_bytes=150)
+    kw = dict(min_freq_bin=-bins, max_freq_bin=bins, fft_size=fft_size, time_threshold=T)
+    sd = _gpu(rx_params, **kw)
+    consumed, recs, tags = sd.detect_host(x)
+    o = oracle.SyncwordDetection(**rx_params, **kw, fft_kind=oracle.FFT_RADIX2, record_metric=True)
+    oc, oout, otags = o.run(x, chunk=1 << 19)
+    assert consumed == oc and len(recs) > 3
+    _assert_bit_exact_vs_oracle(sd, recs, tags, o, oc, otags, bins)
+    # streaming in ring-sized chunks, delayed output included
+    sd2 = _gpu(rx_params, **kw)
+    c2, out2, tags2 = sd2.run(x, chunk=65536, want_output=True)
+    o2 = oracle.SyncwordDetection(**rx_params, **kw, fft_kind=oracle.FFT_RADIX2)
+    oc2, oout2, otags2 = o2.run(x, chunk=65536, want_output=True)
+    assert c2 == oc2 and np.array_equal(out2.view(np.uint32), oout2[:oc2].view(np.uint32))
+    assert [i for _, i, _ in tags2] == [t.index for t in otags2]
+    for (_, _, m), ot in zip(tags2, otags2):
+        assert m["syncword_freq"] == ot.freq and m["syncword_freq_bin"] == ot.freq_bin
+        assert np.float32(m["syncword_phase"]) == np.float32(ot.phase)
+        assert np.float32(m["syncword_amplitude"]) == np.float32(ot.amplitude)
+
+
+def test_other_fft_size_device_output_shards_and_channels(oracle, rx_params):
+    """The remaining entry points with fft_size = 4096: delayed output written on the device, time shards composed
+    on the host, batched channels — all equal to the single offline run."""
+    import torch
+
+    from gr4_packet_modem_b200.sharding import entry_offsets, plan_shards
+    from gr4_packet_modem_b200.stimulus import packet_capture
+
+    F, T = 4096, 768
+    n = 1 << 20
+    x, _ = packet_capture(n, seed=11, esn0_db=8.0, cfo=-0.006, payload_bytes=100)
+    kw = dict(min_freq_bin=-3, max_freq_bin=3, fft_size=F)
+    sd = _gpu(rx_params, **kw)
+    S = sd.stride
+    assert S == F - 297 + 1
+    ref_c, ref_recs, _ = sd.detect_host(x)
+    assert len(ref_recs) > 20
+    # device spans with the delayed output
+    d = torch.from_numpy(x).cuda()
+    out = torch.full((n,), 7 + 7j, dtype=torch.complex64, device="cuda:0")
+    c, recs, _ = sd.detect_device(d.data_ptr(), n, torch.cuda.current_stream().cuda_stream, d_out_ptr=out.data_ptr())
+    torch.cuda.synchronize()
+    assert c == ref_c and np.array_equal(recs.view(np.uint8), ref_recs.view(np.uint8))
+    o = out.cpu().numpy()
+    delay = 2 * T + 1
+    assert np.array_equal(o[delay:c], x[:c - delay]) and np.all(o[c:] == 7 + 7j)
+    # time shards
+    shards = plan_shards(n, 3, F, S, T)
+    ctxs, tables, keep = [], [], []
+    for s in shards:
+        c_ = _gpu(rx_params, **kw)
+        seg = torch.from_numpy(x[s.first_sample:s.first_sample + s.n_samples].copy()).cuda()
+        tables.append(c_.shard_phase1(seg.data_ptr(), s.first_sample, s.n_samples, s.first_block, s.n_blocks,
+                                      s.total_blocks))
+        ctxs.append(c_)
+        keep.append(seg)
+    got = np.concatenate([c_.shard_phase2(j, n // (T + 1) + 2)[0] for c_, j in zip(ctxs, entry_offsets(tables))])
+    assert np.array_equal(got.view(np.uint8), ref_recs.view(np.uint8))
+    # batched channels
+    nch, nc = 3, 300000
+    buf = np.concatenate([x[i * 100000:i * 100000 + nc] for i in range(nch)])
+    db = torch.from_numpy(buf).cuda()
+    consumed, per = sd.detect_channels_device(db.data_ptr(), nch, nc, nc)
+    single = _gpu(rx_params, **kw)
+    for i in range(nch):
+        c1, r1, _ = single.detect_host(buf[i * nc:(i + 1) * nc])
+        assert c1 == consumed and np.array_equal(per[i].view(np.uint8), r1.view(np.uint8))
+
+
+def test_generic_path_at_2048_bit_exact_vs_independent_oracle(oracle, rx_params, monkeypatch):
+    """B200SYNC_FORCE_GENERIC=1 puts the default fft_size on the generic path: there the GPU is bit-identical to the
+    independent arithmetic, and its detections equal those of the hand-scheduled 2048 kernel on the same capture."""
+    from gr4_packet_modem_b200.stimulus import packet_capture
+
+    n = 1 << 20
+    x, _ = packet_capture(n, seed=3, esn0_db=0.0, cfo=0.005, payload_bytes=200)
+    kw = dict(min_freq_bin=-4, max_freq_bin=4)
+    c_t, recs_t, _ = _gpu(rx_params, **kw).detect_host(x)
+    monkeypatch.setenv("B200SYNC_FORCE_GENERIC", "1")
+    sd = _gpu(rx_params, **kw)
+    monkeypatch.delenv("B200SYNC_FORCE_GENERIC")
+    consumed, recs, tags = sd.detect_host(x)
+    o = oracle.SyncwordDetection(**rx_params, **kw, fft_kind=oracle.FFT_RADIX2, record_metric=True)
+    oc, _, otags = o.run(x, chunk=1 << 20)
+    assert consumed == oc == c_t
+    _assert_bit_exact_vs_oracle(sd, recs, tags, o, oc, otags, 4)
+    assert recs["index"].tolist() == recs_t["index"].tolist()

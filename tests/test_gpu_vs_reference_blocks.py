@@ -51,6 +51,26 @@ def test_detection_vs_reference_block(ref, rx_params, bins, esn0, thr, T, cfo):
     assert [t[1] for t in t2] == [t.index for t in rtags]
 
 
+@pytest.mark.parametrize("fft_size,bins", [(1024, 2), (4096, 4)])
+def test_other_fft_sizes_vs_reference_block_bit_for_bit(ref, rx_params, fft_size, bins):
+    """fft_size != 2048: the GPU runs the radix-2 arithmetic that stands in for FFTW under the reference's class here,
+    so every tag value and the delayed output equal the reference block's BIT FOR BIT (no tolerance)."""
+    from gr4_packet_modem_b200 import SyncwordDetection
+    from gr4_packet_modem_b200.stimulus import packet_capture
+
+    x, _ = packet_capture(1 << 19, seed=77, esn0_db=3.0, cfo=0.007, payload_bytes=100)
+    kw = dict(min_freq_bin=-bins, max_freq_bin=bins, time_threshold=768, power_threshold=8.0, fft_size=fft_size)
+    rc, rout, rtags = ref.SyncwordDetection(**rx_params, **kw).run(x, chunk=65536)
+    pos, out, tags = SyncwordDetection(**rx_params, **kw).run(x, chunk=65536, want_output=True)
+    assert pos == rc and len(rtags) >= 20
+    assert np.array_equal(out.view(np.uint32), rout.view(np.uint32))
+    assert [t[1] for t in tags] == [t.index for t in rtags]
+    for (_, _, m), t in zip(tags, rtags):
+        assert m["syncword_freq"] == t.freq and m["syncword_freq_bin"] == t.freq_bin
+        for k in ("amplitude", "phase", "noise_power", "esn0_db", "time_est"):
+            assert np.float32(m["syncword_" + k]).tobytes() == np.float32(getattr(t, k)).tobytes(), k
+
+
 def test_filters_vs_reference_blocks(ref, rx_params):
     from gr4_packet_modem_b200 import (CoarseFrequencyCorrection, CostasLoop, FrontEnd, PfbArbResampler, SymbolFilter,
                                        SyncwordWipeoff)

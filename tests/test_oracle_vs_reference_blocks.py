@@ -55,6 +55,25 @@ def test_syncword_detection_is_the_reference(oracle, ref, rx_params, bins, esn0,
     assert [t.index for t in rtags2] == [t.index for t in rtags if t.index < rc2]
 
 
+@pytest.mark.parametrize("fft_size", [512, 1024, 4096])
+def test_syncword_detection_other_fft_sizes_is_the_reference(oracle, ref, rx_params, fft_size):
+    """fft_size is a setting of the block (PM/syncword_detection.hpp:133): the restatement follows the reference's class
+    bit for bit at other sizes too."""
+    from gr4_packet_modem_b200.stimulus import packet_capture
+
+    x, _ = packet_capture(1 << 17, seed=21, esn0_db=8.0, cfo=0.006, payload_bytes=60)
+    kw = dict(min_freq_bin=-2, max_freq_bin=2, time_threshold=300, power_threshold=8.0, fft_size=fft_size)
+    rc, rout, rtags = ref.SyncwordDetection(**rx_params, **kw).run(x, chunk=30000)
+    oc, oout, otags = oracle.SyncwordDetection(**rx_params, **kw, fft_kind=oracle.FFT_RADIX2).run(x, chunk=30000,
+                                                                                                 want_output=True)
+    assert rc == oc and np.array_equal(_bits(rout), _bits(oout))
+    assert [t.index for t in rtags] == [t.index for t in otags] and len(rtags) >= 10
+    for a, b in zip(rtags, otags):
+        assert a.freq == b.freq and a.freq_bin == b.freq_bin
+        for k in ("amplitude", "phase", "noise_power", "esn0_db", "time_est"):
+            assert np.float32(getattr(a, k)).tobytes() == np.float32(getattr(b, k)).tobytes(), k
+
+
 def test_reference_settings_errors(ref, rx_params):
     """start() throws for min_freq_bin > max_freq_bin and for a syncword longer than the FFT (:145-152)."""
     with pytest.raises(ValueError):
