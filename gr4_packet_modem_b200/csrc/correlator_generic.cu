@@ -13,7 +13,7 @@
 // (ALG/fourier/fft.hpp:70-101) and, bit for bit, the INDEPENDENT arithmetic the tests hold the 2048 kernel to for
 // indices (oracle FftKind::Radix2, also the FFT under the reference's block code in oracle/_ref/librefblocks.so): on
 // this path the metric, the detections and the records are bit-identical to that arithmetic, not merely index-exact.
-// The butterflies run in Stockham (autosort) order — the same butterfly graph on the same operands as the
+// The butterflies run in Stockham (autosort) order, two stages per pass — the same butterfly graph on the same operands as the
 // bit-reversal form, so the same roundings — which keeps every shared-memory access unit-stride or a two-way split:
 //   stage s (sub-transform length m = 2^s, R = N / 2m), butterfly i = r + R k (r < R, k < m):
 //       u = src[i + R k], v = src[i + R k + R], w = tw[m - 1 + k]  ->  dst[i] = u + w v, dst[i + N/2] = u - w v.
@@ -40,21 +40,59 @@ __device__ __forceinline__ float2 cmul_plain(float2 a, float2 b) {
 __device__ __forceinline__ float norm2_plain(float2 z) { return __fadd_rn(__fmul_rn(z.x, z.x), __fmul_rn(z.y, z.y)); }
 
 // in: natural order in `src`, complete and visible (a barrier behind the last write).  Returns the buffer that holds
-// the natural-order transform (src when LOGN is even); a barrier has been passed after its last write.
+// the natural-order transform; a barrier has been passed after its last write.
+// Two radix-2 stages per pass (the four butterflies of a radix-4 step, each with the radix-2 arithmetic above — the
+// intermediate values never leave the registers), one plain radix-2 pass last when LOGN is odd: half the
+// shared-memory traffic and barriers of stage-by-stage passes, the same roundings.
+//   pass over stages s, s+1 (m = 2^s, R' = N / 4m), unit q = r' + R' k (r' < R', k < m), base = q + 3 R' k:
+//     x_j = src[base + j R'];  stage s: a = x0 +- w x2, b = x1 +- w x3, w = tw[m-1+k];
+//     stage s+1: y0, y2 = a0 +- w1 b0, w1 = tw[2m-1+k];  y1, y3 = a1 +- w2 b1, w2 = tw[2m-1+k+m];  dst[q + j N/4] = y_j
 template <int LOGN>
 __device__ __forceinline__ float2* fft_r2(float2* src, float2* dst, const float2* __restrict__ tw_s, int tid) {
     using G = Gen<LOGN>;
+    auto bfly = [](float2 u, float2 v, float2 w, float2& p, float2& q) {
+        const float2 t = cmul_plain(w, v);
+        p = make_float2(__fadd_rn(u.x, t.x), __fadd_rn(u.y, t.y));
+        q = make_float2(__fsub_rn(u.x, t.x), __fsub_rn(u.y, t.y));
+    };
+    int s = 0;
 #pragma unroll 1
-    for (int s = 0; s < LOGN; ++s) {
-        const int m = 1 << s, lr = LOGN - 1 - s, R = 1 << lr;
+    for (; s + 1 < LOGN; s += 2) {
+        const int m = 1 << s, lr = LOGN - 2 - s, Rp = 1 << lr;
+        constexpr int UPT = G::N / 4 / G::NT > 0 ? G::N / 4 / G::NT : 1;   // units per thread
+#pragma unroll
+        for (int i = 0; i < UPT; ++i) {
+            const int q = tid + i * G::NT;
+            if (G::N / 4 >= G::NT || q < G::N / 4) {
+                const int k = q >> lr;
+                const float2* x = src + q + 3 * Rp * k;
+                const float2 x0 = x[0], x1 = x[Rp], x2 = x[2 * Rp], x3 = x[3 * Rp];
+                const float2 w = tw_s[m - 1 + k], w1 = tw_s[2 * m - 1 + k], w2 = tw_s[3 * m - 1 + k];
+                float2 a0, a1, b0, b1, y0, y1, y2, y3;
+                bfly(x0, x2, w, a0, a1);
+                bfly(x1, x3, w, b0, b1);
+                bfly(a0, b0, w1, y0, y2);
+                bfly(a1, b1, w2, y1, y3);
+                dst[q] = y0;
+                dst[q + G::N / 4] = y1;
+                dst[q + G::N / 2] = y2;
+                dst[q + 3 * G::N / 4] = y3;
+            }
+        }
+        __syncthreads();
+        float2* t = src;
+        src = dst;
+        dst = t;
+    }
+    if (s < LOGN) {   // LOGN odd: the last stage on its own, m = N/2, R = 1
+        constexpr int m = G::N / 2;
 #pragma unroll
         for (int i = 0; i < G::BPT; ++i) {
-            const int bf = tid + i * G::NT;
-            const int k = bf >> lr;
-            const float2 u = src[bf + R * k], v = src[bf + R * k + R];
-            const float2 t = cmul_plain(tw_s[m - 1 + k], v);
-            dst[bf] = make_float2(__fadd_rn(u.x, t.x), __fadd_rn(u.y, t.y));
-            dst[bf + G::N / 2] = make_float2(__fsub_rn(u.x, t.x), __fsub_rn(u.y, t.y));
+            const int bf = tid + i * G::NT;   // = k
+            float2 p, q;
+            bfly(src[2 * bf], src[2 * bf + 1], tw_s[m - 1 + bf], p, q);
+            dst[bf] = p;
+            dst[bf + G::N / 2] = q;
         }
         __syncthreads();
         float2* t = src;
