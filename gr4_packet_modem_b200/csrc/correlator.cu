@@ -136,6 +136,21 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
                 tmem_st8(tm_base + kTmH + 32 * k + 16 * pi, r);
             }
         }
+        if (K <= kTmHypA && g == (ngr > 1 ? ngr - 2 : 0)) {
+            // few hypotheses: FFT A's inter-pass factors take the two free template slots (fft_a_tm)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int k1 = 1 + 8 * hf + e;
+                    r[e] = k1 < 16 ? tw_s[kTwS + k1 * 16 + (tid >> 3)] : make_float2(0.f, 0.f);
+                }
+                tmem_st8(tm_base + kTmA1 + 16 * hf, r);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) r[e] = tw_s[kTwL + (tid >> 4) * 256 + (tid & 15) + 16 * (8 * hf + e)];
+                tmem_st8(tm_base + kTmA2 + 16 * hf, r);
+            }
+        }
         if (g == ngr - 1) {  // inter-pass factors of FFT B, the entries fft_b reads from shared memory
 #pragma unroll
             for (int pi = 0; pi < 2; ++pi) {
@@ -186,8 +201,33 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
         const long long s0 = (b0 + bb) * (long long)S;  // absolute first sample of the block
         const float2* src = in + ch * in_chan_stride + (s0 - in_base);
         float2 v[16], xs[16];
+        // The first and last L - 1 samples of a block are also the neighbouring blocks' (overlap-save): those rows are
+        // loaded with the default policy so that the second reader — another group of this CTA, microseconds
+        // later — finds them in L2; the rows in between are read once and stream through (evict-first).
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) v[n1] = __ldcs(src + 128 * n1 + tid);
+        for (int n1 = 0; n1 < 16; ++n1) {
+#ifdef B200_NO_OVERLAP_L2
+            v[n1] = __ldcs(src + 128 * n1 + tid);
+#else
+            // (rows 0-2 and 13-15 cover the overlap of the default syncword, L = 297; a pure cache hint for any other)
+            constexpr bool kSharedRow[16] = {1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1};
+            v[n1] = kSharedRow[n1] ? __ldg(src + 128 * n1 + tid) : __ldcs(src + 128 * n1 + tid);
+#endif
+        }
+#ifdef B200_L2_PREFETCH   // measured SLOWER (K = 1: 4.82 vs 4.47 ms at 2^30; K = 9: 18.8 vs 18.3): register pressure, off by default
+        if (!split && (tid & 15) == 0 && blk + blk_step < nb) {
+            // this group's NEXT block on its way into L2 while the current one is transformed (one request per
+            // 128-byte line): with few hypotheses a block lasts about one DRAM latency
+            long long bbn = blk + blk_step, chn = 0;
+            if constexpr (BATCH) {
+                chn = bbn / nb_chan;
+                bbn -= chn * nb_chan;
+            }
+            const float2* nsrc = in + chn * in_chan_stride + ((b0 + bbn) * (long long)S - in_base) + tid;
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + 128 * n1));
+        }
+#endif
         if (out_delayed != nullptr && (!split || g == 0)) {
             // block contract: out[n] = in[n - delay] (PM/syncword_detection.hpp:318-319).  Only output items
             // [out_lo, out_hi) are stored: out_hi = the number of items the call publishes (:346) — nothing is
@@ -197,11 +237,12 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
             for (int n1 = 0; n1 < 16; ++n1) {
                 const int i = 128 * n1 + tid;
                 const long long o = s0 + i + delay;
-                if (i < S && o >= out_lo && o < out_hi) out_delayed[o - out_base] = v[n1];
+                if (i < S && o >= out_lo && o < out_hi) __stcs(out_delayed + (o - out_base), v[n1]);   // written once, read by a later stage
             }
         }
         if constexpr (kCorrTwoBuf) group_sync(bar_id);  // previous block's last reads of xb2 are done
-        fft_a<kCorrTwoBuf>(v, xs, tw_s, xb, tid, bar_id, xb2);
+        if (kCorrTmem && !kCorrTwoBuf && K <= kTmHypA) fft_a_tm(v, xs, xb, tid, bar_id, tm_base);   // uniform over the launch
+        else fft_a<kCorrTwoBuf>(v, xs, tw_s, xb, tid, bar_id, xb2);
 
         float best[16];
 #pragma unroll
@@ -275,7 +316,7 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
             for (int m1 = 0; m1 < 16; ++m1) {
                 const int m = 128 * m1 + tid;
                 const int kk = (kFft - m) & (kFft - 1);
-                if (kk < S) zdst[kk] = best[m1];
+                if (kk < S) __stcs(zdst + kk, best[m1]);
             }
 #ifdef B200_GM_FLAGS   // measured dead end, see gm_supported() in b200sync_internal.h
             if (gm != nullptr) {

@@ -213,6 +213,61 @@ __device__ __forceinline__ void fft_a(float2 (&v)[16], float2 (&xs)[16], const f
     group_sync(bar_id);  // exchange buffer free again
 }
 
+// ---- FFT A with its inter-pass factors in TMEM (correlate_kernel, K <= kTmHypA) ---------------------------
+// Same passes, same table entries, same multiplies as fft_a (bit-identical): the 15 + 16 factors of a thread come
+// from its TMEM lane (columns kTmA1 / kTmA2 of the layout below) instead of shared memory.
+__device__ __forceinline__ void fft_a_tm(float2 (&v)[16], float2 (&xs)[16], float2* __restrict__ xb, int tid,
+                                         int bar_id, uint32_t tm_tw) {
+    constexpr int TmA1 = 256, TmA2 = 288;   // == kTmA1, kTmA2 (declared with the layout further down)
+    float2 t[8];
+    // pass A1
+    tmem_ld8(tm_tw + TmA1, t);
+    dft16(v);
+    tmem_wait_ld();
+    tmem_use(t);
+#pragma unroll
+    for (int k1 = 0; k1 < 9; ++k1) {
+        float2 val = v[bitrev4(k1)];
+        if (k1 != 0) val = cmul(val, t[k1 > 0 ? k1 - 1 : 0]);
+        xb[k1 * kXchgStrideA + tid] = val;
+    }
+    tmem_ld8(tm_tw + TmA1 + 16, t);
+    tmem_wait_ld();
+    tmem_use(t);
+#pragma unroll
+    for (int k1 = 9; k1 < 16; ++k1) xb[k1 * kXchgStrideA + tid] = cmul(v[bitrev4(k1)], t[k1 - 9]);
+    group_sync(bar_id);
+    // pass A2
+    const int n3 = tid >> 4, k1 = tid & 15;
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = xb[k1 * kXchgStrideA + n2 * 8 + n3];
+    tmem_ld8(tm_tw + TmA2, t);
+    group_sync(bar_id);
+    dft16(v);
+    tmem_wait_ld();
+    tmem_use(t);
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) xb[(k1 + 16 * k2) * kXchgStrideP + n3] = cmul(v[bitrev4(k2)], t[k2]);
+    tmem_ld8(tm_tw + TmA2 + 16, t);
+    tmem_wait_ld();
+    tmem_use(t);
+#pragma unroll
+    for (int k2 = 8; k2 < 16; ++k2) xb[(k1 + 16 * k2) * kXchgStrideP + n3] = cmul(v[bitrev4(k2)], t[k2 - 8]);
+    group_sync(bar_id);
+    // pass A3
+#pragma unroll
+    for (int pi = 0; pi < 2; ++pi) {
+        float2 w[8];
+        const int p = tid + 128 * pi;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) w[d] = xb[p * kXchgStrideP + d];
+        dft8(w);
+#pragma unroll
+        for (int k3 = 0; k3 < 8; ++k3) xs[pi * 8 + k3] = w[bitrev3(k3)];
+    }
+    group_sync(bar_id);  // exchange buffer free again
+}
+
 // ---- FFT B: y[pi*8 + f3] = Y[(tid + 128 pi) + 256 f3] -> c[m1] = C[128 m1 + tid] ------
 // y is destroyed.  The exchange buffer must be free on entry and is free on return.
 //
@@ -288,6 +343,13 @@ __device__ __forceinline__ void fft_b(float2 (&y)[16], float2 (&c)[16], const fl
 //   [ 64, 320)  conj template spectra of the first kTmHyp = 8 hypotheses, 32 columns each (layout of hperm)
 //   [320, 512)  block spectrum of each of the 6 FFT groups, 32 columns per group
 constexpr int kTmT1 = 0, kTmT2 = 32, kTmH = 64, kTmHyp = 8, kTmXs = 320, kTmCols = 512;
+// With K <= kTmHypA hypotheses the last two template slots are free and hold FFT A's inter-pass factors instead
+// (fft_a_tm): then the forward transform, too, keeps only its two exchanges on the LSU pipe.  It is half of the
+// work at K = 1, the one HBM-relevant configuration.
+//   [256, 288)  pass-A1 factors: entry k1-1 = Wt[8 (tid >> 3) k1], k1 = 1..15
+//   [288, 320)  pass-A2 factors: entry k2 = Wt[(tid >> 4) ((tid & 15) + 16 k2)], k2 = 0..15
+constexpr int kTmHypA = 6, kTmA1 = 256, kTmA2 = 288;
+static_assert(kTmH + 32 * kTmHypA <= kTmA1 && kTmA2 + 32 <= kTmXs, "FFT A's factors live in the last two template slots");
 
 // load_h(pi, h): fills h[0..8) with the conj template points of half pi (a tcgen05.ld or eight global loads)
 template <class LoadH>
