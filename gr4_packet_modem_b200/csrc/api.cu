@@ -329,7 +329,7 @@ int do_start(b200sync_sd* sd) {
     if (sd->generic && !generic_fft_supported(sd->fft_size))
         return fail(B200SYNC_EUNSUPPORTED, "fft_size outside [64, 8192] is not implemented on the GPU path");
     sd->K = static_cast<uint32_t>(sd->max_bin - sd->min_bin + 1);
-    if (sd->K > (uint32_t)kMaxHyp) return fail(B200SYNC_EUNSUPPORTED, "too many frequency hypotheses (max 129)");
+    if (sd->K > (uint32_t)kMaxHyp) return fail(B200SYNC_EUNSUPPORTED, "too many frequency hypotheses (max 601)");
     if (sd->time_threshold > (uint64_t)kMaxTimeThresholdSeq)
         return fail(B200SYNC_EUNSUPPORTED, "time_threshold > 4095 is not implemented on the GPU path");
     if (!(sd->power_threshold > 0.0f)) return fail(B200SYNC_EINVAL, "power_threshold must be positive");

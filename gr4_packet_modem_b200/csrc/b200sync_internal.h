@@ -18,7 +18,8 @@ constexpr int kGroupThreads = 128; // threads cooperating on one FFT block
 #endif
 constexpr int kCorrThreads = B200_CORR_THREADS;  // 6 FFT groups per CTA, 1 persistent CTA per SM
 constexpr int kGenericFlag = 1 << 30;  // or-ed into the `fft` argument of the launchers: fft_size 2048 on the generic path
-constexpr int kMaxHyp = 129;       // max frequency hypotheses (min/max_freq_bin = -/+64)
+constexpr int kMaxHyp = 601;       // max frequency hypotheses: min/max_freq_bin = -/+300 spans the whole band for the default
+                                   // syncword (bin spacing pi / 297 rad/sample); sizes a shared-memory array of refine_kernel
 constexpr int kMaxTimeThreshold = 1023;  // parallel chain kernels keep one bitmap word per lane; the time-sharded and
                                          // batched-channel entry points need them
 constexpr int kMaxTimeThresholdSeq = 4095;  // beyond 1023 the peak walk runs in order (one warp): any capture, slower

@@ -193,7 +193,7 @@ def test_settings_the_gpu_path_refuses(rx_params):
     with pytest.raises(B200SyncError, match="fft_size outside \\[64, 8192\\]"):
         _gpu(rx_params, fft_size=16384)
     with pytest.raises(B200SyncError, match="too many frequency hypotheses"):
-        _gpu(rx_params, min_freq_bin=-65, max_freq_bin=65)
+        _gpu(rx_params, min_freq_bin=-301, max_freq_bin=301)
     with pytest.raises(B200SyncError, match="time_threshold > 4095"):
         _gpu(rx_params, time_threshold=4096)
     # time_threshold in (1023, 4095] works for one stream, but not for the entry points built on the chain tables
@@ -606,3 +606,19 @@ def test_generic_path_at_2048_bit_exact_vs_independent_oracle(oracle, rx_params,
     assert consumed == oc == c_t
     _assert_bit_exact_vs_oracle(sd, recs, tags, o, oc, otags, 4)
     assert recs["index"].tolist() == recs_t["index"].tolist()
+
+
+def test_many_hypotheses_bit_exact_vs_mirror_oracle(oracle, rx_params):
+    """K = 257 (min/max_freq_bin = -/+128, beyond round 1's limit of 129 hypotheses; the reference takes any range):
+    metric, detections and records bit for bit, winners far from bin 0 included (CFO 1.2 rad/sample = bin 113)."""
+    from gr4_packet_modem_b200.stimulus import packet_capture
+
+    n = 1 << 18
+    x, _ = packet_capture(n, seed=8, esn0_db=10.0, cfo=1.2, payload_bytes=60)
+    kw = dict(min_freq_bin=-128, max_freq_bin=128)
+    sd = _gpu(rx_params, **kw)
+    consumed, recs, tags = sd.detect_host(x)
+    o = oracle.SyncwordDetection(**rx_params, **kw, fft_kind=oracle.FFT_MIRROR, record_metric=True)
+    oc, _, otags = o.run(x, chunk=1 << 18)
+    assert consumed == oc and len(recs) > 10 and abs(int(np.median(recs["freq_bin"])) - 113) <= 1
+    _assert_bit_exact_vs_oracle(sd, recs, tags, o, oc, otags, 128)
