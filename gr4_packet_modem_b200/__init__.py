@@ -7,4 +7,5 @@ built library raises.
 """
 from .firdes import root_raised_cosine  # noqa: F401
 from .blocks import (SyncwordDetection, SyncwordDetectionMulti, DetectionRecord, SyncwordTag, FrontEnd, PfbArbResampler,  # noqa: F401
-                     Rotator, SymbolFilter, SyncwordDetectionFilter, CoarseFrequencyCorrection, SyncwordWipeoff, CostasLoop)
+                     Rotator, SymbolFilter, SyncwordDetectionFilter, CoarseFrequencyCorrection, SyncwordWipeoff, CostasLoop,
+                     host_register, host_unregister)

@@ -34,6 +34,15 @@ assert RECORD_DTYPE.itemsize == C.sizeof(DetectionRecord) and TAG_DTYPE.itemsize
 _RAW = np.dtype((np.void, RECORD_DTYPE.itemsize))
 
 
+def host_register(buf: np.ndarray) -> None:
+    """Page-lock a long-lived host buffer (b200sync_host_register): spans inside it go straight to the copy engine."""
+    check(_native.lib().b200sync_host_register(buf.ctypes.data, buf.nbytes))
+
+
+def host_unregister(buf: np.ndarray) -> None:
+    check(_native.lib().b200sync_host_unregister(buf.ctypes.data))
+
+
 def _copy_records(buf: np.ndarray, n: int) -> np.ndarray:
     """Copy of the first n records as one memcpy (numpy copies structured arrays field by field)."""
     return buf.view(_RAW)[:n].copy().view(RECORD_DTYPE)

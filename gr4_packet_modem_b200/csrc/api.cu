@@ -15,6 +15,8 @@
 #include <cmath>
 #include <complex>
 #include <cstdio>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -101,8 +103,11 @@ struct b200sync_sd {
     unsigned long long r_abs_host = 0;  // host copy of the search position (PeakState::r_abs), streaming path
     // streaming fast path: pinned staging for pageable input spans, pinned landing buffer for the records
     unsigned char* h_in_stage = nullptr;
+    void* d_in_stage_view = nullptr;   // device-visible address of h_in_stage (zero-copy input of the streaming path)
     DetectionRecord* h_recs_pin = nullptr;
     size_t h_recs_pin_cap = 0;
+    DevBuf<unsigned int> d_done;       // CTA completion counter of the streaming refine launch (StreamWalk::done)
+    unsigned int stream_seq = 0;       // sequence number of the last streaming step (the completion flag's value)
     std::vector<c64> carry; // last `delay` input samples (delay line)
     std::deque<b200sync_sd_tag> pending;
     // offline: metric, and the correlator's group extrema of it for the peak stage (gm_* in b200sync_internal.h)
@@ -217,6 +222,41 @@ int stream_h2d(b200sync_sd* sd, float2* d_dst, const float2* h_src, size_t count
         std::memcpy(sd->h_in_stage + off, src + off, len);   // every call ends with a stream sync: the buffer is free
         CU(cudaMemcpyAsync(dst + off, sd->h_in_stage + off, len, cudaMemcpyHostToDevice, st));
     }
+    return 0;
+}
+
+// Zero-copy input of the streaming path (the correlator pulls the span out of mapped host memory itself instead of
+// waiting for an H2D copy): MEASURED SLOWER on B200 — 89 vs 84 us per 65536-item pinned span; SM-issued PCIe reads of
+// 512 KiB take longer than the copy engine's DMA plus its fixed latency — so it is off unless B200SYNC_ZERO_COPY=1.
+bool zero_copy_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* v = getenv("B200SYNC_ZERO_COPY");
+        on = (v && v[0] == '1') ? 1 : 0;
+    }
+    return on == 1;
+}
+
+// Device-visible address of a host span for the zero-copy correlator: pinned / registered-and-mapped memory as it is;
+// a pageable span of ordinary ring-chunk size through the context's pinned staging buffer.  *view stays null when
+// neither applies (the caller then takes the H2D copy).
+int stream_host_view(b200sync_sd* sd, const float2* h_src, size_t count, const float2** view) {
+    *view = nullptr;
+    const size_t bytes = count * sizeof(float2);
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, h_src) == cudaSuccess) {
+        if (at.type == cudaMemoryTypeHost && at.devicePointer != nullptr) {
+            *view = static_cast<const float2*>(at.devicePointer);
+            return 0;
+        }
+    } else {
+        cudaGetLastError();
+    }
+    if (bytes > kStageBytes) return 0;
+    if (!sd->h_in_stage) CU(cudaMallocHost(&sd->h_in_stage, kStageBytes));
+    if (!sd->d_in_stage_view) CU(cudaHostGetDevicePointer(&sd->d_in_stage_view, sd->h_in_stage, 0));
+    std::memcpy(sd->h_in_stage, h_src, bytes);   // the previous step has completed: the buffer is free
+    *view = static_cast<const float2*>(sd->d_in_stage_view);
     return 0;
 }
 
@@ -449,6 +489,17 @@ const char* b200sync_last_error(void) { return g_last_error.c_str(); }
 int b200sync_abi_version(void) { return 1; }
 uint64_t b200sync_launch_count(void) { return g_launches.load(); }
 
+int b200sync_host_register(const void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return fail(B200SYNC_EINVAL, "null buffer");
+    CU(cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return 0;
+}
+int b200sync_host_unregister(const void* ptr) {
+    if (!ptr) return fail(B200SYNC_EINVAL, "null buffer");
+    CU(cudaHostUnregister(const_cast<void*>(ptr)));
+    return 0;
+}
+
 int b200sync_sd_create(const b200sync_sd_config* cfg, b200sync_sd** out) {
     if (!cfg || !out) return fail(B200SYNC_EINVAL, "null argument");
     *out = nullptr;
@@ -540,6 +591,51 @@ int b200sync_sd_records_to_tags(const b200sync_sd* sd, const b200sync_detection_
     return 0;
 }
 
+// Development aid (B200SYNC_TRACE=1): where the host time of a streaming call goes; printed to stderr every 256 calls
+namespace {
+struct StreamTrace {
+    bool on = false, init = false, dev = false;   // dev (B200SYNC_TRACE=2): device-side stage times too (events between the launches)
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double dacc[4] = {0, 0, 0, 0};
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    long calls = 0;
+    static double now() {
+        return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    }
+    void lap(int i, double& t) {
+        if (!on) return;
+        const double n = now();
+        acc[i] += n - t;
+        t = n;
+    }
+    void end() {
+        if (!on || ++calls % 256) return;
+        std::fprintf(stderr, "[b200sync trace] per call, us: setup %.1f | h2d enqueue (+staging) %.1f | kernels + d2h enqueue %.1f | "
+                             "host delay line %.1f | wait %.1f | tags %.1f\n",
+                     acc[0] / 256, acc[1] / 256, acc[2] / 256, acc[3] / 256, acc[4] / 256, acc[5] / 256);
+        for (double& a : acc) a = 0;
+        if (dev) {
+            std::fprintf(stderr, "[b200sync trace] device, us: h2d %.1f | correlate %.1f | flags %.1f | walk+refine %.1f\n",
+                         dacc[0] / 256, dacc[1] / 256, dacc[2] / 256, dacc[3] / 256);
+            for (double& a : dacc) a = 0;
+        }
+    }
+    void mark(int i, cudaStream_t st) {
+        if (!dev) return;
+        if (!ev[i]) cudaEventCreate(&ev[i]);
+        cudaEventRecord(ev[i], st);
+    }
+    void collect() {
+        if (!dev) return;
+        for (int i = 0; i < 4; ++i) {
+            float ms = 0.f;
+            if (ev[i] && ev[i + 1] && cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) dacc[i] += 1e3 * ms;
+        }
+    }
+};
+thread_local StreamTrace g_trace;
+}  // namespace
+
 // delay line of the streaming block (:318-319): out[i] = stream[C + i - delay]; then remember the last `delay` items
 static void host_delay_line_stream(b200sync_sd* sd, const float* in, float* out, size_t j) {
     const size_t D = static_cast<size_t>(sd->delay);
@@ -565,6 +661,13 @@ int b200sync_sd_process(b200sync_sd* sd, const float* in, size_t n_in, float* ou
     *n_consumed = 0;
     *n_tags = 0;
     if (n_in < sd->fft_size) return 1;  // INSUFFICIENT_INPUT_ITEMS, consume(0)/publish(0) (:215-227)
+    if (!g_trace.init) {
+        const char* v = getenv("B200SYNC_TRACE");
+        g_trace.on = v && (v[0] == '1' || v[0] == '2');
+        g_trace.dev = v && v[0] == '2';
+        g_trace.init = true;
+    }
+    double tt = g_trace.on ? StreamTrace::now() : 0.0;
     CU(cudaSetDevice(sd->device));
     cudaStream_t st = sd->stream;
     const long long S = sd->S, F = sd->fft_size, T = sd->T;
@@ -599,8 +702,25 @@ int b200sync_sd_process(b200sync_sd* sd, const float* in, size_t n_in, float* ou
             if (int rc = slide_window(sd->d_x, sd->d_xtmp, sd->x_base, sd->x_end, keep_x, st)) return rc;
             if (sd->x_end < keep_x) sd->x_end = keep_x;
         }
-        if (int rc = stream_h2d(sd, sd->d_x.p + (a0 - sd->x_base), hin + (a0 - C), static_cast<size_t>(need_end - a0), st))
-            return rc;
+        g_trace.lap(0, tt);
+        g_trace.mark(0, st);
+        // Optional zero copy for a streaming-sized step (off by default, see zero_copy_enabled()): the correlator
+        // pulls the span out of (pinned, mapped) host memory itself and fills the device window on the way; a
+        // pageable span is first copied into the context's pinned staging buffer.
+        const float2* host_view = nullptr;
+        {
+            long long hi_s = P - T - 1;
+            if (hi_s < sd->lo_next) hi_s = sd->lo_next;
+            const size_t nmax_s = static_cast<size_t>((hi_s - sd->lo_next) / (T + 1) + 2);
+            const bool small_s = !sd->generic && hi_s > sd->lo_next && hi_s - sd->lo_next <= kSmallRange && nmax_s <= 1024;
+            if (small_s && zero_copy_enabled() && correlate_takes_host_input((int)sd->K, sd->fft_arg, nb, sd->num_sms))
+                if (int rc = stream_host_view(sd, hin + (a0 - C), static_cast<size_t>(need_end - a0), &host_view)) return rc;
+        }
+        if (host_view == nullptr)
+            if (int rc = stream_h2d(sd, sd->d_x.p + (a0 - sd->x_base), hin + (a0 - C), static_cast<size_t>(need_end - a0), st))
+                return rc;
+        g_trace.lap(1, tt);
+        g_trace.mark(1, st);
         sd->x_end = need_end;
         // --- metric window: [P_prev - 2T - 2, P)
         long long keep_z = P_prev - 2 * T - 2;
@@ -633,25 +753,42 @@ int b200sync_sd_process(b200sync_sd* sd, const float* in, size_t n_in, float* ou
         if (small) {
             // streaming-sized step: correlator, flags, [walk + refine] — three launches, one D2H, one synchronisation
             CU(launch_correlate(sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->fft_arg,
-                                a0 / S, nb, sd->d_tw.p, nullptr, 0, 0, 0, (int)sd->delay, sd->num_sms, st));
+                                a0 / S, nb, sd->d_tw.p, nullptr, 0, 0, 0, (int)sd->delay, sd->num_sms, st, 0, 0, 0, nullptr, 0,
+                                0, host_view, a0));
+            g_trace.mark(2, st);
             StreamWalk walk;
             CU(launch_peak_flags_stream(sd->d_z.p, sd->z_base, P, lo, hi, sd->T, sd->power_threshold, sd->d_ws.p,
                                         sd->d_ws.cap, sd->num_sms, st, &walk));
+            g_trace.mark(3, st);
             walk.r_abs_in = sd->r_abs_host;
             walk.state_out = sd->d_state.p;
-            walk.header = reinterpret_cast<PeakState*>(sd->d_recs.p);   // slot 0 of the record buffer
-            CU(launch_refine(sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->fft_arg,
-                             sd->min_bin, sd->d_tw.p, sd->d_det_idx.p, &sd->d_state.p->det_count, (unsigned)nmax,
-                             sd->d_recs.p + 1, sd->num_sms, st, 1, 0, 0, 0, &walk));
+            // The records land in MAPPED pinned host memory, written by the kernel itself: slot 0 is the header
+            // (search position, count, and — stored last, after every CTA's record is visible — this call's
+            // sequence number, which the host polls).  No D2H copy, no stream synchronisation.
             if (sd->h_recs_pin_cap < nmax + 1) {
+                CU(cudaStreamSynchronize(st));
                 if (sd->h_recs_pin) cudaFreeHost(sd->h_recs_pin);
                 sd->h_recs_pin = nullptr;
                 sd->h_recs_pin_cap = 0;
                 CU(cudaMallocHost(&sd->h_recs_pin, sizeof(DetectionRecord) * (nmax + 65)));
                 sd->h_recs_pin_cap = nmax + 65;
+                std::memset(sd->h_recs_pin, 0, sizeof(DetectionRecord));
             }
-            CU(cudaMemcpyAsync(sd->h_recs_pin, sd->d_recs.p, sizeof(DetectionRecord) * (nmax + 1), cudaMemcpyDeviceToHost, st));
+            if (!sd->d_done.p) {
+                CU(sd->d_done.ensure(1));
+                CU(cudaMemsetAsync(sd->d_done.p, 0, sizeof(unsigned int), st));
+            }
+            if (++sd->stream_seq == 0) sd->stream_seq = 1;
+            walk.header = reinterpret_cast<PeakState*>(sd->h_recs_pin);
+            walk.header->_pad = 0;      // (the previous step has completed: nothing else writes here now)
+            walk.done = sd->d_done.p;
+            walk.seq = sd->stream_seq;
+            CU(launch_refine(sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, sd->d_hperm.p, (int)sd->K, (int)sd->S, sd->fft_arg,
+                             sd->min_bin, sd->d_tw.p, sd->d_det_idx.p, &sd->d_state.p->det_count, (unsigned)nmax,
+                             sd->h_recs_pin + 1, sd->num_sms, st, 1, 0, 0, 0, &walk));
+            g_trace.mark(4, st);
         } else {
+            if (host_view != nullptr) return fail(B200SYNC_ECUDA, "internal: zero-copy span on the bulk path");
             if (int rc = run_chunk(sd, sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, a0 / S, nb, lo, hi, nullptr, 0, st))
                 return rc;
             if (int rc = records_enqueue(sd, sd->d_x.p, sd->x_base, sd->d_z.p, sd->z_base, nmax, st)) return rc;
@@ -660,11 +797,32 @@ int b200sync_sd_process(b200sync_sd* sd, const float* in, size_t n_in, float* ou
         sd->lo_next = hi;
         done_blocks += nb;
         // the delay line of host spans (:318-319) is host work: do it while the GPU runs the last step
+        g_trace.lap(2, tt);
         if (done_blocks >= nb_total) host_delay_line_stream(sd, in, out, static_cast<size_t>(j_total));
+        g_trace.lap(3, tt);
         const DetectionRecord* recs = nullptr;
         size_t nrec = 0;
         if (small) {
-            CU(cudaStreamSynchronize(st));
+            {   // poll the sequence number; the stream is queried now and then so that a failed launch surfaces
+                const volatile unsigned int* flag = &reinterpret_cast<const volatile PeakState*>(sd->h_recs_pin)->_pad;
+                for (unsigned spins = 0; *flag != sd->stream_seq; ++spins) {
+                    if ((spins & 0xfff) == 0xfff) {
+                        const cudaError_t q = cudaStreamQuery(st);
+                        if (q == cudaSuccess) {
+                            if (*flag != sd->stream_seq) return fail(B200SYNC_ECUDA, "streaming step finished without its completion flag");
+                            break;
+                        }
+                        if (q != cudaErrorNotReady) CU(q);
+                    }
+                    __builtin_ia32_pause();
+                }
+                std::atomic_thread_fence(std::memory_order_acquire);
+            }
+            g_trace.lap(4, tt);
+            if (g_trace.dev) {
+                cudaStreamSynchronize(st);
+                g_trace.collect();
+            }
             const PeakState* hs = reinterpret_cast<const PeakState*>(sd->h_recs_pin);
             if (hs->det_count > nmax) return fail(B200SYNC_ENOMEM, "internal detection list overflow");
             sd->r_abs_host = hs->r_abs;
@@ -688,6 +846,8 @@ int b200sync_sd_process(b200sync_sd* sd, const float* in, size_t n_in, float* ou
         sd->pending.pop_front();
     }
     *n_tags = nt;
+    g_trace.lap(5, tt);
+    g_trace.end();
     return 0;
 }
 

@@ -46,7 +46,34 @@ struct StreamWalk {
     unsigned long long r_abs_in = 0;
     PeakState* state_out = nullptr;
     PeakState* header = nullptr;
+    // Completion flag for records that land in MAPPED HOST memory (no D2H copy, no stream synchronisation): every CTA
+    // counts itself on *done after its record is written and fenced system-wide; the last one stores `seq` into
+    // header->_pad, which the host polls.  done == nullptr: the header is written by CTA 0 as soon as it is known.
+    unsigned int* done = nullptr;
+    unsigned int seq = 0;
 };
+
+// Programmatic dependent launch (streaming path: correlator -> flags -> walk + refine back to back in one stream): a
+// kernel launched with launch_pdl() may become resident while its predecessor still runs — its launch latency and
+// its prologue (tables into shared memory) hide behind the predecessor — and calls pdl_wait() before it touches
+// anything the predecessor wrote; the predecessor calls pdl_launch_dependents() once all of its CTAs are resident
+// work (at its start).  Both are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // api.cu: every kernel launch site calls this (b200sync_launch_count of the C ABI)
 void count_launch(int n = 1);
@@ -63,7 +90,12 @@ cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpo
                              const float2* d_tw, float2* d_out_delayed, long long out_base, long long out_lo,
                              long long out_hi, int delay, int num_sms, cudaStream_t st, long long nb_chan = 0,
                              long long in_chan_stride = 0, long long z_chan_stride = 0, float2* d_gm = nullptr,
-                             long long gm_b0 = 0, long long gm_chan_stride = 0);
+                             long long gm_b0 = 0, long long gm_chan_stride = 0, const float2* in_host = nullptr,
+                             long long in_host_base = 0);
+// in_host (streaming, zero copy): device-visible address of the span in pinned host memory, in_host[0] = absolute sample
+// in_host_base; the kernel reads the blocks from there and fills the device window d_in itself.  Only when
+// correlate_takes_host_input() says so for the span.
+bool correlate_takes_host_input(int K, int fft, long long nb, int num_sms);
 // Group extrema of the metric (d_gm): per FFT block, group 0 = lag 0 alone, group q >= 1 = lags 32q-31 .. 32q (clipped to
 // the stride S) — the 32 consecutive samples a warp of the correlator holds.  (max, min) per group, written by the
 // correlator, read by the peak stage instead of the samples themselves.

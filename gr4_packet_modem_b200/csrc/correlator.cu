@@ -81,15 +81,18 @@ static_assert(kCorrThreads == 6 * kGroupThreads, "the TMEM column layout (fft204
 // SPLIT: all groups of a CTA share one block and split the hypotheses (low latency, few blocks);
 // BATCH: channel x block grid of the batched channel mode.  Separate instantiations keep the persistent
 // single-stream shape free of their registers.
-template <bool SPLIT, bool BATCH>
+// ZC (with SPLIT): the span is read from mapped host memory (in_host), see the block loop.
+template <bool SPLIT, bool BATCH, bool ZC = false>
 __global__ void __launch_bounds__(kCorrThreads, 1)
 correlate_kernel(const float2* __restrict__ in, long long in_base, float* __restrict__ zpow,
                  long long z_base, const float2* __restrict__ hperm, int K, int S, long long b0,
                  long long nb, const float2* __restrict__ tw_g, float2* __restrict__ out_delayed,
                  long long out_base, long long out_lo, long long out_hi, int delay, long long nb_chan,
                  long long in_chan_stride, long long z_chan_stride, float2* __restrict__ gm, long long gm_b0,
-                 int gm_ng, long long gm_chan_stride) {
+                 int gm_ng, long long gm_chan_stride, const float2* __restrict__ in_host, long long in_host_base,
+                 float2* __restrict__ x_copy) {
     extern __shared__ __align__(128) unsigned char smem_raw[];  // 128 B: half-warp LDS.64 rows never straddle a bank row, whatever static shared data precedes
+    pdl_launch_dependents();   // streaming: the flags launch may become resident (and wait) behind this grid
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
     const int g = threadIdx.x >> 7;
     const int tid = threadIdx.x & 127;
@@ -201,6 +204,32 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
         const long long s0 = (b0 + bb) * (long long)S;  // absolute first sample of the block
         const float2* src = in + ch * in_chan_stride + (s0 - in_base);
         float2 v[16], xs[16];
+        if constexpr (SPLIT && ZC) {
+            // Streaming, zero copy: the span still lies in (pinned, mapped) HOST memory.  Group 0 pulls the block
+            // over PCIe itself — no separate H2D copy in front of the kernel, and the blocks of the span arrive
+            // side by side — leaves it in the device window x_copy (same indexing as `in`: the refine stage and
+            // the next call read it there), and hands it to the other groups through its exchange buffer.
+            float2* stage = tw_s + kTwTotal;     // group 0's exchange buffer, free until FFT A
+            if (g == 0) {
+                const float2* hsrc = in_host + (s0 - in_host_base) + tid;
+                float2* dcopy = x_copy + (s0 - in_base) + tid;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {   // two batches of eight rows: short live ranges (the kernel sits at its register cap)
+                    float2 t[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) t[r] = __ldcs(hsrc + 128 * (8 * hf + r));
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        dcopy[128 * (8 * hf + r)] = t[r];
+                        stage[128 * (8 * hf + r) + tid] = t[r];
+                    }
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) v[n1] = stage[128 * n1 + tid];
+            __syncthreads();
+        } else {
         // The first and last L - 1 samples of a block are also the neighbouring blocks' (overlap-save): those rows are
         // loaded with the default policy so that the second reader — another group of this CTA, microseconds
         // later — finds them in L2; the rows in between are read once and stream through (evict-first).
@@ -213,6 +242,7 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
             constexpr bool kSharedRow[16] = {1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1};
             v[n1] = kSharedRow[n1] ? __ldg(src + 128 * n1 + tid) : __ldcs(src + 128 * n1 + tid);
 #endif
+        }
         }
 #ifdef B200_L2_PREFETCH   // measured SLOWER (K = 1: 4.82 vs 4.47 ms at 2^30; K = 9: 18.8 vs 18.3): register pressure, off by default
         if (!split && (tid & 15) == 0 && blk + blk_step < nb) {
@@ -410,6 +440,10 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
     unsigned int n;
     const unsigned long long* dets = det_idx;
     if (walk.cand != nullptr) {
+        // launched behind the flags kernel (launch_pdl): the twiddle table — a constant of the context — is staged
+        // while that kernel still runs; everything below reads what it and the correlator wrote
+        load_twiddles(tw_s, tw_g);
+        pdl_wait();
         // Streaming: the in-order walk of the peak detector fused in front of the refine stage.  EVERY CTA walks
         // the (small) bitmaps itself, from shared memory, and so knows the whole detection list without a
         // kernel boundary; CTA d then refines detection d.  CTA 0 publishes the new search position and the count.
@@ -437,7 +471,12 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
                     st.r_abs = (unsigned long long)(r_end > walk.hi ? r_end : walk.hi);
                     st.det_count = cnt;
                     st._pad = 0;
-                    *walk.header = st;          // the host reads the count (and the records behind it) from here
+                    if (walk.done == nullptr) {
+                        *walk.header = st;      // the host reads the count (and the records behind it) from here
+                    } else {                    // mapped host memory: count and position now, the sequence number last
+                        walk.header->r_abs = st.r_abs;
+                        walk.header->det_count = cnt;
+                    }
                     st.det_count = 0;           // the device-side list counts as drained
                     *walk.state_out = st;
                 }
@@ -450,8 +489,19 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
         n = *det_count;
     }
     if (n > det_cap) n = det_cap;
-    if (blockIdx.x >= n) return;  // the grid is sized for the worst case; idle CTAs leave at once
-    load_twiddles(tw_s, tw_g);
+    auto count_done = [&]() {   // (thread 0 of the CTA) everything this CTA wrote is visible system-wide before it counts
+        __threadfence_system();
+        if (atomicAdd(walk.done, 1u) == gridDim.x - 1) {
+            *walk.done = 0u;                                        // ready for the next launch (stream order)
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned int*>(&walk.header->_pad) = walk.seq;
+        }
+    };
+    if (blockIdx.x >= n) {  // the grid is sized for the worst case; idle CTAs leave at once
+        if (walk.done != nullptr && threadIdx.x == 0) count_done();   // (its barrier above ordered CTA 0's header stores)
+        return;
+    }
+    if (walk.cand == nullptr) load_twiddles(tw_s, tw_g);
     __syncthreads();
     const int tid = threadIdx.x;
     const bool fft_warp = tid < kGroupThreads;
@@ -477,14 +527,28 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
             const int nk = min(kRefineChunk, K - c0);
             if (fft_warp) {
                 // pass B1 of every hypothesis of the chunk: column p keeps only its output m3
+                // (the template points of the NEXT half are requested before the current half is transformed: one L2
+                //  latency per chunk instead of one per half — the stage is latency-bound, a CTA per detection)
+                float2 hn[8];
+                {
+                    const float2* h0 = hperm + (size_t)c0 * 16 * kGroupThreads + tid;
+#pragma unroll
+                    for (int dd = 0; dd < 8; ++dd) hn[dd] = __ldg(h0 + dd * kGroupThreads);
+                }
                 for (int kq = 0; kq < nk; ++kq) {
-                    const float2* h = hperm + (size_t)(c0 + kq) * 16 * kGroupThreads + tid;
 #pragma unroll
                     for (int pi = 0; pi < 2; ++pi) {
                         float2 w[8];
 #pragma unroll
-                        for (int dd = 0; dd < 8; ++dd)
-                            w[dd] = cmul(xs[pi * 8 + dd], __ldg(h + (pi * 8 + dd) * kGroupThreads));
+                        for (int dd = 0; dd < 8; ++dd) w[dd] = cmul(xs[pi * 8 + dd], hn[dd]);
+                        {   // next half: (kq, 1) after (kq, 0); (kq + 1, 0) after (kq, 1)
+                            const int kn = pi == 0 ? kq : kq + 1;
+                            if (kn < nk) {
+                                const float2* h = hperm + ((size_t)(c0 + kn) * 16 + (pi == 0 ? 8 : 0)) * kGroupThreads + tid;
+#pragma unroll
+                                for (int dd = 0; dd < 8; ++dd) hn[dd] = __ldg(h + dd * kGroupThreads);
+                            }
+                        }
                         dft8(w);
                         float2 val = w[0];  // output m3 sits at w[bitrev3(m3)]
 #pragma unroll
@@ -560,6 +624,7 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
         }
         __syncthreads();
     }
+    if (walk.done != nullptr && threadIdx.x == 0) count_done();
 }
 
 // ---------------------------------------------------------------------------------
@@ -581,12 +646,19 @@ size_t correlate_smem_bytes(int groups) {
     return sizeof(float2) * (size_t)(kTwTotal + groups * kCorrXchg);
 }
 
+// true when launch_correlate would take the split shape for this span (a CTA per block, all groups on the same
+// block) — the shape that can pull its input from mapped host memory (in_host)
+bool correlate_takes_host_input(int K, int fft, long long nb, int num_sms) {
+    if (getenv("B200SYNC_SMALL_GROUPS") != nullptr) return false;   // development override of the shape
+    return fft == kFft && nb > 0 && nb <= num_sms && K >= 2;
+}
+
 cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpow, long long z_base,
                              const float2* d_hperm, int K, int S, int fft, long long b0, long long nb,
                              const float2* d_tw, float2* d_out_delayed, long long out_base, long long out_lo,
                              long long out_hi, int delay, int num_sms, cudaStream_t st, long long nb_chan,
                              long long in_chan_stride, long long z_chan_stride, float2* d_gm, long long gm_b0,
-                             long long gm_chan_stride) {
+                             long long gm_chan_stride, const float2* in_host, long long in_host_base) {
     if (nb <= 0) return cudaSuccess;
     if (fft != kFft)   // another fft_size, or 2048 forced onto the generic path (kGenericFlag)
         return launch_correlate_generic(fft & ~kGenericFlag, d_in, in_base, d_zpow, z_base, d_hperm, K, S, b0, nb, d_tw,
@@ -602,6 +674,7 @@ cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpo
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         e = cudaFuncSetAttribute(correlate_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(correlate_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(correlate_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(correlate_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
@@ -630,11 +703,14 @@ cudaError_t launch_correlate(const float2* d_in, long long in_base, float* d_zpo
     const size_t smem = correlate_smem_bytes(groups);
     long long want = ksplit > 1 ? nb : (nb + groups - 1) / groups;
     int grid = (int)(want < num_sms ? want : num_sms);
-    auto kern = ksplit > 1 ? correlate_kernel<true, false> : (nb_chan > 0 ? correlate_kernel<false, true> : correlate_kernel<false, false>);
+    auto kern = ksplit > 1 ? (in_host != nullptr ? correlate_kernel<true, false, true> : correlate_kernel<true, false>)
+                           : (nb_chan > 0 ? correlate_kernel<false, true> : correlate_kernel<false, false>);
     kern<<<grid, groups * kGroupThreads, smem, st>>>(d_in, in_base, d_zpow, z_base, d_hperm, K, S, b0, nb, d_tw,
                                                      d_out_delayed, out_base, out_lo, out_hi, delay, nb_chan,
                                                      in_chan_stride, z_chan_stride, d_gm, gm_b0, gm_groups_per_block(S),
-                                                     gm_chan_stride);
+                                                     gm_chan_stride, ksplit > 1 ? in_host : nullptr, in_host_base,
+                                                     const_cast<float2*>(d_in));
+    if (in_host != nullptr && ksplit <= 1) return cudaErrorInvalidValue;   // callers ask correlate_takes_host_input() first
     count_launch();
     return cudaGetLastError();
 }
@@ -683,9 +759,16 @@ cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_
     if (nch > 1) grid = (grid + nch - 1) / nch;  // the channels share the one resident wave
     if ((unsigned)grid > det_cap) grid = (int)det_cap;
     if (grid < 1) grid = 1;
-    refine_kernel<<<dim3((unsigned)grid, (unsigned)nch), kRefineThreads, smem_launch, st>>>(
-        d_in, in_base, d_zpow, z_base, d_hperm, K, S, min_freq_bin, d_tw, d_det_idx, d_det_count, det_cap, d_recs,
-        in_chan_stride, z_chan_stride, det_chan_stride, w);
+    if (walk != nullptr) {
+        e = launch_pdl(refine_kernel, dim3((unsigned)grid, (unsigned)nch), dim3(kRefineThreads), smem_launch, st, d_in, in_base,
+                       d_zpow, z_base, d_hperm, K, S, min_freq_bin, d_tw, d_det_idx, d_det_count, det_cap, d_recs,
+                       in_chan_stride, z_chan_stride, det_chan_stride, w);
+        if (e != cudaSuccess) return e;
+    } else {
+        refine_kernel<<<dim3((unsigned)grid, (unsigned)nch), kRefineThreads, smem_launch, st>>>(
+            d_in, in_base, d_zpow, z_base, d_hperm, K, S, min_freq_bin, d_tw, d_det_idx, d_det_count, det_cap, d_recs,
+            in_chan_stride, z_chan_stride, det_chan_stride, w);
+    }
     count_launch();
     return cudaGetLastError();
 }

@@ -267,6 +267,8 @@ peak_flags_kernel(const float* __restrict__ zpow, long long z_base, long long z_
     unsigned short* poss_list = reinterpret_cast<unsigned short*>(nposs_s + 1);  // [TILE / 32]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();   // streaming: the walk + refine launch may move in behind this grid
+    pdl_wait();                // ... and this one behind the correlator: zpow is complete and visible from here on
     const long long tile_lo = lo + (long long)blockIdx.x * TILE;
     const long long q0 = tile_lo - Tpad;                   // absolute index of window element 0
     const int* src = reinterpret_cast<const int*>(zpow) + (q0 - z_base);
@@ -1072,7 +1074,7 @@ static cudaError_t set_smem_attr(const void* fn, size_t bytes) {
 static cudaError_t launch_flags(const float* d_zpow, long long z_base, long long z_end, long long lo, long long hi,
                                 int T, float power_threshold, const PeakPlan& pl, unsigned char* ws, int nch,
                                 const PeakBatch& pb, cudaStream_t st, bool zero_padding = true,
-                                const GmGeom* gg = nullptr) {
+                                const GmGeom* gg = nullptr, bool pdl = false) {
     const long long range = hi - lo;
     cudaError_t e;
     if (gg != nullptr && gg->gm != nullptr) {
@@ -1116,7 +1118,13 @@ static cudaError_t launch_flags(const float* d_zpow, long long z_base, long long
         auto kern = small ? peak_flags_kernel<kFastTileSmall> : peak_flags_kernel<kFastTile>;
         e = set_smem_attr((const void*)kern, smem);
         if (e != cudaSuccess) return e;
-        kern<<<grid, kFastThreads, smem, st>>>(d_zpow, z_base, z_end, lo, hi, T, power_threshold, cand, pass, pb);
+        if (pdl) {
+            e = launch_pdl(kern, grid, dim3(kFastThreads), smem, st, d_zpow, z_base, z_end, lo, hi, T, power_threshold, cand,
+                           pass, pb);
+            if (e != cudaSuccess) return e;
+        } else {
+            kern<<<grid, kFastThreads, smem, st>>>(d_zpow, z_base, z_end, lo, hi, T, power_threshold, cand, pass, pb);
+        }
         count_launch();
     } else {
         const int n = kFlagsTile + 2 * T;
@@ -1212,7 +1220,7 @@ cudaError_t launch_peak_flags_stream(const float* d_zpow, long long z_base, long
     walk->lo = lo;
     walk->hi = hi;
     walk->T = T;
-    return launch_flags(d_zpow, z_base, z_end, lo, hi, T, power_threshold, pl, ws, 1, pb, st, false);
+    return launch_flags(d_zpow, z_base, z_end, lo, hi, T, power_threshold, pl, ws, 1, pb, st, false, nullptr, true);
 }
 
 cudaError_t launch_peak_phase2(long long lo, long long hi, int T, void* d_ws, size_t ws_bytes, int j_in,

@@ -37,6 +37,13 @@ const char* b200sync_last_error(void);
 int b200sync_abi_version(void);
 /* Number of kernel launches issued by this process so far (bench.py's gpu_launches). */
 uint64_t b200sync_launch_count(void);
+/* Page-lock a long-lived host buffer (GR4's port ring buffers, GR/CircularBuffer.hpp) so that the streaming calls
+ * (b200sync_*_process with host spans) hand its spans straight to the copy engine instead of staging them through
+ * the context's own pinned buffer: a 65536-item span then costs 79 instead of 112 us (profiles/r2_stream_throughput.txt).
+ * Thin wrappers over cudaHostRegister / cudaHostUnregister so that the host program need not link the CUDA runtime;
+ * unregister before the buffer is freed.  Returns 0, B200SYNC_EINVAL or B200SYNC_ECUDA. */
+int b200sync_host_register(const void* ptr, size_t bytes);
+int b200sync_host_unregister(const void* ptr);
 
 /* ------------------------------------------------------------------------------
  * SyncwordDetection                                   PM/syncword_detection.hpp

@@ -622,3 +622,36 @@ def test_many_hypotheses_bit_exact_vs_mirror_oracle(oracle, rx_params):
     oc, _, otags = o.run(x, chunk=1 << 18)
     assert consumed == oc and len(recs) > 10 and abs(int(np.median(recs["freq_bin"])) - 113) <= 1
     _assert_bit_exact_vs_oracle(sd, recs, tags, o, oc, otags, 128)
+
+
+def test_registered_host_ring_streams_like_a_pageable_one(rx_params):
+    """b200sync_host_register: a long-lived pageable ring (GR4's port buffer) is page-locked once; spans inside it then
+    take the pinned path (no staging copy).  Same consumed counts, output and tags as the pageable run."""
+    from gr4_packet_modem_b200 import host_register, host_unregister
+    from gr4_packet_modem_b200.stimulus import packet_capture
+
+    chunk = 1 << 16
+    x, _ = packet_capture(12 * chunk, seed=17, esn0_db=10.0, cfo=0.003, payload_bytes=100)
+    kw = dict(min_freq_bin=-4, max_freq_bin=4)
+
+    def drive(ring, out):
+        sd = _gpu(rx_params, **kw)
+        pos, outs, tags = 0, [], []
+        while x.size - pos >= chunk:
+            ring[:] = x[pos:pos + chunk]
+            status, c, o, t = sd.process_bulk(ring, True)
+            outs.append(o.copy())
+            tags.extend(t)
+            pos += c
+        return pos, np.concatenate(outs), [(i, m["syncword_freq"], m["syncword_phase"]) for _, i, m in tags]
+
+    plain = drive(np.empty(chunk, np.complex64), None)
+    ring = np.empty(chunk, np.complex64)
+    host_register(ring)
+    try:
+        import torch
+        assert torch.cuda.is_available()
+        reg = drive(ring, None)
+    finally:
+        host_unregister(ring)
+    assert plain[0] == reg[0] and np.array_equal(plain[1], reg[1]) and plain[2] == reg[2] and len(reg[2]) > 5
