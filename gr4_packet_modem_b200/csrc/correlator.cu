@@ -413,7 +413,9 @@ __device__ __forceinline__ float2 pick(const float2 (&v)[N], int idx) {
     return r;
 }
 
-__global__ void __launch_bounds__(kRefineThreads)
+// STREAM: the in-order peak walk fused in front (streaming path); its own instantiation, so the bulk form carries none of it
+template <bool STREAM>
+__global__ void __maxnreg__(88)   // 160 threads: 3 CTAs per SM (what shared memory allows); ptxas 12.9 otherwise wanders between 88 and 164 registers with the surrounding code
 refine_kernel(const float2* __restrict__ in, long long in_base, const float* __restrict__ zpow,
               long long z_base, const float2* __restrict__ hperm, int K, int S, int min_freq_bin,
               const float2* __restrict__ tw_g, const unsigned long long* __restrict__ det_idx,
@@ -439,7 +441,7 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
     __shared__ unsigned int n_walk;
     unsigned int n;
     const unsigned long long* dets = det_idx;
-    if (walk.cand != nullptr) {
+    if constexpr (STREAM) {
         // launched behind the flags kernel (launch_pdl): the twiddle table — a constant of the context — is staged
         // while that kernel still runs; everything below reads what it and the correlator wrote
         load_twiddles(tw_s, tw_g);
@@ -498,10 +500,10 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
         }
     };
     if (blockIdx.x >= n) {  // the grid is sized for the worst case; idle CTAs leave at once
-        if (walk.done != nullptr && threadIdx.x == 0) count_done();   // (its barrier above ordered CTA 0's header stores)
+        if (STREAM && walk.done != nullptr && threadIdx.x == 0) count_done();   // (its barrier above ordered CTA 0's header stores)
         return;
     }
-    if (walk.cand == nullptr) load_twiddles(tw_s, tw_g);
+    if constexpr (!STREAM) load_twiddles(tw_s, tw_g);
     __syncthreads();
     const int tid = threadIdx.x;
     const bool fft_warp = tid < kGroupThreads;
@@ -527,28 +529,14 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
             const int nk = min(kRefineChunk, K - c0);
             if (fft_warp) {
                 // pass B1 of every hypothesis of the chunk: column p keeps only its output m3
-                // (the template points of the NEXT half are requested before the current half is transformed: one L2
-                //  latency per chunk instead of one per half — the stage is latency-bound, a CTA per detection)
-                float2 hn[8];
-                {
-                    const float2* h0 = hperm + (size_t)c0 * 16 * kGroupThreads + tid;
-#pragma unroll
-                    for (int dd = 0; dd < 8; ++dd) hn[dd] = __ldg(h0 + dd * kGroupThreads);
-                }
                 for (int kq = 0; kq < nk; ++kq) {
+                    const float2* h = hperm + (size_t)(c0 + kq) * 16 * kGroupThreads + tid;
 #pragma unroll
                     for (int pi = 0; pi < 2; ++pi) {
                         float2 w[8];
 #pragma unroll
-                        for (int dd = 0; dd < 8; ++dd) w[dd] = cmul(xs[pi * 8 + dd], hn[dd]);
-                        {   // next half: (kq, 1) after (kq, 0); (kq + 1, 0) after (kq, 1)
-                            const int kn = pi == 0 ? kq : kq + 1;
-                            if (kn < nk) {
-                                const float2* h = hperm + ((size_t)(c0 + kn) * 16 + (pi == 0 ? 8 : 0)) * kGroupThreads + tid;
-#pragma unroll
-                                for (int dd = 0; dd < 8; ++dd) hn[dd] = __ldg(h + dd * kGroupThreads);
-                            }
-                        }
+                        for (int dd = 0; dd < 8; ++dd)
+                            w[dd] = cmul(xs[pi * 8 + dd], __ldg(h + (pi * 8 + dd) * kGroupThreads));
                         dft8(w);
                         float2 val = w[0];  // output m3 sits at w[bitrev3(m3)]
 #pragma unroll
@@ -624,7 +612,7 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
         }
         __syncthreads();
     }
-    if (walk.done != nullptr && threadIdx.x == 0) count_done();
+    if (STREAM && walk.done != nullptr && threadIdx.x == 0) count_done();
 }
 
 // ---------------------------------------------------------------------------------
@@ -743,7 +731,8 @@ cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        e = cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
@@ -751,7 +740,7 @@ cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_
     // one-third-full wave that took as long as the first
     static int per_sm = 0;
     if (per_sm == 0) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, refine_kernel, kRefineThreads, smem_base);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, refine_kernel<false>, kRefineThreads, smem_base);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
     }
@@ -760,12 +749,12 @@ cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_
     if ((unsigned)grid > det_cap) grid = (int)det_cap;
     if (grid < 1) grid = 1;
     if (walk != nullptr) {
-        e = launch_pdl(refine_kernel, dim3((unsigned)grid, (unsigned)nch), dim3(kRefineThreads), smem_launch, st, d_in, in_base,
+        e = launch_pdl(refine_kernel<true>, dim3((unsigned)grid, (unsigned)nch), dim3(kRefineThreads), smem_launch, st, d_in, in_base,
                        d_zpow, z_base, d_hperm, K, S, min_freq_bin, d_tw, d_det_idx, d_det_count, det_cap, d_recs,
                        in_chan_stride, z_chan_stride, det_chan_stride, w);
         if (e != cudaSuccess) return e;
     } else {
-        refine_kernel<<<dim3((unsigned)grid, (unsigned)nch), kRefineThreads, smem_launch, st>>>(
+        refine_kernel<false><<<dim3((unsigned)grid, (unsigned)nch), kRefineThreads, smem_launch, st>>>(
             d_in, in_base, d_zpow, z_base, d_hperm, K, S, min_freq_bin, d_tw, d_det_idx, d_det_count, det_cap, d_recs,
             in_chan_stride, z_chan_stride, det_chan_stride, w);
     }
