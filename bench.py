@@ -370,6 +370,7 @@ def measure_chain(args, log2n: int, steps: int, warmup: int, e2e: bool, cpu: boo
     sf_taps = pfb_matched_filter_taps()
     sd = SyncwordDetection(**rx_settings(args.bins, args.thr), device=0)
     fe = FrontEnd(rate=rate, taps=fe_taps, phase_incr=0.005)
+    fe_fma = FrontEnd(rate=rate, taps=fe_taps, phase_incr=0.005, fp_contract=True)   # opt-in mode, timed beside the default
     # PM/packet_receiver.hpp:94-115: CoarseFrequencyCorrection(delay 26) -> SymbolFilter(delay 44), fused
     sf = SymbolFilter(sf_taps, 32, 4, delay=44, fused_cfc_delay=None if args.no_cfc else 26)
     n_y = fe.max_output(n)
@@ -420,6 +421,17 @@ def measure_chain(args, log2n: int, steps: int, warmup: int, e2e: bool, cpu: boo
     sd_ms = statistics.mean(t[1] for t in timed)
     sf_ms = statistics.mean(t[2] for t in timed)
     cl_ms = statistics.mean(t[3] for t in timed)
+    # the opt-in fused-multiply-add front end (b200sync_fe_config::fp_contract), the stage alone, same input and buffers
+    fma_ms = []
+    for i in range(warmup + steps):
+        fe_fma.restart()
+        ev[0].record()
+        fe_fma.process_device(raw.data_ptr(), n, y.data_ptr(), n_y, stream)
+        ev[1].record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            fma_ms.append(ev[0].elapsed_time(ev[1]))
+    fe_fma_ms = statistics.mean(fma_ms)
     peaks = load_peaks()
     rec = {
         "metric": "complex Msps (cf32) through RX sync (fused front end + SyncwordDetection + "
@@ -435,6 +447,10 @@ def measure_chain(args, log2n: int, steps: int, warmup: int, e2e: bool, cpu: boo
         "gpu_launches": int(launches),
         "stage_ms": {"frontend": fe_ms, "syncword_detection": sd_ms, "symbol_filter_incl_host_plan": sf_ms,
                      "wipeoff_costas_loop": cl_ms},
+        "frontend_fp_contract": {"ms": fe_fma_ms, "value_with_it": c_in / ((ms_per_step - fe_ms + fe_fma_ms) * 1e-3) / 1e6,
+                                 "note": "opt-in b200sync_fe_config::fp_contract = 1: fused multiply-add per tap (one rounding "
+                                         "instead of the reference's two, relative L2 difference ~1e-7); `value` above is the "
+                                         "bit-exact default, value_with_it = the same step with this front end instead"},
         "roofline": hbm_roofline("frontend_kernel", 16.0 * n_out, fe_ms, peaks,
                                  "16 B/sample (8 in + 8 out); 2 x 40 taps x 2 x (mul, add) = 320 separately rounded "
                                  "FP32 instructions per output (bit-exact std::inner_product order): FP32-issue bound",
@@ -638,7 +654,7 @@ def measure_detect(args, bins: int, log2n: int, esn0: float, cfo: float, steps: 
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        c, recs, _ = sd.detect_device(x.data_ptr(), n, stream, d_out_ptr=out.data_ptr() if with_output else 0)
+        c, recs, _ = sd.detect_device(x.data_ptr(), n, stream, d_out_ptr=out.data_ptr() if with_output else 0, copy=False)
         if i >= warmup:
             tm.append(sd.last_timings())
     e1.record()
@@ -819,7 +835,8 @@ def main():
 
     def step_device():
         if world == 1:
-            c, recs, _ = sd.detect_device(x.data_ptr(), n_per, stream, d_out_ptr=d_out.data_ptr() if with_out else 0)
+            # (records and tags as views into the context's buffers — valid until the next call, like processBulk's spans)
+            c, recs, _ = sd.detect_device(x.data_ptr(), n_per, stream, d_out_ptr=d_out.data_ptr() if with_out else 0, copy=False)
             return c, len(recs)
         if with_out:
             sd.shard_output(d_out.data_ptr(), out_first, out_len)

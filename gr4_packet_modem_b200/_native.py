@@ -108,6 +108,8 @@ class FeConfig(C.Structure):
         ("device", C.c_int32),
         ("rate_is_f64", C.c_uint32),
         ("rate_f64", C.c_double),
+        ("fp_contract", C.c_uint32),
+        ("_reserved", C.c_uint32),
     ]
 
 

@@ -125,7 +125,16 @@ __device__ __forceinline__ void rot_factors(const FeParams& P, long long nt, flo
     }
 }
 
-template <bool WIDE>
+// FMA (b200sync_fe_config::fp_contract): every multiply-accumulate of the filter as ONE fused operation (FFMA2, a third of
+// the issue slots and half the FP32 pipe passes) instead of std::inner_product's separately rounded multiply and add —
+// not bit-identical to the reference any more (one rounding per tap instead of two), opt-in.
+template <bool FMA>
+__device__ __forceinline__ float2 fe_mac(float2 acc, float2 h, float t) {
+    if constexpr (FMA) return __ffma2_rn(h, make_float2(t, t), acc);
+    else return __fadd2_rn(acc, make_float2(__fmul_rn(h.x, t), __fmul_rn(h.y, t)));
+}
+
+template <bool WIDE, bool FMA>
 __global__ void __launch_bounds__(kFeThreads, 4)
 frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (tap, diff tap)*/) {
     using FT = FeTime<WIDE>;
@@ -237,8 +246,8 @@ frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (t
                     // each half rounded like the multiply-then-add of std::inner_product.  (A packed
                     // multiply as well would be 2 slots, but ptxas 12.9 contracts mul.rn.f32x2 +
                     // add.rn.f32x2 into FFMA2 even with --fmad=false, which changes the rounding.)
-                    af[r] = __fadd2_rn(af[r], make_float2(__fmul_rn(h.x, t.x), __fmul_rn(h.y, t.x)));
-                    ad[r] = __fadd2_rn(ad[r], make_float2(__fmul_rn(h.x, t.y), __fmul_rn(h.y, t.y)));
+                    af[r] = fe_mac<FMA>(af[r], h, t.x);
+                    ad[r] = fe_mac<FMA>(ad[r], h, t.y);
                 }
                 // x[c0-1-(k+kk+1)] replaces the element leaving the window
                 W[(-(kk + 1)) & (kFeR - 1)] = xin[fe_skew(b - (k + kk + 1))];
@@ -249,13 +258,12 @@ frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (t
 #pragma unroll
             for (int r = 0; r < kFeR; ++r) {
                 const float2 h = xin[fe_skew(b + r - k)];
-                af[r] = __fadd2_rn(af[r], make_float2(__fmul_rn(h.x, t.x), __fmul_rn(h.y, t.x)));
-                ad[r] = __fadd2_rn(ad[r], make_float2(__fmul_rn(h.x, t.y), __fmul_rn(h.y, t.y)));
+                af[r] = fe_mac<FMA>(af[r], h, t.x);
+                ad[r] = fe_mac<FMA>(ad[r], h, t.y);
             }
         }
 #pragma unroll
-        for (int r = 0; r < kFeR; ++r)
-            y[r] = __fadd2_rn(af[r], make_float2(__fmul_rn(acc[r], ad[r].x), __fmul_rn(acc[r], ad[r].y)));
+        for (int r = 0; r < kFeR; ++r) y[r] = fe_mac<FMA>(af[r], ad[r], acc[r]);
     } else {
 #pragma unroll
         for (int r = 0; r < kFeR; ++r) {
@@ -269,12 +277,10 @@ frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (t
                 const long long a = cr - 1 - k;
                 const float2 h = staged ? xin[fe_skew((int)(a - lo))] : sample(a);
                 const float2 t = tp[k];
-                af.x = __fadd_rn(af.x, __fmul_rn(h.x, t.x));
-                af.y = __fadd_rn(af.y, __fmul_rn(h.y, t.x));
-                ad.x = __fadd_rn(ad.x, __fmul_rn(h.x, t.y));
-                ad.y = __fadd_rn(ad.y, __fmul_rn(h.y, t.y));
+                af = fe_mac<FMA>(af, h, t.x);
+                ad = fe_mac<FMA>(ad, h, t.y);
             }
-            y[r] = make_float2(__fadd_rn(af.x, __fmul_rn(acc[r], ad.x)), __fadd_rn(af.y, __fmul_rn(acc[r], ad.y)));
+            y[r] = fe_mac<FMA>(af, ad, acc[r]);
         }
     }
     float2* dst = P.out + (nt - P.out_base);
@@ -326,6 +332,7 @@ struct b200sync_fe {
     float rate = 1.0f, phase_incr = 0.0f;
     double rate_f64 = 1.0;      // TRate = double (rate_is_f64)
     bool wide = false;
+    bool fma = false;           // fp_contract: fused multiply-add in the filter (not bit-identical to the reference)
     std::vector<float> taps;
     uint32_t fs = 32;
     bool do_resample = true, do_rotate = true;
@@ -499,7 +506,8 @@ int fe_run(b200sync_fe* fe, const float2* d_in, size_t n_in, float2* d_out, size
         const size_t smem = fe->do_resample
                                 ? sizeof(float2) * (static_cast<size_t>(P.fs) * P.arm + static_cast<size_t>(kFeXinSlots))
                                 : 0;
-        auto kern = fe->wide ? frontend_kernel<true> : frontend_kernel<false>;
+        auto kern = fe->wide ? (fe->fma ? frontend_kernel<true, true> : frontend_kernel<true, false>)
+                             : (fe->fma ? frontend_kernel<false, true> : frontend_kernel<false, false>);
         FCU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = static_cast<unsigned>((n_out + kFeTileOut - 1) / kFeTileOut);
         kern<<<grid, kFeThreads, smem, st>>>(P, reinterpret_cast<const float2*>(fe->d_taps));
@@ -534,6 +542,7 @@ int b200sync_fe_create(const b200sync_fe_config* cfg, b200sync_fe** out) {
     if (!fe) return fe_fail(B200SYNC_ENOMEM, "out of memory");
     fe->rate = cfg->rate;
     fe->wide = cfg->rate_is_f64 != 0;
+    fe->fma = cfg->fp_contract != 0;
     fe->rate_f64 = fe->wide ? cfg->rate_f64 : static_cast<double>(cfg->rate);
     fe->phase_incr = cfg->phase_incr;
     if (cfg->taps && cfg->n_taps) fe->taps.assign(cfg->taps, cfg->taps + cfg->n_taps);

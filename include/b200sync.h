@@ -277,6 +277,11 @@ typedef struct b200sync_fe_config {
     int32_t device;
     uint32_t rate_is_f64;      /* 1: TRate = double — the rate is rate_f64, `rate` is ignored; the timing recurrence */
     double rate_f64;           /*    then runs in double like PfbArbResampler<.., double> (test/qa_pfb_arb_resampler.cpp) */
+    uint32_t fp_contract;      /* 0 (default): every tap a separately rounded multiply and add, the order of std::inner_product
+                                *    (:147-160) — the resampled stream is BIT-EXACT.  1: fused multiply-add per tap (what
+                                *    GCC's -ffp-contract=fast makes of the reference on an FMA machine): one rounding per tap,
+                                *    relative L2 difference ~1e-7, the kernel 2x faster.                                   */
+    uint32_t _reserved;
 } b200sync_fe_config;
 
 typedef struct b200sync_fe b200sync_fe;

@@ -196,3 +196,25 @@ def test_reference_qa_pfb_arb_resampler_double():
     k = np.arange(1000, y.size)
     expected = np.exp(1j * (np.angle(y[1000]) + freq / rate * (k - 1000)))
     assert np.max(np.abs(y[1000:] - expected)) < 3e-3
+
+
+def test_fp_contract_mode_is_opt_in_and_within_tolerance(oracle):
+    """b200sync_fe_config::fp_contract = 1 (fused multiply-add per tap, 2x faster): same item counts, output within
+    1e-6 relative L2 of the bit-exact default — inside north_star's 1e-5 bar for filter outputs — and the default
+    stays bit-exact vs the oracle's std::inner_product order."""
+    from gr4_packet_modem_b200 import PfbArbResampler
+
+    x = _signal(200000, 4)
+    rate = float(np.float32(1.0 + 1.2e-6))
+    c0, exact = PfbArbResampler(rate, taps()).process_bulk(x)
+    fast_blk = PfbArbResampler(rate, taps(), fp_contract=True)
+    a = []
+    for p in range(0, x.size, 50000):
+        a.append(fast_blk.process_bulk(x[p:p + 50000])[1])
+    fast = np.concatenate(a)
+    o = oracle.PfbArbResampler(rate, taps(), 32, use_double=False)
+    oc, oy = o.process_bulk(x, x.size + 1000)
+    assert c0 == oc and np.array_equal(exact.view(np.uint32), oy.view(np.uint32))
+    assert fast.size == exact.size
+    rel = np.linalg.norm(fast.astype(np.complex128) - exact) / np.linalg.norm(exact.astype(np.complex128))
+    assert 0.0 < rel < 1e-6, rel
