@@ -360,7 +360,7 @@ int do_start(b200sync_sd* sd) {
     sd->L = static_cast<uint32_t>((sd->syncword.size() - 1) * sd->sps + sd->rrc_taps.size());
     if (sd->L > sd->fft_size) return fail(B200SYNC_EINVAL, "fft_size too small");
     if ((sd->fft_size & (sd->fft_size - 1)) != 0)
-        return fail(B200SYNC_EINVAL, "FFT size must be 2^N");   // ALG/fourier/fftw.hpp:182-184
+        return fail(B200SYNC_EINVAL, "Input data must have 2^N samples, input size: ");   // the text of ALG/fourier/fftw.hpp:182-184 (sic)
     {
         const char* fg = getenv("B200SYNC_FORCE_GENERIC");     // tests / A-B runs: fft_size 2048 on the generic path too
         sd->generic = sd->fft_size != (uint32_t)kFft || (fg && fg[0] == '1');

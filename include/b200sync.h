@@ -51,7 +51,8 @@ int b200sync_host_unregister(const void* ptr);
 
 /* The reflected settings of the block, PM/syncword_detection.hpp:131-141, 361-372. */
 typedef struct b200sync_sd_config {
-    uint32_t fft_size;            /* default 2048 (only 2048 is implemented)            */
+    uint32_t fft_size;            /* default 2048; any power of two in [64, 8192] (2048: the hand-scheduled kernel;
+                                   * others: the generic radix-2 path, correlator_generic.cu)          */
     uint32_t samples_per_symbol;  /* default 4                                          */
     const float* rrc_taps;        /* rrc_taps                                           */
     uint32_t n_rrc_taps;

@@ -188,7 +188,7 @@ def test_settings_the_gpu_path_refuses(rx_params):
     import torch
     from gr4_packet_modem_b200.blocks import B200SyncError
 
-    with pytest.raises(B200SyncError, match="FFT size must be 2\\^N"):      # the reference throws too (fftw.hpp:182-184)
+    with pytest.raises(B200SyncError, match="Input data must have 2\\^N samples"):      # the reference throws too (fftw.hpp:182-184)
         _gpu(rx_params, fft_size=3000)
     with pytest.raises(B200SyncError, match="fft_size outside \\[64, 8192\\]"):
         _gpu(rx_params, fft_size=16384)
