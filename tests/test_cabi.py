@@ -78,3 +78,24 @@ def test_product_does_not_reference_oracle():
                 for line in txt.splitlines():
                     code = line.split("//")[0].split("#")[0] if not f.endswith(".py") else line.split("#")[0]
                     assert "pyoracle" not in code and "liboracle" not in code and "oracle/" not in code, (f, line)
+
+
+def test_plugin_packaging_compiles_against_the_stand_in_runtime(tmp_path):
+    """blocks/b200_plugin.cpp (GR_PLUGIN + addBlockType for the ten shells, GR/plugin.hpp:40-98 and
+    python/bindings/register_syncword_detection.cpp:5-10): its GR4 branch compiles against the stand-in runtime of
+    oracle/ref_stub — the same stand-in the reference's own block headers compile against — and registers every shell."""
+    import shutil
+    import subprocess
+
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    obj = tmp_path / "plugin.o"
+    subprocess.run([cxx, "-std=c++23", "-c", "-o", str(obj), "-I" + os.path.join(ROOT, "oracle", "ref_stub"),
+                    "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "gr4_packet_modem_b200", "blocks"),
+                    os.path.join(ROOT, "gr4_packet_modem_b200", "blocks", "b200_plugin.cpp")], check=True)
+    syms = subprocess.run(["nm", "-C", str(obj)], capture_output=True, text=True, check=True).stdout
+    for name in ("SyncwordDetectionB200", "SyncwordDetectionFilterB200", "SymbolFilterB200", "CoarseFrequencyCorrectionB200",
+                 "SyncwordWipeoffB200", "CostasLoopB200", "PfbArbResamplerB200T<float>", "PfbArbResamplerB200T<double>",
+                 "RotatorB200", "RxFrontEndB200"):
+        assert f"addBlockType<gr::packet_modem::{name}>" in syms, name
