@@ -306,9 +306,18 @@ int collect_records(b200sync_sd* sd, const float2* d_in, long long in_base, cons
     const unsigned n = sd->h_state->det_count;
     if (n == 0) return 0;
     if (n > sd->d_det_idx.cap) return fail(B200SYNC_ENOMEM, "internal detection list overflow");
-    out.resize(n);
-    CU(cudaMemcpyAsync(out.data(), sd->d_recs.p, sizeof(DetectionRecord) * n, cudaMemcpyDeviceToHost, st));
+    // through the context's pinned landing buffer: a D2H copy into pageable memory (the vector) runs at a fraction of
+    // the link rate and blocks in the driver (2 MB of records: 0.25 ms against 0.05)
+    if (sd->h_recs_pin_cap < n) {
+        if (sd->h_recs_pin) cudaFreeHost(sd->h_recs_pin);
+        sd->h_recs_pin = nullptr;
+        sd->h_recs_pin_cap = 0;
+        CU(cudaMallocHost(&sd->h_recs_pin, sizeof(DetectionRecord) * (static_cast<size_t>(n) + n / 4 + 64)));
+        sd->h_recs_pin_cap = static_cast<size_t>(n) + n / 4 + 64;
+    }
+    CU(cudaMemcpyAsync(sd->h_recs_pin, sd->d_recs.p, sizeof(DetectionRecord) * n, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    out.assign(sd->h_recs_pin, sd->h_recs_pin + n);
     return 0;
 }
 
