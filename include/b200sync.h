@@ -427,10 +427,11 @@ int b200sync_cl_info(const b200sync_cl* c, float* k1, float* k2);
  * has_syncword (a "syncword_phase" key) does set_phase(sw.syncword_phase) before its item (:102-107).
  * The stretches between such tags are independent and run one GPU thread each; the loop state at the end
  * of the span stays on the device for the next call.  in == out is allowed for device spans.
- * Cost model: the run time of a call is the recurrence of its LONGEST stretch on one thread (about 8 ns per symbol),
- * whatever the number of stretches — the throughput comes from many packets per span (2^28 symbols with one tag per
- * 24 832 samples: 1.9 ms).  A span without any tag is a single stretch: 2^20 untagged symbols take about 8 ms, so feed
- * untagged streams in spans of ordinary ring-chunk size, as GR4 does. */
+ * Cost model: the run time of a call is the recurrence of its LONGEST stretch on one thread (about 0.3 us per symbol:
+ * a chain of dependent sin/cos, multiply and loop-filter operations), whatever the number of stretches — the throughput
+ * comes from many packets per span (2^28 symbols, one tag per 6208 symbols: 1.9 ms).  A span without any tag is a
+ * single stretch: 65536 untagged symbols take about 20 ms.  In the receiver the loop only ever sees packets
+ * (PayloadMetadataInsert drops what lies between them, PM/packet_receiver.hpp:203-214), each opened by a tag. */
 int b200sync_cl_process(b200sync_cl* c, const float* in, size_t n, const b200sync_stream_tag* in_tags,
                         size_t n_in_tags, float* out);
 int b200sync_cl_process_device(b200sync_cl* c, const void* d_in, size_t n, const b200sync_stream_tag* in_tags,
