@@ -653,7 +653,23 @@ static void host_delay_line_stream(b200sync_sd* sd, const float* in, float* out,
         c64* cout = reinterpret_cast<c64*>(out);
         const size_t from_carry = std::min(D, j);
         std::memcpy(cout, sd->carry.data(), from_carry * sizeof(c64));
-        if (j > D) std::memcpy(cout + D, cin, (j - D) * sizeof(c64));
+        if (j > D) {
+            // large spans (a flowgraph edge with a 2^18 .. 2^20-item buffer): the copy is spread over a few threads,
+            // one memcpy would take as long as everything the GPU does for the span
+            const size_t cnt = j - D;
+            const size_t nth = std::min<size_t>({4, std::max(1u, std::thread::hardware_concurrency() / 2), cnt >> 17});
+            if (nth <= 1) {
+                std::memcpy(cout + D, cin, cnt * sizeof(c64));
+            } else {
+                std::vector<std::thread> pool;
+                for (size_t t = 1; t < nth; ++t) {
+                    const size_t i0 = cnt * t / nth, i1 = cnt * (t + 1) / nth;
+                    pool.emplace_back([=] { std::memcpy(cout + D + i0, cin + i0, (i1 - i0) * sizeof(c64)); });
+                }
+                std::memcpy(cout + D, cin, (cnt / nth) * sizeof(c64));
+                for (auto& th : pool) th.join();
+            }
+        }
     }
     if (j >= D) {
         std::memcpy(sd->carry.data(), cin + (j - D), D * sizeof(c64));

@@ -66,7 +66,19 @@ __device__ __forceinline__ float2* fft_r2(float2* src, float2* dst, const float2
             if (G::N / 4 >= G::NT || q < G::N / 4) {
                 const int k = q >> lr;
                 const float2* x = src + q + 3 * Rp * k;
-                const float2 x0 = x[0], x1 = x[Rp], x2 = x[2 * Rp], x3 = x[3 * Rp];
+                float2 x0, x1, x2, x3;
+                if (lr == 0) {   // last pass of an even log2 N: the four inputs are contiguous — two 128-bit loads
+                    const float4 lo4 = reinterpret_cast<const float4*>(x)[0], hi4 = reinterpret_cast<const float4*>(x)[1];
+                    x0 = make_float2(lo4.x, lo4.y);
+                    x1 = make_float2(lo4.z, lo4.w);
+                    x2 = make_float2(hi4.x, hi4.y);
+                    x3 = make_float2(hi4.z, hi4.w);
+                } else {
+                    x0 = x[0];
+                    x1 = x[Rp];
+                    x2 = x[2 * Rp];
+                    x3 = x[3 * Rp];
+                }
                 const float2 w = tw_s[m - 1 + k], w1 = tw_s[2 * m - 1 + k], w2 = tw_s[3 * m - 1 + k];
                 float2 a0, a1, b0, b1, y0, y1, y2, y3;
                 bfly(x0, x2, w, a0, a1);
@@ -90,7 +102,8 @@ __device__ __forceinline__ float2* fft_r2(float2* src, float2* dst, const float2
         for (int i = 0; i < G::BPT; ++i) {
             const int bf = tid + i * G::NT;   // = k
             float2 p, q;
-            bfly(src[2 * bf], src[2 * bf + 1], tw_s[m - 1 + bf], p, q);
+            const float4 uv = reinterpret_cast<const float4*>(src)[bf];   // (src[2 bf], src[2 bf + 1]) as one 128-bit load
+            bfly(make_float2(uv.x, uv.y), make_float2(uv.z, uv.w), tw_s[m - 1 + bf], p, q);
             dst[bf] = p;
             dst[bf + G::N / 2] = q;
         }
