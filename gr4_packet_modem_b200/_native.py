@@ -131,6 +131,7 @@ def lib():
     vp, sz, psz = C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)
     L.b200sync_host_register.argtypes = [vp, sz]
     L.b200sync_host_unregister.argtypes = [vp]
+    L.b200sync_sd_set_auto_register.argtypes = [vp, C.c_int]
     L.b200sync_sd_create.argtypes = [C.POINTER(SdConfig), C.POINTER(vp)]
     L.b200sync_sd_destroy.argtypes = [vp]
     L.b200sync_sd_start.argtypes = [vp]

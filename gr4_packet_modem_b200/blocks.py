@@ -118,6 +118,10 @@ class SyncwordDetection:
             pass
 
     # -- processBulk -------------------------------------------------------------------
+    def set_auto_register(self, on: bool = True) -> None:
+        """Page-lock the pages of every pageable input span handed to process_bulk (b200sync_sd_set_auto_register)."""
+        check(_native.lib().b200sync_sd_set_auto_register(self._h, int(bool(on))))
+
     def process_bulk(self, in_span, want_output: bool = True, max_tags: int = 4096):
         """One processBulk(inSpan, outSpan) call with host spans.
 

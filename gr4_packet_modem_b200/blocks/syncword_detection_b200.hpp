@@ -70,6 +70,9 @@ public:
     float power_threshold = 9.5;
     // extra, not in the reference: which CUDA device runs this block instance
     int device = 0;
+    // extra: page-lock the pages of the input ring as its spans arrive (b200sync_sd_set_auto_register): the spans then
+    // go straight to the copy engine (0.85 instead of 0.55 Gsps at 65536-item spans); the ring must outlive this block
+    bool register_input_ring = false;
 
     SyncwordDetectionB200() = default;
     SyncwordDetectionB200(const SyncwordDetectionB200&) = delete;
@@ -97,6 +100,7 @@ public:
         cfg.power_threshold = power_threshold;
         cfg.device = device;
         if (b200sync_sd_create(&cfg, &_ctx) != 0) throw gr::exception(b200sync_last_error());
+        if (register_input_ring) b200sync_sd_set_auto_register(_ctx, 1);
         _items_consumed = 0;
         in.min_samples = fft_size;  // :200-201
         out.min_samples = fft_size;

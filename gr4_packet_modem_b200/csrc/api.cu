@@ -103,7 +103,11 @@ struct b200sync_sd {
     unsigned long long r_abs_host = 0;  // host copy of the search position (PeakState::r_abs), streaming path
     // streaming fast path: pinned staging for pageable input spans, pinned landing buffer for the records
     unsigned char* h_in_stage = nullptr;
-    void* d_in_stage_view = nullptr;   // device-visible address of h_in_stage (zero-copy input of the streaming path)
+    void* d_in_stage_view = nullptr;
+    // auto-registration of pageable input spans (b200sync_sd_set_auto_register): disjoint page-aligned ranges this context
+    // has page-locked, sorted by address; ranges whose registration failed once are not tried again
+    int auto_register = -1;            // -1: take B200SYNC_AUTO_REGISTER from the environment at first use
+    std::vector<std::pair<uintptr_t, uintptr_t>> reg_ranges, reg_failed;   // device-visible address of h_in_stage (zero-copy input of the streaming path)
     DetectionRecord* h_recs_pin = nullptr;
     size_t h_recs_pin_cap = 0;
     DevBuf<unsigned int> d_done;       // CTA completion counter of the streaming refine launch (StreamWalk::done)
@@ -199,6 +203,43 @@ int run_chunk(b200sync_sd* sd, const float2* d_in, long long in_base, float* d_z
 }
 
 
+// Page-lock the pages of a pageable span (b200sync_sd_set_auto_register).  Spans of a ring overlap in every way, so only
+// the pages not yet covered by this context's ranges are registered; true when the whole span is page-locked afterwards.
+bool auto_register_span(b200sync_sd* sd, const void* p, size_t bytes) {
+    if (sd->auto_register < 0) {
+        const char* v = getenv("B200SYNC_AUTO_REGISTER");
+        sd->auto_register = (v && v[0] == '1') ? 1 : 0;
+    }
+    if (sd->auto_register != 1 || bytes == 0) return false;
+    const uintptr_t page = 4096;
+    uintptr_t lo = reinterpret_cast<uintptr_t>(p) & ~(page - 1);
+    const uintptr_t hi = (reinterpret_cast<uintptr_t>(p) + bytes + page - 1) & ~(page - 1);
+    for (const auto& f : sd->reg_failed)
+        if (lo < f.second && f.first < hi) return false;
+    auto& rr = sd->reg_ranges;
+    // register the gaps of [lo, hi) between the existing ranges
+    std::vector<std::pair<uintptr_t, uintptr_t>> gaps;
+    uintptr_t cur = lo;
+    for (const auto& r : rr) {
+        if (r.second <= cur) continue;
+        if (r.first >= hi) break;
+        if (r.first > cur) gaps.emplace_back(cur, r.first);
+        cur = std::max(cur, r.second);
+        if (cur >= hi) break;
+    }
+    if (cur < hi) gaps.emplace_back(cur, hi);
+    for (const auto& g : gaps) {
+        if (cudaHostRegister(reinterpret_cast<void*>(g.first), g.second - g.first, cudaHostRegisterPortable) != cudaSuccess) {
+            cudaGetLastError();
+            sd->reg_failed.emplace_back(g.first, g.second);
+            return false;
+        }
+        rr.emplace_back(g.first, g.second);
+        std::sort(rr.begin(), rr.end());
+    }
+    return true;
+}
+
 // H2D of a host span for the streaming path.  Pinned / registered memory goes straight to the copy engine; a
 // pageable span of ordinary ring-chunk size is staged through the context's own pinned buffer piece by piece (the
 // memcpy of piece i+1 overlaps the DMA of piece i) instead of through the driver's internal staging.
@@ -210,6 +251,7 @@ int stream_h2d(b200sync_sd* sd, float2* d_dst, const float2* h_src, size_t count
         if (cudaPointerGetAttributes(&at, h_src) == cudaSuccess) pinned = (at.type == cudaMemoryTypeHost);
         else cudaGetLastError();
     }
+    if (!pinned && bytes <= kStageBytes && auto_register_span(sd, h_src, bytes)) pinned = true;
     if (pinned || bytes > kStageBytes) {
         CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
         return 0;
@@ -503,6 +545,11 @@ int b200sync_host_register(const void* ptr, size_t bytes) {
     CU(cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
     return 0;
 }
+int b200sync_sd_set_auto_register(b200sync_sd* sd, int on) {
+    if (!sd) return fail(B200SYNC_EINVAL, "null context");
+    sd->auto_register = on ? 1 : 0;
+    return 0;
+}
 int b200sync_host_unregister(const void* ptr) {
     if (!ptr) return fail(B200SYNC_EINVAL, "null buffer");
     CU(cudaHostUnregister(const_cast<void*>(ptr)));
@@ -548,6 +595,8 @@ void b200sync_sd_destroy(b200sync_sd* sd) {
     }
     for (auto& e : sd->ev)
         if (e) cudaEventDestroy(e);
+    for (const auto& r : sd->reg_ranges)
+        if (cudaHostUnregister(reinterpret_cast<void*>(r.first)) != cudaSuccess) cudaGetLastError();
     if (sd->h_state) cudaFreeHost(sd->h_state);
     if (sd->h_in_stage) cudaFreeHost(sd->h_in_stage);
     if (sd->h_recs_pin) cudaFreeHost(sd->h_recs_pin);

@@ -19,13 +19,15 @@ x = DeviceStimulus(seed=1, esn0_db=20.0, cfo=0.005).generate(n, torch.device("cu
 L = _native.lib()
 tags = (SyncwordTag * 4096)()
 # ---- ring mode: the span lives in a fixed ring slot the producer has just written (GR4's CircularBuffer)
-for pinned in (False, True):
+for pinned in (False, "auto", True):
     chunk = 1 << 16
-    ring = torch.empty(chunk, dtype=torch.complex64, pin_memory=pinned).numpy()
-    out = torch.empty(chunk, dtype=torch.complex64, pin_memory=pinned).numpy()
+    ring = torch.empty(chunk, dtype=torch.complex64, pin_memory=(pinned is True)).numpy()
+    out = torch.empty(chunk, dtype=torch.complex64, pin_memory=(pinned is True)).numpy()
     out[:] = 0
     for rep in range(2):
         sd = SyncwordDetection(unit_energy_rrc(), SYNCWORD, BPSK, -4, 4, 768, 9.5)
+        if pinned == "auto":
+            sd.set_auto_register(True)    # pageable ring, page-locked by the context itself as its spans arrive
         nc, nt = C.c_size_t(0), C.c_size_t(0)
         pos = calls = ntags = 0
         busy = 0.0

@@ -634,8 +634,10 @@ def test_registered_host_ring_streams_like_a_pageable_one(rx_params):
     x, _ = packet_capture(12 * chunk, seed=17, esn0_db=10.0, cfo=0.003, payload_bytes=100)
     kw = dict(min_freq_bin=-4, max_freq_bin=4)
 
-    def drive(ring, out):
+    def drive(ring, out, auto=False):
         sd = _gpu(rx_params, **kw)
+        if auto:
+            sd.set_auto_register(True)
         pos, outs, tags = 0, [], []
         while x.size - pos >= chunk:
             ring[:] = x[pos:pos + chunk]
@@ -655,3 +657,12 @@ def test_registered_host_ring_streams_like_a_pageable_one(rx_params):
     finally:
         host_unregister(ring)
     assert plain[0] == reg[0] and np.array_equal(plain[1], reg[1]) and plain[2] == reg[2] and len(reg[2]) > 5
+    # b200sync_sd_set_auto_register: the context page-locks the ring itself, span by span (a view that starts inside a
+    # page and spans of changing length exercise the bookkeeping of overlapping ranges), and releases it at destroy
+    import torch
+
+    big = np.empty(chunk + 3000, np.complex64)
+    ring2 = big[777:777 + chunk]
+    auto = drive(ring2, None, auto=True)
+    assert auto[0] == plain[0] and np.array_equal(auto[1], plain[1]) and auto[2] == plain[2]
+    assert not torch.from_numpy(big).is_pinned()   # released again when the context went away
