@@ -63,6 +63,7 @@ struct FeParams {
     double theta;            // effective rotation per sample
     float amp_eps;           // |incr| - 1
     float2 wr[kFeR];         // (cos, sin)(r * theta), r = 0..R-1: rotation of output r relative to output 0
+    float neg_zero;          // -0.0f, opaque to the compiler (fe_mac)
 };
 
 // WIDE = false: TRate = float, units 2^-24, 64-bit products.  WIDE = true: TRate = double, units 2^-52, 128-bit.
@@ -128,10 +129,15 @@ __device__ __forceinline__ void rot_factors(const FeParams& P, long long nt, flo
 // FMA (b200sync_fe_config::fp_contract): every multiply-accumulate of the filter as ONE fused operation (FFMA2, a third of
 // the issue slots and half the FP32 pipe passes) instead of std::inner_product's separately rounded multiply and add —
 // not bit-identical to the reference any more (one rounding per tap instead of two), opt-in.
+// Bit-exact form: the product must be rounded on its own before the add.  A packed multiply feeding a packed add is
+// contracted into FFMA2 by ptxas (and so is fma(h, t, -0.0f) with a LITERAL -0, which it first folds into a multiply);
+// with the -0 in a register whose value the compiler cannot see (nz, a kernel parameter), the FFMA2 stays a rounded
+// product — fma(a, b, -0) == a * b bit for bit, signed zeros included — and the add stays an add: 2 issue slots per
+// complex multiply-accumulate instead of the 3 of two scalar multiplies + one packed add.
 template <bool FMA>
-__device__ __forceinline__ float2 fe_mac(float2 acc, float2 h, float t) {
+__device__ __forceinline__ float2 fe_mac(float2 acc, float2 h, float t, float nz) {
     if constexpr (FMA) return __ffma2_rn(h, make_float2(t, t), acc);
-    else return __fadd2_rn(acc, make_float2(__fmul_rn(h.x, t), __fmul_rn(h.y, t)));
+    else return __fadd2_rn(acc, __ffma2_rn(h, make_float2(t, t), make_float2(nz, nz)));
 }
 
 template <bool WIDE, bool FMA>
@@ -246,8 +252,8 @@ frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (t
                     // each half rounded like the multiply-then-add of std::inner_product.  (A packed
                     // multiply as well would be 2 slots, but ptxas 12.9 contracts mul.rn.f32x2 +
                     // add.rn.f32x2 into FFMA2 even with --fmad=false, which changes the rounding.)
-                    af[r] = fe_mac<FMA>(af[r], h, t.x);
-                    ad[r] = fe_mac<FMA>(ad[r], h, t.y);
+                    af[r] = fe_mac<FMA>(af[r], h, t.x, P.neg_zero);
+                    ad[r] = fe_mac<FMA>(ad[r], h, t.y, P.neg_zero);
                 }
                 // x[c0-1-(k+kk+1)] replaces the element leaving the window
                 W[(-(kk + 1)) & (kFeR - 1)] = xin[fe_skew(b - (k + kk + 1))];
@@ -258,12 +264,12 @@ frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (t
 #pragma unroll
             for (int r = 0; r < kFeR; ++r) {
                 const float2 h = xin[fe_skew(b + r - k)];
-                af[r] = fe_mac<FMA>(af[r], h, t.x);
-                ad[r] = fe_mac<FMA>(ad[r], h, t.y);
+                af[r] = fe_mac<FMA>(af[r], h, t.x, P.neg_zero);
+                ad[r] = fe_mac<FMA>(ad[r], h, t.y, P.neg_zero);
             }
         }
 #pragma unroll
-        for (int r = 0; r < kFeR; ++r) y[r] = fe_mac<FMA>(af[r], ad[r], acc[r]);
+        for (int r = 0; r < kFeR; ++r) y[r] = fe_mac<FMA>(af[r], ad[r], acc[r], P.neg_zero);
     } else {
 #pragma unroll
         for (int r = 0; r < kFeR; ++r) {
@@ -277,10 +283,10 @@ frontend_kernel(const FeParams P, const float2* __restrict__ td_g /*[fs][arm] (t
                 const long long a = cr - 1 - k;
                 const float2 h = staged ? xin[fe_skew((int)(a - lo))] : sample(a);
                 const float2 t = tp[k];
-                af = fe_mac<FMA>(af, h, t.x);
-                ad = fe_mac<FMA>(ad, h, t.y);
+                af = fe_mac<FMA>(af, h, t.x, P.neg_zero);
+                ad = fe_mac<FMA>(ad, h, t.y, P.neg_zero);
             }
-            y[r] = fe_mac<FMA>(af, ad, acc[r]);
+            y[r] = fe_mac<FMA>(af, ad, acc[r], P.neg_zero);
         }
     }
     float2* dst = P.out + (nt - P.out_base);
@@ -501,6 +507,7 @@ int fe_run(b200sync_fe* fe, const float2* d_in, size_t n_in, float2* d_out, size
         P.do_rotate = fe->do_rotate;
         P.theta = fe->theta;
         P.amp_eps = fe->amp_eps;
+        P.neg_zero = -0.0f;
         for (int r = 0; r < kFeR; ++r)
             P.wr[r] = make_float2(static_cast<float>(std::cos(r * fe->theta)), static_cast<float>(std::sin(r * fe->theta)));
         const size_t smem = fe->do_resample

@@ -315,7 +315,8 @@ symbol_filter_fast_kernel(const SfParams P, const float* __restrict__ taps_g /*[
 #pragma unroll
             for (int r = 0; r < kSfR; ++r) {
                 const int k = r * SPS - j;
-                if (k >= 0 && k < ARM)  // two scalar multiplies + one packed FP32x2 add (see frontend.cu on FFMA2)
+                if (k >= 0 && k < ARM)  // two scalar multiplies + one packed FP32x2 add (see frontend.cu on FFMA2; the opaque -0 form
+                                        // of fe_mac measured no faster here: this kernel waits on its loads, not on issue slots)
                     acc[r] = __fadd2_rn(acc[r], make_float2(__fmul_rn(t[k], h.x), __fmul_rn(t[k], h.y)));
             }
         }
