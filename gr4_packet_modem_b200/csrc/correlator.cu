@@ -244,6 +244,20 @@ correlate_kernel(const float2* __restrict__ in, long long in_base, float* __rest
 #endif
         }
         }
+#ifdef B200_BULK_PREFETCH   // measured SLOWER as well (K = 1: 4.68 vs 4.47 ms, K = 9: 18.7 vs 18.3): off by default
+        if constexpr (!SPLIT && !BATCH) {
+            // this group's NEXT block on its way into L2 while the current one is transformed: ONE bulk prefetch
+            // (cp.async.bulk.prefetch.L2, the TMA engine walks the 16 KiB) issued by one thread of the group — with
+            // few hypotheses a block lasts about one DRAM latency and only ~2.5 of the 6 groups of an SM have
+            // loads in flight at any time.  (Sixteen per-line prefetch instructions per 16 lanes cost registers
+            // and were slower: B200_L2_PREFETCH below.)
+            if (tid == 0 && blk + blk_step < nb) {
+                const float2* nsrc = in + ((b0 + blk + blk_step) * (long long)S - in_base);
+                if ((reinterpret_cast<uintptr_t>(nsrc) & 15) == 0)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nsrc), "r"((int)(kFft * sizeof(float2))) : "memory");
+            }
+        }
+#endif
 #ifdef B200_L2_PREFETCH   // measured SLOWER (K = 1: 4.82 vs 4.47 ms at 2^30; K = 9: 18.8 vs 18.3): register pressure, off by default
         if (!split && (tid & 15) == 0 && blk + blk_step < nb) {
             // this group's NEXT block on its way into L2 while the current one is transformed (one request per
