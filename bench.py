@@ -142,7 +142,7 @@ def binding_roof(K: int) -> tuple:
                             "matters (SURVEY §8d); see profiles/r2_ncu_summary_k1.md for the measured split")
     return "fp32_pipe", (f"K={K}: {flop_per_sample(K):.0f} nominal flop/sample, far above the ridge — bound by the FP32 "
                          "pipe (packed FFMA2/FADD2 occupy it two passes each; ncu: math-pipe-throttle is the top "
-                         "stall, LSU wavefronts 70 %, DRAM 9 %), not by HBM")
+                         "stall, LSU wavefronts 71 %, DRAM 15 %), not by HBM")
 
 
 def measured_fp32_peak():
@@ -452,8 +452,9 @@ def measure_chain(args, log2n: int, steps: int, warmup: int, e2e: bool, cpu: boo
                                          "instead of the reference's two, relative L2 difference ~1e-7); `value` above is the "
                                          "bit-exact default, value_with_it = the same step with this front end instead"},
         "roofline": hbm_roofline("frontend_kernel", 16.0 * n_out, fe_ms, peaks,
-                                 "16 B/sample (8 in + 8 out); 2 x 40 taps x 2 x (mul, add) = 320 separately rounded "
-                                 "FP32 instructions per output (bit-exact std::inner_product order): FP32-issue bound",
+                                 "16 B/sample (8 in + 8 out); 2 x 40 taps x (rounded packed product, packed add) = 160 "
+                                 "FP32x2 instructions per output (bit-exact std::inner_product order) + ~150 of timing, "
+                                 "rotator and staging: FP32 pipe 52 % / issue 70 %",
                                  bound="fp32_issue"),
         "roofline_syncword_detection": hbm_roofline("correlate_kernel + peak stage + refine", 16.0 * consumed, sd_ms,
                                                     peaks, binding_roof(K)[1], bound=binding_roof(K)[0]),
