@@ -71,8 +71,10 @@ public:
     // extra, not in the reference: which CUDA device runs this block instance
     int device = 0;
     // extra: page-lock the pages of the input ring as its spans arrive (b200sync_sd_set_auto_register): the spans then
-    // go straight to the copy engine (0.85 instead of 0.55 Gsps at 65536-item spans); the ring must outlive this block
-    bool register_input_ring = false;
+    // go straight to the copy engine (0.8 instead of 0.55 Gsps at 65536-item spans).  On by default in the shell: a GR4
+    // port's CircularBuffer is shared-owned by its readers (GR/CircularBuffer.hpp), so the ring outlives this block, which
+    // releases the pages in its destructor; a failed registration (RLIMIT_MEMLOCK) falls back to the staged copy
+    bool register_input_ring = true;
 
     SyncwordDetectionB200() = default;
     SyncwordDetectionB200(const SyncwordDetectionB200&) = delete;

@@ -203,8 +203,8 @@ int run_chunk(b200sync_sd* sd, const float2* d_in, long long in_base, float* d_z
 }
 
 
-// Page-lock the pages of a pageable span (b200sync_sd_set_auto_register).  Spans of a ring overlap in every way, so only
-// the pages not yet covered by this context's ranges are registered; true when the whole span is page-locked afterwards.
+// Page-lock the pages of a pageable span (b200sync_sd_set_auto_register); true when the whole span lies inside ONE
+// registration of this context afterwards.
 bool auto_register_span(b200sync_sd* sd, const void* p, size_t bytes) {
     if (sd->auto_register < 0) {
         const char* v = getenv("B200SYNC_AUTO_REGISTER");
@@ -217,26 +217,29 @@ bool auto_register_span(b200sync_sd* sd, const void* p, size_t bytes) {
     for (const auto& f : sd->reg_failed)
         if (lo < f.second && f.first < hi) return false;
     auto& rr = sd->reg_ranges;
-    // register the gaps of [lo, hi) between the existing ranges
-    std::vector<std::pair<uintptr_t, uintptr_t>> gaps;
-    uintptr_t cur = lo;
+    // One registration must cover the whole span (a copy may not straddle two registrations), so every range of this
+    // context that overlaps or touches [lo, hi) is released and the union registered as ONE range: a ring converges to
+    // a single registration after one pass, a capture walked front to back to one that grows with it.
+    uintptr_t ulo = lo, uhi = hi;
+    std::vector<std::pair<uintptr_t, uintptr_t>> keep, merge;
     for (const auto& r : rr) {
-        if (r.second <= cur) continue;
-        if (r.first >= hi) break;
-        if (r.first > cur) gaps.emplace_back(cur, r.first);
-        cur = std::max(cur, r.second);
-        if (cur >= hi) break;
+        if (r.second < lo || r.first > hi) keep.push_back(r);
+        else merge.push_back(r);
     }
-    if (cur < hi) gaps.emplace_back(cur, hi);
-    for (const auto& g : gaps) {
-        if (cudaHostRegister(reinterpret_cast<void*>(g.first), g.second - g.first, cudaHostRegisterPortable) != cudaSuccess) {
-            cudaGetLastError();
-            sd->reg_failed.emplace_back(g.first, g.second);
-            return false;
-        }
-        rr.emplace_back(g.first, g.second);
-        std::sort(rr.begin(), rr.end());
+    if (merge.size() == 1 && merge[0].first <= lo && merge[0].second >= hi) return true;   // already inside one range
+    for (const auto& r : merge) {
+        ulo = std::min(ulo, r.first);
+        uhi = std::max(uhi, r.second);
+        if (cudaHostUnregister(reinterpret_cast<void*>(r.first)) != cudaSuccess) cudaGetLastError();
     }
+    rr = keep;
+    if (cudaHostRegister(reinterpret_cast<void*>(ulo), uhi - ulo, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        sd->reg_failed.emplace_back(ulo, uhi);
+        return false;
+    }
+    rr.emplace_back(ulo, uhi);
+    std::sort(rr.begin(), rr.end());
     return true;
 }
 
@@ -247,11 +250,19 @@ int stream_h2d(b200sync_sd* sd, float2* d_dst, const float2* h_src, size_t count
     const size_t bytes = count * sizeof(float2);
     bool pinned = false;
     if (bytes <= kStageBytes) {
-        cudaPointerAttributes at{};
-        if (cudaPointerGetAttributes(&at, h_src) == cudaSuccess) pinned = (at.type == cudaMemoryTypeHost);
-        else cudaGetLastError();
+        if (auto_register_span(sd, h_src, bytes)) {
+            pinned = true;   // inside ONE registration of this context
+        } else {
+            cudaPointerAttributes at{};
+            if (cudaPointerGetAttributes(&at, h_src) == cudaSuccess) pinned = (at.type == cudaMemoryTypeHost);
+            else cudaGetLastError();
+            // the first byte may lie in a range this context registered while the span runs past its end (a later
+            // registration failed): such a span takes the staged copy
+            const uintptr_t a = reinterpret_cast<uintptr_t>(h_src), b = a + bytes;
+            for (const auto& r : sd->reg_ranges)
+                if (a < r.second && r.first < b && !(r.first <= a && b <= r.second)) pinned = false;
+        }
     }
-    if (!pinned && bytes <= kStageBytes && auto_register_span(sd, h_src, bytes)) pinned = true;
     if (pinned || bytes > kStageBytes) {
         CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
         return 0;

@@ -666,3 +666,12 @@ def test_registered_host_ring_streams_like_a_pageable_one(rx_params):
     auto = drive(ring2, None, auto=True)
     assert auto[0] == plain[0] and np.array_equal(auto[1], plain[1]) and auto[2] == plain[2]
     assert not torch.from_numpy(big).is_pinned()   # released again when the context went away
+    # a capture walked front to back (every span starts inside the previous registration and runs past its end: the
+    # registration has to grow, a copy may not straddle two of them)
+    sd = _gpu(rx_params, **kw)
+    sd.set_auto_register(True)
+    xs = x.copy()
+    c_w, out_w, tags_w = sd.run(xs, chunk=50000, want_output=True)
+    c_p, out_p, tags_p = _gpu(rx_params, **kw).run(x, chunk=50000, want_output=True)
+    assert c_w == c_p and np.array_equal(out_w, out_p) and [t[1] for t in tags_w] == [t[1] for t in tags_p]
+    del sd
