@@ -1327,18 +1327,26 @@ int b200sync_sd_detect_channels_device(b200sync_sd* sd, const void* d_in, size_t
     CU(cudaMemcpyAsync(sd->h_chan_state, sd->d_chan_state.p, sizeof(PeakState) * n_channels, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     // exact-size record copies, then the reference's "tag already published" filter per channel
-    std::vector<DetectionRecord>& h = sd->h_recs;
     size_t total = 0;
     for (size_t c = 0; c < n_channels; ++c) {
         if (sd->h_chan_state[c].det_count > cap) return fail(B200SYNC_ENOMEM, "internal detection list overflow");
         total += sd->h_chan_state[c].det_count;
     }
-    h.resize(total);
+    // into the context's pinned landing buffer: one copy per channel into pageable memory blocks in the driver
+    // (64 channels: 2 ms of a 24 ms step)
+    if (sd->h_recs_pin_cap < total) {
+        if (sd->h_recs_pin) cudaFreeHost(sd->h_recs_pin);
+        sd->h_recs_pin = nullptr;
+        sd->h_recs_pin_cap = 0;
+        CU(cudaMallocHost(&sd->h_recs_pin, sizeof(DetectionRecord) * (total + total / 4 + 64)));
+        sd->h_recs_pin_cap = total + total / 4 + 64;
+    }
+    const DetectionRecord* h = sd->h_recs_pin;
     size_t off = 0;
     for (size_t c = 0; c < n_channels; ++c) {
         const size_t cnt = sd->h_chan_state[c].det_count;
         if (cnt)
-            CU(cudaMemcpyAsync(h.data() + off, sd->d_chan_recs.p + c * cap, sizeof(DetectionRecord) * cnt,
+            CU(cudaMemcpyAsync(sd->h_recs_pin + off, sd->d_chan_recs.p + c * cap, sizeof(DetectionRecord) * cnt,
                                cudaMemcpyDeviceToHost, st));
         off += cnt;
     }
