@@ -844,7 +844,7 @@ def main():
         table = sd.shard_phase1(x.data_ptr(), seg0, seg_n, fb, nbk, total_blocks, stream)
         # T+1 small integers per rank, exchanged as host bytes: the only exchange of the path
         j = entry_offset(table)
-        recs, _ = sd.shard_phase2(j, max_recs)
+        recs, _ = sd.shard_phase2(j, max_recs, copy=False)
         return nbk * S, len(recs)
 
     def barrier():

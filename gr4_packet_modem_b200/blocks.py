@@ -295,13 +295,14 @@ class SyncwordDetection:
                                               total_blocks, table.ctypes.data, table.size))
         return table
 
-    def shard_phase2(self, entry_offset: int, max_recs: int):
+    def shard_phase2(self, entry_offset: int, max_recs: int, copy: bool = True):
+        """copy=False: records and tags are views into the context's buffers, valid until the next call (detect_device)."""
         L = _native.lib()
         recs = self._rec_buffer(max(max_recs, 1))
         nr = C.c_size_t(0)
         check(L.b200sync_sd_shard_phase2(self._h, entry_offset, recs.ctypes.data, max_recs, C.byref(nr)))
-        r = _copy_records(recs, nr.value)
-        return r, self.records_to_tags(r)
+        r = _copy_records(recs, nr.value) if copy else recs[:nr.value]
+        return r, self.records_to_tags(r, reuse=not copy)
 
     def last_timings(self) -> dict:
         """Device milliseconds of the stages of the last offline call (CUDA events)."""
