@@ -71,10 +71,11 @@ public:
     // extra, not in the reference: which CUDA device runs this block instance
     int device = 0;
     // extra: page-lock the pages of the input ring as its spans arrive (b200sync_sd_set_auto_register): the spans then
-    // go straight to the copy engine (0.8 instead of 0.55 Gsps at 65536-item spans).  On by default in the shell: a GR4
-    // port's CircularBuffer is shared-owned by its readers (GR/CircularBuffer.hpp), so the ring outlives this block, which
-    // releases the pages in its destructor; a failed registration (RLIMIT_MEMLOCK) falls back to the staged copy
-    bool register_input_ring = true;
+    // go straight to the copy engine (0.8 instead of 0.55 Gsps at 65536-item spans).  OPT-IN: it is only safe when the
+    // memory behind the spans outlives this block — true for a GR4 port's CircularBuffer (shared-owned by its readers,
+    // GR/CircularBuffer.hpp), NOT for a caller that hands in temporary buffers: a freed and re-allocated buffer would
+    // still be mapped to its old pages for the copy engine.  A failed registration falls back to the staged copy.
+    bool register_input_ring = false;
 
     SyncwordDetectionB200() = default;
     SyncwordDetectionB200(const SyncwordDetectionB200&) = delete;

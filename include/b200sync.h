@@ -46,8 +46,9 @@ int b200sync_host_register(const void* ptr, size_t bytes);
 int b200sync_host_unregister(const void* ptr);
 /* The same without knowing the rings: when on (or with B200SYNC_AUTO_REGISTER=1 in the environment), a SyncwordDetection
  * context page-locks the pages of every pageable input span it is handed by b200sync_sd_process — a flowgraph's ring is
- * covered after one pass over it — and releases them in b200sync_sd_destroy.  Off by default: the buffers must outlive the
- * context (GR4's do: an edge's buffer lives as long as the graph), and page-locked memory counts against RLIMIT_MEMLOCK. */
+ * covered after one pass over it — and releases them in b200sync_sd_destroy.  Off by default: the buffers MUST outlive the
+ * context (GR4's do: an edge's buffer lives as long as the graph; a buffer freed and re-allocated at the same address would
+ * still be mapped to its old pages for the copy engine), and page-locked memory counts against RLIMIT_MEMLOCK. */
 int b200sync_sd_set_auto_register(struct b200sync_sd* sd, int on);
 
 /* ------------------------------------------------------------------------------
