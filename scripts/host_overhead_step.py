@@ -1,3 +1,5 @@
+"""Development aid: where the host time of one bulk step goes — the C call (kernels + record copy), the copy of the
+records into a fresh array, output_tag() on them.  Usage: python scripts/host_overhead_step.py   (one B200, 2^30 samples)"""
 import sys, time, ctypes as C
 sys.path.insert(0, ".")
 import torch, numpy as np
