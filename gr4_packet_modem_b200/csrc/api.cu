@@ -263,9 +263,15 @@ int stream_h2d(b200sync_sd* sd, float2* d_dst, const float2* h_src, size_t count
                 if (a < r.second && r.first < b && !(r.first <= a && b <= r.second)) pinned = false;
         }
     }
-    if (pinned || bytes > kStageBytes) {
+    if (bytes > kStageBytes) {
         CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
         return 0;
+    }
+    if (pinned) {
+        // (a span that runs from page-locked into pageable memory, or across two registrations — e.g. a ring whose
+        //  mirror mapping was registered separately — may be refused: such a span takes the staged copy below)
+        if (cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st) == cudaSuccess) return 0;
+        cudaGetLastError();
     }
     if (!sd->h_in_stage) CU(cudaMallocHost(&sd->h_in_stage, kStageBytes));
     const unsigned char* src = reinterpret_cast<const unsigned char*>(h_src);
