@@ -447,10 +447,13 @@ refine_kernel(const float2* __restrict__ in, long long in_base, const float* __r
     }
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
     float2* xb = tw_s + kTwTotal;
-    float2* b1out = xb + kXchgFloat2;                      // [kRefineChunk][256]
-    float2* b2out = b1out + kRefineChunk * 256;            // [kRefineChunk][16]
-    float2* corr_s = b2out + kRefineChunk * 16;            // [kMaxHyp + 1]
-    float* xpow = reinterpret_cast<float*>(corr_s + kMaxHyp + 1);  // [2048]
+    // (sized by the launch for THIS K — refine_smem_float2(K) — not for the largest one: with few hypotheses a fourth
+    //  CTA fits on the SM, and the stage is latency-bound, a CTA per detection)
+    const int chunk_alloc = K < kRefineChunk ? K : kRefineChunk;
+    float2* b1out = xb + kXchgFloat2;                      // [chunk_alloc][256]
+    float2* b2out = b1out + chunk_alloc * 256;             // [chunk_alloc][16]
+    float2* corr_s = b2out + chunk_alloc * 16;             // [K + 1]
+    float* xpow = reinterpret_cast<float*>(corr_s + K + 1 + ((K + 1) & 1));  // [2048] (16-byte aligned)
     __shared__ float noise_s;
     __shared__ unsigned int n_walk;
     unsigned int n;
@@ -729,10 +732,13 @@ cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_
                                      d_det_idx, d_det_count, det_cap, d_recs, num_sms, st, nch, in_chan_stride,
                                      z_chan_stride, det_chan_stride);
     }
-    const size_t smem_base = sizeof(float2) * (size_t)(kTwTotal + kXchgFloat2 + kRefineChunk * (256 + 16) + kMaxHyp + 1) +
-                             sizeof(float) * kFft;
-    // the attribute (and the occupancy figure) is for the largest streaming walk: 2^19-sample bitmaps + the list
-    const size_t smem = smem_base + 2 * sizeof(uint32_t) * ((1u << 19) / 32 + 1) + sizeof(unsigned long long) * 1024;
+    auto refine_smem = [](int k) {   // the kernel's carve-up: tables, exchange buffer, chunk outputs, K + 1 correlations, |X|^2
+        const int chunk = k < kRefineChunk ? k : kRefineChunk;
+        return sizeof(float2) * (size_t)(kTwTotal + kXchgFloat2 + chunk * (256 + 16) + k + 1 + ((k + 1) & 1)) + sizeof(float) * kFft;
+    };
+    const size_t smem_base = refine_smem(K);
+    // the attribute is for the largest K and the largest streaming walk: 2^19-sample bitmaps + the list
+    const size_t smem = refine_smem(kMaxHyp) + 2 * sizeof(uint32_t) * ((1u << 19) / 32 + 1) + sizeof(unsigned long long) * 1024;
     size_t smem_launch = smem_base;
     StreamWalk w{};
     if (walk != nullptr) {
@@ -750,13 +756,15 @@ cudaError_t launch_refine(const float2* d_in, long long in_base, const float* d_
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    // exactly one resident wave (shared memory allows 3 CTAs per SM): a grid of 4 per SM ran a second,
-    // one-third-full wave that took as long as the first
-    static int per_sm = 0;
+    // exactly one resident wave (shared memory allows 3 CTAs per SM at K >= 7, 4 below): a grid of 4 per SM where 3 fit
+    // ran a second, one-third-full wave that took as long as the first
+    static int per_sm_k[kMaxHyp + 1] = {};   // resident CTAs per SM for K hypotheses (benign race: same value)
+    int per_sm = per_sm_k[K];
     if (per_sm == 0) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, refine_kernel<false>, kRefineThreads, smem_base);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
+        per_sm_k[K] = per_sm;
     }
     int grid = num_sms * per_sm;
     if (nch > 1) grid = (grid + nch - 1) / nch;  // the channels share the one resident wave
